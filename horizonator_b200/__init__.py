@@ -1,0 +1,294 @@
+"""horizonator_b200 -- B200-native (sm_100a CUDA) renderer behind dkogan/horizonator's interfaces.
+
+The product is the C-ABI shared library ``horizonator_b200/lib/libhorizonator.so`` (headers in
+``include/``).  This module is the host-side mirror of the reference's Python binding
+(/root/reference/horizonator-pywrap.c): the same type name, constructor arguments, ``render()``
+arguments, return values and error behaviour, implemented with ctypes on top of the C ABI.
+
+There is no CPU fallback: importing works anywhere the library file exists, but constructing a
+``horizonator`` without a CUDA device raises ``RuntimeError``, and a missing library raises
+``ImportError`` at import time.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIBRARY_PATH = os.path.join(_HERE, "lib", "libhorizonator.so")
+
+HORIZONATOR_ZNEAR_DEFAULT = 100.0   # include/horizonator.h
+HORIZONATOR_ZFAR_DEFAULT = 40000.0
+
+
+class dem_context_t(C.Structure):
+    """include/dem.h: horizonator_dem_context_t (352 bytes)."""
+    _fields_ = [
+        ("dems", (C.c_void_p * 4) * 4),
+        ("mmap_sizes", (C.c_size_t * 4) * 4),
+        ("mmap_fd", (C.c_int * 4) * 4),
+        ("origin_dem_lon_lat", C.c_int * 2),
+        ("origin_dem_cellij", C.c_int * 2),
+        ("Ndems_ij", C.c_int * 2),
+        ("radius_cells", C.c_int),
+        ("cells_per_deg", C.c_int),
+    ]
+
+
+class _offscreen_t(C.Structure):
+    _fields_ = [
+        ("inited", C.c_bool),
+        ("frameBufID", C.c_uint32),
+        ("renderBufID", C.c_uint32),
+        ("depthBufID", C.c_uint32),
+        ("width", C.c_int),
+        ("height", C.c_int),
+    ]
+
+
+class context_t(C.Structure):
+    """include/horizonator.h: horizonator_context_t (472 bytes)."""
+    _fields_ = [
+        ("Ntriangles", C.c_int),
+        ("render_texture", C.c_bool),
+        ("use_glut", C.c_bool),
+        ("glut_window", C.c_int),
+        ("uniforms", C.c_int32 * 17),
+        ("program", C.c_uint32),
+        ("viewer_lat", C.c_float),
+        ("viewer_lon", C.c_float),
+        ("dems", dem_context_t),
+        ("offscreen", _offscreen_t),
+    ]
+
+
+class view_t(C.Structure):
+    """include/horizonator-batch.h: horizonator_view_t."""
+    _fields_ = [
+        ("lat", C.c_float), ("lon", C.c_float),
+        ("viewer_z", C.c_float),
+        ("az_deg0", C.c_float), ("az_deg1", C.c_float),
+    ]
+
+
+def _declare(lib):
+    P = C.POINTER
+    ctx = P(context_t)
+    f, d, i, b, vp, cp = C.c_float, C.c_double, C.c_int, C.c_bool, C.c_void_p, C.c_char_p
+    sigs = {
+        "horizonator_init": (b, [ctx, f, f, P(f), i, i, i, f, b, b, b, cp, cp, cp, cp, b]),
+        "horizonator_deinit": (None, [ctx]),
+        "horizonator_resized": (b, [ctx, i, i]),
+        "horizonator_pan_zoom": (b, [ctx, f, f]),
+        "horizonator_move": (b, [ctx, P(f), f, f]),
+        "horizonator_set_zextents": (b, [ctx, f, f, f, f]),
+        "horizonator_redraw": (b, [ctx]),
+        "horizonator_pick": (b, [ctx, P(f), P(f), i, i]),
+        "horizonator_render_offscreen": (b, [ctx, vp, vp]),
+        "horizonator_x_from_az": (b, [P(d), P(d), d, d, d, i]),
+        "horizonator_project": (b, [P(d), P(d), P(d), d, d, d, d, d, d, d, d, d, i, i]),
+        "horizonator_unproject": (b, [P(f), P(f), i, i, d, d, d, d, d, d, d, i, i]),
+        "horizonator_dem_init": (b, [P(dem_context_t), f, f, i, f, cp, b]),
+        "horizonator_dem_deinit": (None, [P(dem_context_t)]),
+        "horizonator_dem_sample": (C.c_int16, [P(dem_context_t), i, i]),
+        "horizonator_dem_bounds_latlon_deg": (None, [P(dem_context_t), P(f), P(f), P(f), P(f)]),
+        "horizonator_render_batch_device": (b, [ctx, i, P(view_t), vp, vp, vp]),
+        "horizonator_render_batch": (b, [ctx, i, P(view_t), vp, vp]),
+        "horizonator_render_wedge_device": (b, [ctx, i, i, vp, vp, vp]),
+        "horizonator_download_mosaic": (b, [ctx, vp]),
+        "horizonator_time_mosaic": (b, [ctx, i, P(f)]),
+        "horizonator_last_render_stats": (b, [ctx, P(C.c_uint * 4)]),
+    }
+    for name, (res, args) in sigs.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    return lib
+
+
+#: every symbol include/*.h declares (tests check that the library exports each of them)
+EXPORTED_SYMBOLS = (
+    "horizonator_init", "horizonator_deinit", "horizonator_resized", "horizonator_pan_zoom",
+    "horizonator_move", "horizonator_set_zextents", "horizonator_redraw", "horizonator_pick",
+    "horizonator_render_offscreen", "horizonator_x_from_az", "horizonator_project",
+    "horizonator_unproject",
+    "horizonator_dem_init", "horizonator_dem_deinit", "horizonator_dem_sample",
+    "horizonator_dem_bounds_latlon_deg",
+    "horizonator_render_batch_device", "horizonator_render_batch", "horizonator_render_wedge_device",
+    "horizonator_download_mosaic", "horizonator_time_mosaic", "horizonator_last_render_stats",
+)
+
+if not os.path.exists(LIBRARY_PATH):
+    raise ImportError(
+        "%s is missing: build it with `python -m horizonator_b200.build` (needs nvcc). "
+        "horizonator_b200 has no CPU fallback." % LIBRARY_PATH)
+
+lib = _declare(C.CDLL(LIBRARY_PATH))
+
+
+def _enc(s):
+    return None if s is None else os.fsencode(s)
+
+
+class horizonator:
+    """SRTM terrain renderer: mirror of the reference's Python type ``horizonator.horizonator``.
+
+    Arguments, defaults and semantics as /root/reference/horizonator-pywrap.c:49-125 and
+    horizonator.docstring.  The constructor loads the DEMs around (lat, lon) and is relatively
+    slow; ``render()`` is fast.
+    """
+
+    def __init__(self, lat, lon, width, height,
+                 render_texture=False, SRTM1=False,
+                 dir_dems=None, dir_tiles=None, tiles_name=None, tiles_url_fmt=None,
+                 allow_downloads=True, render_radius_cells=-1, render_radius_m=-1.):
+        self._ctx = context_t()
+        if render_radius_cells < 0 and render_radius_m < 0:
+            render_radius_cells = 1000                      # pywrap.c:65,98-99
+        elif render_radius_cells > 0 and render_radius_m > 0:
+            raise RuntimeError("both render_radius_cells,render_radius_m cannot be >0")
+        if width < 0 or height < 0:
+            raise OverflowError("width, height must be unsigned")   # format "II"
+        if not lib.horizonator_init(C.byref(self._ctx), lat, lon, None,
+                                    int(width), int(height),
+                                    int(render_radius_cells), float(render_radius_m),
+                                    True, bool(render_texture), bool(SRTM1),
+                                    _enc(dir_dems), _enc(dir_tiles), _enc(tiles_name), _enc(tiles_url_fmt),
+                                    bool(allow_downloads)):
+            raise RuntimeError("horizonator_init() failed")
+
+    def __del__(self):
+        ctx = getattr(self, "_ctx", None)
+        if ctx is not None and lib is not None:
+            lib.horizonator_deinit(C.byref(ctx))
+
+    def close(self):
+        lib.horizonator_deinit(C.byref(self._ctx))
+
+    def __str__(self):
+        # pywrap.c:133-156: "%.9S" = the first 9 characters of str(float)
+        return "Looking out from %s,%s" % (str(float(self._ctx.viewer_lat))[:9], str(float(self._ctx.viewer_lon))[:9])
+
+    # ------------------------------------------------------------------ reference API
+    def render(self, az_deg0, az_deg1, lat=-1000., lon=-1000.,
+               return_image=True, return_range=True, az_extents_use_pixel_centers=False,
+               znear=HORIZONATOR_ZNEAR_DEFAULT, zfar=HORIZONATOR_ZFAR_DEFAULT,
+               znear_color=-1., zfar_color=-1.):
+        """Mirror of render() at horizonator-pywrap.c:158-279.
+
+        Returns (image, ranges), or just one of them, or () -- image: (H,W,3) uint8 in B,G,R order,
+        ranges: (H,W) float32 with -1 where no terrain is seen; top row first.
+        """
+        if znear_color < 0.:
+            znear_color = znear
+        if zfar_color < 0.:
+            zfar_color = zfar
+        if not return_image and not return_range:
+            return ()
+        W, H = self._ctx.offscreen.width, self._ctx.offscreen.height
+        if az_extents_use_pixel_centers:
+            az_per_pixel = (az_deg1 - az_deg0) / float(W - 1)
+            az_deg0 -= az_per_pixel / 2.
+            az_deg1 += az_per_pixel / 2.
+        if not lib.horizonator_pan_zoom(C.byref(self._ctx), az_deg0, az_deg1):
+            raise RuntimeError("horizonator_pan_zoom() failed")
+        if lat > -1000.:
+            if not lib.horizonator_move(C.byref(self._ctx), None, lat, lon):
+                raise RuntimeError("horizonator_move() failed")
+        if not lib.horizonator_set_zextents(C.byref(self._ctx), znear, zfar, znear_color, zfar_color):
+            raise RuntimeError("horizonator_set_zextents() failed")
+        image = np.empty((H, W, 3), dtype=np.uint8) if return_image else None
+        ranges = np.empty((H, W), dtype=np.float32) if return_range else None
+        if not lib.horizonator_render_offscreen(C.byref(self._ctx),
+                                                image.ctypes.data if image is not None else None,
+                                                ranges.ctypes.data if ranges is not None else None):
+            raise RuntimeError("horizonator_render_offscreen() failed")
+        if return_image and not return_range:
+            return image
+        if return_range and not return_image:
+            return ranges
+        return image, ranges
+
+    # ------------------------------------------------------------------ additions (horizonator-batch.h)
+    @property
+    def width(self):
+        return self._ctx.offscreen.width
+
+    @property
+    def height(self):
+        return self._ctx.offscreen.height
+
+    @property
+    def context(self):
+        """The underlying horizonator_context_t (ctypes structure)."""
+        return self._ctx
+
+    @staticmethod
+    def _views(views):
+        arr = (view_t * len(views))()
+        for k, v in enumerate(views):
+            lat, lon, az0, az1 = v[0], v[1], v[2], v[3]
+            z = v[4] if len(v) > 4 else -1.
+            arr[k] = view_t(lat, lon, z, az0, az1)
+        return arr
+
+    def set_zextents(self, znear, zfar, znear_color=-1., zfar_color=-1.):
+        if znear_color < 0.:
+            znear_color = znear
+        if zfar_color < 0.:
+            zfar_color = zfar
+        if not lib.horizonator_set_zextents(C.byref(self._ctx), znear, zfar, znear_color, zfar_color):
+            raise RuntimeError("horizonator_set_zextents() failed")
+
+    def render_batch(self, views, return_image=True, return_range=True):
+        """views: sequence of (lat, lon, az_deg0, az_deg1[, viewer_z]).  Host arrays (n,H,W,3), (n,H,W)."""
+        n, W, H = len(views), self.width, self.height
+        image = np.empty((n, H, W, 3), dtype=np.uint8) if return_image else None
+        ranges = np.empty((n, H, W), dtype=np.float32) if return_range else None
+        if not lib.horizonator_render_batch(C.byref(self._ctx), n, self._views(views),
+                                            image.ctypes.data if image is not None else None,
+                                            ranges.ctypes.data if ranges is not None else None):
+            raise RuntimeError("horizonator_render_batch() failed")
+        return image, ranges
+
+    def render_batch_device(self, views, d_images=0, d_ranges=0, stream=0):
+        """Device-pointer variant: d_images / d_ranges are integer device addresses (e.g. tensor.data_ptr()),
+        stream an integer cudaStream_t (0 = the context's own stream, synchronous)."""
+        if not lib.horizonator_render_batch_device(C.byref(self._ctx), len(views), self._views(views),
+                                                   d_images or None, d_ranges or None, stream or None):
+            raise RuntimeError("horizonator_render_batch_device() failed")
+
+    def render_wedge_device(self, x0, x1, d_image=0, d_ranges=0, stream=0):
+        if not lib.horizonator_render_wedge_device(C.byref(self._ctx), int(x0), int(x1),
+                                                   d_image or None, d_ranges or None, stream or None):
+            raise RuntimeError("horizonator_render_wedge_device() failed")
+
+    def pan_zoom(self, az_deg0, az_deg1):
+        if not lib.horizonator_pan_zoom(C.byref(self._ctx), az_deg0, az_deg1):
+            raise RuntimeError("horizonator_pan_zoom() failed")
+
+    def move(self, lat, lon, viewer_z=None):
+        z = C.c_float(-1. if viewer_z is None else viewer_z)
+        if not lib.horizonator_move(C.byref(self._ctx), C.byref(z), lat, lon):
+            raise RuntimeError("horizonator_move() failed")
+        return z.value
+
+    def mosaic(self):
+        """The decoded DEM square as the GPU holds it: (2R, 2R) int16, [j north][i east]."""
+        n = 2 * self._ctx.dems.radius_cells
+        out = np.empty((n, n), dtype=np.int16)
+        if not lib.horizonator_download_mosaic(C.byref(self._ctx), out.ctypes.data):
+            raise RuntimeError("horizonator_download_mosaic() failed")
+        return out
+
+    def time_mosaic(self, reps=10):
+        ms = C.c_float(0)
+        if not lib.horizonator_time_mosaic(C.byref(self._ctx), reps, C.byref(ms)):
+            raise RuntimeError("horizonator_time_mosaic() failed")
+        return ms.value
+
+    def last_render_stats(self):
+        out = (C.c_uint * 4)()
+        if not lib.horizonator_last_render_stats(C.byref(self._ctx), C.byref(out)):
+            raise RuntimeError("horizonator_last_render_stats() failed")
+        return {"big_triangles": out[0], "big_capacity": out[1], "launches": out[2], "device": out[3]}

@@ -1,0 +1,728 @@
+// hz_api.cpp -- the C ABI of include/horizonator.h and include/horizonator-batch.h.
+//
+// Replaces the host side of /root/reference/horizonator-lib.c: where that file drives an OpenGL context, this
+// one owns a block of device state per context (the decoded DEM square, the visibility buffer, output and
+// staging buffers, one CUDA stream) and enqueues the kernels of hz_kernels.cu.  The caller-visible struct has
+// no room for a pointer, so the state lives in a process-wide table and `ctx->program` holds its handle.
+//
+// No CPU rendering path exists: without a usable CUDA device horizonator_init() fails.
+#include "horizonator.h"
+#include "horizonator-batch.h"
+#include "util.h"
+#include "hz_device.h"
+
+#include <cmath>
+#include <cstddef>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <thread>
+#include <vector>
+
+namespace {
+
+#define CUDA_TRY(expr)                                                              \
+    do {                                                                            \
+        cudaError_t e__ = (expr);                                                   \
+        if(e__ != cudaSuccess)                                                      \
+        {                                                                           \
+            MSG("CUDA error: %s failed: %s", #expr, cudaGetErrorString(e__));       \
+            return false;                                                           \
+        }                                                                           \
+    } while(0)
+
+constexpr int   TANEL_SLOTS     = 8;
+constexpr float PI_F            = 3.14159265358979f;       // vertex.glsl:31
+constexpr unsigned BIG_CAPACITY = 1u << 20;
+
+// what the reference keeps in GL uniforms
+struct ViewState
+{
+    float viewer_cell_i = 0, viewer_cell_j = 0, viewer_z = 0, cos_viewer_lat = 1;
+    float az_deg0 = -45.f, az_deg1 = 45.f;
+};
+
+struct Slot
+{
+    int device = 0;
+    cudaStream_t stream = nullptr;
+
+    // terrain
+    int N = 0, pitch = 0, cpd = 0;
+    int16_t* d_mosaic = nullptr;
+    HzTiles  tiles{};
+    float *d_e = nullptr, *d_n = nullptr;
+
+    // target
+    int W = 0, H = 0;
+    unsigned long long* d_vis = nullptr;
+    uint8_t* d_image  = nullptr;
+    float*   d_ranges = nullptr;
+    uint8_t* h_image  = nullptr;     // pinned staging for the host-pointer API
+    float*   h_ranges = nullptr;
+    size_t   target_pixels = 0;      // capacity of the buffers above
+
+    // tan(elevation) per row, computed on the host like the reference's read-back does
+    float*   d_tanel = nullptr;      // [TANEL_SLOTS][H]
+    float*   h_tanel = nullptr;      // pinned, same shape
+    struct { bool valid; float daz; int W, H; } tanel_key[TANEL_SLOTS] = {};
+    int      tanel_next = 0;
+
+    uint32_t* d_big_queue = nullptr;
+    uint32_t* d_big_count = nullptr;
+
+    ViewState view;
+    float znear = HORIZONATOR_ZNEAR_DEFAULT, zfar = HORIZONATOR_ZFAR_DEFAULT;
+    float znear_color = HORIZONATOR_ZNEAR_DEFAULT, zfar_color = HORIZONATOR_ZFAR_DEFAULT;
+
+    bool have_render = false;        // d_vis holds a complete full-width render (for pick)
+    unsigned launches_last = 0;
+};
+
+std::mutex          g_table_mutex;
+std::vector<Slot*>  g_table;         // handle = index + 1
+
+Slot* slot_of(const horizonator_context_t* ctx)
+{
+    if(ctx == nullptr || ctx->Ntriangles <= 0 || ctx->program == 0) return nullptr;
+    std::lock_guard<std::mutex> lock(g_table_mutex);
+    if(ctx->program > g_table.size()) return nullptr;
+    return g_table[ctx->program - 1];
+}
+
+struct DeviceGuard
+{
+    int prev = -1;
+    bool ok = false;
+    explicit DeviceGuard(int dev)
+    {
+        if(cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        ok = cudaSetDevice(dev) == cudaSuccess;
+    }
+    ~DeviceGuard() { if(prev >= 0) cudaSetDevice(prev); }
+};
+
+void free_target(Slot& s)
+{
+    cudaFree(s.d_vis);    s.d_vis = nullptr;
+    cudaFree(s.d_image);  s.d_image = nullptr;
+    cudaFree(s.d_ranges); s.d_ranges = nullptr;
+    cudaFree(s.d_tanel);  s.d_tanel = nullptr;
+    cudaFreeHost(s.h_image);  s.h_image = nullptr;
+    cudaFreeHost(s.h_ranges); s.h_ranges = nullptr;
+    cudaFreeHost(s.h_tanel);  s.h_tanel = nullptr;
+    s.target_pixels = 0;
+    for(auto& k : s.tanel_key) k.valid = false;
+}
+
+bool alloc_target(Slot& s, int W, int H)
+{
+    free_target(s);
+    const size_t px = (size_t)W * (size_t)H;
+    CUDA_TRY(cudaMalloc(&s.d_vis, px * sizeof(unsigned long long)));
+    CUDA_TRY(cudaMalloc(&s.d_image, px * 3));
+    CUDA_TRY(cudaMalloc(&s.d_ranges, px * sizeof(float)));
+    CUDA_TRY(cudaMalloc(&s.d_tanel, (size_t)TANEL_SLOTS * H * sizeof(float)));
+    CUDA_TRY(cudaMallocHost(&s.h_image, px * 3));
+    CUDA_TRY(cudaMallocHost(&s.h_ranges, px * sizeof(float)));
+    CUDA_TRY(cudaMallocHost(&s.h_tanel, (size_t)TANEL_SLOTS * H * sizeof(float)));
+    s.W = W; s.H = H; s.target_pixels = px;
+    s.have_render = false;
+    return true;
+}
+
+void destroy_slot(Slot* s)
+{
+    if(s == nullptr) return;
+    DeviceGuard g(s->device);
+    if(s->stream) cudaStreamSynchronize(s->stream);
+    free_target(*s);
+    cudaFree(s->d_mosaic);
+    for(int i = 0; i < 4; i++) for(int j = 0; j < 4; j++) cudaFree((void*)s->tiles.tile[i][j]);
+    cudaFree(s->d_e); cudaFree(s->d_n);
+    cudaFree(s->d_big_queue); cudaFree(s->d_big_count);
+    if(s->stream) cudaStreamDestroy(s->stream);
+    delete s;
+}
+
+// vertex.glsl:34-38 on the host, in float (round() = round-half-even, oracle rule F9)
+float unwrap_near_rad(float x, float near)
+{
+    const float d = (x - near) / (2.f * PI_F);
+    return (d - rintf(d)) * 2.f * PI_F + near;
+}
+
+// lib:1007-1012: tan(elevation) of each GL row as the reference's read-back computes it -- rows of the
+// lower half directly, rows of the upper half as the negated value of their mirror row.
+void fill_tanel(float* out, int W, int H, float az_deg0, float az_deg1)
+{
+    const float aspect = (float)W / (float)H;
+    for(int y = 0; y < H; y++)
+    {
+        const int   ysrc   = (y < H / 2 || ((H & 1) && y == H / 2)) ? y : H - 1 - y;
+        const float el_ndc = ((float)ysrc + 0.5f) / (float)H * 2.f - 1.f;
+        const float el     = el_ndc * (az_deg1 - az_deg0) / 2.f / aspect * M_PI / 180.0f;
+        const float t      = tanf(el);
+        out[y] = (ysrc != y) ? -t : t;
+    }
+}
+
+// returns the device pointer of the row table for this window, uploading it if it is not cached
+bool tanel_for(Slot& s, float az_deg0, float az_deg1, cudaStream_t st, const float** d_out)
+{
+    const float daz = az_deg1 - az_deg0;
+    for(int k = 0; k < TANEL_SLOTS; k++)
+        if(s.tanel_key[k].valid && s.tanel_key[k].W == s.W && s.tanel_key[k].H == s.H &&
+           memcmp(&s.tanel_key[k].daz, &daz, sizeof(float)) == 0)
+        {
+            *d_out = s.d_tanel + (size_t)k * s.H;
+            return true;
+        }
+    const int k = s.tanel_next;
+    s.tanel_next = (s.tanel_next + 1) % TANEL_SLOTS;
+    // the pinned row may still be in flight from an earlier upload, the device row may still be in use
+    CUDA_TRY(cudaStreamSynchronize(st));
+    if(st != s.stream) CUDA_TRY(cudaStreamSynchronize(s.stream));
+    fill_tanel(s.h_tanel + (size_t)k * s.H, s.W, s.H, az_deg0, az_deg1);
+    CUDA_TRY(cudaMemcpyAsync(s.d_tanel + (size_t)k * s.H, s.h_tanel + (size_t)k * s.H,
+                             (size_t)s.H * sizeof(float), cudaMemcpyHostToDevice, st));
+    s.tanel_key[k] = { true, daz, s.W, s.H };
+    *d_out = s.d_tanel + (size_t)k * s.H;
+    return true;
+}
+
+// enqueue one render of columns [x0,x1) into d_image / d_ranges (device, either may be null)
+bool enqueue_render(Slot& s, const ViewState& vs, int x0, int x1,
+                    uint8_t* d_image, float* d_ranges, cudaStream_t st)
+{
+    HzView v{};
+    v.mosaic = s.d_mosaic; v.N = s.N; v.pitch = s.pitch;
+    v.e_tab = s.d_e; v.n_tab = s.d_n;
+    v.viewer_cell_i = vs.viewer_cell_i; v.viewer_cell_j = vs.viewer_cell_j; v.viewer_z = vs.viewer_z;
+    v.deg_per_cell = 1.0f / (float)s.cpd;                                // lib:577
+    v.cos_viewer_lat = vs.cos_viewer_lat;
+
+    // vertex.glsl:139-150, float
+    const float az_rad0 = vs.az_deg0 * 0.017453292519943295f;            // radians()
+    float       az_rad1 = vs.az_deg1 * 0.017453292519943295f;
+    az_rad1 = unwrap_near_rad(az_rad1 - az_rad0, PI_F) + az_rad0;
+    v.az_center      = (az_rad0 + az_rad1) / 2.f;
+    v.az_ndc_per_rad = 2.0f / (az_rad1 - az_rad0);
+    v.aspect         = (float)s.W / (float)s.H;                          // lib:658-659
+
+    v.znear = s.znear; v.zfar = s.zfar; v.znear_color = s.znear_color; v.zfar_color = s.zfar_color;
+    v.W = s.W; v.H = s.H; v.x0 = x0; v.x1 = x1;
+    v.vis = s.d_vis;
+    v.big_queue = s.d_big_queue; v.big_count = s.d_big_count; v.big_capacity = BIG_CAPACITY;
+
+    // conservative block culling (hz_kernels.cu: hz_block_dead)
+    const float far_m = s.zfar * 1.001f + 1.0f;
+    v.cull_d2_far = far_m * far_m;
+    {
+        // azimuths that can land in columns [x0-1, x1+1): x_ndc = (az - center) * az_ndc_per_rad
+        const double k = (double)v.az_ndc_per_rad;
+        const double ndc_lo = 2.0 * (double)(x0 - 1) / (double)s.W - 1.0;
+        const double ndc_hi = 2.0 * (double)(x1 + 1) / (double)s.W - 1.0;
+        const double a_lo = (double)v.az_center + ndc_lo / k, a_hi = (double)v.az_center + ndc_hi / k;
+        v.cull_az_mid  = (float)(0.5 * (a_lo + a_hi));
+        v.cull_az_half = (float)(0.5 * fabs(a_hi - a_lo)) + 2e-3f;
+        if(!(v.cull_az_half < 3.1f) || !std::isfinite(v.cull_az_half)) v.cull_az_half = 4.0f;   // no test
+    }
+
+    const float* d_tanel = nullptr;
+    if(d_ranges && !tanel_for(s, vs.az_deg0, vs.az_deg1, st, &d_tanel)) return false;
+
+    CUDA_TRY(hz_launch_prepare(v, st));
+    CUDA_TRY(hz_launch_march(v, st));
+    CUDA_TRY(hz_launch_big(v, st));
+    s.launches_last = 3;
+    if(d_image || d_ranges)
+    {
+        HzResolve r{};
+        r.vis = s.d_vis; r.Wt = x1 - x0; r.H = s.H;
+        r.tanel = d_tanel; r.znear = s.znear; r.zfar = s.zfar;
+        r.image = d_image; r.ranges = d_ranges;
+        CUDA_TRY(hz_launch_resolve(r, st));
+        s.launches_last = 4;
+    }
+    s.have_render = (x0 == 0 && x1 == s.W);
+    return true;
+}
+
+// lib:765-789, float as written there.  The four samples come from the host mmaps (dem.h).
+bool compute_move(const horizonator_context_t* ctx, float* viewer_z, float lat, float lon, ViewState& vs)
+{
+    const horizonator_dem_context_t* d = &ctx->dems;
+    const float vci = (lon - (float)d->origin_dem_lon_lat[0]) * (float)d->cells_per_deg - (float)d->origin_dem_cellij[0];
+    const float vcj = (lat - (float)d->origin_dem_lon_lat[1]) * (float)d->cells_per_deg - (float)d->origin_dem_cellij[1];
+    const int i0 = (int)floorf(vci), j0 = (int)floorf(vcj);
+    float z;
+    if(viewer_z == nullptr || *viewer_z < 0)
+    {
+        // a little above the ground so that the bumps right next to the eye don't fill the view
+        z = (float)((double)fmaxf(fmaxf((float)horizonator_dem_sample(d, i0,     j0),
+                                        (float)horizonator_dem_sample(d, i0 + 1, j0)),
+                                  fmaxf((float)horizonator_dem_sample(d, i0,     j0 + 1),
+                                        (float)horizonator_dem_sample(d, i0 + 1, j0 + 1))) + 1.0);
+        if(viewer_z != nullptr) *viewer_z = z;
+    }
+    else
+        z = *viewer_z;
+    vs.viewer_cell_i  = vci;
+    vs.viewer_cell_j  = vcj;
+    vs.viewer_z       = z;
+    vs.cos_viewer_lat = cosf((float)((double)lat * M_PI / (double)180.0f));   // lib:799
+    return true;
+}
+
+// multi-threaded copy out of the pinned staging buffers: a single thread cannot keep up with PCIe
+void copy_out(void* dst, const void* src, size_t bytes)
+{
+    const size_t chunk = 1u << 20;
+    const unsigned hw = std::thread::hardware_concurrency();
+    size_t nthreads = bytes / (4 * chunk);
+    if(nthreads > 8) nthreads = 8;
+    if(hw && nthreads > hw) nthreads = hw;
+    if(nthreads <= 1) { memcpy(dst, src, bytes); return; }
+    std::vector<std::thread> pool;
+    const size_t per = (bytes + nthreads - 1) / nthreads;
+    for(size_t t = 0; t < nthreads; t++)
+    {
+        const size_t off = t * per;
+        if(off >= bytes) break;
+        const size_t len = (off + per <= bytes) ? per : bytes - off;
+        pool.emplace_back([=] { memcpy((char*)dst + off, (const char*)src + off, len); });
+    }
+    for(auto& th : pool) th.join();
+}
+
+} // namespace
+
+extern "C" {
+
+bool horizonator_init(horizonator_context_t* ctx,
+                      float viewer_lat, float viewer_lon, float* viewer_z,
+                      int offscreen_width, int offscreen_height,
+                      int render_radius_cells, float render_radius_m,
+                      bool use_glut, bool render_texture, bool SRTM1,
+                      const char* dir_dems, const char* dir_tiles,
+                      const char* tiles_name, const char* tiles_url_fmt,
+                      bool allow_downloads)
+{
+    (void)dir_tiles; (void)tiles_name; (void)tiles_url_fmt; (void)allow_downloads;
+    memset(ctx, 0, sizeof(*ctx));
+
+    if(render_texture)
+    {
+        MSG("render_texture=true (OpenStreetMap texturing) is not supported by the CUDA renderer");
+        return false;
+    }
+    if(offscreen_width > 0 && offscreen_height <= 0)
+    {
+        MSG("offscreen_width > 0 needs offscreen_height > 0");
+        return false;
+    }
+    if(dir_dems == nullptr)                                             // lib:94-97
+        dir_dems = SRTM1 ? "~/.horizonator/DEMs_SRTM1" : "~/.horizonator/DEMs_SRTM3";
+
+    int ndev = 0;
+    if(cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0)
+    {
+        MSG("No usable CUDA device: libhorizonator renders on the GPU only (there is no CPU path)");
+        return false;
+    }
+    int dev = 0;
+    if(const char* env = getenv("HORIZONATOR_DEVICE")) dev = atoi(env);
+    else if(cudaGetDevice(&dev) != cudaSuccess) dev = 0;
+
+    if(!horizonator_dem_init(&ctx->dems, viewer_lat, viewer_lon, render_radius_cells, render_radius_m, dir_dems, SRTM1))
+    {
+        MSG("Couldn't init DEMs. Giving up");
+        return false;
+    }
+
+    Slot* s = new Slot;
+    s->device = dev;
+    bool ok = false;
+    do
+    {
+        DeviceGuard guard(dev);
+        if(!guard.ok) { MSG("cudaSetDevice(%d) failed", dev); break; }
+        auto fail = [](cudaError_t e, const char* what) {
+            if(e != cudaSuccess) MSG("CUDA error: %s: %s", what, cudaGetErrorString(e));
+            return e != cudaSuccess;
+        };
+        if(fail(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking), "cudaStreamCreate")) break;
+
+        const horizonator_dem_context_t* d = &ctx->dems;
+        s->cpd = d->cells_per_deg;
+        s->N   = 2 * d->radius_cells;
+        s->pitch = ((s->N + 2) + 63) / 64 * 64;
+
+        // raw tiles to the device (16 spare bytes: k_mosaic's aligned 32-bit loads may touch them)
+        s->tiles.cpd = s->cpd;
+        s->tiles.origin_cell[0] = d->origin_dem_cellij[0]; s->tiles.origin_cell[1] = d->origin_dem_cellij[1];
+        s->tiles.ntiles[0] = d->Ndems_ij[0];               s->tiles.ntiles[1] = d->Ndems_ij[1];
+        bool bad = false;
+        for(int i = 0; i < d->Ndems_ij[0] && !bad; i++)
+            for(int j = 0; j < d->Ndems_ij[1] && !bad; j++)
+            {
+                if(d->dems[i][j] == nullptr) continue;
+                uint8_t* p = nullptr;
+                bad = fail(cudaMalloc(&p, d->mmap_sizes[i][j] + 16), "cudaMalloc(tile)") ||
+                      fail(cudaMemcpyAsync(p, d->dems[i][j], d->mmap_sizes[i][j], cudaMemcpyHostToDevice, s->stream),
+                           "cudaMemcpy(tile)");
+                s->tiles.tile[i][j] = p;
+            }
+        if(bad) break;
+
+        if(fail(cudaMalloc(&s->d_mosaic, (size_t)s->N * s->pitch * sizeof(int16_t)), "cudaMalloc(mosaic)")) break;
+        if(fail(cudaMalloc(&s->d_e, (size_t)s->N * sizeof(float)), "cudaMalloc")) break;
+        if(fail(cudaMalloc(&s->d_n, (size_t)s->N * sizeof(float)), "cudaMalloc")) break;
+        if(fail(cudaMalloc(&s->d_big_queue, (size_t)BIG_CAPACITY * sizeof(uint32_t)), "cudaMalloc")) break;
+        if(fail(cudaMalloc(&s->d_big_count, sizeof(uint32_t)), "cudaMalloc")) break;
+        if(fail(hz_launch_mosaic(s->tiles, s->d_mosaic, s->N, s->pitch, s->stream), "k_mosaic")) break;
+
+        // without an offscreen size the reference opens a 1024x1024 window (lib:142)
+        const int W = offscreen_width > 0 ? offscreen_width : 1024;
+        const int H = offscreen_width > 0 ? offscreen_height : 1024;
+        if(!alloc_target(*s, W, H)) break;
+        if(fail(cudaStreamSynchronize(s->stream), "DEM upload/decode")) break;
+        ok = true;
+    } while(0);
+
+    if(!ok)
+    {
+        destroy_slot(s);
+        horizonator_dem_deinit(&ctx->dems);
+        memset(ctx, 0, sizeof(*ctx));
+        return false;
+    }
+
+    {
+        std::lock_guard<std::mutex> lock(g_table_mutex);
+        size_t k = 0;
+        while(k < g_table.size() && g_table[k] != nullptr) k++;
+        if(k == g_table.size()) g_table.push_back(s); else g_table[k] = s;
+        ctx->program = (uint32_t)(k + 1);
+    }
+
+    const int n1 = 2 * ctx->dems.radius_cells - 1;
+    ctx->Ntriangles     = n1 * n1 * 2;                                  // lib:202-203
+    ctx->render_texture = false;
+    ctx->use_glut       = use_glut;
+    ctx->glut_window    = 1;
+    // the 17 GL uniform locations of the reference: no meaning here, -1 = "no such uniform"
+    memset(&ctx->uniform_aspect, 0xFF,
+           offsetof(horizonator_context_t, uniform_zfar_color) + sizeof(int32_t) - offsetof(horizonator_context_t, uniform_aspect));
+    if(offscreen_width > 0)
+    {
+        ctx->offscreen.inited = true;
+        ctx->offscreen.width  = offscreen_width;
+        ctx->offscreen.height = offscreen_height;
+    }
+
+    horizonator_move(ctx, viewer_z, viewer_lat, viewer_lon);           // lib:611
+    horizonator_set_zextents(ctx, HORIZONATOR_ZNEAR_DEFAULT, HORIZONATOR_ZFAR_DEFAULT,
+                             HORIZONATOR_ZNEAR_DEFAULT, HORIZONATOR_ZFAR_DEFAULT);
+    horizonator_pan_zoom(ctx, -45.f, 45.f);                             // lib:670
+    return true;
+}
+
+void horizonator_deinit(horizonator_context_t* ctx)
+{
+    if(ctx == nullptr) return;
+    Slot* s = nullptr;
+    if(ctx->Ntriangles > 0 && ctx->program != 0)
+    {
+        std::lock_guard<std::mutex> lock(g_table_mutex);
+        if(ctx->program <= g_table.size())
+        {
+            s = g_table[ctx->program - 1];
+            g_table[ctx->program - 1] = nullptr;
+        }
+    }
+    destroy_slot(s);
+    if(ctx->Ntriangles > 0) horizonator_dem_deinit(&ctx->dems);
+    ctx->Ntriangles  = 0;
+    ctx->program     = 0;
+    ctx->glut_window = 0;
+    ctx->offscreen.inited = false;
+}
+
+bool horizonator_resized(const horizonator_context_t* ctx, int width, int height)
+{
+    Slot* s = slot_of(ctx);
+    if(s == nullptr) return false;
+    if(ctx->offscreen.inited)
+    {
+        MSG("Resizing an offscreen context is not supported");          // the reference asserts here
+        return false;
+    }
+    if(width <= 0 || height <= 0) return false;
+    DeviceGuard g(s->device);
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    return alloc_target(*s, width, height);
+}
+
+bool horizonator_pan_zoom(const horizonator_context_t* ctx, float az_deg0, float az_deg1)
+{
+    Slot* s = slot_of(ctx);
+    if(s == nullptr) return false;
+    s->view.az_deg0 = az_deg0;      // stored as given, like the uniforms at lib:833-834
+    s->view.az_deg1 = az_deg1;
+    return true;
+}
+
+bool horizonator_move(horizonator_context_t* ctx, float* viewer_z, float viewer_lat, float viewer_lon)
+{
+    Slot* s = slot_of(ctx);
+    if(s == nullptr) return false;
+    const float az0 = s->view.az_deg0, az1 = s->view.az_deg1;
+    if(!compute_move(ctx, viewer_z, viewer_lat, viewer_lon, s->view)) return false;
+    s->view.az_deg0 = az0; s->view.az_deg1 = az1;
+    ctx->viewer_lat = viewer_lat;                                       // lib:812-813
+    ctx->viewer_lon = viewer_lon;
+    return true;
+}
+
+bool horizonator_set_zextents(horizonator_context_t* ctx,
+                              float znear, float zfar, float znear_color, float zfar_color)
+{
+    Slot* s = slot_of(ctx);
+    if(s == nullptr) return false;
+    if(!(znear > 0.0f && znear_color > 0.0f && zfar > 0.0f && zfar_color > 0.0f)) return false;   // lib:875-877
+    s->znear = znear; s->zfar = zfar; s->znear_color = znear_color; s->zfar_color = zfar_color;
+    return true;
+}
+
+bool horizonator_redraw(const horizonator_context_t* ctx)
+{
+    Slot* s = slot_of(ctx);
+    if(s == nullptr) return false;
+    DeviceGuard g(s->device);
+    if(!enqueue_render(*s, s->view, 0, s->W, s->d_image, s->d_ranges, s->stream)) return false;
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    return true;
+}
+
+bool horizonator_render_offscreen(const horizonator_context_t* ctx, char* image, float* ranges)
+{
+    Slot* s = slot_of(ctx);
+    if(s == nullptr) return false;
+    if(!ctx->offscreen.inited)
+    {
+        MSG("Prior to calling horizonator_render_offscreen(), the context must have been inited for offscreen rendering with horizonator_init(offscreen_width,height > 0)");
+        return false;
+    }
+    DeviceGuard g(s->device);
+    const size_t px = (size_t)s->W * s->H;
+    if(!enqueue_render(*s, s->view, 0, s->W,
+                       image ? s->d_image : nullptr, ranges ? s->d_ranges : nullptr, s->stream)) return false;
+    if(image)  CUDA_TRY(cudaMemcpyAsync(s->h_image,  s->d_image,  px * 3, cudaMemcpyDeviceToHost, s->stream));
+    if(ranges) CUDA_TRY(cudaMemcpyAsync(s->h_ranges, s->d_ranges, px * sizeof(float), cudaMemcpyDeviceToHost, s->stream));
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    if(image)  copy_out(image,  s->h_image,  px * 3);
+    if(ranges) copy_out(ranges, s->h_ranges, px * sizeof(float));
+    return true;
+}
+
+bool horizonator_pick(const horizonator_context_t* ctx, float* lat, float* lon, int x, int y)
+{
+    Slot* s = slot_of(ctx);
+    if(s == nullptr || !s->have_render) return false;
+    if(x < 0 || y < 0 || x >= s->W || y >= s->H) return false;
+    DeviceGuard g(s->device);
+    unsigned long long key = 0;
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    CUDA_TRY(cudaMemcpy(&key, s->d_vis + (size_t)(s->H - 1 - y) * s->W + x, sizeof(key), cudaMemcpyDeviceToHost));
+    const float depth = (float)((double)(unsigned)(key >> 40) * (1.0 / 16777215.0));
+    if(depth >= 1.0f) return false;                                     // lib:1272
+    // lib:1282-1295: the depth is treated as horizontal distance
+    const double range_en = depth * (s->zfar - s->znear) + s->znear;
+    return horizonator_unproject(lat, lon, x, y, -1., range_en,
+                                 ctx->viewer_lat, s->view.cos_viewer_lat, ctx->viewer_lon,
+                                 s->view.az_deg0, s->view.az_deg1, s->W, s->H);
+}
+
+// ---- pure host geometry (lib:1053-1213): double precision, no device involved ----------------------------
+
+static double unwrap_near_rad_d(double x, double near)
+{
+    const double d = (x - near) / (2. * M_PI);
+    return (d - round(d)) * 2. * M_PI + near;
+}
+
+bool horizonator_x_from_az(double* x, double* az_ndc_per_rad,
+                           double az_rad, double az_rad0, double az_rad1, int width)
+{
+    az_rad1 = unwrap_near_rad_d(az_rad1 - az_rad0, M_PI) + az_rad0;
+    const double center = (az_rad0 + az_rad1) / 2.;
+    az_rad = unwrap_near_rad_d(az_rad, center);
+    const double per_rad = 2.0 / (az_rad1 - az_rad0);
+    const double az_ndc  = (az_rad - center) * per_rad;
+    if(!(-1. <= az_ndc && az_ndc <= 1.)) return false;
+    if(az_ndc_per_rad != nullptr) *az_ndc_per_rad = per_rad;
+    *x = (az_ndc + 1.) / 2. * width - 0.5;                               // NDC [-1,1] -> pixel (-0.5, W-0.5)
+    return true;
+}
+
+bool horizonator_project(double* x, double* y, double* range,
+                         double lat_viewer, double cos_lat_viewer, double lon_viewer, double ele_viewer,
+                         double lat, double lon, double ele,
+                         double az_rad0, double az_rad1, int width, int height)
+{
+    const float Rearth = 6371000.0;
+    const double dlat = (lat - lat_viewer) * M_PI / 180;
+    const double dlon = (lon - lon_viewer) * M_PI / 180;
+    const double east  = dlon * Rearth * cos_lat_viewer;
+    const double north = dlat * Rearth;
+    const double d2 = east * east + north * north;
+
+    double per_rad;
+    if(!horizonator_x_from_az(x, &per_rad, atan2(east, north), az_rad0, az_rad1, width)) return false;
+
+    const double h = ele - ele_viewer;
+    *range = sqrt(d2 + h * h);
+    const double aspect = (double)width / (double)height;
+    const double el_ndc = atan2(h, sqrt(d2)) * aspect * per_rad;
+    if(!(-1. <= el_ndc && el_ndc <= 1.)) return false;
+    *y = (-el_ndc + 1.) / 2. * height - 0.5;
+    return true;
+}
+
+bool horizonator_unproject(float* lat, float* lon, int x, int y,
+                           double range_enh, double range_en,
+                           double lat_viewer, double cos_lat_viewer, double lon_viewer,
+                           double az_deg0, double az_deg1, int width, int height)
+{
+    if(1 != (range_enh > 0.) + (range_en > 0.)) return false;
+    const float Rearth = 6371000.0;
+    // mixed float/double exactly as lib:1185-1186
+    const float az_ndc = ((float)x + 0.5f) / (float)width * 2.f - 1.f;
+    const float az     = (az_ndc * (az_deg1 - az_deg0) / 2.f + (az_deg1 + az_deg0) / 2.f) * M_PI / 180.0f;
+    if(range_en <= 0)
+    {
+        const double aspect = (double)width / (double)height;
+        const double el_ndc = ((double)y + 0.5) / (double)height * 2. - 1.;
+        const double el     = el_ndc * (az_deg1 - az_deg0) / 2. / aspect * M_PI / 180.0;
+        range_en = cos(el) * range_enh;
+    }
+    const float e = range_en * sinf(az);
+    const float n = range_en * cosf(az);
+    *lon = lon_viewer + e / Rearth / M_PI * 180. / cos_lat_viewer;
+    *lat = lat_viewer + n / Rearth / M_PI * 180.;
+    return true;
+}
+
+// ---- additive API (include/horizonator-batch.h) -----------------------------------------------------------
+
+bool horizonator_render_batch_device(const horizonator_context_t* ctx, int n, const horizonator_view_t* views,
+                                     void* d_images, void* d_ranges, void* stream)
+{
+    Slot* s = slot_of(ctx);
+    if(s == nullptr || n < 0 || (n > 0 && views == nullptr)) return false;
+    DeviceGuard g(s->device);
+    cudaStream_t st = stream ? (cudaStream_t)stream : s->stream;
+    const size_t px = (size_t)s->W * s->H;
+    for(int k = 0; k < n; k++)
+    {
+        ViewState vs;
+        float z = views[k].viewer_z;
+        if(!compute_move(ctx, &z, views[k].lat, views[k].lon, vs)) return false;
+        vs.az_deg0 = views[k].az_deg0; vs.az_deg1 = views[k].az_deg1;
+        if(!enqueue_render(*s, vs, 0, s->W,
+                           d_images ? (uint8_t*)d_images + (size_t)k * px * 3 : nullptr,
+                           d_ranges ? (float*)d_ranges + (size_t)k * px : nullptr, st)) return false;
+    }
+    s->have_render = false;     // d_vis no longer matches the context's own view
+    if(stream == nullptr) CUDA_TRY(cudaStreamSynchronize(st));
+    return true;
+}
+
+bool horizonator_render_batch(const horizonator_context_t* ctx, int n, const horizonator_view_t* views,
+                              char* images, float* ranges)
+{
+    Slot* s = slot_of(ctx);
+    if(s == nullptr || n < 0 || (n > 0 && views == nullptr)) return false;
+    DeviceGuard g(s->device);
+    const size_t px = (size_t)s->W * s->H;
+    for(int k = 0; k < n; k++)
+    {
+        ViewState vs;
+        float z = views[k].viewer_z;
+        if(!compute_move(ctx, &z, views[k].lat, views[k].lon, vs)) return false;
+        vs.az_deg0 = views[k].az_deg0; vs.az_deg1 = views[k].az_deg1;
+        if(!enqueue_render(*s, vs, 0, s->W, images ? s->d_image : nullptr, ranges ? s->d_ranges : nullptr, s->stream))
+            return false;
+        if(images) CUDA_TRY(cudaMemcpyAsync(s->h_image,  s->d_image,  px * 3, cudaMemcpyDeviceToHost, s->stream));
+        if(ranges) CUDA_TRY(cudaMemcpyAsync(s->h_ranges, s->d_ranges, px * sizeof(float), cudaMemcpyDeviceToHost, s->stream));
+        CUDA_TRY(cudaStreamSynchronize(s->stream));
+        if(images) copy_out(images + (size_t)k * px * 3, s->h_image, px * 3);
+        if(ranges) copy_out(ranges + (size_t)k * px, s->h_ranges, px * sizeof(float));
+    }
+    s->have_render = false;
+    return true;
+}
+
+bool horizonator_render_wedge_device(const horizonator_context_t* ctx, int x0, int x1,
+                                     void* d_image, void* d_ranges, void* stream)
+{
+    Slot* s = slot_of(ctx);
+    if(s == nullptr) return false;
+    if(x0 < 0 || x1 > s->W || x0 >= x1)
+    {
+        MSG("wedge columns [%d,%d) are not inside [0,%d)", x0, x1, s->W);
+        return false;
+    }
+    DeviceGuard g(s->device);
+    cudaStream_t st = stream ? (cudaStream_t)stream : s->stream;
+    if(!enqueue_render(*s, s->view, x0, x1, (uint8_t*)d_image, (float*)d_ranges, st)) return false;
+    if(stream == nullptr) CUDA_TRY(cudaStreamSynchronize(st));
+    return true;
+}
+
+bool horizonator_download_mosaic(const horizonator_context_t* ctx, int16_t* mosaic)
+{
+    Slot* s = slot_of(ctx);
+    if(s == nullptr || mosaic == nullptr) return false;
+    DeviceGuard g(s->device);
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    CUDA_TRY(cudaMemcpy2D(mosaic, (size_t)s->N * sizeof(int16_t), s->d_mosaic, (size_t)s->pitch * sizeof(int16_t),
+                          (size_t)s->N * sizeof(int16_t), s->N, cudaMemcpyDeviceToHost));
+    return true;
+}
+
+bool horizonator_time_mosaic(const horizonator_context_t* ctx, int reps, float* ms_per_run)
+{
+    Slot* s = slot_of(ctx);
+    if(s == nullptr || reps <= 0 || ms_per_run == nullptr) return false;
+    DeviceGuard g(s->device);
+    cudaEvent_t a, b;
+    CUDA_TRY(cudaEventCreate(&a));
+    CUDA_TRY(cudaEventCreate(&b));
+    CUDA_TRY(hz_launch_mosaic(s->tiles, s->d_mosaic, s->N, s->pitch, s->stream));      // warm-up
+    CUDA_TRY(cudaEventRecord(a, s->stream));
+    for(int k = 0; k < reps; k++) CUDA_TRY(hz_launch_mosaic(s->tiles, s->d_mosaic, s->N, s->pitch, s->stream));
+    CUDA_TRY(cudaEventRecord(b, s->stream));
+    CUDA_TRY(cudaEventSynchronize(b));
+    float ms = 0;
+    CUDA_TRY(cudaEventElapsedTime(&ms, a, b));
+    cudaEventDestroy(a); cudaEventDestroy(b);
+    *ms_per_run = ms / (float)reps;
+    return true;
+}
+
+bool horizonator_last_render_stats(const horizonator_context_t* ctx, unsigned int out[4])
+{
+    Slot* s = slot_of(ctx);
+    if(s == nullptr) return false;
+    DeviceGuard g(s->device);
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    unsigned int count = 0;
+    CUDA_TRY(cudaMemcpy(&count, s->d_big_count, sizeof(count), cudaMemcpyDeviceToHost));
+    out[0] = count; out[1] = BIG_CAPACITY; out[2] = s->launches_last; out[3] = (unsigned)s->device;
+    return true;
+}
+
+} // extern "C"

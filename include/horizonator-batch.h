@@ -1,0 +1,68 @@
+/* horizonator-batch.h -- additive entry points of the B200-native libhorizonator.
+ *
+ * The reference (dkogan/horizonator) has no counterpart for these: its only render call is
+ * horizonator_render_offscreen() (horizonator.h:165-169), one view at a time into host
+ * memory.  horizonator.h keeps that ABI untouched; everything new lives here.
+ *
+ * Same conventions: plain C, plain pointers and sizes, `bool` returns with a MSG() line on
+ * stderr on failure.  "Device pointer" means memory of the CUDA device the context was
+ * created on (e.g. torch tensor .data_ptr()); `stream` is a cudaStream_t passed as void*
+ * (NULL = the context's own stream; the call then waits for completion before returning,
+ * otherwise it only enqueues work and the caller synchronises).
+ */
+#pragma once
+
+#include "horizonator.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* one view of a batch: an eye position inside the loaded DEM square and an azimuth window */
+typedef struct
+{
+    float lat, lon;
+    float viewer_z;          /* < 0: highest of the 4 surrounding samples + 1 m (as horizonator_move) */
+    float az_deg0, az_deg1;  /* as horizonator_pan_zoom */
+} horizonator_view_t;
+
+/* Renders n views with the context's current z extents and image size (W x H).
+ * d_images: n*H*W*3 bytes (B,G,R, top row first) or NULL; d_ranges: n*H*W floats or NULL;
+ * both DEVICE pointers.  Leaves the context's own eye/azimuth state as it was. */
+bool horizonator_render_batch_device(const horizonator_context_t* ctx,
+                                     int n, const horizonator_view_t* views,
+                                     void* d_images, void* d_ranges,
+                                     void* stream);
+
+/* Same, into HOST memory (images/ranges as in horizonator_render_offscreen, n of each). */
+bool horizonator_render_batch(const horizonator_context_t* ctx,
+                              int n, const horizonator_view_t* views,
+                              char* images, float* ranges);
+
+/* Renders only columns [x0, x1) of the context's current W x H panorama (current eye, azimuth
+ * window and z extents) into DEVICE slabs d_image: H*(x1-x0)*3 bytes, d_ranges: H*(x1-x0)
+ * floats (either may be NULL).  The columns are bit-identical to the same columns of a full
+ * render: the projection, the quarter-width triangle discard (geometry.glsl:21-27) and the
+ * depth test all use the full window; only the set of pixels written differs.  This is the
+ * unit of work for splitting one giant panorama across GPUs by azimuth wedge. */
+bool horizonator_render_wedge_device(const horizonator_context_t* ctx,
+                                     int x0, int x1,
+                                     void* d_image, void* d_ranges,
+                                     void* stream);
+
+/* Copies the decoded DEM square (2R x 2R int16, row j = north index, column i = east index,
+ * tightly packed) from the device to host memory.  For tests of the decode/stitch kernel. */
+bool horizonator_download_mosaic(const horizonator_context_t* ctx, int16_t* mosaic);
+
+/* Re-runs the decode/stitch kernel `reps` times and reports the mean device time per run in
+ * milliseconds (CUDA events on the context's stream).  For benchmarks of the init path. */
+bool horizonator_time_mosaic(const horizonator_context_t* ctx, int reps, float* ms_per_run);
+
+/* Counters of the most recent render on this context: out[0] = triangles that were queued
+ * for the large-triangle kernel, out[1] = queue capacity, out[2] = kernel launches the
+ * render issued, out[3] = CUDA device ordinal. */
+bool horizonator_last_render_stats(const horizonator_context_t* ctx, unsigned int out[4]);
+
+#ifdef __cplusplus
+}
+#endif

@@ -1,0 +1,196 @@
+"""oracle/binding.py -- TEST INFRASTRUCTURE.  ctypes access to the CPU oracle.
+
+Only tests/, __graft_entry__.smoke() and bench.py's CPU-baseline legs may import this.
+
+  Oracle      liboracle.so: the CPU restatement (horizonator_oracle.c + gl_pipeline.c)
+  Reference   _ref/libhorizonator_ref.so: the reference's own horizonator-lib.c + dem.c, compiled
+              unmodified from /root/reference on the fake GL of oracle/fakegl (prebuilt .so travels)
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ORACLE_SO = os.path.join(HERE, "liboracle.so")
+REF_SO = os.path.join(HERE, "_ref", "libhorizonator_ref.so")
+
+
+def build(ref=True):
+    """make liboracle.so (+ _ref when /root/reference is present)."""
+    targets = ["liboracle.so"] + (["ref"] if ref else [])
+    subprocess.run(["make", "-s", "-C", HERE] + targets, check=True)
+
+
+def have_ref():
+    return os.path.exists(REF_SO)
+
+
+class Oracle:
+    """CPU restatement; same call sequence as the reference's Python type."""
+    _lib = None
+
+    @classmethod
+    def lib(cls):
+        if cls._lib is None:
+            if not os.path.exists(ORACLE_SO):
+                build(ref=False)
+            L = C.CDLL(ORACLE_SO)
+            f, i, b, vp = C.c_float, C.c_int, C.c_bool, C.c_void_p
+            L.oracle_init.restype = vp
+            L.oracle_init.argtypes = [f, f, C.POINTER(f), i, i, i, f, b, C.c_char_p]
+            L.oracle_deinit.argtypes = [vp]
+            L.oracle_move.restype = b
+            L.oracle_move.argtypes = [vp, C.POINTER(f), f, f]
+            L.oracle_pan_zoom.restype = b
+            L.oracle_pan_zoom.argtypes = [vp, f, f]
+            L.oracle_set_zextents.restype = b
+            L.oracle_set_zextents.argtypes = [vp, f, f, f, f]
+            L.oracle_render_offscreen.restype = b
+            L.oracle_render_offscreen.argtypes = [vp, vp, vp]
+            L.oracle_dem_sample.restype = C.c_int16
+            L.oracle_dem_sample.argtypes = [vp, i, i]
+            L.oracle_get_dem_geometry.argtypes = [vp, C.POINTER(C.c_int * 8)]
+            L.oracle_get_viewer.argtypes = [vp, C.POINTER(C.c_float * 4)]
+            L.oracle_set_threads.argtypes = [vp, i]
+            cls._lib = L
+        return cls._lib
+
+    def __init__(self, lat, lon, width, height, SRTM1=False, dir_dems=None,
+                 render_radius_cells=-1, render_radius_m=-1., viewer_z=None, threads=1):
+        L = self.lib()
+        z = C.c_float(-1. if viewer_z is None else viewer_z)
+        self.h = L.oracle_init(lat, lon, C.byref(z), width, height, render_radius_cells, render_radius_m,
+                               SRTM1, os.fsencode(dir_dems))
+        if not self.h:
+            raise RuntimeError("oracle_init() failed")
+        self.viewer_z = z.value
+        self.W, self.H = width, height
+        L.oracle_set_threads(self.h, threads)
+
+    def close(self):
+        if self.h:
+            self.lib().oracle_deinit(self.h)
+            self.h = None
+
+    def __del__(self):
+        self.close()
+
+    def move(self, lat, lon, viewer_z=None):
+        z = C.c_float(-1. if viewer_z is None else viewer_z)
+        assert self.lib().oracle_move(self.h, C.byref(z), lat, lon)
+        return z.value
+
+    def dem_geometry(self):
+        out = (C.c_int * 8)()
+        self.lib().oracle_get_dem_geometry(self.h, C.byref(out))
+        return dict(origin_dem_lon_lat=(out[0], out[1]), origin_dem_cellij=(out[2], out[3]),
+                    Ndems_ij=(out[4], out[5]), radius_cells=out[6], cells_per_deg=out[7])
+
+    def viewer(self):
+        out = (C.c_float * 4)()
+        self.lib().oracle_get_viewer(self.h, C.byref(out))
+        return dict(viewer_cell_i=out[0], viewer_cell_j=out[1], viewer_z=out[2], cos_viewer_lat=out[3])
+
+    def dem_sample(self, i, j):
+        return self.lib().oracle_dem_sample(self.h, i, j)
+
+    def mosaic(self):
+        n = 2 * self.dem_geometry()["radius_cells"]
+        L = self.lib()
+        return np.array([[L.oracle_dem_sample(self.h, i, j) for i in range(n)] for j in range(n)], dtype=np.int16)
+
+    def render(self, az_deg0, az_deg1, lat=-1000., lon=-1000., znear=100., zfar=40000.,
+               znear_color=-1., zfar_color=-1.):
+        L = self.lib()
+        if znear_color < 0:
+            znear_color = znear
+        if zfar_color < 0:
+            zfar_color = zfar
+        assert L.oracle_pan_zoom(self.h, az_deg0, az_deg1)
+        if lat > -1000.:
+            self.move(lat, lon)
+        if not L.oracle_set_zextents(self.h, znear, zfar, znear_color, zfar_color):
+            raise RuntimeError("oracle_set_zextents() failed")
+        image = np.empty((self.H, self.W, 3), np.uint8)
+        ranges = np.empty((self.H, self.W), np.float32)
+        assert L.oracle_render_offscreen(self.h, image.ctypes.data, ranges.ctypes.data)
+        return image, ranges
+
+
+class Reference:
+    """The reference's horizonator-lib.c + dem.c (unmodified) on the fake GL.  One live instance at a time:
+    the fake GL, like the code it serves, keeps one current program/framebuffer."""
+    _lib = None
+
+    @classmethod
+    def lib(cls):
+        if cls._lib is None:
+            L = C.CDLL(REF_SO)
+            f, d, i, b, vp, cp = C.c_float, C.c_double, C.c_int, C.c_bool, C.c_void_p, C.c_char_p
+            L.horizonator_init.restype = b
+            L.horizonator_init.argtypes = [vp, f, f, C.POINTER(f), i, i, i, f, b, b, b, cp, cp, cp, cp, b]
+            L.horizonator_move.restype = b
+            L.horizonator_move.argtypes = [vp, C.POINTER(f), f, f]
+            L.horizonator_pan_zoom.restype = b
+            L.horizonator_pan_zoom.argtypes = [vp, f, f]
+            L.horizonator_set_zextents.restype = b
+            L.horizonator_set_zextents.argtypes = [vp, f, f, f, f]
+            L.horizonator_render_offscreen.restype = b
+            L.horizonator_render_offscreen.argtypes = [vp, vp, vp]
+            L.horizonator_pick.restype = b
+            L.horizonator_pick.argtypes = [vp, C.POINTER(f), C.POINTER(f), i, i]
+            L.horizonator_dem_sample.restype = C.c_int16
+            L.horizonator_dem_sample.argtypes = [vp, i, i]
+            L.horizonator_dem_init.restype = b
+            L.horizonator_dem_init.argtypes = [vp, f, f, i, f, cp, b]
+            L.horizonator_dem_deinit.argtypes = [vp]
+            L.horizonator_x_from_az.restype = b
+            L.horizonator_x_from_az.argtypes = [C.POINTER(d), C.POINTER(d), d, d, d, i]
+            L.horizonator_project.restype = b
+            L.horizonator_project.argtypes = [C.POINTER(d)] * 3 + [d] * 9 + [i, i]
+            L.horizonator_unproject.restype = b
+            L.horizonator_unproject.argtypes = [C.POINTER(f), C.POINTER(f), i, i] + [d] * 7 + [i, i]
+            L.fakegl_set_threads.argtypes = [i]
+            cls._lib = L
+        return cls._lib
+
+    def __init__(self, lat, lon, width, height, SRTM1=False, dir_dems=None,
+                 render_radius_cells=-1, render_radius_m=-1., viewer_z=None, threads=1):
+        from horizonator_b200 import context_t   # layout only; no product code runs
+        L = self.lib()
+        L.fakegl_set_threads(threads)
+        self.ctx = context_t()
+        z = C.c_float(-1. if viewer_z is None else viewer_z)
+        if not L.horizonator_init(C.byref(self.ctx), lat, lon, C.byref(z), width, height,
+                                  render_radius_cells, render_radius_m, True, False, SRTM1,
+                                  os.fsencode(dir_dems), None, None, None, False):
+            raise RuntimeError("reference horizonator_init() failed")
+        self.viewer_z = z.value
+        self.W, self.H = width, height
+
+    def move(self, lat, lon, viewer_z=None):
+        z = C.c_float(-1. if viewer_z is None else viewer_z)
+        assert self.lib().horizonator_move(C.byref(self.ctx), C.byref(z), lat, lon)
+        return z.value
+
+    def dem_sample(self, i, j):
+        return self.lib().horizonator_dem_sample(C.byref(self.ctx.dems), i, j)
+
+    def render(self, az_deg0, az_deg1, lat=-1000., lon=-1000., znear=100., zfar=40000.,
+               znear_color=-1., zfar_color=-1.):
+        L = self.lib()
+        if znear_color < 0:
+            znear_color = znear
+        if zfar_color < 0:
+            zfar_color = zfar
+        assert L.horizonator_pan_zoom(C.byref(self.ctx), az_deg0, az_deg1)
+        if lat > -1000.:
+            self.move(lat, lon)
+        if not L.horizonator_set_zextents(C.byref(self.ctx), znear, zfar, znear_color, zfar_color):
+            raise RuntimeError("reference horizonator_set_zextents() failed")
+        image = np.empty((self.H, self.W, 3), np.uint8)
+        ranges = np.empty((self.H, self.W), np.float32)
+        assert L.horizonator_render_offscreen(C.byref(self.ctx), image.ctypes.data, ranges.ctypes.data)
+        return image, ranges

@@ -1,0 +1,298 @@
+"""GPU parity tests proper: the CUDA path, called through the C ABI (ctypes mirror in horizonator_b200),
+against the CPU oracle on the same seeded synthetic tiles.  Run on the B200 box: pytest -m gpu.
+
+Bars (BASELINE.json north_star): DEM mosaic bit-exact; coverage agreement >= 99.5 %; range within 1e-4
+relative where both hit (exceptions only on silhouette edges, inside the same 0.5 % budget); red +-1 LSB.
+Sharded (wedge, batch) renders must equal the unsharded ones bit-for-bit, and repeated renders too.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+from conftest import C1_LAT, C1_LON
+from compare import compare_renders
+
+pytestmark = pytest.mark.gpu
+
+
+def _torch_cuda():
+    import torch
+    assert torch.cuda.is_available(), "gpu-marked test running without a CUDA device"
+    return torch
+
+
+@pytest.fixture(scope="module")
+def hz():
+    import horizonator_b200
+    return horizonator_b200
+
+
+def _oracle(tiles, W, H, R, lat=C1_LAT, lon=C1_LON, **kw):
+    from oracle.binding import Oracle
+    return Oracle(lat, lon, W, H, SRTM1=False, dir_dems=tiles, render_radius_cells=R, threads=os.cpu_count() or 1, **kw)
+
+
+# ------------------------------------------------------------------------------------------ K1: mosaic
+
+@pytest.mark.parametrize("R", [1, 5, 48, 600, 1200])
+def test_mosaic_bit_exact(hz, tiles_c1, R):
+    """k_mosaic vs dem.c:264-309 restated (oracle) for every cell of the square."""
+    h = hz.horizonator(C1_LAT, C1_LON, 64, 16, dir_dems=tiles_c1, render_radius_cells=R)
+    got = h.mosaic()
+    if R <= 48:
+        o = _oracle(tiles_c1, 64, 16, R)
+        want = o.mosaic()
+    else:
+        # large squares: assemble the expectation from the raw tiles with numpy (same rule as dem.c)
+        want = _numpy_mosaic(tiles_c1, h.context.dems)
+    assert got.dtype == np.int16 and got.shape == (2 * R, 2 * R)
+    assert np.array_equal(got, want)
+    # and the host-side sampler of the product agrees with the device copy on a scattered subset
+    rs = np.random.default_rng(R)
+    for _ in range(200):
+        i, j = int(rs.integers(0, 2 * R)), int(rs.integers(0, 2 * R))
+        assert hz.lib.horizonator_dem_sample(C.byref(h.context.dems), i, j) == got[j, i]
+
+
+def _numpy_mosaic(tiles_dir, dems):
+    from tools.synth import tile_name
+    cpd, R = dems.cells_per_deg, dems.radius_cells
+    N = 2 * R
+    oi, oj = dems.origin_dem_cellij[0], dems.origin_dem_cellij[1]
+    lon0, lat0 = dems.origin_dem_lon_lat[0], dems.origin_dem_lon_lat[1]
+    out = np.zeros((N, N), np.int16)
+    gi = np.arange(N) + oi
+    gj = np.arange(N) + oj
+
+    def split(g):
+        t = g // cpd
+        c = g - t * cpd
+        z = c == 0
+        t = np.where(z, t - 1, t)
+        c = np.where(z, cpd, c)
+        neg = t < 0
+        return np.where(neg, 0, t), np.where(neg, 0, c)
+
+    ti, ci = split(gi)
+    tj, cj = split(gj)
+    cache = {}
+    for a in np.unique(ti):
+        for b in np.unique(tj):
+            path = os.path.join(tiles_dir, tile_name(lat0 + int(b), lon0 + int(a)))
+            if os.path.exists(path) and os.path.getsize(path) > 0:
+                cache[(a, b)] = np.fromfile(path, dtype=">i2").reshape(cpd + 1, cpd + 1)
+            else:
+                cache[(a, b)] = None
+            cols = np.where(ti == a)[0]
+            rows = np.where(tj == b)[0]
+            if cache[(a, b)] is None:
+                continue
+            sub = cache[(a, b)][np.ix_(cpd - cj[rows], ci[cols])]
+            out[np.ix_(rows, cols)] = np.maximum(sub, 0)
+    return out
+
+
+def test_mosaic_missing_and_empty_tiles(hz, tiles_holes):
+    h = hz.horizonator(C1_LAT, C1_LON, 64, 16, dir_dems=tiles_holes, render_radius_cells=300)
+    got = h.mosaic()
+    want = _numpy_mosaic(tiles_holes, h.context.dems)
+    assert np.array_equal(got, want)
+    assert (got[:300, 300:] == 0).all() or (got[300:, :300] == 0).all()   # at least one quadrant is sea
+
+
+# ------------------------------------------------------------------------------------------ render parity
+
+SCENES = [
+    # name,            W,    H,  R,   az0,     az1,    znear, zfar,   znc,  zfc
+    ("circle_small",   360,  60, 48,  -180.05, 179.95, 100., 100000., -1., -1.),
+    ("quarter",        256,  96, 96,   30.0,   120.0,  50.,  20000.,  200., 10000.),
+    ("seam_odd_h",     300,  75, 64,   150.0,  210.0,  100., 40000.,  -1., -1.),
+    ("narrow_zoom",    400, 100, 200,  80.0,   100.0,  100., 40000.,  -1., -1.),
+    ("circle_mid",    1800, 300, 400, -180.05, 179.95, 100., 100000., -1., -1.),
+    ("near_clip",      360,  90, 64,  -90.0,   90.0,   5.,   3000.,   -1., -1.),
+]
+
+
+@pytest.mark.parametrize("scene", SCENES, ids=[s[0] for s in SCENES])
+def test_render_matches_oracle(hz, tiles_c1, scene):
+    name, W, H, R, az0, az1, znear, zfar, znc, zfc = scene
+    h = hz.horizonator(C1_LAT, C1_LON, W, H, dir_dems=tiles_c1, render_radius_cells=R)
+    img, rng = h.render(az0, az1, znear=znear, zfar=zfar, znear_color=znc, zfar_color=zfc)
+    o = _oracle(tiles_c1, W, H, R)
+    img_o, rng_o = o.render(az0, az1, znear=znear, zfar=zfar, znear_color=znc, zfar_color=zfc)
+    s = compare_renders(img, rng, img_o, rng_o)
+    print(name, s)
+    assert s["hit_fraction_ref"] > 0.01, "scene shows no terrain: not a test"
+    assert s["ok"], s
+
+
+def test_config1_full_size(hz, tiles_c1):
+    """BASELINE config 1 at full size: R=1200, 3600x300, az [-180.05,179.95], znear 100, zfar 100000."""
+    W, H, R = 3600, 300, 1200
+    h = hz.horizonator(C1_LAT, C1_LON, W, H, dir_dems=tiles_c1, render_radius_cells=R)
+    img, rng = h.render(-180.05, 179.95, znear=100., zfar=100000.)
+    o = _oracle(tiles_c1, W, H, R)
+    img_o, rng_o = o.render(-180.05, 179.95, znear=100., zfar=100000.)
+    s = compare_renders(img, rng, img_o, rng_o)
+    print("config1", s, h.last_render_stats())
+    assert s["ok"], s
+
+
+def test_render_moved_viewer_and_holes(hz, tiles_holes):
+    W, H, R = 512, 128, 500
+    lat, lon = C1_LAT - 0.05, C1_LON + 0.03
+    h = hz.horizonator(C1_LAT, C1_LON, W, H, dir_dems=tiles_holes, render_radius_cells=R)
+    img, rng = h.render(-60., 60., lat=lat, lon=lon, znear=100., zfar=60000.)
+    o = _oracle(tiles_holes, W, H, R)
+    img_o, rng_o = o.render(-60., 60., lat=lat, lon=lon, znear=100., zfar=60000.)
+    s = compare_renders(img, rng, img_o, rng_o)
+    print("moved+holes", s)
+    assert s["ok"], s
+
+
+def test_flat_world_analytic(hz, tmp_path):
+    """All tiles missing => elevation 0 everywhere.  Eye 50 m up: ground pixel at elevation el<0 has slant
+    range h/sin|el| (linear interpolation inside a cell is exact on a plane through... the eye-centred
+    projection is not linear, so allow 1e-3) and the reported range is slant/cos(el) (reference quirk Q1)."""
+    W, H, R = 720, 120, 300
+    d = str(tmp_path)
+    import horizonator_b200 as hb
+    ctx = hb.context_t()
+    z = C.c_float(50.0)
+    assert hb.lib.horizonator_init(C.byref(ctx), C1_LAT, C1_LON, C.byref(z), W, H, R, -1.0, True, False, False,
+                                   os.fsencode(d), None, None, None, False)
+    try:
+        assert hb.lib.horizonator_pan_zoom(C.byref(ctx), -180.05, 179.95)
+        assert hb.lib.horizonator_set_zextents(C.byref(ctx), 100., 20000., 100., 20000.)
+        img = np.empty((H, W, 3), np.uint8)
+        rng = np.empty((H, W), np.float32)
+        assert hb.lib.horizonator_render_offscreen(C.byref(ctx), img.ctypes.data, rng.ctypes.data)
+    finally:
+        hb.lib.horizonator_deinit(C.byref(ctx))
+    deg_per_px = 360.0 / W
+    rows = np.arange(H)
+    el = np.radians((1 - (2 * rows + 1) / H) * (360.0 / (2 * (W / H))))
+    assert abs(np.degrees(el[0]) - (H / 2 - 0.5) * deg_per_px) < 1e-9
+    up = el >= 0
+    assert (rng[up] == -1).all() and (img[up] == (255, 0, 0)).all()
+    for r in np.where(~up)[0]:
+        slant = 50.0 / np.sin(-el[r])
+        row = rng[r]
+        if 100.0 * 1.01 < slant < 20000.0 * 0.99 and slant * np.cos(el[r]) < 0.8 * R * 92.6 * np.cos(np.radians(35)):
+            # the first/last column may be empty: triangles straddling the window seam are dropped, not
+            # split (geometry.glsl:15-27)
+            assert (row[1:-1] > 0).all(), (r, slant)
+            np.testing.assert_allclose(row[1:-1], slant / np.cos(el[r]), rtol=2e-3)
+        elif slant < 99.0:
+            assert (row == -1).all()
+
+
+# ------------------------------------------------------------------------------------------ determinism, shards
+
+def test_repeatable(hz, tiles_c1):
+    h = hz.horizonator(C1_LAT, C1_LON, 900, 150, dir_dems=tiles_c1, render_radius_cells=300)
+    a = h.render(-180.05, 179.95, zfar=100000.)
+    for _ in range(3):
+        b = h.render(-180.05, 179.95, zfar=100000.)
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+
+
+def test_wedges_equal_full_render(hz, tiles_c1):
+    torch = _torch_cuda()
+    W, H, R = 1200, 200, 300
+    h = hz.horizonator(C1_LAT, C1_LON, W, H, dir_dems=tiles_c1, render_radius_cells=R)
+    img, rng = h.render(-180.05, 179.95, zfar=100000.)
+    for G in (2, 3, 8):
+        edges = [W * g // G for g in range(G + 1)]
+        out_i = np.empty_like(img)
+        out_r = np.empty_like(rng)
+        for g in range(G):
+            x0, x1 = edges[g], edges[g + 1]
+            di = torch.empty((H, x1 - x0, 3), dtype=torch.uint8, device="cuda")
+            dr = torch.empty((H, x1 - x0), dtype=torch.float32, device="cuda")
+            h.render_wedge_device(x0, x1, di.data_ptr(), dr.data_ptr())
+            torch.cuda.synchronize()
+            out_i[:, x0:x1] = di.cpu().numpy()
+            out_r[:, x0:x1] = dr.cpu().numpy()
+        assert np.array_equal(out_i, img), G
+        assert np.array_equal(out_r, rng), G
+
+
+def test_batch_equals_loop(hz, tiles_c1):
+    torch = _torch_cuda()
+    W, H, R = 600, 100, 200
+    h = hz.horizonator(C1_LAT, C1_LON, W, H, dir_dems=tiles_c1, render_radius_cells=R)
+    h.set_zextents(100., 50000.)
+    views = [(C1_LAT + 0.01 * k, C1_LON - 0.01 * k, -180.05 + 10 * k, 179.95 + 10 * k) for k in range(4)]
+    bi, br = h.render_batch(views)
+    di = torch.empty((len(views), H, W, 3), dtype=torch.uint8, device="cuda")
+    dr = torch.empty((len(views), H, W), dtype=torch.float32, device="cuda")
+    h.render_batch_device(views, di.data_ptr(), dr.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    assert np.array_equal(di.cpu().numpy(), bi) and np.array_equal(dr.cpu().numpy(), br)
+    for k, (lat, lon, a0, a1) in enumerate(views):
+        i1, r1 = h.render(a0, a1, lat=lat, lon=lon, zfar=50000.)
+        assert np.array_equal(i1, bi[k]) and np.array_equal(r1, br[k]), k
+
+
+# ------------------------------------------------------------------------------------------ API behaviour
+
+def test_python_api_shapes_and_errors(hz, tiles_c1):
+    h = hz.horizonator(C1_LAT, C1_LON, 128, 32, dir_dems=tiles_c1, render_radius_cells=32)
+    assert str(h).startswith("Looking out from 35.00")
+    assert h.render(0, 90, return_image=False, return_range=False) == ()
+    im = h.render(0, 90, return_range=False)
+    assert im.shape == (32, 128, 3) and im.dtype == np.uint8
+    r = h.render(0, 90, return_image=False)
+    assert r.shape == (32, 128) and r.dtype == np.float32
+    a = h.render(0, 90)
+    b = h.render(0 + 45. / 127, 90 - 45. / 127 * 0, az_extents_use_pixel_centers=False)
+    assert isinstance(a, tuple) and len(a) == 2 and isinstance(b, tuple)
+    with pytest.raises(RuntimeError):
+        h.render(0, 90, znear=-5.)                        # set_zextents refuses non-positive values
+    with pytest.raises(RuntimeError):
+        hz.horizonator(C1_LAT, C1_LON, 64, 16, dir_dems=tiles_c1, render_radius_cells=10, render_radius_m=5000.)
+    with pytest.raises(RuntimeError):
+        hz.horizonator(C1_LAT, C1_LON, 64, 16, dir_dems=tiles_c1, render_texture=True, render_radius_cells=10)
+    # pixel-centre convention widens the window by half a pixel each side (pywrap.c:204-212)
+    c = h.render(0., 90., az_extents_use_pixel_centers=True)
+    half = 90. / 127 / 2
+    d = h.render(0. - half, 90. + half)
+    assert np.array_equal(c[0], d[0]) and np.array_equal(c[1], d[1])
+
+
+def test_pick_matches_reference_formula(hz, tiles_c1):
+    W, H, R = 360, 60, 64
+    h = hz.horizonator(C1_LAT, C1_LON, W, H, dir_dems=tiles_c1, render_radius_cells=R)
+    img, rng = h.render(-180.05, 179.95, zfar=100000.)
+    ys, xs = np.where(rng > 0)
+    assert len(ys) > 10
+    lat, lon = C.c_float(), C.c_float()
+    for k in range(0, len(ys), max(1, len(ys) // 25)):
+        x, y = int(xs[k]), int(ys[k])
+        assert hz.lib.horizonator_pick(C.byref(h.context), C.byref(lat), C.byref(lon), x, y)
+        # the picked point lies within the loaded square, in the direction of the pixel's azimuth
+        az = np.radians(-180.05 + (x + 0.5) / W * 360.0)
+        de = (lon.value - C1_LON) * np.cos(np.radians(C1_LAT))
+        dn = lat.value - C1_LAT
+        assert abs(np.arctan2(de, dn) - az + 2 * np.pi * np.round((az - np.arctan2(de, dn)) / (2 * np.pi))) < 0.05
+    ys, xs = np.where(rng < 0)
+    assert not hz.lib.horizonator_pick(C.byref(h.context), C.byref(lat), C.byref(lon), int(xs[0]), int(ys[0]))
+
+
+def test_windowed_context_redraw_and_resize(hz, tiles_c1):
+    import horizonator_b200 as hb
+    ctx = hb.context_t()
+    assert hb.lib.horizonator_init(C.byref(ctx), C1_LAT, C1_LON, None, 0, 0, 32, -1.0, False, False, False,
+                                   os.fsencode(tiles_c1), None, None, None, False)
+    try:
+        assert not ctx.offscreen.inited and ctx.Ntriangles == 2 * 63 * 63
+        assert hb.lib.horizonator_redraw(C.byref(ctx))
+        assert hb.lib.horizonator_resized(C.byref(ctx), 640, 200)
+        assert hb.lib.horizonator_redraw(C.byref(ctx))
+        assert not hb.lib.horizonator_render_offscreen(C.byref(ctx), None, None)
+    finally:
+        hb.lib.horizonator_deinit(C.byref(ctx))
+        hb.lib.horizonator_deinit(C.byref(ctx))      # idempotent
