@@ -1,0 +1,382 @@
+#!/usr/bin/env python
+"""bench.py -- panoramas/s of the render hot path on N B200s (BASELINE.json metric), one JSON line.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+
+Workload (N=1 and per rank for N>1): BASELINE.json configs[1] ("C2") -- synthetic SRTM1 tiles N32..N35 x
+W119..W116, viewer (34+1/7200, -117+1/7200), render_radius_m = 150 km (R = 5858 cells, 137 M vertices, 274 M
+triangles), 3600x600 panorama + range image, az [-180.05, 179.95], znear 100 m, zfar 150 km.  A step is one
+panorama per rank; with N>1 the ranks render different viewpoints of the SURVEY 8d "C5" grid against their
+own copy of the DEM (weak scaling, no collective on the data path; NCCL only for the barrier/max of times).
+
+value      device-resident throughput: outputs stay in HBM, CUDA events on the stream the kernels run on
+e2e        the same through the reference-facing call horizonator_render_offscreen() (host buffers in, D2H inside)
+roofline   k_march, the dominant kernel: algorithmic bytes (2*(2R)^2 + 7*W*H per panorama) / its mean
+           launch duration measured live with CUDA events; peak = MEASURED_PEAKS.json hbm_gbs
+cpu_baseline  the CPU oracle timed on the host cores (rank 0, N=1), a bounded sample of the same workload
+
+--impl reference: the reference's own horizonator-lib.c + dem.c (compiled unmodified, oracle/_ref) rendering
+the same workload on the host cores through a software GL restatement (no GL driver can run in this image).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+C2 = dict(lat=34.0 + 1.0 / 7200.0, lon=-117.0 + 1.0 / 7200.0, W=3600, H=600, radius_m=150000.0,
+          az0=-180.05, az1=179.95, znear=100.0, zfar=150000.0, R=5858)
+TILES_DIR = os.environ.get("HZ_BENCH_TILES", "/tmp/hz_tiles_c2")
+
+
+def algorithmic_bytes(R, W, H):
+    return 2 * (2 * R) ** 2 + 7 * W * H
+
+
+def measured_peak_gbs():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, smmax, reasons = [], [], set()
+        for t, line in self.lines:
+            if t < t0 - 0.05 or t > t1 + 0.15:
+                continue
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); smmax.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples in the timed region"]}
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(smmax), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def ensure_tiles(rank, barrier):
+    from tools import synth
+    if rank == 0:
+        synth.config2_tiles(TILES_DIR)
+    barrier()
+    return TILES_DIR
+
+
+def viewpoints(n_ranks, rank, steps):
+    """Rank 0 / N=1 renders the C2 viewpoint itself.  Other ranks take points of the 64x64 grid spanning the
+    central 1 x 1 degree, one fixed point per rank: same work per rank, different data."""
+    if n_ranks == 1 or rank == 0:
+        return [(C2["lat"], C2["lon"])] * steps
+    g = 64
+    k = (rank * 977) % (g * g)
+    lat = 33.5 + (k // g + 0.5) / g + 1.0 / 7200.0
+    lon = -117.5 + (k % g + 0.5) / g + 1.0 / 7200.0
+    return [(lat, lon)] * steps
+
+
+# ------------------------------------------------------------------------------------------------ our arm
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the renderer has no CPU path")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    tiles = ensure_tiles(rank, barrier)
+    import horizonator_b200 as hz
+
+    t_init = time.time()
+    h = hz.horizonator(C2["lat"], C2["lon"], C2["W"], C2["H"], SRTM1=True, dir_dems=tiles,
+                       render_radius_m=C2["radius_m"])
+    t_init = time.time() - t_init
+    R = h.context.dems.radius_cells
+    W, H = C2["W"], C2["H"]
+    h.set_zextents(C2["znear"], C2["zfar"])
+    K, Wm = args.steps, args.warmup
+    pts = viewpoints(world, rank, K + Wm)
+    views = [(la, lo, C2["az0"], C2["az1"]) for la, lo in pts]
+
+    d_img = torch.empty((H, W, 3), dtype=torch.uint8, device="cuda")
+    d_rng = torch.empty((H, W), dtype=torch.float32, device="cuda")
+    stream = torch.cuda.current_stream()
+
+    # ---- device-resident throughput ----
+    for k in range(Wm):
+        h.render_batch_device(views[k:k + 1], d_img.data_ptr(), d_rng.data_ptr(), stream.cuda_stream)
+    torch.cuda.synchronize()
+    h.profile(True)
+    h.profile_read()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    barrier()
+    torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    wall0 = time.time()
+    ev0.record(stream)
+    for k in range(K):
+        h.render_batch_device(views[Wm + k:Wm + k + 1], d_img.data_ptr(), d_rng.data_ptr(), stream.cuda_stream)
+    ev1.record(stream)
+    torch.cuda.synchronize()
+    barrier()
+    wall1 = time.time()
+    ms_total = ev0.elapsed_time(ev1)
+    prof = h.profile_read()
+    h.profile(False)
+    clocks = sampler.stop(wall0, wall1) if rank == 0 else None
+    stats = h.last_render_stats()
+
+    t = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total_max = float(t.item())
+    value = world * K / (ms_total_max / 1e3)
+
+    # ---- end to end through the reference-facing call, host buffers ----
+    import numpy as np
+    import ctypes as C
+    img = np.empty((H, W, 3), np.uint8)
+    rng = np.empty((H, W), np.float32)
+    ctx = C.byref(h.context)
+
+    def e2e_step(la, lo):
+        # what horizonator-pywrap.c's render() does per call, minus the numpy allocation
+        assert hz.lib.horizonator_pan_zoom(ctx, C2["az0"], C2["az1"])
+        assert hz.lib.horizonator_move(ctx, None, la, lo)
+        assert hz.lib.horizonator_set_zextents(ctx, C2["znear"], C2["zfar"], C2["znear"], C2["zfar"])
+        assert hz.lib.horizonator_render_offscreen(ctx, img.ctypes.data, rng.ctypes.data)
+
+    for k in range(Wm):
+        e2e_step(*pts[k])
+    barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for k in range(K):
+        e2e_step(*pts[Wm + k])
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * K / float(t.item())
+    hit_fraction = float((rng > 0).mean())
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peak, peak_src = measured_peak_gbs()
+    alg = algorithmic_bytes(R, W, H)
+    march_s = prof["march"] / 1e3
+    achieved = alg / march_s / 1e9 if march_s > 0 else 0.0
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "r01_march_dram_bytes.json")
+    if os.path.exists(tp):
+        try:
+            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+
+    mosaic_ms = h.time_mosaic(5)
+    out = {
+        "metric": "panoramas/sec (SRTM1, 3600x600 px)",
+        "value": value, "unit": "panoramas/s",
+        "n_gpus": world, "steps": K, "warmup": Wm,
+        "ms_per_step": ms_total_max / K,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {
+            "workload": "BASELINE configs[1]: single viewpoint per GPU, synthetic SRTM1 4x4 tiles, 150 km radius "
+                        "(R=%d cells, %d triangles), 3600x600 panorama + range image" % (R, h.context.Ntriangles),
+            "az_deg": [C2["az0"], C2["az1"]], "znear_m": C2["znear"], "zfar_m": C2["zfar"],
+            "panoramas_per_step_per_gpu": 1,
+            "l2": "inputs larger than L2: the int16 DEM square is %.0f MB, read once per panorama" % (2 * (2 * R) ** 2 / 1e6),
+            "parallelism": "viewpoint batch, 1 panorama per GPU per step, DEM replicated, no data-path collective",
+        },
+        "e2e": {"value": e2e_value, "unit": "panoramas/s",
+                "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 7 * W * H,
+                "note": "horizonator_pan_zoom+move+set_zextents+render_offscreen into host buffers; per-step inputs "
+                        "are 7 scalars passed as kernel arguments (no H2D copy), outputs 7*W*H bytes D2H"},
+        "gpu_launches": K * stats["launches"],
+        "roofline": {"bound": "hbm", "kernel": "k_march", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": alg,
+                     "kernel_ms": {k: prof[k] for k in ("prepare", "march", "big", "resolve")},
+                     "note": "k_march is instruction-bound (2 atan + rsqrt per vertex, 274 M triangles), not HBM-bound"},
+        "clocks": clocks,
+        "aux": {"init_s": t_init, "mosaic_decode_ms": mosaic_ms,
+                "mosaic_decode_gbs": 4 * (2 * R) ** 2 / (mosaic_ms / 1e3) / 1e9,
+                "big_triangles": stats["big_triangles"], "terrain_pixel_fraction": hit_fraction},
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        out["cpu_baseline"] = cpu_baseline(tiles, use_ref=False, steps=3)
+    print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------------------ CPU legs
+
+def cpu_baseline(tiles, use_ref, steps=1, warmup=0, budget_s=25.0):
+    """Times the CPU oracle (or the reference build) on the C2 workload with all host threads.
+    Bounded: renders are timed until `steps` are done or the budget is spent."""
+    from oracle import binding
+    cores = os.cpu_count() or 1
+    cls = binding.Reference if use_ref else binding.Oracle
+    o = cls(C2["lat"], C2["lon"], C2["W"], C2["H"], SRTM1=True, dir_dems=tiles,
+            render_radius_m=C2["radius_m"], threads=cores)
+    for _ in range(warmup):
+        o.render(C2["az0"], C2["az1"], znear=C2["znear"], zfar=C2["zfar"])
+    times = []
+    t_start = time.perf_counter()
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        o.render(C2["az0"], C2["az1"], znear=C2["znear"], zfar=C2["zfar"])
+        times.append(time.perf_counter() - t0)
+        if time.perf_counter() - t_start > budget_s:
+            break
+    mean = sum(times) / len(times)
+    return {"value": 1.0 / mean, "unit": "panoramas/s", "cores": cores,
+            "kind": "reference" if use_ref else "port",
+            "sample": "%d full C2 panorama(s) (3600x600, 274 M triangles), steady state (DEM loaded), %.2f s each; "
+                      "%s, OpenMP over %d threads" %
+                      (len(times), mean,
+                       "reference horizonator-lib.c+dem.c unmodified on the software-GL restatement (oracle/_ref)"
+                       if use_ref else "CPU restatement of the reference GL path (oracle/)", cores),
+            "ms_per_render": mean * 1e3}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if rank != 0:
+        return
+    from tools import synth
+    from oracle import binding
+    synth.config2_tiles(TILES_DIR)
+    use_ref = binding.have_ref()
+    if not os.path.exists(binding.ORACLE_SO):
+        binding.build(ref=False)
+    # bounded: every step is one full C2 panorama; the run stops early once ~4 minutes are spent
+    cores = os.cpu_count() or 1
+    cls = binding.Reference if use_ref else binding.Oracle
+    o = cls(C2["lat"], C2["lon"], C2["W"], C2["H"], SRTM1=True, dir_dems=TILES_DIR,
+            render_radius_m=C2["radius_m"], threads=cores)
+    budget = float(os.environ.get("HZ_REF_BUDGET_S", "200"))
+    t_begin = time.perf_counter()
+    done_w = 0
+    for _ in range(args.warmup):
+        o.render(C2["az0"], C2["az1"], znear=C2["znear"], zfar=C2["zfar"])
+        done_w += 1
+        if time.perf_counter() - t_begin > budget / 4:
+            break
+    times = []
+    for _ in range(args.steps):
+        t0 = time.perf_counter()
+        o.render(C2["az0"], C2["az1"], znear=C2["znear"], zfar=C2["zfar"])
+        times.append(time.perf_counter() - t0)
+        if time.perf_counter() - t_begin > budget:
+            break
+    mean = sum(times) / len(times)
+    value = 1.0 / mean
+    kind = "reference" if use_ref else "port"
+    sample = ("%d of the requested %d steps timed (budget %.0f s), each one full C2 panorama (3600x600, R=5858, "
+              "274 M triangles) into host buffers, %.2f s each; %s; OpenMP over %d host threads; "
+              "1 process regardless of --gpus" %
+              (len(times), args.steps, budget, mean,
+               "the reference's horizonator-lib.c + dem.c compiled unmodified (oracle/_ref) on a software-GL "
+               "restatement of the driver (no GL driver exists in this image; real llvmpipe not measurable)"
+               if use_ref else "CPU restatement of the reference GL path (oracle/)", cores))
+    out = {
+        "impl": "reference",
+        "metric": "panoramas/sec (SRTM1, 3600x600 px)",
+        "value": value, "unit": "panoramas/s",
+        "n_gpus": world, "steps": len(times), "warmup": done_w,
+        "ms_per_step": mean * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "BASELINE configs[1]: single viewpoint, synthetic SRTM1 4x4 tiles, 150 km radius "
+                               "(R=5858 cells, 274482450 triangles), 3600x600 panorama + range image",
+                   "az_deg": [C2["az0"], C2["az1"]], "znear_m": C2["znear"], "zfar_m": C2["zfar"]},
+        "cpu_baseline": {"value": value, "unit": "panoramas/s", "cores": cores, "kind": kind, "sample": sample},
+        "e2e": {"value": value, "unit": "panoramas/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(out), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "b200":
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

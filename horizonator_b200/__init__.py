@@ -98,6 +98,8 @@ def _declare(lib):
         "horizonator_download_mosaic": (b, [ctx, vp]),
         "horizonator_time_mosaic": (b, [ctx, i, P(f)]),
         "horizonator_last_render_stats": (b, [ctx, P(C.c_uint * 4)]),
+        "horizonator_profile_enable": (b, [ctx, b]),
+        "horizonator_profile_read": (b, [ctx, P(f * 4), P(i)]),
     }
     for name, (res, args) in sigs.items():
         fn = getattr(lib, name)
@@ -116,6 +118,7 @@ EXPORTED_SYMBOLS = (
     "horizonator_dem_bounds_latlon_deg",
     "horizonator_render_batch_device", "horizonator_render_batch", "horizonator_render_wedge_device",
     "horizonator_download_mosaic", "horizonator_time_mosaic", "horizonator_last_render_stats",
+    "horizonator_profile_enable", "horizonator_profile_read",
 )
 
 if not os.path.exists(LIBRARY_PATH):
@@ -286,6 +289,19 @@ class horizonator:
         if not lib.horizonator_time_mosaic(C.byref(self._ctx), reps, C.byref(ms)):
             raise RuntimeError("horizonator_time_mosaic() failed")
         return ms.value
+
+    def profile(self, on=True):
+        """Record CUDA events around every kernel of every render from now on (see profile_read)."""
+        if not lib.horizonator_profile_enable(C.byref(self._ctx), bool(on)):
+            raise RuntimeError("horizonator_profile_enable() failed")
+
+    def profile_read(self):
+        """Mean device ms per render of each kernel since the last read, and the number of renders."""
+        ms = (C.c_float * 4)()
+        n = C.c_int(0)
+        if not lib.horizonator_profile_read(C.byref(self._ctx), C.byref(ms), C.byref(n)):
+            raise RuntimeError("horizonator_profile_read() failed")
+        return {"prepare": ms[0], "march": ms[1], "big": ms[2], "resolve": ms[3], "renders": n.value}
 
     def last_render_stats(self):
         out = (C.c_uint * 4)()

@@ -77,6 +77,11 @@ struct Slot
 
     bool have_render = false;        // d_vis holds a complete full-width render (for pick)
     unsigned launches_last = 0;
+
+    // optional per-kernel timing: 5 events per recorded render
+    bool profiling = false;
+    std::vector<cudaEvent_t> prof_events;
+    size_t prof_used = 0;
 };
 
 std::mutex          g_table_mutex;
@@ -139,6 +144,7 @@ void destroy_slot(Slot* s)
     free_target(*s);
     cudaFree(s->d_mosaic);
     for(int i = 0; i < 4; i++) for(int j = 0; j < 4; j++) cudaFree((void*)s->tiles.tile[i][j]);
+    for(cudaEvent_t e : s->prof_events) cudaEventDestroy(e);
     cudaFree(s->d_e); cudaFree(s->d_n);
     cudaFree(s->d_big_queue); cudaFree(s->d_big_count);
     if(s->stream) cudaStreamDestroy(s->stream);
@@ -232,9 +238,25 @@ bool enqueue_render(Slot& s, const ViewState& vs, int x0, int x1,
     const float* d_tanel = nullptr;
     if(d_ranges && !tanel_for(s, vs.az_deg0, vs.az_deg1, st, &d_tanel)) return false;
 
+    cudaEvent_t* ev = nullptr;
+    if(s.profiling)
+    {
+        while(s.prof_events.size() < s.prof_used + 5)
+        {
+            cudaEvent_t e;
+            CUDA_TRY(cudaEventCreate(&e));
+            s.prof_events.push_back(e);
+        }
+        ev = &s.prof_events[s.prof_used];
+        s.prof_used += 5;
+    }
+    if(ev) CUDA_TRY(cudaEventRecord(ev[0], st));
     CUDA_TRY(hz_launch_prepare(v, st));
+    if(ev) CUDA_TRY(cudaEventRecord(ev[1], st));
     CUDA_TRY(hz_launch_march(v, st));
+    if(ev) CUDA_TRY(cudaEventRecord(ev[2], st));
     CUDA_TRY(hz_launch_big(v, st));
+    if(ev) CUDA_TRY(cudaEventRecord(ev[3], st));
     s.launches_last = 3;
     if(d_image || d_ranges)
     {
@@ -245,6 +267,7 @@ bool enqueue_render(Slot& s, const ViewState& vs, int x0, int x1,
         CUDA_TRY(hz_launch_resolve(r, st));
         s.launches_last = 4;
     }
+    if(ev) CUDA_TRY(cudaEventRecord(ev[4], st));
     s.have_render = (x0 == 0 && x1 == s.W);
     return true;
 }
@@ -710,6 +733,38 @@ bool horizonator_time_mosaic(const horizonator_context_t* ctx, int reps, float* 
     CUDA_TRY(cudaEventElapsedTime(&ms, a, b));
     cudaEventDestroy(a); cudaEventDestroy(b);
     *ms_per_run = ms / (float)reps;
+    return true;
+}
+
+bool horizonator_profile_enable(const horizonator_context_t* ctx, bool on)
+{
+    Slot* s = slot_of(ctx);
+    if(s == nullptr) return false;
+    s->profiling = on;
+    return true;
+}
+
+bool horizonator_profile_read(const horizonator_context_t* ctx, float out_ms[4], int* renders)
+{
+    Slot* s = slot_of(ctx);
+    if(s == nullptr || out_ms == nullptr || renders == nullptr) return false;
+    DeviceGuard g(s->device);
+    double sum[4] = {0, 0, 0, 0};
+    const size_t n = s->prof_used / 5;
+    for(size_t r = 0; r < n; r++)
+    {
+        cudaEvent_t* ev = &s->prof_events[5 * r];
+        CUDA_TRY(cudaEventSynchronize(ev[4]));
+        for(int k = 0; k < 4; k++)
+        {
+            float ms = 0;
+            CUDA_TRY(cudaEventElapsedTime(&ms, ev[k], ev[k + 1]));
+            sum[k] += ms;
+        }
+    }
+    for(int k = 0; k < 4; k++) out_ms[k] = n ? (float)(sum[k] / (double)n) : 0.f;
+    *renders = (int)n;
+    s->prof_used = 0;
     return true;
 }
 

@@ -58,6 +58,14 @@ bool horizonator_download_mosaic(const horizonator_context_t* ctx, int16_t* mosa
  * milliseconds (CUDA events on the context's stream).  For benchmarks of the init path. */
 bool horizonator_time_mosaic(const horizonator_context_t* ctx, int reps, float* ms_per_run);
 
+/* Per-kernel device times.  While enabled, every render records CUDA events around each of
+ * its kernels on the stream it runs on.  horizonator_profile_read() waits for them and reports
+ * the MEAN duration in milliseconds per render of: out_ms[0] k_prepare (clear + axis tables),
+ * [1] k_march (mesh + projection + cull + small-triangle raster), [2] k_big (large triangles),
+ * [3] k_resolve (keys -> image + ranges), over the *renders recorded since the last read. */
+bool horizonator_profile_enable(const horizonator_context_t* ctx, bool on);
+bool horizonator_profile_read(const horizonator_context_t* ctx, float out_ms[4], int* renders);
+
 /* Counters of the most recent render on this context: out[0] = triangles that were queued
  * for the large-triangle kernel, out[1] = queue capacity, out[2] = kernel launches the
  * render issued, out[3] = CUDA device ordinal. */
