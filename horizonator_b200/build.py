@@ -51,6 +51,10 @@ def build_library(force=False, extra_flags=(), verbose=False):
         if verbose:
             print(" ".join(cmd))
         subprocess.run(cmd, check=True)
+    # the SONAME is libhorizonator.so.0: give the dynamic loader that name too
+    link = out + ".0"
+    if not os.path.islink(link) and not os.path.exists(link):
+        os.symlink(os.path.basename(out), link)
     return out
 
 
