@@ -258,12 +258,13 @@ def run_b200(args):
         "roofline": {"bound": "hbm", "kernel": "k_march", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": alg,
-                     "kernel_ms": {k: prof[k] for k in ("prepare", "march", "big", "resolve")},
+                     "kernel_ms": {k: prof[k] for k in ("prepare", "march", "raster", "big", "resolve")},
                      "note": "k_march is instruction-bound (2 atan + rsqrt per vertex, 274 M triangles), not HBM-bound"},
         "clocks": clocks,
         "aux": {"init_s": t_init, "mosaic_decode_ms": mosaic_ms,
                 "mosaic_decode_gbs": 4 * (2 * R) ** 2 / (mosaic_ms / 1e3) / 1e9,
-                "big_triangles": stats["big_triangles"], "terrain_pixel_fraction": hit_fraction},
+                "triangles_rasterised": stats["triangles_rasterised"], "big_bands": stats["big_bands"],
+                "terrain_pixel_fraction": hit_fraction},
     }
     if world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline(tiles, use_ref=False, steps=3)

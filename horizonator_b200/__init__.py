@@ -97,9 +97,9 @@ def _declare(lib):
         "horizonator_render_wedge_device": (b, [ctx, i, i, vp, vp, vp]),
         "horizonator_download_mosaic": (b, [ctx, vp]),
         "horizonator_time_mosaic": (b, [ctx, i, P(f)]),
-        "horizonator_last_render_stats": (b, [ctx, P(C.c_uint * 4)]),
+        "horizonator_last_render_stats": (b, [ctx, P(C.c_uint * 5)]),
         "horizonator_profile_enable": (b, [ctx, b]),
-        "horizonator_profile_read": (b, [ctx, P(f * 4), P(i)]),
+        "horizonator_profile_read": (b, [ctx, P(f * 5), P(i)]),
     }
     for name, (res, args) in sigs.items():
         fn = getattr(lib, name)
@@ -297,14 +297,16 @@ class horizonator:
 
     def profile_read(self):
         """Mean device ms per render of each kernel since the last read, and the number of renders."""
-        ms = (C.c_float * 4)()
+        ms = (C.c_float * 5)()
         n = C.c_int(0)
         if not lib.horizonator_profile_read(C.byref(self._ctx), C.byref(ms), C.byref(n)):
             raise RuntimeError("horizonator_profile_read() failed")
-        return {"prepare": ms[0], "march": ms[1], "big": ms[2], "resolve": ms[3], "renders": n.value}
+        return {"prepare": ms[0], "march": ms[1], "raster": ms[2], "big": ms[3], "resolve": ms[4],
+                "renders": n.value}
 
     def last_render_stats(self):
-        out = (C.c_uint * 4)()
+        out = (C.c_uint * 5)()
         if not lib.horizonator_last_render_stats(C.byref(self._ctx), C.byref(out)):
             raise RuntimeError("horizonator_last_render_stats() failed")
-        return {"big_triangles": out[0], "big_capacity": out[1], "launches": out[2], "device": out[3]}
+        return {"big_bands": out[0], "big_capacity": out[1], "launches": out[2], "device": out[3],
+                "triangles_rasterised": out[4]}

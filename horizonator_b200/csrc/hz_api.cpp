@@ -33,7 +33,8 @@ namespace {
 
 constexpr int   TANEL_SLOTS     = 8;
 constexpr float PI_F            = 3.14159265358979f;       // vertex.glsl:31
-constexpr unsigned BIG_CAPACITY = 1u << 20;
+constexpr unsigned BIG_CAPACITY = 1u << 21;      // (triangle, band) pairs; overflow is drawn inline
+constexpr int   PROF_EVENTS     = 6;            // 5 kernels per render
 
 // what the reference keeps in GL uniforms
 struct ViewState
@@ -68,8 +69,9 @@ struct Slot
     struct { bool valid; float daz; int W, H; } tanel_key[TANEL_SLOTS] = {};
     int      tanel_next = 0;
 
-    uint32_t* d_big_queue = nullptr;
-    uint32_t* d_big_count = nullptr;
+    uint32_t* d_tri_queue = nullptr;   // one slot per triangle of the mesh: cannot overflow
+    uint2*    d_big_queue = nullptr;
+    uint32_t* d_counters  = nullptr;   // [0] big_count, [1] tri_count, [2] work_count
 
     ViewState view;
     float znear = HORIZONATOR_ZNEAR_DEFAULT, zfar = HORIZONATOR_ZFAR_DEFAULT;
@@ -78,7 +80,7 @@ struct Slot
     bool have_render = false;        // d_vis holds a complete full-width render (for pick)
     unsigned launches_last = 0;
 
-    // optional per-kernel timing: 5 events per recorded render
+    // optional per-kernel timing: PROF_EVENTS events per recorded render
     bool profiling = false;
     std::vector<cudaEvent_t> prof_events;
     size_t prof_used = 0;
@@ -146,7 +148,7 @@ void destroy_slot(Slot* s)
     for(int i = 0; i < 4; i++) for(int j = 0; j < 4; j++) cudaFree((void*)s->tiles.tile[i][j]);
     for(cudaEvent_t e : s->prof_events) cudaEventDestroy(e);
     cudaFree(s->d_e); cudaFree(s->d_n);
-    cudaFree(s->d_big_queue); cudaFree(s->d_big_count);
+    cudaFree(s->d_tri_queue); cudaFree(s->d_big_queue); cudaFree(s->d_counters);
     if(s->stream) cudaStreamDestroy(s->stream);
     delete s;
 }
@@ -219,7 +221,9 @@ bool enqueue_render(Slot& s, const ViewState& vs, int x0, int x1,
     v.znear = s.znear; v.zfar = s.zfar; v.znear_color = s.znear_color; v.zfar_color = s.zfar_color;
     v.W = s.W; v.H = s.H; v.x0 = x0; v.x1 = x1;
     v.vis = s.d_vis;
-    v.big_queue = s.d_big_queue; v.big_count = s.d_big_count; v.big_capacity = BIG_CAPACITY;
+    v.tri_queue = s.d_tri_queue; v.tri_count = s.d_counters + 1;
+    v.big_queue = s.d_big_queue; v.big_count = s.d_counters + 0; v.big_capacity = BIG_CAPACITY;
+    v.work_count = s.d_counters + 2;
 
     // conservative block culling (hz_kernels.cu: hz_block_dead)
     const float far_m = s.zfar * 1.001f + 1.0f;
@@ -241,23 +245,25 @@ bool enqueue_render(Slot& s, const ViewState& vs, int x0, int x1,
     cudaEvent_t* ev = nullptr;
     if(s.profiling)
     {
-        while(s.prof_events.size() < s.prof_used + 5)
+        while(s.prof_events.size() < s.prof_used + PROF_EVENTS)
         {
             cudaEvent_t e;
             CUDA_TRY(cudaEventCreate(&e));
             s.prof_events.push_back(e);
         }
         ev = &s.prof_events[s.prof_used];
-        s.prof_used += 5;
+        s.prof_used += PROF_EVENTS;
     }
     if(ev) CUDA_TRY(cudaEventRecord(ev[0], st));
     CUDA_TRY(hz_launch_prepare(v, st));
     if(ev) CUDA_TRY(cudaEventRecord(ev[1], st));
     CUDA_TRY(hz_launch_march(v, st));
     if(ev) CUDA_TRY(cudaEventRecord(ev[2], st));
-    CUDA_TRY(hz_launch_big(v, st));
+    CUDA_TRY(hz_launch_raster(v, st));
     if(ev) CUDA_TRY(cudaEventRecord(ev[3], st));
-    s.launches_last = 3;
+    CUDA_TRY(hz_launch_big(v, st));
+    if(ev) CUDA_TRY(cudaEventRecord(ev[4], st));
+    s.launches_last = 4;
     if(d_image || d_ranges)
     {
         HzResolve r{};
@@ -265,9 +271,9 @@ bool enqueue_render(Slot& s, const ViewState& vs, int x0, int x1,
         r.tanel = d_tanel; r.znear = s.znear; r.zfar = s.zfar;
         r.image = d_image; r.ranges = d_ranges;
         CUDA_TRY(hz_launch_resolve(r, st));
-        s.launches_last = 4;
+        s.launches_last = 5;
     }
-    if(ev) CUDA_TRY(cudaEventRecord(ev[4], st));
+    if(ev) CUDA_TRY(cudaEventRecord(ev[5], st));
     s.have_render = (x0 == 0 && x1 == s.W);
     return true;
 }
@@ -402,8 +408,12 @@ bool horizonator_init(horizonator_context_t* ctx,
         if(fail(cudaMalloc(&s->d_mosaic, (size_t)s->N * s->pitch * sizeof(int16_t)), "cudaMalloc(mosaic)")) break;
         if(fail(cudaMalloc(&s->d_e, (size_t)s->N * sizeof(float)), "cudaMalloc")) break;
         if(fail(cudaMalloc(&s->d_n, (size_t)s->N * sizeof(float)), "cudaMalloc")) break;
-        if(fail(cudaMalloc(&s->d_big_queue, (size_t)BIG_CAPACITY * sizeof(uint32_t)), "cudaMalloc")) break;
-        if(fail(cudaMalloc(&s->d_big_count, sizeof(uint32_t)), "cudaMalloc")) break;
+        {
+            const size_t n1 = (size_t)s->N - 1;
+            if(fail(cudaMalloc(&s->d_tri_queue, 2 * n1 * n1 * sizeof(uint32_t)), "cudaMalloc(triangle list)")) break;
+        }
+        if(fail(cudaMalloc(&s->d_big_queue, (size_t)BIG_CAPACITY * sizeof(uint2)), "cudaMalloc")) break;
+        if(fail(cudaMalloc(&s->d_counters, 4 * sizeof(uint32_t)), "cudaMalloc")) break;
         if(fail(hz_launch_mosaic(s->tiles, s->d_mosaic, s->N, s->pitch, s->stream), "k_mosaic")) break;
 
         // without an offscreen size the reference opens a 1024x1024 window (lib:142)
@@ -744,39 +754,40 @@ bool horizonator_profile_enable(const horizonator_context_t* ctx, bool on)
     return true;
 }
 
-bool horizonator_profile_read(const horizonator_context_t* ctx, float out_ms[4], int* renders)
+bool horizonator_profile_read(const horizonator_context_t* ctx, float out_ms[5], int* renders)
 {
     Slot* s = slot_of(ctx);
     if(s == nullptr || out_ms == nullptr || renders == nullptr) return false;
     DeviceGuard g(s->device);
-    double sum[4] = {0, 0, 0, 0};
-    const size_t n = s->prof_used / 5;
+    double sum[PROF_EVENTS - 1] = {};
+    const size_t n = s->prof_used / PROF_EVENTS;
     for(size_t r = 0; r < n; r++)
     {
-        cudaEvent_t* ev = &s->prof_events[5 * r];
-        CUDA_TRY(cudaEventSynchronize(ev[4]));
-        for(int k = 0; k < 4; k++)
+        cudaEvent_t* ev = &s->prof_events[PROF_EVENTS * r];
+        CUDA_TRY(cudaEventSynchronize(ev[PROF_EVENTS - 1]));
+        for(int k = 0; k < PROF_EVENTS - 1; k++)
         {
             float ms = 0;
             CUDA_TRY(cudaEventElapsedTime(&ms, ev[k], ev[k + 1]));
             sum[k] += ms;
         }
     }
-    for(int k = 0; k < 4; k++) out_ms[k] = n ? (float)(sum[k] / (double)n) : 0.f;
+    for(int k = 0; k < PROF_EVENTS - 1; k++) out_ms[k] = n ? (float)(sum[k] / (double)n) : 0.f;
     *renders = (int)n;
     s->prof_used = 0;
     return true;
 }
 
-bool horizonator_last_render_stats(const horizonator_context_t* ctx, unsigned int out[4])
+bool horizonator_last_render_stats(const horizonator_context_t* ctx, unsigned int out[5])
 {
     Slot* s = slot_of(ctx);
     if(s == nullptr) return false;
     DeviceGuard g(s->device);
     CUDA_TRY(cudaStreamSynchronize(s->stream));
-    unsigned int count = 0;
-    CUDA_TRY(cudaMemcpy(&count, s->d_big_count, sizeof(count), cudaMemcpyDeviceToHost));
-    out[0] = count; out[1] = BIG_CAPACITY; out[2] = s->launches_last; out[3] = (unsigned)s->device;
+    unsigned int counters[3] = {0, 0, 0};
+    CUDA_TRY(cudaMemcpy(counters, s->d_counters, sizeof(counters), cudaMemcpyDeviceToHost));
+    out[0] = counters[0]; out[1] = BIG_CAPACITY; out[2] = s->launches_last; out[3] = (unsigned)s->device;
+    out[4] = counters[1];
     return true;
 }
 

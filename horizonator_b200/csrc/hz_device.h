@@ -52,10 +52,14 @@ struct HzView
     int x0, x1;
     unsigned long long* vis;     // [H][x1-x0], GL row order (row 0 = bottom)
 
-    // triangles too big for the streaming kernel
-    uint32_t* big_queue;         // triangle ids
+    // triangles that passed k_march's integer tests (worst case: all of them)
+    uint32_t* tri_queue;
+    uint32_t* tri_count;
+    // (triangle, band of rows) pairs too big for one thread of k_raster
+    uint2*    big_queue;
     uint32_t* big_count;
     uint32_t  big_capacity;
+    uint32_t* work_count;        // k_march's work-item dispenser
 
     // conservative culling of whole mesh blocks (never changes the image)
     float cull_d2_far;           // blocks entirely farther (horizontally) than sqrt(this) are skipped
@@ -73,17 +77,11 @@ struct HzResolve
     float*   ranges;             // [H][Wt] top row first, or nullptr
 };
 
-// counters the march kernel maintains (device memory, zeroed by hz_launch_prepare)
-struct HzStats
-{
-    unsigned int big_triangles;      // == *big_count
-    unsigned int big_overflow;       // pushed past capacity -> rasterised inline instead
-};
-
 // All launches are asynchronous on `stream`.
 cudaError_t hz_launch_mosaic (const HzTiles& t, int16_t* mosaic, int N, int pitch, cudaStream_t stream);
 cudaError_t hz_launch_prepare(const HzView& v, cudaStream_t stream);   // clear vis, axis tables, queue
-cudaError_t hz_launch_march  (const HzView& v, cudaStream_t stream);   // project + cull + rasterise
+cudaError_t hz_launch_march  (const HzView& v, cudaStream_t stream);   // mesh + project + cull -> triangle list
+cudaError_t hz_launch_raster (const HzView& v, cudaStream_t stream);   // set-up + rasterise the list
 cudaError_t hz_launch_big    (const HzView& v, cudaStream_t stream);   // queued large triangles
 cudaError_t hz_launch_resolve(const HzResolve& r, cudaStream_t stream);
 

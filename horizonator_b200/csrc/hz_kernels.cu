@@ -3,10 +3,11 @@
 //   k_mosaic   (init)    raw big-endian .hgt tiles -> one int16 mosaic        replaces dem.c:264-309 called
 //                                                                              (2R)^2 times at horizonator-lib.c:435-439
 //   k_prepare  (render)  clear visibility keys, per-column/row metre tables    glClear, lib:896; vertex.glsl:128-130
-//   k_march    (render)  mesh generation + projection + cull + rasterisation   lib:496-508 (index pattern),
-//                        of every triangle whose clipped bounding box is small   vertex.glsl, geometry.glsl, GL raster,
-//                                                                              depth test, fragment.glsl
-//   k_big      (render)  the few triangles with large bounding boxes           same stages, one CTA per triangle
+//   k_march    (render)  mesh generation + projection + exact integer cull       lib:496-508 (index pattern), vertex.glsl,
+//                        -> list of triangles that can produce a fragment        GL cull/clip
+//   k_raster   (render)  set-up + rasterisation + depth test of the survivors    vertex.glsl, geometry.glsl, GL raster,
+//                        (one thread per triangle)                               depth test, fragment.glsl
+//   k_big      (render)  the few triangles with large bounding boxes           same stages, one warp per band of rows
 //   k_resolve  (render)  keys -> BGR8 image + float range image, top row first lib:936-1048
 //
 // The mesh is never materialised: triangle t of the reference's index buffer is (cell = t>>1, half = t&1)
@@ -141,7 +142,7 @@ k_prepare(const __grid_constant__ HzView P)
         P.e_tab[k] = (f - P.viewer_cell_i) * P.deg_per_cell * HZ_REARTH_F * HZ_PI_F / 180.f * P.cos_viewer_lat;
         P.n_tab[k] = (f - P.viewer_cell_j) * P.deg_per_cell * HZ_REARTH_F * HZ_PI_F / 180.f;
     }
-    if(tid == 0) *P.big_count = 0;
+    if(tid == 0) { *P.big_count = 0; *P.tri_count = 0; *P.work_count = 0; }
 }
 
 cudaError_t hz_launch_prepare(const HzView& v, cudaStream_t stream)
@@ -156,11 +157,11 @@ cudaError_t hz_launch_prepare(const HzView& v, cudaStream_t stream)
 }
 
 // ================================================================================================
-// projection and triangle set-up shared by k_march and k_big
+// projection and triangle set-up shared by k_march, k_raster and k_big
 // ================================================================================================
 
-#define HZ_GUARD_PX   4194304.0f      /* 2^22: triangles reaching beyond are dropped (oracle rule F5) */
-#define HZ_SNAP_LIMIT 1073741824.0f   /* 2^30 */
+#define HZ_GUARD_PX   2097152.0f      /* 2^21: triangles reaching beyond are dropped (oracle rule F5) */
+#define HZ_SNAP_LIMIT 536870912.0f    /* 2^29 = guard band in 1/256 pixel */
 
 struct HzVtx
 {
@@ -183,7 +184,8 @@ __device__ __forceinline__ void hz_project(const HzView& P, float e, float n, fl
     v.z  = z;
 }
 
-// window coordinate -> 1/256 pixel fixed point (oracle rule F2), saturated so later integer math cannot overflow
+// window coordinate -> 1/256 pixel fixed point (oracle rule F2), saturated at the guard band so that the
+// integer math downstream cannot overflow (triangles touching the guard band are dropped anyway)
 __device__ __forceinline__ int hz_snap(float a)
 {
     float t = a * 256.0f;
@@ -192,20 +194,27 @@ __device__ __forceinline__ int hz_snap(float a)
     return (int)t;
 }
 
+// triangle number -> its three vertices (row j, column i), lib:496-508
+__device__ __forceinline__ void hz_tri_vertices(unsigned int id, int N, int vj[3], int vi[3])
+{
+    const unsigned int cell = id >> 1;
+    const int j = (int)(cell / (unsigned int)(N - 1)), i = (int)(cell % (unsigned int)(N - 1));
+    vj[0] = j; vi[0] = i;
+    if((id & 1u) == 0) { vj[1] = j + 1; vi[1] = i + 1; vj[2] = j + 1; vi[2] = i;     }
+    else               { vj[1] = j;     vi[1] = i + 1; vj[2] = j + 1; vi[2] = i + 1; }
+}
+
 struct HzTri
 {
-    // integer edge functions on snapped positions, E_k(P) = dx_k*(Py - Y_k) - dy_k*(Px - X_k)
-    long long X[3], Y[3];
-    long long dx[3], dy[3];
-    long long bias[3];
+    int X0, Y0, X1, Y1, X2, Y2;      // snapped window positions, 1/256 pixel
     int px0, px1, py0, py1;          // clipped pixel bounding box (inclusive)
+    float xw0, yw0, xw1, yw1, xw2, yw2;
     // attribute planes through the unsnapped float vertices, anchored at vertex 0 (oracle rule F6)
-    float x0w, y0w, z0w, r0;
-    float dzdx, dzdy, drdx, drdy;
+    float z0w, r0, dzdx, dzdy, drdx, drdy;
     unsigned int id;
 };
 
-// geometry.glsl:21-27, back-face cull and bounding box.  Returns false if the triangle produces nothing.
+// geometry.glsl:21-27, guard band, back-face cull, bounding box.  False if the triangle produces nothing.
 __device__ __forceinline__ bool
 hz_tri_bounds(const HzView& P, const HzVtx& a, const HzVtx& b, const HzVtx& c, HzTri& T)
 {
@@ -214,36 +223,29 @@ hz_tri_bounds(const HzView& P, const HzVtx& a, const HzVtx& b, const HzVtx& c, H
     if(xmax - xmin > 0.5f) return false;                                     // geometry.glsl:21-27
 
     const float halfW = 0.5f * (float)P.W, halfH = 0.5f * (float)P.H;
-    const float xw0 = a.xn * halfW + halfW, yw0 = a.yn * halfH + halfH;      // viewport transform (F1)
-    const float xw1 = b.xn * halfW + halfW, yw1 = b.yn * halfH + halfH;
-    const float xw2 = c.xn * halfW + halfW, yw2 = c.yn * halfH + halfH;
-    if(!(fabsf(xw0) < HZ_GUARD_PX && fabsf(yw0) < HZ_GUARD_PX &&
-         fabsf(xw1) < HZ_GUARD_PX && fabsf(yw1) < HZ_GUARD_PX &&
-         fabsf(xw2) < HZ_GUARD_PX && fabsf(yw2) < HZ_GUARD_PX)) return false; // F5
+    T.xw0 = a.xn * halfW + halfW; T.yw0 = a.yn * halfH + halfH;              // viewport transform (F1)
+    T.xw1 = b.xn * halfW + halfW; T.yw1 = b.yn * halfH + halfH;
+    T.xw2 = c.xn * halfW + halfW; T.yw2 = c.yn * halfH + halfH;
+    if(!(fabsf(T.xw0) < HZ_GUARD_PX && fabsf(T.yw0) < HZ_GUARD_PX &&
+         fabsf(T.xw1) < HZ_GUARD_PX && fabsf(T.yw1) < HZ_GUARD_PX &&
+         fabsf(T.xw2) < HZ_GUARD_PX && fabsf(T.yw2) < HZ_GUARD_PX)) return false;   // F5
 
-    T.X[0] = hz_snap(xw0); T.Y[0] = hz_snap(yw0);
-    T.X[1] = hz_snap(xw1); T.Y[1] = hz_snap(yw1);
-    T.X[2] = hz_snap(xw2); T.Y[2] = hz_snap(yw2);
+    T.X0 = hz_snap(T.xw0); T.Y0 = hz_snap(T.yw0);
+    T.X1 = hz_snap(T.xw1); T.Y1 = hz_snap(T.yw1);
+    T.X2 = hz_snap(T.xw2); T.Y2 = hz_snap(T.yw2);
 
     // GL_CULL_FACE, front = counter-clockwise, y up (lib:184; F3)
-    const long long area = (T.X[1] - T.X[0]) * (T.Y[2] - T.Y[0]) - (T.X[2] - T.X[0]) * (T.Y[1] - T.Y[0]);
+    const long long area = (long long)(T.X1 - T.X0) * (T.Y2 - T.Y0) - (long long)(T.X2 - T.X0) * (T.Y1 - T.Y0);
     if(area <= 0) return false;
 
-    const long long bx0 = min(min(T.X[0], T.X[1]), T.X[2]), bx1 = max(max(T.X[0], T.X[1]), T.X[2]);
-    const long long by0 = min(min(T.Y[0], T.Y[1]), T.Y[2]), by1 = max(max(T.Y[0], T.Y[1]), T.Y[2]);
-    long long px0 = (bx0 + 127) >> 8, px1 = (bx1 - 128) >> 8;
-    long long py0 = (by0 + 127) >> 8, py1 = (by1 - 128) >> 8;
-    if(px0 < P.x0)     px0 = P.x0;
-    if(px1 > P.x1 - 1) px1 = P.x1 - 1;
-    if(py0 < 0)        py0 = 0;
-    if(py1 > P.H - 1)  py1 = P.H - 1;
-    if(px0 > px1 || py0 > py1) return false;
-    T.px0 = (int)px0; T.px1 = (int)px1; T.py0 = (int)py0; T.py1 = (int)py1;
-
-    T.x0w = xw0; T.y0w = yw0;
-    // stash the other two window positions in the plane slots until hz_tri_planes() runs
-    T.dzdx = xw1; T.dzdy = yw1; T.drdx = xw2; T.drdy = yw2;
-    return true;
+    const int bx0 = min(min(T.X0, T.X1), T.X2), bx1 = max(max(T.X0, T.X1), T.X2);
+    const int by0 = min(min(T.Y0, T.Y1), T.Y2), by1 = max(max(T.Y0, T.Y1), T.Y2);
+    // pixel centres sit at 256*p + 128
+    T.px0 = max((bx0 + 127) >> 8, P.x0);
+    T.px1 = min((bx1 - 128) >> 8, P.x1 - 1);
+    T.py0 = max((by0 + 127) >> 8, 0);
+    T.py1 = min((by1 - 128) >> 8, P.H - 1);
+    return T.px0 <= T.px1 && T.py0 <= T.py1;
 }
 
 // vertex.glsl:155,159-160 for one vertex: window depth and red channel
@@ -262,14 +264,13 @@ __device__ __forceinline__ void
 hz_tri_planes(const HzView& P, HzTri& T,
               float e0, float n0, float z0, float e1, float n1, float z1, float e2, float n2, float z2)
 {
-    const float xw1 = T.dzdx, yw1 = T.dzdy, xw2 = T.drdx, yw2 = T.drdy;
     float zw0, zw1, zw2, r0, r1, r2;
     hz_depth_shade(P, e0, n0, z0, zw0, r0);
     hz_depth_shade(P, e1, n1, z1, zw1, r1);
     hz_depth_shade(P, e2, n2, z2, zw2, r2);
 
-    const float ax = xw1 - T.x0w, ay = yw1 - T.y0w;
-    const float bx = xw2 - T.x0w, by = yw2 - T.y0w;
+    const float ax = T.xw1 - T.xw0, ay = T.yw1 - T.yw0;
+    const float bx = T.xw2 - T.xw0, by = T.yw2 - T.yw0;
     const float det = ax * by - bx * ay;
     const float inv = 1.0f / det;
     const float az = zw1 - zw0, bz = zw2 - zw0;
@@ -279,23 +280,34 @@ hz_tri_planes(const HzView& P, HzTri& T,
     T.drdx = (ar * by - br * ay) * inv;
     T.drdy = (br * ax - ar * bx) * inv;
     T.z0w = zw0; T.r0 = r0;
+}
 
+// complete set-up of triangle `id` from the mosaic; false if it produces nothing
+__device__ __forceinline__ bool hz_tri_setup(const HzView& P, unsigned int id, HzTri& T, bool with_planes)
+{
+    int vj[3], vi[3];
+    hz_tri_vertices(id, P.N, vj, vi);
+    float e[3], n[3];
+    HzVtx v[3];
     #pragma unroll
     for(int k = 0; k < 3; k++)
     {
-        const int k1 = (k + 1) % 3;
-        T.dx[k] = T.X[k1] - T.X[k];
-        T.dy[k] = T.Y[k1] - T.Y[k];
-        // F4: the edge owns its boundary iff it runs downwards, or is horizontal running leftwards
-        T.bias[k] = (T.dy[k] < 0 || (T.dy[k] == 0 && T.dx[k] < 0)) ? 0 : 1;
+        e[k] = __ldg(P.e_tab + vi[k]);
+        n[k] = __ldg(P.n_tab + vj[k]);
+        const float z = (float)__ldg(P.mosaic + (size_t)vj[k] * P.pitch + vi[k]);
+        hz_project(P, e[k], n[k], z, v[k]);
     }
+    if(!hz_tri_bounds(P, v[0], v[1], v[2], T)) return false;
+    T.id = id;
+    if(with_planes) hz_tri_planes(P, T, e[0], n[0], v[0].z, e[1], n[1], v[1].z, e[2], n[2], v[2].z);
+    return true;
 }
 
 // depth test + colour write for one covered pixel centre
 __device__ __forceinline__ void hz_fragment(const HzView& P, const HzTri& T, int px, int py)
 {
     const float cx = (float)px + 0.5f, cy = (float)py + 0.5f;
-    const float ddx = cx - T.x0w, ddy = cy - T.y0w;
+    const float ddx = cx - T.xw0, ddy = cy - T.yw0;
     const float zw = T.z0w + (T.dzdx * ddx + T.dzdy * ddy);
     if(!(zw >= 0.0f && zw <= 1.0f)) return;                                  // F5: view-volume clip per fragment
     const unsigned int q = (unsigned int)((double)zw * 16777215.0 + 0.5);   // F7
@@ -307,50 +319,80 @@ __device__ __forceinline__ void hz_fragment(const HzView& P, const HzTri& T, int
     atomicMin(&P.vis[(size_t)py * (size_t)(P.x1 - P.x0) + (size_t)(px - P.x0)], key);
 }
 
-__device__ __forceinline__ bool hz_inside(const HzTri& T, long long Px, long long Py)
+// Edge functions E_k(P) = dx_k*(Py - Y_k) - dy_k*(Px - X_k) on the snapped positions (F3); an edge owns its
+// boundary iff it runs downwards, or is horizontal running leftwards (F4).  I = int when every term fits in
+// 32 bits (triangle smaller than 128 pixels), long long otherwise.
+template <typename I>
+struct HzEdges
 {
-    const long long E0 = T.dx[0] * (Py - T.Y[0]) - T.dy[0] * (Px - T.X[0]);
-    const long long E1 = T.dx[1] * (Py - T.Y[1]) - T.dy[1] * (Px - T.X[1]);
-    const long long E2 = T.dx[2] * (Py - T.Y[2]) - T.dy[2] * (Px - T.X[2]);
-    return E0 >= T.bias[0] && E1 >= T.bias[1] && E2 >= T.bias[2];
+    I dx0, dy0, dx1, dy1, dx2, dy2;
+    I b0, b1, b2;
+    __device__ __forceinline__ explicit HzEdges(const HzTri& T)
+    {
+        dx0 = (I)T.X1 - T.X0; dy0 = (I)T.Y1 - T.Y0;
+        dx1 = (I)T.X2 - T.X1; dy1 = (I)T.Y2 - T.Y1;
+        dx2 = (I)T.X0 - T.X2; dy2 = (I)T.Y0 - T.Y2;
+        b0 = (dy0 < 0 || (dy0 == 0 && dx0 < 0)) ? 0 : 1;
+        b1 = (dy1 < 0 || (dy1 == 0 && dx1 < 0)) ? 0 : 1;
+        b2 = (dy2 < 0 || (dy2 == 0 && dx2 < 0)) ? 0 : 1;
+    }
+    __device__ __forceinline__ bool inside(const HzTri& T, int px, int py) const
+    {
+        const I Px = (I)px * 256 + 128, Py = (I)py * 256 + 128;
+        const I E0 = dx0 * (Py - T.Y0) - dy0 * (Px - T.X0);
+        const I E1 = dx1 * (Py - T.Y1) - dy1 * (Px - T.X1);
+        const I E2 = dx2 * (Py - T.Y2) - dy2 * (Px - T.X2);
+        return E0 >= b0 && E1 >= b1 && E2 >= b2;
+    }
+};
+
+__device__ __forceinline__ bool hz_tri_is_small(const HzTri& T)
+{
+    const int bx0 = min(min(T.X0, T.X1), T.X2), bx1 = max(max(T.X0, T.X1), T.X2);
+    const int by0 = min(min(T.Y0, T.Y1), T.Y2), by1 = max(max(T.Y0, T.Y1), T.Y2);
+    return (bx1 - bx0) < 32768 && (by1 - by0) < 32768;      // every difference < 2^15 => products < 2^30
 }
 
 // ================================================================================================
-// k_march
+// k_march: mesh generation + projection + conservative-exact triangle filter
 // ================================================================================================
 //
 // One warp walks a strip of the mosaic northwards.  Lane l owns vertex columns c0+2l and c0+2l+1 (one aligned
 // 32-bit load per row) and the two cells to their right; the right-hand neighbour's column arrives by
 // shuffle, the previous row stays in registers, so every vertex is projected once per strip (plus one shared
-// column between strips and one shared row between segments).  A cell whose snapped bounding box holds no
-// pixel centre of the target is finished after a few integer instructions -- that is ~90% of them.  The
-// others are compacted through a per-warp shared-memory queue so that the (long) triangle set-up and
-// rasterisation code runs with all 32 lanes busy.
+// column between strips and one shared row between segments).  Only the snapped window position of a vertex
+// is kept.  A cell whose snapped bounding box holds no pixel centre of the target is finished after a few
+// integer instructions -- about 90% of them.  For the others both triangles get the same integer tests the
+// rasteriser will apply (pixel centre inside the bounding box, inside the target, counter-clockwise), and
+// the numbers of the survivors are appended to a global list through a per-warp shared-memory stage (one
+// global atomic per ~64 survivors).  k_raster then sets those triangles up and draws them with every lane busy.
+//
+// Work items (strip x 64-row segment) are handed out through an atomic counter, ordered outwards from the
+// eye: the expensive items next to the eye start first and the cheap far field fills in behind them.
 
 #define HZ_WARPS_PER_CTA 8
-#define HZ_QUEUE_SLOTS   64
-#define HZ_QUEUE_WORDS   13
-#define HZ_SMALL_MAX_PIX 32        /* clipped bounding boxes above this go to k_big */
+#define HZ_STAGE_SLOTS   192       /* < 64 pending + at most 4*32 new per row */
+#define HZ_STAGE_FLUSH   64
+#define HZ_SMALL_MAX_PIX 8         /* k_raster draws bounding boxes up to this many pixels itself */
+#define HZ_BAND_ROWS     8         /* bigger ones are cut into bands of rows for k_big */
 
-struct HzLaneVtx { int X, Y; float xn, yn, z; };
+struct HzLaneVtx { int X, Y; };
 
-__device__ __forceinline__ void hz_lane_vertex(const HzView& P, float e, float n, float z, float halfW, float halfH, HzLaneVtx& o)
+__device__ __forceinline__ HzLaneVtx hz_lane_vertex(const HzView& P, float e, float n, float z, float halfW, float halfH)
 {
     HzVtx v;
     hz_project(P, e, n, z, v);
-    o.xn = v.xn; o.yn = v.yn; o.z = z;
+    HzLaneVtx o;
     o.X = hz_snap(v.xn * halfW + halfW);
     o.Y = hz_snap(v.yn * halfH + halfH);
+    return o;
 }
 
 __device__ __forceinline__ HzLaneVtx hz_shfl_down1(const HzLaneVtx& v)
 {
     HzLaneVtx o;
-    o.X  = __shfl_down_sync(0xffffffffu, v.X, 1);
-    o.Y  = __shfl_down_sync(0xffffffffu, v.Y, 1);
-    o.xn = __shfl_down_sync(0xffffffffu, v.xn, 1);
-    o.yn = __shfl_down_sync(0xffffffffu, v.yn, 1);
-    o.z  = __shfl_down_sync(0xffffffffu, v.z, 1);
+    o.X = __shfl_down_sync(0xffffffffu, v.X, 1);
+    o.Y = __shfl_down_sync(0xffffffffu, v.Y, 1);
     return o;
 }
 
@@ -365,81 +407,18 @@ hz_cell_alive(const HzView& P, const HzLaneVtx& a, const HzLaneVtx& b, const HzL
     return px0 <= px1 && py0 <= py1 && px1 >= P.x0 && px0 < P.x1 && py1 >= 0 && py0 < P.H;
 }
 
-// rasterise one triangle of a cell inside k_march
-__device__ __forceinline__ void
-hz_march_triangle(const HzView& P, unsigned int id,
-                  const HzVtx& a, const HzVtx& b, const HzVtx& c,
-                  float ea, float na, float eb, float nb, float ec, float nc)
+// the rasteriser's integer tests for one triangle (hz_tri_bounds without the float-only seam/guard tests,
+// which k_raster applies; a triangle that fails here cannot produce a fragment there)
+__device__ __forceinline__ bool
+hz_tri_alive(const HzView& P, const HzLaneVtx& a, const HzLaneVtx& b, const HzLaneVtx& c)
 {
-    HzTri T;
-    if(!hz_tri_bounds(P, a, b, c, T)) return;
-    T.id = id;
-    const int bw = T.px1 - T.px0 + 1, bh = T.py1 - T.py0 + 1;
-    if((long long)bw * bh > HZ_SMALL_MAX_PIX)
-    {
-        const unsigned int slot = atomicAdd(P.big_count, 1u);
-        if(slot < P.big_capacity) { P.big_queue[slot] = id; return; }
-        // queue full: fall through and do it here (slow but correct)
-    }
-    hz_tri_planes(P, T, ea, na, a.z, eb, nb, b.z, ec, nc, c.z);
-    for(int py = T.py0; py <= T.py1; py++)
-    {
-        const long long Py = (long long)py * 256 + 128;
-        for(int px = T.px0; px <= T.px1; px++)
-            if(hz_inside(T, (long long)px * 256 + 128, Py)) hz_fragment(P, T, px, py);
-    }
-}
-
-// one queued cell: both of its triangles, in the reference's order (lib:496-508)
-__device__ __forceinline__ void hz_march_cell(const HzView& P, const float* q /* this lane's entry */, int stride)
-{
-    HzVtx v00, v01, v10, v11;     // vJI: J = row offset, I = column offset
-    v00.xn = q[0 * stride]; v00.yn = q[1 * stride]; v00.z = q[2 * stride];
-    v01.xn = q[3 * stride]; v01.yn = q[4 * stride]; v01.z = q[5 * stride];
-    v10.xn = q[6 * stride]; v10.yn = q[7 * stride]; v10.z = q[8 * stride];
-    v11.xn = q[9 * stride]; v11.yn = q[10 * stride]; v11.z = q[11 * stride];
-    const unsigned int ji = __float_as_uint(q[12 * stride]);
-    const int j = (int)(ji >> 16), i = (int)(ji & 0xFFFFu);
-
-    const float e0 = __ldg(P.e_tab + i), e1 = __ldg(P.e_tab + i + 1);
-    const float n0 = __ldg(P.n_tab + j), n1 = __ldg(P.n_tab + j + 1);
-    const unsigned int id = 2u * ((unsigned int)j * (unsigned int)(P.N - 1) + (unsigned int)i);
-
-    // (j,i), (j+1,i+1), (j+1,i)
-    hz_march_triangle(P, id,      v00, v11, v10, e0, n0, e1, n1, e0, n1);
-    // (j,i), (j,i+1), (j+1,i+1)
-    hz_march_triangle(P, id + 1u, v00, v01, v11, e0, n0, e1, n0, e1, n1);
-}
-
-__device__ __forceinline__ void
-hz_queue_push(float* qbase, int& qcount, bool alive, int lane,
-              const HzLaneVtx& v00, const HzLaneVtx& v01, const HzLaneVtx& v10, const HzLaneVtx& v11, int j, int i)
-{
-    const unsigned int ballot = __ballot_sync(0xffffffffu, alive);
-    if(alive)
-    {
-        const int slot = qcount + __popc(ballot & ((1u << lane) - 1u));
-        float* q = qbase + slot;
-        q[0 * HZ_QUEUE_SLOTS] = v00.xn; q[1 * HZ_QUEUE_SLOTS] = v00.yn; q[2 * HZ_QUEUE_SLOTS] = v00.z;
-        q[3 * HZ_QUEUE_SLOTS] = v01.xn; q[4 * HZ_QUEUE_SLOTS] = v01.yn; q[5 * HZ_QUEUE_SLOTS] = v01.z;
-        q[6 * HZ_QUEUE_SLOTS] = v10.xn; q[7 * HZ_QUEUE_SLOTS] = v10.yn; q[8 * HZ_QUEUE_SLOTS] = v10.z;
-        q[9 * HZ_QUEUE_SLOTS] = v11.xn; q[10 * HZ_QUEUE_SLOTS] = v11.yn; q[11 * HZ_QUEUE_SLOTS] = v11.z;
-        q[12 * HZ_QUEUE_SLOTS] = __uint_as_float(((unsigned int)j << 16) | (unsigned int)i);
-    }
-    qcount += __popc(ballot);
-}
-
-__device__ __forceinline__ void hz_queue_drain(const HzView& P, float* qbase, int& qcount, int lane, bool flush)
-{
-    __syncwarp();
-    while(qcount >= 32 || (flush && qcount > 0))
-    {
-        const int take = qcount >= 32 ? 32 : qcount;
-        const int base = qcount - take;
-        if(lane < take) hz_march_cell(P, qbase + base + lane, HZ_QUEUE_SLOTS);
-        qcount = base;
-        __syncwarp();
-    }
+    const int bx0 = min(min(a.X, b.X), c.X), bx1 = max(max(a.X, b.X), c.X);
+    const int by0 = min(min(a.Y, b.Y), c.Y), by1 = max(max(a.Y, b.Y), c.Y);
+    const int px0 = (bx0 + 127) >> 8, px1 = (bx1 - 128) >> 8;
+    const int py0 = (by0 + 127) >> 8, py1 = (by1 - 128) >> 8;
+    if(!(px0 <= px1 && py0 <= py1 && px1 >= P.x0 && px0 < P.x1 && py1 >= 0 && py0 < P.H)) return false;
+    const long long area = (long long)(b.X - a.X) * (c.Y - a.Y) - (long long)(c.X - a.X) * (b.Y - a.Y);
+    return area > 0;
 }
 
 // conservative test: can any triangle of the block [c_lo..c_hi] x [r_lo..r_hi] (vertex indices) reach the target?
@@ -457,8 +436,8 @@ __device__ __forceinline__ bool hz_block_dead(const HzView& P, int c_lo, int c_h
     if(P.cull_az_half < 3.2f && (ne != 0.f || nn != 0.f))
     {
         // the rectangle does not contain the eye: its azimuths form an interval bounded by corner azimuths.
-        // Measure every corner relative to the middle of the interval of interest and relative to the first
-        // corner (so wrap-around is handled): dead iff the whole fan lies outside +-cull_az_half.
+        // Measure every corner relative to the first one (the fan is < pi wide, so no wrap inside it) and the
+        // first one relative to the middle of the interval of interest.
         const float ce[4] = { e_lo, e_hi, e_lo, e_hi };
         const float cn[4] = { n_lo, n_lo, n_hi, n_hi };
         const float a0 = atan2f(ce[0], cn[0]);
@@ -467,15 +446,13 @@ __device__ __forceinline__ bool hz_block_dead(const HzView& P, int c_lo, int c_h
         for(int k = 1; k < 4; k++)
         {
             float d = atan2f(ce[k], cn[k]) - a0;
-            d -= 6.28318530717958648f * rintf(d * 0.15915494309189535f);     // into [-pi, pi]: fan is < pi wide
+            d -= 6.28318530717958648f * rintf(d * 0.15915494309189535f);
             lo = fminf(lo, d); hi = fmaxf(hi, d);
         }
         float m = a0 - P.cull_az_mid;
-        m -= 6.28318530717958648f * rintf(m * 0.15915494309189535f);         // a0 relative to the window middle
-        // block interval relative to the window middle is [m+lo, m+hi] (mod 2pi); margin for rounding
+        m -= 6.28318530717958648f * rintf(m * 0.15915494309189535f);
         const float margin = 1e-3f;
         const float blo = m + lo - margin, bhi = m + hi + margin;
-        // alive iff it overlaps [-half, half] in any of the relevant turns
         bool alive = false;
         #pragma unroll
         for(int turn = -1; turn <= 1; turn++)
@@ -488,88 +465,181 @@ __device__ __forceinline__ bool hz_block_dead(const HzView& P, int c_lo, int c_h
     return false;
 }
 
-__global__ void __launch_bounds__(HZ_WARPS_PER_CTA * 32)
+// k-th element of the sequence c, c+1, c-1, c+2, c-2, ... restricted to [0, n)
+__device__ __forceinline__ int hz_outward(int c, int k, int n)
+{
+    const int m = min(c, n - 1 - c);
+    if(k <= 2 * m) return (k & 1) ? c + (k + 1) / 2 : c - k / 2;
+    return (n - 1 - c > c) ? c + (k - m) : c - (k - m);
+}
+
+__device__ __forceinline__ void hz_stage_flush(const HzView& P, unsigned int* stage, int& count, int lane)
+{
+    __syncwarp();
+    if(count > 0)
+    {
+        unsigned int base = 0;
+        if(lane == 0) base = atomicAdd(P.tri_count, (unsigned int)count);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        for(int k = lane; k < count; k += 32) P.tri_queue[base + k] = stage[k];
+        count = 0;
+    }
+    __syncwarp();
+}
+
+__global__ void __launch_bounds__(HZ_WARPS_PER_CTA * 32, 4)
 k_march(const __grid_constant__ HzView P)
 {
-    __shared__ float s_queue[HZ_WARPS_PER_CTA][HZ_QUEUE_WORDS * HZ_QUEUE_SLOTS];
+    __shared__ unsigned int s_stage[HZ_WARPS_PER_CTA][HZ_STAGE_SLOTS];
 
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int N = P.N;
     const int n_strips = (N - 1 + HZ_STRIP_CELLS - 1) / HZ_STRIP_CELLS;
     const int n_segs   = (N - 1 + HZ_SEG_ROWS - 1) / HZ_SEG_ROWS;
-    const long long wg = (long long)blockIdx.x * HZ_WARPS_PER_CTA + wib;
-    if(wg >= (long long)n_strips * n_segs) return;
-    const int seg = (int)(wg / n_strips), strip = (int)(wg % n_strips);
+    const unsigned int n_items = (unsigned int)n_strips * (unsigned int)n_segs;
+    const int strip_eye = min(max((int)P.viewer_cell_i / HZ_STRIP_CELLS, 0), n_strips - 1);
+    const int seg_eye   = min(max((int)P.viewer_cell_j / HZ_SEG_ROWS, 0), n_segs - 1);
 
-    const int c0 = strip * HZ_STRIP_CELLS;                   // first vertex column of the strip (even)
-    const int r0 = seg * HZ_SEG_ROWS;                        // first vertex row
-    const int r1 = min(r0 + HZ_SEG_ROWS, N - 1);             // last vertex row (inclusive)
-    const int c_last = min(c0 + HZ_STRIP_CELLS, N - 1);      // last vertex column any cell of the strip touches
-
-    if(hz_block_dead(P, c0, c_last, r0, r1)) return;
-
-    float* qbase = s_queue[wib];
-    int qcount = 0;
-
+    unsigned int* stage = s_stage[wib];
+    int count = 0;
     const float halfW = 0.5f * (float)P.W, halfH = 0.5f * (float)P.H;
 
-    // this lane's two vertex columns (clamped for loads; cells beyond the mesh are masked below)
-    const int colA = c0 + 2 * lane, colB = colA + 1;
-    const int ldA = min(colA, N - 1), ldB = min(colB, N - 1);
-    const float eA = __ldg(P.e_tab + ldA), eB = __ldg(P.e_tab + ldB);
-    // cell 0 spans columns colA..colB, cell 1 spans colB..colA+2 (the neighbour lane's first column)
-    const bool cell0_ok = (lane < 31) && (colB <= N - 1);
-    const bool cell1_ok = (lane < 31) && (colA + 2 <= N - 1);
-
-    // mosaic rows are pitch-aligned and colA is even: one 32-bit load fetches both heights
-    const int16_t* mrow = P.mosaic + (size_t)r0 * P.pitch + min(colA, P.pitch - 2);
-
-    HzLaneVtx pA, pB, pC;   // previous row
+    for(;;)
     {
-        const unsigned int zz = __ldg((const unsigned int*)mrow);
-        const float n = __ldg(P.n_tab + r0);
-        hz_lane_vertex(P, eA, n, (float)(short)(zz & 0xFFFFu), halfW, halfH, pA);
-        hz_lane_vertex(P, eB, n, (float)(short)(zz >> 16),     halfW, halfH, pB);
-        pC = hz_shfl_down1(pA);
+        unsigned int item = 0;
+        if(lane == 0) item = atomicAdd(P.work_count, 1u);
+        item = __shfl_sync(0xffffffffu, item, 0);
+        if(item >= n_items) break;
+        const int seg   = hz_outward(seg_eye,   (int)(item / (unsigned int)n_strips), n_segs);
+        const int strip = hz_outward(strip_eye, (int)(item % (unsigned int)n_strips), n_strips);
+
+        const int c0 = strip * HZ_STRIP_CELLS;                   // first vertex column of the strip (even)
+        const int r0 = seg * HZ_SEG_ROWS;                        // first vertex row
+        const int r1 = min(r0 + HZ_SEG_ROWS, N - 1);             // last vertex row (inclusive)
+        const int c_last = min(c0 + HZ_STRIP_CELLS, N - 1);      // last vertex column any cell of the strip touches
+        if(hz_block_dead(P, c0, c_last, r0, r1)) continue;
+
+        // this lane's two vertex columns (clamped for loads; cells beyond the mesh are masked below)
+        const int colA = c0 + 2 * lane, colB = colA + 1;
+        const float eA = __ldg(P.e_tab + min(colA, N - 1)), eB = __ldg(P.e_tab + min(colB, N - 1));
+        // cell 0 spans columns colA..colB, cell 1 spans colB..colA+2 (the neighbour lane's first column)
+        const bool cell0_ok = (lane < 31) && (colB <= N - 1);
+        const bool cell1_ok = (lane < 31) && (colA + 2 <= N - 1);
+
+        // mosaic rows are pitch-aligned and colA is even: one 32-bit load fetches both heights
+        const int16_t* mrow = P.mosaic + (size_t)r0 * P.pitch + min(colA, P.pitch - 2);
+
+        HzLaneVtx pA, pB, pC;   // previous row
+        {
+            const unsigned int zz = __ldg((const unsigned int*)mrow);
+            const float n = __ldg(P.n_tab + r0);
+            pA = hz_lane_vertex(P, eA, n, (float)(short)(zz & 0xFFFFu), halfW, halfH);
+            pB = hz_lane_vertex(P, eB, n, (float)(short)(zz >> 16),     halfW, halfH);
+            pC = hz_shfl_down1(pA);
+        }
+
+        unsigned int zz_next = (r0 + 1 <= r1) ? __ldg((const unsigned int*)(mrow + P.pitch)) : 0u;
+        float n_next = (r0 + 1 <= r1) ? __ldg(P.n_tab + r0 + 1) : 0.f;
+        for(int j = r0 + 1; j <= r1; j++)
+        {
+            const unsigned int zz = zz_next;
+            const float n = n_next;
+            if(j + 1 <= r1)
+            {
+                zz_next = __ldg((const unsigned int*)(mrow + (size_t)(j + 1 - r0) * P.pitch));
+                n_next  = __ldg(P.n_tab + j + 1);
+            }
+            const HzLaneVtx cA = hz_lane_vertex(P, eA, n, (float)(short)(zz & 0xFFFFu), halfW, halfH);
+            const HzLaneVtx cB = hz_lane_vertex(P, eB, n, (float)(short)(zz >> 16),     halfW, halfH);
+            const HzLaneVtx cC = hz_shfl_down1(cA);
+
+            // cell (j-1, colA): corners pA pB / cA cB ; cell (j-1, colB): corners pB pC / cB cC
+            unsigned int m = 0;
+            if(cell0_ok && hz_cell_alive(P, pA, pB, cA, cB))
+            {
+                if(hz_tri_alive(P, pA, cB, cA)) m |= 1u;     // (j-1,i), (j,i+1), (j,i)
+                if(hz_tri_alive(P, pA, pB, cB)) m |= 2u;     // (j-1,i), (j-1,i+1), (j,i+1)
+            }
+            if(cell1_ok && hz_cell_alive(P, pB, pC, cB, cC))
+            {
+                if(hz_tri_alive(P, pB, cC, cB)) m |= 4u;
+                if(hz_tri_alive(P, pB, pC, cC)) m |= 8u;
+            }
+            if(__any_sync(0xffffffffu, m != 0))
+            {
+                const unsigned int id0 = 2u * ((unsigned int)(j - 1) * (unsigned int)(N - 1) + (unsigned int)colA);
+                const unsigned int lt = (1u << lane) - 1u;
+                #pragma unroll
+                for(int b = 0; b < 4; b++)
+                {
+                    const bool on = (m >> b) & 1u;
+                    const unsigned int ballot = __ballot_sync(0xffffffffu, on);
+                    if(on) stage[count + __popc(ballot & lt)] = id0 + (unsigned int)b;
+                    count += __popc(ballot);
+                }
+                if(count >= HZ_STAGE_FLUSH) hz_stage_flush(P, stage, count, lane);
+            }
+            pA = cA; pB = cB; pC = cC;
+        }
     }
-
-    unsigned int zz_next = (r0 + 1 <= r1) ? __ldg((const unsigned int*)(mrow + P.pitch)) : 0u;
-    for(int j = r0 + 1; j <= r1; j++)
-    {
-        const unsigned int zz = zz_next;
-        if(j + 1 <= r1) zz_next = __ldg((const unsigned int*)(mrow + (size_t)(j + 1 - r0) * P.pitch));
-        const float n = __ldg(P.n_tab + j);
-
-        HzLaneVtx cA, cB, cC;
-        hz_lane_vertex(P, eA, n, (float)(short)(zz & 0xFFFFu), halfW, halfH, cA);
-        hz_lane_vertex(P, eB, n, (float)(short)(zz >> 16),     halfW, halfH, cB);
-        cC = hz_shfl_down1(cA);
-
-        // cell (j-1, colA): corners pA pB / cA cB ; cell (j-1, colB): corners pB pC / cB cC
-        const bool alive0 = cell0_ok && hz_cell_alive(P, pA, pB, cA, cB);
-        hz_queue_push(qbase, qcount, alive0, lane, pA, pB, cA, cB, j - 1, colA);
-        hz_queue_drain(P, qbase, qcount, lane, false);
-        const bool alive1 = cell1_ok && hz_cell_alive(P, pB, pC, cB, cC);
-        hz_queue_push(qbase, qcount, alive1, lane, pB, pC, cB, cC, j - 1, colB);
-        hz_queue_drain(P, qbase, qcount, lane, false);
-
-        pA = cA; pB = cB; pC = cC;
-    }
-    hz_queue_drain(P, qbase, qcount, lane, true);
+    hz_stage_flush(P, stage, count, lane);
 }
 
 cudaError_t hz_launch_march(const HzView& v, cudaStream_t stream)
 {
-    const int n_strips = (v.N - 1 + HZ_STRIP_CELLS - 1) / HZ_STRIP_CELLS;
-    const int n_segs   = (v.N - 1 + HZ_SEG_ROWS - 1) / HZ_SEG_ROWS;
-    const long long warps = (long long)n_strips * n_segs;
-    const unsigned blocks = (unsigned)((warps + HZ_WARPS_PER_CTA - 1) / HZ_WARPS_PER_CTA);
-    k_march<<<blocks, HZ_WARPS_PER_CTA * 32, 0, stream>>>(v);
+    // persistent: 4 CTAs of 8 warps per SM, the warps pull (strip, segment) items until none are left
+    k_march<<<148 * 4, HZ_WARPS_PER_CTA * 32, 0, stream>>>(v);
     return cudaGetLastError();
 }
 
 // ================================================================================================
-// k_big: one CTA per queued triangle, threads spread over its clipped bounding box
+// k_raster: one thread per surviving triangle
+// ================================================================================================
+
+template <typename I>
+__device__ __forceinline__ void hz_draw_box(const HzView& P, const HzTri& T)
+{
+    const HzEdges<I> E(T);
+    for(int py = T.py0; py <= T.py1; py++)
+        for(int px = T.px0; px <= T.px1; px++)
+            if(E.inside(T, px, py)) hz_fragment(P, T, px, py);
+}
+
+__global__ void __launch_bounds__(256)
+k_raster(const __grid_constant__ HzView P)
+{
+    const unsigned int count = *P.tri_count;
+    const unsigned int nth = gridDim.x * blockDim.x;
+    for(unsigned int t = blockIdx.x * blockDim.x + threadIdx.x; t < count; t += nth)
+    {
+        HzTri T;
+        const unsigned int id = P.tri_queue[t];
+        if(!hz_tri_setup(P, id, T, true)) continue;
+        const int bw = T.px1 - T.px0 + 1, bh = T.py1 - T.py0 + 1;
+        if((long long)bw * bh > HZ_SMALL_MAX_PIX)
+        {
+            const unsigned int bands = (unsigned int)((bh + HZ_BAND_ROWS - 1) / HZ_BAND_ROWS);
+            const unsigned int slot = atomicAdd(P.big_count, bands);
+            if(slot + bands <= P.big_capacity)
+            {
+                for(unsigned int b = 0; b < bands; b++) P.big_queue[slot + b] = make_uint2(id, b);
+                continue;
+            }
+            // queue full: draw it here (slow but correct)
+        }
+        if(hz_tri_is_small(T)) hz_draw_box<int>(P, T);
+        else                   hz_draw_box<long long>(P, T);
+    }
+}
+
+cudaError_t hz_launch_raster(const HzView& v, cudaStream_t stream)
+{
+    k_raster<<<148 * 8, 256, 0, stream>>>(v);
+    return cudaGetLastError();
+}
+
+// ================================================================================================
+// k_big: one warp per (triangle, band of rows), lanes spread over the band's pixels
 // ================================================================================================
 
 __global__ void __launch_bounds__(256)
@@ -577,40 +647,34 @@ k_big(const __grid_constant__ HzView P)
 {
     unsigned int count = *P.big_count;
     if(count > P.big_capacity) count = P.big_capacity;
-    const int N = P.N;
-
-    for(unsigned int t = blockIdx.x; t < count; t += gridDim.x)
+    const unsigned int lane = threadIdx.x & 31;
+    const unsigned int nwarps = gridDim.x * (blockDim.x >> 5);
+    for(unsigned int t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); t < count; t += nwarps)
     {
-        const unsigned int id = P.big_queue[t];
-        const unsigned int cell = id >> 1;
-        const int j = (int)(cell / (unsigned int)(N - 1)), i = (int)(cell % (unsigned int)(N - 1));
-        // lib:496-508
-        int vj[3], vi[3];
-        vj[0] = j; vi[0] = i;
-        if((id & 1u) == 0) { vj[1] = j + 1; vi[1] = i + 1; vj[2] = j + 1; vi[2] = i;     }
-        else               { vj[1] = j;     vi[1] = i + 1; vj[2] = j + 1; vi[2] = i + 1; }
-
-        float e[3], n[3];
-        HzVtx v[3];
-        #pragma unroll
-        for(int k = 0; k < 3; k++)
-        {
-            e[k] = __ldg(P.e_tab + vi[k]);
-            n[k] = __ldg(P.n_tab + vj[k]);
-            const float z = (float)__ldg(P.mosaic + (size_t)vj[k] * P.pitch + vi[k]);
-            hz_project(P, e[k], n[k], z, v[k]);
-        }
+        const uint2 entry = P.big_queue[t];
         HzTri T;
-        if(!hz_tri_bounds(P, v[0], v[1], v[2], T)) continue;      // cannot happen: k_march already accepted it
-        T.id = id;
-        hz_tri_planes(P, T, e[0], n[0], v[0].z, e[1], n[1], v[1].z, e[2], n[2], v[2].z);
-
-        const long long bw = T.px1 - T.px0 + 1, bh = T.py1 - T.py0 + 1;
-        const long long npix = bw * bh;
-        for(long long p = threadIdx.x; p < npix; p += blockDim.x)
+        if(!hz_tri_setup(P, entry.x, T, true)) continue;      // cannot happen: k_raster accepted it
+        const int y0 = T.py0 + (int)entry.y * HZ_BAND_ROWS;
+        const int y1 = min(y0 + HZ_BAND_ROWS - 1, T.py1);
+        const int bw = T.px1 - T.px0 + 1;
+        const int npix = bw * (y1 - y0 + 1);
+        if(hz_tri_is_small(T))
         {
-            const int py = T.py0 + (int)(p / bw), px = T.px0 + (int)(p % bw);
-            if(hz_inside(T, (long long)px * 256 + 128, (long long)py * 256 + 128)) hz_fragment(P, T, px, py);
+            const HzEdges<int> E(T);
+            for(int p = (int)lane; p < npix; p += 32)
+            {
+                const int py = y0 + p / bw, px = T.px0 + p % bw;
+                if(E.inside(T, px, py)) hz_fragment(P, T, px, py);
+            }
+        }
+        else
+        {
+            const HzEdges<long long> E(T);
+            for(int p = (int)lane; p < npix; p += 32)
+            {
+                const int py = y0 + p / bw, px = T.px0 + p % bw;
+                if(E.inside(T, px, py)) hz_fragment(P, T, px, py);
+            }
         }
     }
 }

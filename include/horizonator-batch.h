@@ -61,15 +61,17 @@ bool horizonator_time_mosaic(const horizonator_context_t* ctx, int reps, float* 
 /* Per-kernel device times.  While enabled, every render records CUDA events around each of
  * its kernels on the stream it runs on.  horizonator_profile_read() waits for them and reports
  * the MEAN duration in milliseconds per render of: out_ms[0] k_prepare (clear + axis tables),
- * [1] k_march (mesh + projection + cull + small-triangle raster), [2] k_big (large triangles),
- * [3] k_resolve (keys -> image + ranges), over the *renders recorded since the last read. */
+ * [1] k_march (mesh + projection + cull -> triangle list), [2] k_raster (set-up + rasterise
+ * the list), [3] k_big (large triangles), [4] k_resolve (keys -> image + ranges), over the
+ * *renders recorded since the last read. */
 bool horizonator_profile_enable(const horizonator_context_t* ctx, bool on);
-bool horizonator_profile_read(const horizonator_context_t* ctx, float out_ms[4], int* renders);
+bool horizonator_profile_read(const horizonator_context_t* ctx, float out_ms[5], int* renders);
 
-/* Counters of the most recent render on this context: out[0] = triangles that were queued
- * for the large-triangle kernel, out[1] = queue capacity, out[2] = kernel launches the
- * render issued, out[3] = CUDA device ordinal. */
-bool horizonator_last_render_stats(const horizonator_context_t* ctx, unsigned int out[4]);
+/* Counters of the most recent render on this context: out[0] = (triangle, row band) pairs
+ * queued for the large-triangle kernel, out[1] = that queue's capacity, out[2] = kernel
+ * launches the render issued, out[3] = CUDA device ordinal, out[4] = triangles that passed
+ * the cull and were rasterised. */
+bool horizonator_last_render_stats(const horizonator_context_t* ctx, unsigned int out[5]);
 
 #ifdef __cplusplus
 }

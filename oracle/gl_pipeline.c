@@ -17,7 +17,8 @@
  *       Two triangles sharing an edge therefore never both produce the pixel.
  *   F5  clipping to the view volume: w is 1 for every vertex, so interpolation is affine and
  *       clipping is applied per fragment: outside the viewport or zw outside [0,1] => dropped.
- *       A triangle with a vertex beyond +-2^22 pixels (or a non-finite one) is dropped.
+ *       A triangle with a vertex beyond +-2^21 pixels (or a non-finite one) is dropped
+ *       (keeps the 64-bit edge functions on 1/256-pixel coordinates free of overflow).
  *   F6  zw and the red channel are interpolated as planes through the UNSNAPPED float
  *       vertices, anchored at the triangle's first vertex, evaluated at the pixel centre.
  *   F7  GL_DEPTH_COMPONENT renderbuffer = 24-bit unsigned normalised: q = floor(zw*(2^24-1)+.5);
@@ -136,7 +137,7 @@ typedef struct
 } glp_vtx_t;
 
 #define SUBPIXEL   256
-#define GUARD_PX   4194304.0f   /* 2^22 (F5) */
+#define GUARD_PX   2097152.0f   /* 2^21 (F5) */
 
 static inline int64_t snap(float a)                                          /* F2 */
 {
