@@ -98,6 +98,8 @@ def _declare(lib):
         "horizonator_download_mosaic": (b, [ctx, vp]),
         "horizonator_time_mosaic": (b, [ctx, i, P(f)]),
         "horizonator_last_render_stats": (b, [ctx, P(C.c_uint * 5)]),
+        "horizonator_host_alloc": (vp, [C.c_size_t]),
+        "horizonator_host_free": (None, [vp]),
         "horizonator_profile_enable": (b, [ctx, b]),
         "horizonator_profile_read": (b, [ctx, P(f * 5), P(i)]),
     }
@@ -119,6 +121,7 @@ EXPORTED_SYMBOLS = (
     "horizonator_render_batch_device", "horizonator_render_batch", "horizonator_render_wedge_device",
     "horizonator_download_mosaic", "horizonator_time_mosaic", "horizonator_last_render_stats",
     "horizonator_profile_enable", "horizonator_profile_read",
+    "horizonator_host_alloc", "horizonator_host_free",
 )
 
 if not os.path.exists(LIBRARY_PATH):
@@ -290,6 +293,14 @@ class horizonator:
             raise RuntimeError("horizonator_time_mosaic() failed")
         return ms.value
 
+    def render_into(self, image, ranges):
+        """horizonator_render_offscreen() with the current state into caller-owned arrays (either may be
+        None): no allocation, and DMA speed when the arrays come from pinned_array()."""
+        if not lib.horizonator_render_offscreen(C.byref(self._ctx),
+                                                image.ctypes.data if image is not None else None,
+                                                ranges.ctypes.data if ranges is not None else None):
+            raise RuntimeError("horizonator_render_offscreen() failed")
+
     def profile(self, on=True):
         """Record CUDA events around every kernel of every render from now on (see profile_read)."""
         if not lib.horizonator_profile_enable(C.byref(self._ctx), bool(on)):
@@ -310,3 +321,25 @@ class horizonator:
             raise RuntimeError("horizonator_last_render_stats() failed")
         return {"big_bands": out[0], "big_capacity": out[1], "launches": out[2], "device": out[3],
                 "triangles_rasterised": out[4]}
+
+
+class _PinnedBlock:
+    def __init__(self, nbytes):
+        self.ptr = lib.horizonator_host_alloc(nbytes)
+        if not self.ptr:
+            raise MemoryError("horizonator_host_alloc(%d) failed" % nbytes)
+
+    def __del__(self):
+        if getattr(self, "ptr", None) and lib is not None:
+            lib.horizonator_host_free(self.ptr)
+            self.ptr = None
+
+
+def pinned_array(shape, dtype):
+    """numpy array in page-locked host memory (horizonator_host_alloc); freed with the array."""
+    dtype = np.dtype(dtype)
+    n = int(np.prod(shape)) * dtype.itemsize
+    block = _PinnedBlock(max(n, 1))
+    buf = (C.c_uint8 * max(n, 1)).from_address(block.ptr)
+    buf._hz_block = block                 # keeps the allocation alive as long as any view of it
+    return np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)

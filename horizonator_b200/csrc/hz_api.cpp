@@ -16,7 +16,6 @@
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
-#include <thread>
 #include <vector>
 
 namespace {
@@ -59,8 +58,6 @@ struct Slot
     unsigned long long* d_vis = nullptr;
     uint8_t* d_image  = nullptr;
     float*   d_ranges = nullptr;
-    uint8_t* h_image  = nullptr;     // pinned staging for the host-pointer API
-    float*   h_ranges = nullptr;
     size_t   target_pixels = 0;      // capacity of the buffers above
 
     // tan(elevation) per row, computed on the host like the reference's read-back does
@@ -115,8 +112,6 @@ void free_target(Slot& s)
     cudaFree(s.d_image);  s.d_image = nullptr;
     cudaFree(s.d_ranges); s.d_ranges = nullptr;
     cudaFree(s.d_tanel);  s.d_tanel = nullptr;
-    cudaFreeHost(s.h_image);  s.h_image = nullptr;
-    cudaFreeHost(s.h_ranges); s.h_ranges = nullptr;
     cudaFreeHost(s.h_tanel);  s.h_tanel = nullptr;
     s.target_pixels = 0;
     for(auto& k : s.tanel_key) k.valid = false;
@@ -130,8 +125,6 @@ bool alloc_target(Slot& s, int W, int H)
     CUDA_TRY(cudaMalloc(&s.d_image, px * 3));
     CUDA_TRY(cudaMalloc(&s.d_ranges, px * sizeof(float)));
     CUDA_TRY(cudaMalloc(&s.d_tanel, (size_t)TANEL_SLOTS * H * sizeof(float)));
-    CUDA_TRY(cudaMallocHost(&s.h_image, px * 3));
-    CUDA_TRY(cudaMallocHost(&s.h_ranges, px * sizeof(float)));
     CUDA_TRY(cudaMallocHost(&s.h_tanel, (size_t)TANEL_SLOTS * H * sizeof(float)));
     s.W = W; s.H = H; s.target_pixels = px;
     s.have_render = false;
@@ -304,25 +297,13 @@ bool compute_move(const horizonator_context_t* ctx, float* viewer_z, float lat, 
     return true;
 }
 
-// multi-threaded copy out of the pinned staging buffers: a single thread cannot keep up with PCIe
-void copy_out(void* dst, const void* src, size_t bytes)
+// Device -> caller's host buffer on `st`.  Page-locked destinations (cudaHostAlloc / cudaHostRegister /
+// horizonator_host_alloc) are written by DMA at PCIe speed; for ordinary pageable memory the driver stages the
+// copy itself, which measured faster here than a private pinned bounce buffer plus memcpy.
+bool copy_to_host(void* dst, const void* src, size_t bytes, cudaStream_t st)
 {
-    const size_t chunk = 1u << 20;
-    const unsigned hw = std::thread::hardware_concurrency();
-    size_t nthreads = bytes / (4 * chunk);
-    if(nthreads > 8) nthreads = 8;
-    if(hw && nthreads > hw) nthreads = hw;
-    if(nthreads <= 1) { memcpy(dst, src, bytes); return; }
-    std::vector<std::thread> pool;
-    const size_t per = (bytes + nthreads - 1) / nthreads;
-    for(size_t t = 0; t < nthreads; t++)
-    {
-        const size_t off = t * per;
-        if(off >= bytes) break;
-        const size_t len = (off + per <= bytes) ? per : bytes - off;
-        pool.emplace_back([=] { memcpy((char*)dst + off, (const char*)src + off, len); });
-    }
-    for(auto& th : pool) th.join();
+    CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, st));
+    return true;
 }
 
 } // namespace
@@ -552,11 +533,9 @@ bool horizonator_render_offscreen(const horizonator_context_t* ctx, char* image,
     const size_t px = (size_t)s->W * s->H;
     if(!enqueue_render(*s, s->view, 0, s->W,
                        image ? s->d_image : nullptr, ranges ? s->d_ranges : nullptr, s->stream)) return false;
-    if(image)  CUDA_TRY(cudaMemcpyAsync(s->h_image,  s->d_image,  px * 3, cudaMemcpyDeviceToHost, s->stream));
-    if(ranges) CUDA_TRY(cudaMemcpyAsync(s->h_ranges, s->d_ranges, px * sizeof(float), cudaMemcpyDeviceToHost, s->stream));
+    if(image  && !copy_to_host(image,  s->d_image,  px * 3, s->stream)) return false;
+    if(ranges && !copy_to_host(ranges, s->d_ranges, px * sizeof(float), s->stream)) return false;
     CUDA_TRY(cudaStreamSynchronize(s->stream));
-    if(image)  copy_out(image,  s->h_image,  px * 3);
-    if(ranges) copy_out(ranges, s->h_ranges, px * sizeof(float));
     return true;
 }
 
@@ -688,11 +667,9 @@ bool horizonator_render_batch(const horizonator_context_t* ctx, int n, const hor
         vs.az_deg0 = views[k].az_deg0; vs.az_deg1 = views[k].az_deg1;
         if(!enqueue_render(*s, vs, 0, s->W, images ? s->d_image : nullptr, ranges ? s->d_ranges : nullptr, s->stream))
             return false;
-        if(images) CUDA_TRY(cudaMemcpyAsync(s->h_image,  s->d_image,  px * 3, cudaMemcpyDeviceToHost, s->stream));
-        if(ranges) CUDA_TRY(cudaMemcpyAsync(s->h_ranges, s->d_ranges, px * sizeof(float), cudaMemcpyDeviceToHost, s->stream));
+        if(images && !copy_to_host(images + (size_t)k * px * 3, s->d_image, px * 3, s->stream)) return false;
+        if(ranges && !copy_to_host(ranges + (size_t)k * px, s->d_ranges, px * sizeof(float), s->stream)) return false;
         CUDA_TRY(cudaStreamSynchronize(s->stream));
-        if(images) copy_out(images + (size_t)k * px * 3, s->h_image, px * 3);
-        if(ranges) copy_out(ranges + (size_t)k * px, s->h_ranges, px * sizeof(float));
     }
     s->have_render = false;
     return true;
@@ -713,6 +690,23 @@ bool horizonator_render_wedge_device(const horizonator_context_t* ctx, int x0, i
     if(!enqueue_render(*s, s->view, x0, x1, (uint8_t*)d_image, (float*)d_ranges, st)) return false;
     if(stream == nullptr) CUDA_TRY(cudaStreamSynchronize(st));
     return true;
+}
+
+void* horizonator_host_alloc(size_t bytes)
+{
+    void* p = nullptr;
+    if(cudaMallocHost(&p, bytes) != cudaSuccess)
+    {
+        MSG("cudaMallocHost(%zu) failed", bytes);
+        cudaGetLastError();
+        return nullptr;
+    }
+    return p;
+}
+
+void horizonator_host_free(void* p)
+{
+    if(p != nullptr) cudaFreeHost(p);
 }
 
 bool horizonator_download_mosaic(const horizonator_context_t* ctx, int16_t* mosaic)

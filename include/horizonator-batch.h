@@ -12,6 +12,8 @@
  */
 #pragma once
 
+#include <stddef.h>
+
 #include "horizonator.h"
 
 #ifdef __cplusplus
@@ -49,6 +51,13 @@ bool horizonator_render_wedge_device(const horizonator_context_t* ctx,
                                      int x0, int x1,
                                      void* d_image, void* d_ranges,
                                      void* stream);
+
+/* Page-locked host memory for output buffers.  horizonator_render_offscreen() and
+ * horizonator_render_batch() accept any host pointer; into memory from this allocator (or any
+ * other CUDA-registered host memory) the results arrive by DMA at PCIe speed, into ordinary
+ * pageable memory through the driver's staging copy (about 3x slower for a 15 MB result). */
+void* horizonator_host_alloc(size_t bytes);
+void  horizonator_host_free(void* p);
 
 /* Copies the decoded DEM square (2R x 2R int16, row j = north index, column i = east index,
  * tightly packed) from the device to host memory.  For tests of the decode/stitch kernel. */
