@@ -49,7 +49,9 @@ def measured_peak_gbs():
 
 
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """SM clock + clock-event (throttle) reasons sampled DURING the timed region: NVML polled every ~2 ms from a
+    thread (the region can be shorter than nvidia-smi's sampling period); nvidia-smi -lms as the fallback
+    (B200_PROFILING.md clocks line)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
@@ -57,45 +59,87 @@ class ClockSampler:
     def __init__(self, gpu_index):
         self.gpu = gpu_index
         self.proc = None
-        self.lines = []
+        self.samples = []          # (time, sm_mhz, sm_max_mhz, set of reasons)
+        self.stop_flag = False
+        self.thread = None
+        self.how = None
+
+    def _physical_index(self):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            try:
+                return int(vis.split(",")[self.gpu])
+            except (ValueError, IndexError):
+                pass
+        return self.gpu
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+            import pynvml
+            pynvml.nvmlInit()
+            hnd = pynvml.nvmlDeviceGetHandleByIndex(self._physical_index())
+            smmax = float(pynvml.nvmlDeviceGetMaxClockInfo(hnd, pynvml.NVML_CLOCK_SM))
+            names = (("hw_slowdown", pynvml.nvmlClocksEventReasonHwSlowdown),
+                     ("hw_thermal_slowdown", pynvml.nvmlClocksEventReasonHwThermalSlowdown),
+                     ("sw_thermal_slowdown", pynvml.nvmlClocksEventReasonSwThermalSlowdown),
+                     ("sw_power_cap", pynvml.nvmlClocksEventReasonSwPowerCap))
+
+            def poll():
+                while not self.stop_flag:
+                    try:
+                        mhz = float(pynvml.nvmlDeviceGetClockInfo(hnd, pynvml.NVML_CLOCK_SM))
+                        bits = pynvml.nvmlDeviceGetCurrentClocksEventReasons(hnd)
+                        self.samples.append((time.time(), mhz, smmax, {n for n, b in names if bits & b}))
+                    except Exception:
+                        pass
+                    time.sleep(0.002)
+            self.thread = threading.Thread(target=poll, daemon=True)
+            self.thread.start()
+            self.how = "nvml"
+            return
+        except Exception:
+            pass
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self._physical_index()), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
+            self.how = "nvidia-smi"
         except Exception:
             self.proc = None
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.lines.append((time.time(), line.strip()))
-
-    def stop(self, t0, t1):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        sm, smmax, reasons = [], [], set()
-        for t, line in self.lines:
-            if t < t0 - 0.05 or t > t1 + 0.15:
-                continue
             f = [x.strip() for x in line.split(",")]
             if len(f) < 9:
                 continue
             try:
-                sm.append(float(f[1])); smmax.append(float(f[2]))
+                mhz, smmax = float(f[1]), float(f[2])
             except ValueError:
                 continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        if not sm:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples in the timed region"]}
-        sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(smmax), "reasons": sorted(reasons), "samples": len(sm)}
+            names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+            self.samples.append((time.time(), mhz, smmax,
+                                 {n for n, v in zip(names, f[5:9]) if v.lower().startswith("active")}))
+
+    def stop(self, t0, t1):
+        if self.how is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no NVML and no nvidia-smi"]}
+        self.stop_flag = True
+        if self.proc is not None:
+            time.sleep(0.05)
+            self.proc.terminate()
+        elif self.thread is not None:
+            self.thread.join(timeout=1.0)
+        inside = [s for s in self.samples if t0 <= s[0] <= t1]
+        if not inside:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples in the timed region"], "how": self.how}
+        sm = sorted(s[1] for s in inside)
+        reasons = set()
+        for s in inside:
+            reasons |= s[3]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_min_mhz": sm[0], "sm_max_mhz": max(s[2] for s in inside),
+                "reasons": sorted(reasons), "samples": len(inside), "how": self.how}
 
 
 def ensure_tiles(rank, barrier):
@@ -164,7 +208,7 @@ def run_b200(args):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-        time.sleep(0.3)
+        time.sleep(0.05)
     barrier()
     torch.cuda.synchronize()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -379,7 +423,7 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
