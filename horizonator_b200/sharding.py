@@ -1,0 +1,141 @@
+"""Multi-GPU partitioning of the render path: one process per GPU, torch.distributed for the
+plumbing (NCCL on the GPUs, gloo in the CPU tests).
+
+The reference has no counterpart (single thread, single GL context).  Two partitions exist, and neither puts a
+collective on the data path of a render:
+
+* viewpoint batch -- every viewpoint is an independent render against the same read-only DEM square, which each
+  rank loads for itself.  Viewpoints are block-partitioned; outputs stay sharded on the rank that made them.
+  Only reduced products (horizon profiles, a few bytes per image column) are gathered.
+* azimuth wedges  -- one giant panorama: rank g renders columns [edges[g], edges[g+1]) with
+  horizonator_render_wedge_device(), bit-identical to the same columns of an unsharded render, and the slabs
+  are gathered once (all_gather of equal-sized padded slabs + a strided placement).
+
+Everything here except the two render_* drivers is device-agnostic tensor code, so the world_size-2 gloo tests
+exercise exactly what runs over NCCL.
+"""
+import torch
+import torch.distributed as dist
+
+
+def block_partition(n, world, rank):
+    """[lo, hi) of the items rank `rank` owns when n items are dealt out in contiguous, near-equal blocks."""
+    if world <= 0 or not (0 <= rank < world):
+        raise ValueError("bad rank %d of %d" % (rank, world))
+    return n * rank // world, n * (rank + 1) // world
+
+
+def wedge_edges(width, n_wedges):
+    """Column edges of n_wedges near-equal azimuth wedges of a panorama `width` pixels wide."""
+    if n_wedges <= 0 or n_wedges > width:
+        raise ValueError("cannot cut %d columns into %d wedges" % (width, n_wedges))
+    return [width * g // n_wedges for g in range(n_wedges + 1)]
+
+
+def _world(group):
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_world_size(group), dist.get_rank(group)
+    return 1, 0
+
+
+def stitch_wedges(slabs, edges):
+    """slabs[g]: (H, >=w_g, ...) tensor whose first w_g = edges[g+1]-edges[g] columns are wedge g.  Returns the
+    (H, W, ...) panorama."""
+    first = slabs[0]
+    W = edges[-1]
+    out = first.new_empty((first.shape[0], W) + tuple(first.shape[2:]))
+    for g, s in enumerate(slabs):
+        x0, x1 = edges[g], edges[g + 1]
+        out[:, x0:x1] = s[:, :x1 - x0]
+    return out
+
+
+def gather_wedges(local, edges, group=None):
+    """All ranks contribute their wedge `local` (H, w_rank, ...); every rank gets the full (H, W, ...) panorama.
+    Wedges may differ in width by one column; they travel padded to the widest one so that a single all_gather
+    of equal-sized buffers does the exchange."""
+    world, rank = _world(group)
+    if world == 1:
+        return stitch_wedges([local], edges)
+    if len(edges) != world + 1:
+        raise ValueError("need one wedge per rank: %d edges for %d ranks" % (len(edges), world))
+    if local.shape[1] != edges[rank + 1] - edges[rank]:
+        raise ValueError("rank %d holds %d columns, its wedge has %d" % (rank, local.shape[1], edges[rank + 1] - edges[rank]))
+    wmax = max(edges[g + 1] - edges[g] for g in range(world))
+    padded = local.new_zeros((local.shape[0], wmax) + tuple(local.shape[2:]))
+    padded[:, :local.shape[1]] = local
+    slabs = [torch.empty_like(padded) for _ in range(world)]
+    dist.all_gather(slabs, padded.contiguous(), group=group)
+    return stitch_wedges(slabs, edges)
+
+
+def gather_blocks(local, n_total, group=None):
+    """Inverse of block_partition for per-item results: `local` is (n_rank, ...) on every rank; returns
+    (n_total, ...) on every rank.  Meant for reduced products, not for full images."""
+    world, rank = _world(group)
+    if world == 1:
+        return local
+    sizes = [block_partition(n_total, world, r) for r in range(world)]
+    nmax = max(hi - lo for lo, hi in sizes)
+    padded = local.new_zeros((nmax,) + tuple(local.shape[1:]))
+    padded[:local.shape[0]] = local
+    parts = [torch.empty_like(padded) for _ in range(world)]
+    dist.all_gather(parts, padded.contiguous(), group=group)
+    return torch.cat([p[:hi - lo] for p, (lo, hi) in zip(parts, sizes)], dim=0)
+
+
+def horizon_profile(ranges):
+    """Per image column: the row of the topmost terrain pixel (-1 if none) and the range there.
+    ranges: (..., H, W) float tensor as render() returns it (top row first, < 0 where no terrain).
+    Returns (rows int32 (..., W), range float32 (..., W)).  Device-agnostic reference implementation; the CUDA
+    renderer has the same reduction as a kernel (horizonator_horizon_profile_device)."""
+    hit = ranges > 0
+    H = ranges.shape[-2]
+    idx = torch.arange(H, device=ranges.device, dtype=torch.int32).view((1,) * (ranges.dim() - 2) + (H, 1))
+    first = torch.where(hit, idx, torch.full_like(idx, H)).amin(dim=-2)
+    rows = torch.where(first < H, first, torch.full_like(first, -1))
+    rng = torch.gather(ranges, -2, first.clamp(max=H - 1).unsqueeze(-2).long()).squeeze(-2)
+    rng = torch.where(first < H, rng, torch.full_like(rng, -1.0))
+    return rows.to(torch.int32), rng.to(torch.float32)
+
+
+# ---------------------------------------------------------------------------------------------- drivers (GPU)
+
+def render_wedges(h, group=None, return_image=True, return_range=True):
+    """One panorama of h's current view split by azimuth wedge over the ranks of `group`; every rank returns the
+    full (H,W,3) uint8 / (H,W) float32 CUDA tensors.  All ranks must hold contexts of the same DEM, size and view."""
+    world, rank = _world(group)
+    W, H = h.width, h.height
+    edges = wedge_edges(W, world)
+    x0, x1 = edges[rank], edges[rank + 1]
+    dev = torch.device("cuda", torch.cuda.current_device())
+    img = torch.empty((H, x1 - x0, 3), dtype=torch.uint8, device=dev) if return_image else None
+    rng = torch.empty((H, x1 - x0), dtype=torch.float32, device=dev) if return_range else None
+    stream = torch.cuda.current_stream()
+    h.render_wedge_device(x0, x1, img.data_ptr() if return_image else 0, rng.data_ptr() if return_range else 0,
+                          stream.cuda_stream)
+    out = []
+    if return_image:
+        out.append(gather_wedges(img, edges, group))
+    if return_range:
+        out.append(gather_wedges(rng, edges, group))
+    return tuple(out)
+
+
+def render_batch_sharded(h, views, group=None, gather_profiles=True):
+    """Block-partitions `views` over the ranks, renders this rank's share into device memory and returns
+    (local_images, local_ranges, (lo, hi), profiles) -- profiles = (rows, range) of ALL views on every rank
+    when gather_profiles, else None.  The full images never leave the GPU that rendered them."""
+    world, rank = _world(group)
+    lo, hi = block_partition(len(views), world, rank)
+    W, H = h.width, h.height
+    dev = torch.device("cuda", torch.cuda.current_device())
+    img = torch.empty((hi - lo, H, W, 3), dtype=torch.uint8, device=dev)
+    rng = torch.empty((hi - lo, H, W), dtype=torch.float32, device=dev)
+    if hi > lo:
+        h.render_batch_device(views[lo:hi], img.data_ptr(), rng.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    profiles = None
+    if gather_profiles:
+        rows, r = horizon_profile(rng)
+        profiles = (gather_blocks(rows, len(views), group), gather_blocks(r, len(views), group))
+    return img, rng, (lo, hi), profiles
