@@ -98,13 +98,19 @@ def _declare(lib):
         "horizonator_download_mosaic": (b, [ctx, vp]),
         "horizonator_time_mosaic": (b, [ctx, i, P(f)]),
         "horizonator_last_render_stats": (b, [ctx, P(C.c_uint * 5)]),
+        "horizonator_render_counters": (b, [ctx, P(C.c_uint * 16)]),
+        "horizonator_horizon_profile_device": (b, [ctx, vp, i, vp, vp, vp]),
         "horizonator_host_alloc": (vp, [C.c_size_t]),
         "horizonator_host_free": (None, [vp]),
         "horizonator_profile_enable": (b, [ctx, b]),
-        "horizonator_profile_read": (b, [ctx, P(f * 5), P(i)]),
+        "horizonator_profile_read": (b, [ctx, P(f * 6), P(i)]),
     }
     for name, (res, args) in sigs.items():
-        fn = getattr(lib, name)
+        try:
+            fn = getattr(lib, name)
+        except AttributeError:
+            raise ImportError("%s is stale (no symbol %s): rebuild it with `python horizonator_b200/build.py`"
+                              % (LIBRARY_PATH, name)) from None
         fn.restype = res
         fn.argtypes = args
     return lib
@@ -122,11 +128,12 @@ EXPORTED_SYMBOLS = (
     "horizonator_download_mosaic", "horizonator_time_mosaic", "horizonator_last_render_stats",
     "horizonator_profile_enable", "horizonator_profile_read",
     "horizonator_host_alloc", "horizonator_host_free",
+    "horizonator_render_counters", "horizonator_horizon_profile_device",
 )
 
 if not os.path.exists(LIBRARY_PATH):
     raise ImportError(
-        "%s is missing: build it with `python -m horizonator_b200.build` (needs nvcc). "
+        "%s is missing: build it with `python horizonator_b200/build.py` (needs nvcc). "
         "horizonator_b200 has no CPU fallback." % LIBRARY_PATH)
 
 lib = _declare(C.CDLL(LIBRARY_PATH))
@@ -308,19 +315,36 @@ class horizonator:
 
     def profile_read(self):
         """Mean device ms per render of each kernel since the last read, and the number of renders."""
-        ms = (C.c_float * 5)()
+        ms = (C.c_float * 6)()
         n = C.c_int(0)
         if not lib.horizonator_profile_read(C.byref(self._ctx), C.byref(ms), C.byref(n)):
             raise RuntimeError("horizonator_profile_read() failed")
-        return {"prepare": ms[0], "march": ms[1], "raster": ms[2], "big": ms[3], "resolve": ms[4],
-                "renders": n.value}
+        return {"prepare": ms[0], "near": ms[1], "big_near": ms[2], "march": ms[3], "big_far": ms[4],
+                "resolve": ms[5], "renders": n.value}
 
     def last_render_stats(self):
         out = (C.c_uint * 5)()
         if not lib.horizonator_last_render_stats(C.byref(self._ctx), C.byref(out)):
             raise RuntimeError("horizonator_last_render_stats() failed")
-        return {"big_bands": out[0], "big_capacity": out[1], "launches": out[2], "device": out[3],
+        return {"big_entries": out[0], "big_capacity": out[1], "launches": out[2], "device": out[3],
                 "triangles_rasterised": out[4]}
+
+    COUNTER_NAMES = ("tiles", "tiles_far", "tiles_window", "tiles_occluded",
+                     "blocks", "blocks_far", "blocks_window", "blocks_occluded",
+                     "blocks_meshed", "triangles", "big_entries")
+
+    def render_counters(self):
+        """Culling counters of the most recent render (horizonator_render_counters)."""
+        out = (C.c_uint * 16)()
+        if not lib.horizonator_render_counters(C.byref(self._ctx), C.byref(out)):
+            raise RuntimeError("horizonator_render_counters() failed")
+        return dict(zip(self.COUNTER_NAMES, out))
+
+    def horizon_profile_device(self, d_ranges, n, d_rows, d_range, stream=0):
+        """Per-column topmost terrain (row, range) of n device range images; all arguments device addresses."""
+        if not lib.horizonator_horizon_profile_device(C.byref(self._ctx), d_ranges, int(n), d_rows, d_range,
+                                                      stream or None):
+            raise RuntimeError("horizonator_horizon_profile_device() failed")
 
 
 class _PinnedBlock:

@@ -32,14 +32,32 @@ namespace {
 
 constexpr int   TANEL_SLOTS     = 8;
 constexpr float PI_F            = 3.14159265358979f;       // vertex.glsl:31
-constexpr unsigned BIG_CAPACITY = 1u << 21;      // (triangle, band) pairs; overflow is drawn inline
-constexpr int   PROF_EVENTS     = 6;            // 5 kernels per render
+constexpr unsigned BIG_CAPACITY = 1u << 21;      // (triangle, sub-box) pairs per pass; overflow is drawn inline
+constexpr int   PROF_EVENTS     = 7;            // 6 stages per render
+constexpr int   MAX_BANDS       = 6;
+// [0] big_count near, [1] big_count bands, [2+2b] tile_count, [3+2b] block_count of band b, then the stats
+constexpr int   STATS_AT        = 2 + 2 * MAX_BANDS;
+constexpr int   N_COUNTERS      = STATS_AT + HZ_STAT_COUNT;
 
 // what the reference keeps in GL uniforms
 struct ViewState
 {
     float viewer_cell_i = 0, viewer_cell_j = 0, viewer_z = 0, cos_viewer_lat = 1;
     float az_deg0 = -45.f, az_deg1 = 45.f;
+};
+
+// everything one render writes besides its outputs
+struct Scratch
+{
+    cudaStream_t stream = nullptr;     // lanes only
+    cudaEvent_t  done = nullptr;       // lanes only
+    unsigned long long* d_vis = nullptr;
+    float *d_e = nullptr, *d_n = nullptr;
+    uint32_t *d_tile_queue = nullptr, *d_block_queue = nullptr;
+    uint2*    d_big_queue = nullptr;   // [2][BIG_CAPACITY]: near pass, bands
+    uint32_t* d_counters  = nullptr;   // [N_COUNTERS]
+    uint8_t*  d_image  = nullptr;      // lanes only: staging of one view's outputs for the host-pointer batch call
+    float*    d_ranges = nullptr;
 };
 
 struct Slot
@@ -51,11 +69,16 @@ struct Slot
     int N = 0, pitch = 0, cpd = 0;
     int16_t* d_mosaic = nullptr;
     HzTiles  tiles{};
-    float *d_e = nullptr, *d_n = nullptr;
+    short2 *d_mm_block = nullptr, *d_mm_tile = nullptr;   // culling pyramid
+    int nb = 0, nt = 0;
+    int near_rings = 2;
+    int n_bands = 3;
+    int occl_tile_max_pix = 128, occl_block_max_pix = 32;
+    int band_end[MAX_BANDS] = { 12, 48, 1 << 20, 0, 0, 0 };   // ring at which each band ends (exclusive)
+    int n_lanes_max = 8;
 
     // target
     int W = 0, H = 0;
-    unsigned long long* d_vis = nullptr;
     uint8_t* d_image  = nullptr;
     float*   d_ranges = nullptr;
     size_t   target_pixels = 0;      // capacity of the buffers above
@@ -66,9 +89,12 @@ struct Slot
     struct { bool valid; float daz; int W, H; } tanel_key[TANEL_SLOTS] = {};
     int      tanel_next = 0;
 
-    uint32_t* d_tri_queue = nullptr;   // one slot per triangle of the mesh: cannot overflow
-    uint2*    d_big_queue = nullptr;
-    uint32_t* d_counters  = nullptr;   // [0] big_count, [1] tri_count, [2] work_count
+    // Scratch of one render in flight.  `main` serves the single-view entry points (and keeps the last
+    // visibility buffer for horizonator_pick); `lanes` are made on demand by the batch entry points so that
+    // several views of one batch render concurrently, each on its own stream.
+    Scratch main;
+    std::vector<Scratch> lanes;
+    cudaEvent_t fork_ev = nullptr;
 
     ViewState view;
     float znear = HORIZONATOR_ZNEAR_DEFAULT, zfar = HORIZONATOR_ZFAR_DEFAULT;
@@ -108,7 +134,12 @@ struct DeviceGuard
 
 void free_target(Slot& s)
 {
-    cudaFree(s.d_vis);    s.d_vis = nullptr;
+    cudaFree(s.main.d_vis); s.main.d_vis = nullptr;
+    for(Scratch& l : s.lanes)
+    {
+        cudaFree(l.d_vis); cudaFree(l.d_image); cudaFree(l.d_ranges);
+        l.d_vis = nullptr; l.d_image = nullptr; l.d_ranges = nullptr;
+    }
     cudaFree(s.d_image);  s.d_image = nullptr;
     cudaFree(s.d_ranges); s.d_ranges = nullptr;
     cudaFree(s.d_tanel);  s.d_tanel = nullptr;
@@ -121,7 +152,13 @@ bool alloc_target(Slot& s, int W, int H)
 {
     free_target(s);
     const size_t px = (size_t)W * (size_t)H;
-    CUDA_TRY(cudaMalloc(&s.d_vis, px * sizeof(unsigned long long)));
+    CUDA_TRY(cudaMalloc(&s.main.d_vis, px * sizeof(unsigned long long)));
+    for(Scratch& l : s.lanes)
+    {
+        CUDA_TRY(cudaMalloc(&l.d_vis, px * sizeof(unsigned long long)));
+        CUDA_TRY(cudaMalloc(&l.d_image, px * 3));
+        CUDA_TRY(cudaMalloc(&l.d_ranges, px * sizeof(float)));
+    }
     CUDA_TRY(cudaMalloc(&s.d_image, px * 3));
     CUDA_TRY(cudaMalloc(&s.d_ranges, px * sizeof(float)));
     CUDA_TRY(cudaMalloc(&s.d_tanel, (size_t)TANEL_SLOTS * H * sizeof(float)));
@@ -131,17 +168,69 @@ bool alloc_target(Slot& s, int W, int H)
     return true;
 }
 
+void free_scratch(Scratch& c)
+{
+    cudaFree(c.d_vis); cudaFree(c.d_e); cudaFree(c.d_n);
+    cudaFree(c.d_tile_queue); cudaFree(c.d_block_queue); cudaFree(c.d_big_queue); cudaFree(c.d_counters);
+    cudaFree(c.d_image); cudaFree(c.d_ranges);
+    if(c.done) cudaEventDestroy(c.done);
+    if(c.stream) cudaStreamDestroy(c.stream);
+    c = Scratch{};
+}
+
+// everything but the visibility buffer (alloc_target owns that: it depends on the image size)
+bool alloc_scratch(const Slot& s, Scratch& c, bool own_stream)
+{
+    CUDA_TRY(cudaMalloc(&c.d_e, (size_t)s.N * sizeof(float)));
+    CUDA_TRY(cudaMalloc(&c.d_n, (size_t)s.N * sizeof(float)));
+    CUDA_TRY(cudaMalloc(&c.d_tile_queue, (size_t)s.nt * s.nt * sizeof(uint32_t)));
+    CUDA_TRY(cudaMalloc(&c.d_block_queue, (size_t)s.nb * s.nb * sizeof(uint32_t)));
+    CUDA_TRY(cudaMalloc(&c.d_big_queue, 2 * (size_t)BIG_CAPACITY * sizeof(uint2)));
+    CUDA_TRY(cudaMalloc(&c.d_counters, N_COUNTERS * sizeof(uint32_t)));
+    if(own_stream)
+    {
+        CUDA_TRY(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+        CUDA_TRY(cudaEventCreateWithFlags(&c.done, cudaEventDisableTiming));
+    }
+    return true;
+}
+
+// makes sure n lanes exist (n <= n_lanes_max)
+bool ensure_lanes(Slot& s, int n)
+{
+    if(s.fork_ev == nullptr) CUDA_TRY(cudaEventCreateWithFlags(&s.fork_ev, cudaEventDisableTiming));
+    while((int)s.lanes.size() < n)
+    {
+        Scratch c;
+        if(!alloc_scratch(s, c, true) ||
+           cudaMalloc(&c.d_vis, s.target_pixels * sizeof(unsigned long long)) != cudaSuccess ||
+           cudaMalloc(&c.d_image, s.target_pixels * 3) != cudaSuccess ||
+           cudaMalloc(&c.d_ranges, s.target_pixels * sizeof(float)) != cudaSuccess)
+        {
+            MSG("Could not allocate render lane %d", (int)s.lanes.size());
+            cudaGetLastError();
+            free_scratch(c);
+            return false;
+        }
+        s.lanes.push_back(c);
+    }
+    return true;
+}
+
 void destroy_slot(Slot* s)
 {
     if(s == nullptr) return;
     DeviceGuard g(s->device);
     if(s->stream) cudaStreamSynchronize(s->stream);
+    for(Scratch& l : s->lanes) if(l.stream) cudaStreamSynchronize(l.stream);
     free_target(*s);
+    free_scratch(s->main);
+    for(Scratch& l : s->lanes) free_scratch(l);
+    if(s->fork_ev) cudaEventDestroy(s->fork_ev);
     cudaFree(s->d_mosaic);
     for(int i = 0; i < 4; i++) for(int j = 0; j < 4; j++) cudaFree((void*)s->tiles.tile[i][j]);
     for(cudaEvent_t e : s->prof_events) cudaEventDestroy(e);
-    cudaFree(s->d_e); cudaFree(s->d_n);
-    cudaFree(s->d_tri_queue); cudaFree(s->d_big_queue); cudaFree(s->d_counters);
+    cudaFree(s->d_mm_block); cudaFree(s->d_mm_tile);
     if(s->stream) cudaStreamDestroy(s->stream);
     delete s;
 }
@@ -193,12 +282,14 @@ bool tanel_for(Slot& s, float az_deg0, float az_deg1, cudaStream_t st, const flo
 }
 
 // enqueue one render of columns [x0,x1) into d_image / d_ranges (device, either may be null)
-bool enqueue_render(Slot& s, const ViewState& vs, int x0, int x1,
+bool enqueue_render(Slot& s, Scratch& sc, const ViewState& vs, int x0, int x1,
                     uint8_t* d_image, float* d_ranges, cudaStream_t st)
 {
     HzView v{};
     v.mosaic = s.d_mosaic; v.N = s.N; v.pitch = s.pitch;
-    v.e_tab = s.d_e; v.n_tab = s.d_n;
+    v.e_tab = sc.d_e; v.n_tab = sc.d_n;
+    v.mm_block = s.d_mm_block; v.nb = s.nb;
+    v.mm_tile  = s.d_mm_tile;  v.nt = s.nt;
     v.viewer_cell_i = vs.viewer_cell_i; v.viewer_cell_j = vs.viewer_cell_j; v.viewer_z = vs.viewer_z;
     v.deg_per_cell = 1.0f / (float)s.cpd;                                // lib:577
     v.cos_viewer_lat = vs.cos_viewer_lat;
@@ -213,23 +304,24 @@ bool enqueue_render(Slot& s, const ViewState& vs, int x0, int x1,
 
     v.znear = s.znear; v.zfar = s.zfar; v.znear_color = s.znear_color; v.zfar_color = s.zfar_color;
     v.W = s.W; v.H = s.H; v.x0 = x0; v.x1 = x1;
-    v.vis = s.d_vis;
-    v.tri_queue = s.d_tri_queue; v.tri_count = s.d_counters + 1;
-    v.big_queue = s.d_big_queue; v.big_count = s.d_counters + 0; v.big_capacity = BIG_CAPACITY;
-    v.work_count = s.d_counters + 2;
+    v.vis = sc.d_vis;
+    v.stats      = sc.d_counters + STATS_AT;
+    v.tile_queue = sc.d_tile_queue; v.block_queue = sc.d_block_queue;
+    v.occl_tile_max_pix = s.occl_tile_max_pix; v.occl_block_max_pix = s.occl_block_max_pix;
+    v.big_capacity = BIG_CAPACITY;
 
-    // conservative block culling (hz_kernels.cu: hz_block_dead)
-    const float far_m = s.zfar * 1.001f + 1.0f;
-    v.cull_d2_far = far_m * far_m;
+    // the eye's tile, and how many rings of tiles around it form the foreground pass
     {
-        // azimuths that can land in columns [x0-1, x1+1): x_ndc = (az - center) * az_ndc_per_rad
-        const double k = (double)v.az_ndc_per_rad;
-        const double ndc_lo = 2.0 * (double)(x0 - 1) / (double)s.W - 1.0;
-        const double ndc_hi = 2.0 * (double)(x1 + 1) / (double)s.W - 1.0;
-        const double a_lo = (double)v.az_center + ndc_lo / k, a_hi = (double)v.az_center + ndc_hi / k;
-        v.cull_az_mid  = (float)(0.5 * (a_lo + a_hi));
-        v.cull_az_half = (float)(0.5 * fabs(a_hi - a_lo)) + 2e-3f;
-        if(!(v.cull_az_half < 3.1f) || !std::isfinite(v.cull_az_half)) v.cull_az_half = 4.0f;   // no test
+        const int ti = (int)floorf(vs.viewer_cell_i / (float)HZ_TILE_CELLS), tj = (int)floorf(vs.viewer_cell_j / (float)HZ_TILE_CELLS);
+        v.eye_ti = ti < 0 ? 0 : (ti >= s.nt ? s.nt - 1 : ti);
+        v.eye_tj = tj < 0 ? 0 : (tj >= s.nt ? s.nt - 1 : tj);
+        v.near_rings = s.near_rings;
+    }
+
+    // for the depth bound of hz_rect_test: the diagonal of one cell on the ground
+    {
+        const double cn = (double)v.deg_per_cell * 6371000.0 * M_PI / 180.0, ce = cn * fabs((double)vs.cos_viewer_lat);
+        v.cell_diag2 = (float)((ce * ce + cn * cn) * 1.01);
     }
 
     const float* d_tanel = nullptr;
@@ -247,27 +339,46 @@ bool enqueue_render(Slot& s, const ViewState& vs, int x0, int x1,
         ev = &s.prof_events[s.prof_used];
         s.prof_used += PROF_EVENTS;
     }
+    HzView v_near = v, v_far = v;
+    v_near.big_queue = sc.d_big_queue;                 v_near.big_count = sc.d_counters + 0;
+    v_far.big_queue  = sc.d_big_queue + BIG_CAPACITY;  v_far.big_count  = sc.d_counters + 1;
+
     if(ev) CUDA_TRY(cudaEventRecord(ev[0], st));
-    CUDA_TRY(hz_launch_prepare(v, st));
+    CUDA_TRY(hz_launch_prepare(v, sc.d_counters, N_COUNTERS, st));
     if(ev) CUDA_TRY(cudaEventRecord(ev[1], st));
-    CUDA_TRY(hz_launch_march(v, st));
+    CUDA_TRY(hz_launch_near(v_near, st));
     if(ev) CUDA_TRY(cudaEventRecord(ev[2], st));
-    CUDA_TRY(hz_launch_raster(v, st));
+    CUDA_TRY(hz_launch_big(v_near, st));
     if(ev) CUDA_TRY(cudaEventRecord(ev[3], st));
-    CUDA_TRY(hz_launch_big(v, st));
+    int band_launches = 0;
+    {
+        int lo = s.near_rings + 1;
+        for(int b = 0; b < s.n_bands; b++)
+        {
+            HzView vb = v_far;
+            vb.ring_lo = lo; vb.ring_hi = s.band_end[b] > lo ? s.band_end[b] : lo;
+            vb.tile_count = sc.d_counters + 2 + 2 * b; vb.block_count = sc.d_counters + 3 + 2 * b;
+            int n = 0;
+            CUDA_TRY(hz_launch_band(vb, st, &n));
+            band_launches += n;
+            lo = vb.ring_hi;
+        }
+    }
     if(ev) CUDA_TRY(cudaEventRecord(ev[4], st));
-    s.launches_last = 4;
+    CUDA_TRY(hz_launch_big(v_far, st));
+    if(ev) CUDA_TRY(cudaEventRecord(ev[5], st));
+    s.launches_last = 4 + band_launches;
     if(d_image || d_ranges)
     {
         HzResolve r{};
-        r.vis = s.d_vis; r.Wt = x1 - x0; r.H = s.H;
+        r.vis = sc.d_vis; r.Wt = x1 - x0; r.H = s.H;
         r.tanel = d_tanel; r.znear = s.znear; r.zfar = s.zfar;
         r.image = d_image; r.ranges = d_ranges;
         CUDA_TRY(hz_launch_resolve(r, st));
-        s.launches_last = 5;
+        s.launches_last++;
     }
-    if(ev) CUDA_TRY(cudaEventRecord(ev[5], st));
-    s.have_render = (x0 == 0 && x1 == s.W);
+    if(ev) CUDA_TRY(cudaEventRecord(ev[6], st));
+    if(&sc == &s.main) s.have_render = (x0 == 0 && x1 == s.W);
     return true;
 }
 
@@ -387,15 +498,32 @@ bool horizonator_init(horizonator_context_t* ctx,
         if(bad) break;
 
         if(fail(cudaMalloc(&s->d_mosaic, (size_t)s->N * s->pitch * sizeof(int16_t)), "cudaMalloc(mosaic)")) break;
-        if(fail(cudaMalloc(&s->d_e, (size_t)s->N * sizeof(float)), "cudaMalloc")) break;
-        if(fail(cudaMalloc(&s->d_n, (size_t)s->N * sizeof(float)), "cudaMalloc")) break;
+        s->nb = (s->N - 1 + HZ_BLOCK_CELLS - 1) / HZ_BLOCK_CELLS;
+        s->nt = (s->N - 1 + HZ_TILE_CELLS - 1) / HZ_TILE_CELLS;
+        if(const char* env = getenv("HORIZONATOR_NEAR_RINGS")) s->near_rings = atoi(env) < 0 ? 0 : atoi(env);
+        if(const char* env = getenv("HORIZONATOR_OCCL_TILE_PIX"))  s->occl_tile_max_pix  = atoi(env);
+        if(const char* env = getenv("HORIZONATOR_OCCL_BLOCK_PIX")) s->occl_block_max_pix = atoi(env);
+        if(const char* env = getenv("HORIZONATOR_BANDS"))
         {
-            const size_t n1 = (size_t)s->N - 1;
-            if(fail(cudaMalloc(&s->d_tri_queue, 2 * n1 * n1 * sizeof(uint32_t)), "cudaMalloc(triangle list)")) break;
+            // comma-separated rings at which the bands end; the last band always runs to the edge of the mesh
+            int n = 0;
+            for(const char* p = env; *p && n < MAX_BANDS - 1; )
+            {
+                const int r = atoi(p);
+                if(r > 0) s->band_end[n++] = r;
+                while(*p && *p != ',') p++;
+                if(*p == ',') p++;
+            }
+            s->band_end[n++] = 1 << 20;
+            s->n_bands = n;
         }
-        if(fail(cudaMalloc(&s->d_big_queue, (size_t)BIG_CAPACITY * sizeof(uint2)), "cudaMalloc")) break;
-        if(fail(cudaMalloc(&s->d_counters, 4 * sizeof(uint32_t)), "cudaMalloc")) break;
+        if(const char* env = getenv("HORIZONATOR_LANES")) s->n_lanes_max = atoi(env) < 1 ? 1 : (atoi(env) > 32 ? 32 : atoi(env));
+        if(fail(cudaMalloc(&s->d_mm_block, (size_t)s->nb * s->nb * sizeof(short2)), "cudaMalloc(pyramid)")) break;
+        if(fail(cudaMalloc(&s->d_mm_tile, (size_t)s->nt * s->nt * sizeof(short2)), "cudaMalloc(pyramid)")) break;
+        if(!alloc_scratch(*s, s->main, false)) break;
         if(fail(hz_launch_mosaic(s->tiles, s->d_mosaic, s->N, s->pitch, s->stream), "k_mosaic")) break;
+        if(fail(hz_launch_pyramid(s->d_mosaic, s->N, s->pitch, s->d_mm_block, s->nb, s->d_mm_tile, s->nt, s->stream),
+                "k_minmax")) break;
 
         // without an offscreen size the reference opens a 1024x1024 window (lib:142)
         const int W = offscreen_width > 0 ? offscreen_width : 1024;
@@ -515,7 +643,7 @@ bool horizonator_redraw(const horizonator_context_t* ctx)
     Slot* s = slot_of(ctx);
     if(s == nullptr) return false;
     DeviceGuard g(s->device);
-    if(!enqueue_render(*s, s->view, 0, s->W, s->d_image, s->d_ranges, s->stream)) return false;
+    if(!enqueue_render(*s, s->main, s->view, 0, s->W, s->d_image, s->d_ranges, s->stream)) return false;
     CUDA_TRY(cudaStreamSynchronize(s->stream));
     return true;
 }
@@ -531,7 +659,7 @@ bool horizonator_render_offscreen(const horizonator_context_t* ctx, char* image,
     }
     DeviceGuard g(s->device);
     const size_t px = (size_t)s->W * s->H;
-    if(!enqueue_render(*s, s->view, 0, s->W,
+    if(!enqueue_render(*s, s->main, s->view, 0, s->W,
                        image ? s->d_image : nullptr, ranges ? s->d_ranges : nullptr, s->stream)) return false;
     if(image  && !copy_to_host(image,  s->d_image,  px * 3, s->stream)) return false;
     if(ranges && !copy_to_host(ranges, s->d_ranges, px * sizeof(float), s->stream)) return false;
@@ -547,7 +675,7 @@ bool horizonator_pick(const horizonator_context_t* ctx, float* lat, float* lon, 
     DeviceGuard g(s->device);
     unsigned long long key = 0;
     CUDA_TRY(cudaStreamSynchronize(s->stream));
-    CUDA_TRY(cudaMemcpy(&key, s->d_vis + (size_t)(s->H - 1 - y) * s->W + x, sizeof(key), cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(&key, s->main.d_vis + (size_t)(s->H - 1 - y) * s->W + x, sizeof(key), cudaMemcpyDeviceToHost));
     const float depth = (float)((double)(unsigned)(key >> 40) * (1.0 / 16777215.0));
     if(depth >= 1.0f) return false;                                     // lib:1272
     // lib:1282-1295: the depth is treated as horizontal distance
@@ -629,6 +757,74 @@ bool horizonator_unproject(float* lat, float* lon, int x, int y,
 
 // ---- additive API (include/horizonator-batch.h) -----------------------------------------------------------
 
+// Common part of the two batch calls.  The views are dealt round-robin to render lanes, each with its own stream
+// and scratch, so that the (latency-bound) kernel chains of different views overlap; the lanes start after
+// everything already queued on `st` and `st` continues after all of them.  to_host: outputs go through the lane's
+// device staging buffers and a device->host copy on the lane's stream, which overlaps the next views' kernels.
+static bool render_batch_common(const horizonator_context_t* ctx, Slot* s, int n, const horizonator_view_t* views,
+                                uint8_t* images, float* ranges, bool to_host, cudaStream_t st)
+{
+    const size_t px = (size_t)s->W * s->H;
+    std::vector<ViewState> vs((size_t)n);
+    for(int k = 0; k < n; k++)
+    {
+        float z = views[k].viewer_z;
+        if(!compute_move(ctx, &z, views[k].lat, views[k].lon, vs[k])) return false;
+        vs[k].az_deg0 = views[k].az_deg0; vs[k].az_deg1 = views[k].az_deg1;
+    }
+
+    // Lanes need every per-window row table of the batch resident before they start (tanel_for() synchronises
+    // when it has to upload one): resolve them all on `st`, then check that none evicted another.
+    int n_lanes = n < s->n_lanes_max ? n : s->n_lanes_max;
+    if(n_lanes > 1 && ranges != nullptr)
+    {
+        const float* dummy;
+        for(int k = 0; k < n; k++) if(!tanel_for(*s, vs[k].az_deg0, vs[k].az_deg1, st, &dummy)) return false;
+        const int before = s->tanel_next;
+        for(int k = 0; k < n; k++) if(!tanel_for(*s, vs[k].az_deg0, vs[k].az_deg1, st, &dummy)) return false;
+        if(s->tanel_next != before) n_lanes = 1;      // more distinct windows than table slots: one at a time
+    }
+    if(n_lanes > 1 && !ensure_lanes(*s, n_lanes)) n_lanes = 1;
+
+    if(n_lanes <= 1)
+    {
+        for(int k = 0; k < n; k++)
+        {
+            uint8_t* di = images ? (to_host ? s->d_image  : images + (size_t)k * px * 3) : nullptr;
+            float*   dr = ranges ? (to_host ? s->d_ranges : ranges + (size_t)k * px)     : nullptr;
+            if(!enqueue_render(*s, s->main, vs[k], 0, s->W, di, dr, st)) return false;
+            if(to_host)
+            {
+                if(images && !copy_to_host(images + (size_t)k * px * 3, di, px * 3, st)) return false;
+                if(ranges && !copy_to_host(ranges + (size_t)k * px, dr, px * sizeof(float), st)) return false;
+            }
+        }
+        s->have_render = false;     // the visibility buffer no longer matches the context's own view
+        return true;
+    }
+
+    CUDA_TRY(cudaEventRecord(s->fork_ev, st));
+    for(int l = 0; l < n_lanes; l++) CUDA_TRY(cudaStreamWaitEvent(s->lanes[l].stream, s->fork_ev, 0));
+    for(int k = 0; k < n; k++)
+    {
+        Scratch& lane = s->lanes[k % n_lanes];
+        uint8_t* di = images ? (to_host ? lane.d_image  : images + (size_t)k * px * 3) : nullptr;
+        float*   dr = ranges ? (to_host ? lane.d_ranges : ranges + (size_t)k * px)     : nullptr;
+        if(!enqueue_render(*s, lane, vs[k], 0, s->W, di, dr, lane.stream)) return false;
+        if(to_host)
+        {
+            if(images && !copy_to_host(images + (size_t)k * px * 3, di, px * 3, lane.stream)) return false;
+            if(ranges && !copy_to_host(ranges + (size_t)k * px, dr, px * sizeof(float), lane.stream)) return false;
+        }
+    }
+    for(int l = 0; l < n_lanes; l++)
+    {
+        CUDA_TRY(cudaEventRecord(s->lanes[l].done, s->lanes[l].stream));
+        CUDA_TRY(cudaStreamWaitEvent(st, s->lanes[l].done, 0));
+    }
+    return true;
+}
+
 bool horizonator_render_batch_device(const horizonator_context_t* ctx, int n, const horizonator_view_t* views,
                                      void* d_images, void* d_ranges, void* stream)
 {
@@ -636,18 +832,7 @@ bool horizonator_render_batch_device(const horizonator_context_t* ctx, int n, co
     if(s == nullptr || n < 0 || (n > 0 && views == nullptr)) return false;
     DeviceGuard g(s->device);
     cudaStream_t st = stream ? (cudaStream_t)stream : s->stream;
-    const size_t px = (size_t)s->W * s->H;
-    for(int k = 0; k < n; k++)
-    {
-        ViewState vs;
-        float z = views[k].viewer_z;
-        if(!compute_move(ctx, &z, views[k].lat, views[k].lon, vs)) return false;
-        vs.az_deg0 = views[k].az_deg0; vs.az_deg1 = views[k].az_deg1;
-        if(!enqueue_render(*s, vs, 0, s->W,
-                           d_images ? (uint8_t*)d_images + (size_t)k * px * 3 : nullptr,
-                           d_ranges ? (float*)d_ranges + (size_t)k * px : nullptr, st)) return false;
-    }
-    s->have_render = false;     // d_vis no longer matches the context's own view
+    if(!render_batch_common(ctx, s, n, views, (uint8_t*)d_images, (float*)d_ranges, false, st)) return false;
     if(stream == nullptr) CUDA_TRY(cudaStreamSynchronize(st));
     return true;
 }
@@ -658,20 +843,8 @@ bool horizonator_render_batch(const horizonator_context_t* ctx, int n, const hor
     Slot* s = slot_of(ctx);
     if(s == nullptr || n < 0 || (n > 0 && views == nullptr)) return false;
     DeviceGuard g(s->device);
-    const size_t px = (size_t)s->W * s->H;
-    for(int k = 0; k < n; k++)
-    {
-        ViewState vs;
-        float z = views[k].viewer_z;
-        if(!compute_move(ctx, &z, views[k].lat, views[k].lon, vs)) return false;
-        vs.az_deg0 = views[k].az_deg0; vs.az_deg1 = views[k].az_deg1;
-        if(!enqueue_render(*s, vs, 0, s->W, images ? s->d_image : nullptr, ranges ? s->d_ranges : nullptr, s->stream))
-            return false;
-        if(images && !copy_to_host(images + (size_t)k * px * 3, s->d_image, px * 3, s->stream)) return false;
-        if(ranges && !copy_to_host(ranges + (size_t)k * px, s->d_ranges, px * sizeof(float), s->stream)) return false;
-        CUDA_TRY(cudaStreamSynchronize(s->stream));
-    }
-    s->have_render = false;
+    if(!render_batch_common(ctx, s, n, views, (uint8_t*)images, ranges, true, s->stream)) return false;
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
     return true;
 }
 
@@ -687,7 +860,7 @@ bool horizonator_render_wedge_device(const horizonator_context_t* ctx, int x0, i
     }
     DeviceGuard g(s->device);
     cudaStream_t st = stream ? (cudaStream_t)stream : s->stream;
-    if(!enqueue_render(*s, s->view, x0, x1, (uint8_t*)d_image, (float*)d_ranges, st)) return false;
+    if(!enqueue_render(*s, s->main, s->view, x0, x1, (uint8_t*)d_image, (float*)d_ranges, st)) return false;
     if(stream == nullptr) CUDA_TRY(cudaStreamSynchronize(st));
     return true;
 }
@@ -748,7 +921,7 @@ bool horizonator_profile_enable(const horizonator_context_t* ctx, bool on)
     return true;
 }
 
-bool horizonator_profile_read(const horizonator_context_t* ctx, float out_ms[5], int* renders)
+bool horizonator_profile_read(const horizonator_context_t* ctx, float out_ms[6], int* renders)
 {
     Slot* s = slot_of(ctx);
     if(s == nullptr || out_ms == nullptr || renders == nullptr) return false;
@@ -778,10 +951,32 @@ bool horizonator_last_render_stats(const horizonator_context_t* ctx, unsigned in
     if(s == nullptr) return false;
     DeviceGuard g(s->device);
     CUDA_TRY(cudaStreamSynchronize(s->stream));
-    unsigned int counters[3] = {0, 0, 0};
-    CUDA_TRY(cudaMemcpy(counters, s->d_counters, sizeof(counters), cudaMemcpyDeviceToHost));
-    out[0] = counters[0]; out[1] = BIG_CAPACITY; out[2] = s->launches_last; out[3] = (unsigned)s->device;
-    out[4] = counters[1];
+    unsigned int counters[N_COUNTERS] = {};
+    CUDA_TRY(cudaMemcpy(counters, s->main.d_counters, sizeof(counters), cudaMemcpyDeviceToHost));
+    out[0] = counters[0] + counters[1]; out[1] = 2 * BIG_CAPACITY; out[2] = s->launches_last; out[3] = (unsigned)s->device;
+    out[4] = counters[STATS_AT + HZ_STAT_TRIANGLES];
+    return true;
+}
+
+bool horizonator_render_counters(const horizonator_context_t* ctx, unsigned int out[16])
+{
+    Slot* s = slot_of(ctx);
+    if(s == nullptr || out == nullptr) return false;
+    DeviceGuard g(s->device);
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    CUDA_TRY(cudaMemcpy(out, s->main.d_counters + STATS_AT, HZ_STAT_COUNT * sizeof(unsigned int), cudaMemcpyDeviceToHost));
+    return true;
+}
+
+bool horizonator_horizon_profile_device(const horizonator_context_t* ctx, const void* d_ranges, int n,
+                                        void* d_rows, void* d_range, void* stream)
+{
+    Slot* s = slot_of(ctx);
+    if(s == nullptr || n < 0 || d_ranges == nullptr || d_rows == nullptr || d_range == nullptr) return false;
+    DeviceGuard g(s->device);
+    cudaStream_t st = stream ? (cudaStream_t)stream : s->stream;
+    CUDA_TRY(hz_launch_horizon((const float*)d_ranges, n, s->W, s->H, (int*)d_rows, (float*)d_range, st));
+    if(stream == nullptr) CUDA_TRY(cudaStreamSynchronize(st));
     return true;
 }
 

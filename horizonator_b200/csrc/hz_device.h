@@ -25,6 +25,30 @@ struct HzTiles
     int cpd;                     // 1200 / 3600
 };
 
+// ---- culling pyramid over the mosaic (built once at init) -------------------------------------
+// block (bj,bi) = the 4x4 cells whose south-west vertex is (4bj, 4bi): (min,max) height of its 5x5 vertices
+// tile  (tj,ti) = 8x8 blocks = 32x32 cells: (min,max) over its blocks
+constexpr int HZ_BLOCK_CELLS = 4;
+constexpr int HZ_TILE_BLOCKS = 8;
+constexpr int HZ_TILE_CELLS  = HZ_BLOCK_CELLS * HZ_TILE_BLOCKS;
+
+// ---- counters a render leaves behind (diagnostics; bench.py and the tests read them) -----------
+enum HzStat
+{
+    HZ_STAT_TILES = 0,          // tiles of the bands looked at
+    HZ_STAT_TILES_FAR,          //   ... dropped: beyond zfar
+    HZ_STAT_TILES_WINDOW,       //   ... dropped: no pixel centre of the target inside their screen box
+    HZ_STAT_TILES_OCCLUDED,     //   ... dropped: every pixel of their screen box already holds something nearer
+    HZ_STAT_BLOCKS,             // blocks looked at (both passes)
+    HZ_STAT_BLOCKS_FAR,
+    HZ_STAT_BLOCKS_WINDOW,
+    HZ_STAT_BLOCKS_OCCLUDED,
+    HZ_STAT_BLOCKS_MESHED,      // blocks whose 32 triangles were projected and tested exactly
+    HZ_STAT_TRIANGLES,          // triangles that passed the exact integer tests and went to set-up
+    HZ_STAT_BIG_ENTRIES,        // (triangle, sub-box) pairs queued for k_big
+    HZ_STAT_COUNT = 16
+};
+
 // ---- one render ------------------------------------------------------------------------------
 struct HzView
 {
@@ -34,6 +58,9 @@ struct HzView
     int   pitch;                 // elements per row (multiple of 64)
     float* e_tab;                // [N] metres east of the eye for column i   (vertex.glsl:128-130)
     float* n_tab;                // [N] metres north of the eye for row j
+    const short2* mm_block;      // [nb][nb] (min,max) per block
+    const short2* mm_tile;       // [nt][nt] (min,max) per tile
+    int   nb, nt;
 
     // eye
     float viewer_cell_i, viewer_cell_j, viewer_z;
@@ -52,19 +79,25 @@ struct HzView
     int x0, x1;
     unsigned long long* vis;     // [H][x1-x0], GL row order (row 0 = bottom)
 
-    // triangles that passed k_march's integer tests (worst case: all of them)
-    uint32_t* tri_queue;
-    uint32_t* tri_count;
-    // (triangle, band of rows) pairs too big for one thread of k_raster
+    // The mesh is walked outwards from the eye.  Tiles within `near_rings` (Chebyshev distance in tiles) of the
+    // eye's tile go first and completely (k_near + k_big), then bands of rings [ring_lo, ring_hi), each through
+    // k_tiles -> k_blocks -> k_mesh, so that the foreground is in the visibility buffer before what lies behind
+    // it is tested against it.
+    int eye_ti, eye_tj, near_rings;
+    int ring_lo, ring_hi;        // the band this launch works on
+    uint32_t* tile_queue;        // live tiles of the band (tj*nt+ti)
+    uint32_t* tile_count;
+    uint32_t* block_queue;       // live blocks of the band (bj*nb+bi)
+    uint32_t* block_count;
+    int occl_tile_max_pix, occl_block_max_pix;   // largest screen box one thread checks against the visibility buffer
+
+    // (triangle, sub-box) pairs too big for one thread; one queue for the near pass, one for all bands
     uint2*    big_queue;
     uint32_t* big_count;
     uint32_t  big_capacity;
-    uint32_t* work_count;        // k_march's work-item dispenser
+    uint32_t* stats;             // [HZ_STAT_COUNT]
 
-    // conservative culling of whole mesh blocks (never changes the image)
-    float cull_d2_far;           // blocks entirely farther (horizontally) than sqrt(this) are skipped
-    float cull_az_half;          // half-width [rad] of the az interval that can reach columns [x0,x1),
-    float cull_az_mid;           //   centred here; cull_az_half >= pi disables the test
+    float cell_diag2;            // (east cell size)^2 + (north cell size)^2 in metres^2, rounded up
 };
 
 struct HzResolve
@@ -79,12 +112,11 @@ struct HzResolve
 
 // All launches are asynchronous on `stream`.
 cudaError_t hz_launch_mosaic (const HzTiles& t, int16_t* mosaic, int N, int pitch, cudaStream_t stream);
-cudaError_t hz_launch_prepare(const HzView& v, cudaStream_t stream);   // clear vis, axis tables, queue
-cudaError_t hz_launch_march  (const HzView& v, cudaStream_t stream);   // mesh + project + cull -> triangle list
-cudaError_t hz_launch_raster (const HzView& v, cudaStream_t stream);   // set-up + rasterise the list
-cudaError_t hz_launch_big    (const HzView& v, cudaStream_t stream);   // queued large triangles
+cudaError_t hz_launch_pyramid(const int16_t* mosaic, int N, int pitch, short2* mm_block, int nb,
+                              short2* mm_tile, int nt, cudaStream_t stream);
+cudaError_t hz_launch_prepare(const HzView& v, uint32_t* counters, int ncounters, cudaStream_t stream);
+cudaError_t hz_launch_near   (const HzView& v, cudaStream_t stream);   // foreground tiles, no occlusion tests
+cudaError_t hz_launch_band   (const HzView& v, cudaStream_t stream, int* launches);   // one band of the rest: k_tiles, k_blocks, k_mesh
+cudaError_t hz_launch_big    (const HzView& v, cudaStream_t stream);   // queued large triangles of one pass
 cudaError_t hz_launch_resolve(const HzResolve& r, cudaStream_t stream);
-
-// Column strip width of the march kernel, exposed for the tests/docs
-constexpr int HZ_STRIP_CELLS = 62;
-constexpr int HZ_SEG_ROWS    = 64;
+cudaError_t hz_launch_horizon(const float* ranges, int n, int W, int H, int* rows, float* range, cudaStream_t stream);

@@ -2,13 +2,18 @@
 //
 //   k_mosaic   (init)    raw big-endian .hgt tiles -> one int16 mosaic        replaces dem.c:264-309 called
 //                                                                              (2R)^2 times at horizonator-lib.c:435-439
+//   k_minmax_* (init)    (min,max) height per 4x4-cell block and per 32x32-cell tile: the culling pyramid
 //   k_prepare  (render)  clear visibility keys, per-column/row metre tables    glClear, lib:896; vertex.glsl:128-130
-//   k_march    (render)  mesh generation + projection + exact integer cull       lib:496-508 (index pattern), vertex.glsl,
-//                        -> list of triangles that can produce a fragment        GL cull/clip
-//   k_raster   (render)  set-up + rasterisation + depth test of the survivors    vertex.glsl, geometry.glsl, GL raster,
-//                        (one thread per triangle)                               depth test, fragment.glsl
-//   k_big      (render)  the few triangles with large bounding boxes           same stages, one warp per band of rows
+//   k_near     (render)  the tiles around the eye: mesh generation, projection,  lib:496-508 (index pattern), vertex.glsl,
+//                        exact integer cull, set-up and rasterisation             geometry.glsl, GL cull/clip/raster/depth
+//   k_tiles, k_blocks, k_mesh (render)
+//                        the rest of the mesh in bands outwards from the eye: whole tiles, then blocks, are dropped
+//                        by conservative tests (beyond zfar, no pixel centre of the target inside their screen box,
+//                        everything in that box already nearer in the visibility buffer); what is left goes
+//                        through the same exact stages as in k_near
+//   k_big      (render)  the few triangles with large bounding boxes, one warp per 8x64-pixel sub-box
 //   k_resolve  (render)  keys -> BGR8 image + float range image, top row first lib:936-1048
+//   k_horizon  (extra)   range image -> per-column topmost terrain row and its range
 //
 // The mesh is never materialised: triangle t of the reference's index buffer is (cell = t>>1, half = t&1)
 // and its vertices are read straight from the int16 mosaic.
@@ -122,7 +127,7 @@ cudaError_t hz_launch_mosaic(const HzTiles& t, int16_t* mosaic, int N, int pitch
 // ================================================================================================
 
 __global__ void __launch_bounds__(256)
-k_prepare(const __grid_constant__ HzView P)
+k_prepare(const __grid_constant__ HzView P, uint32_t* counters, int ncounters)
 {
     const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const size_t nth = (size_t)gridDim.x * blockDim.x;
@@ -142,17 +147,17 @@ k_prepare(const __grid_constant__ HzView P)
         P.e_tab[k] = (f - P.viewer_cell_i) * P.deg_per_cell * HZ_REARTH_F * HZ_PI_F / 180.f * P.cos_viewer_lat;
         P.n_tab[k] = (f - P.viewer_cell_j) * P.deg_per_cell * HZ_REARTH_F * HZ_PI_F / 180.f;
     }
-    if(tid == 0) { *P.big_count = 0; *P.tri_count = 0; *P.work_count = 0; }
+    if(tid < (size_t)ncounters) counters[tid] = 0;
 }
 
-cudaError_t hz_launch_prepare(const HzView& v, cudaStream_t stream)
+cudaError_t hz_launch_prepare(const HzView& v, uint32_t* counters, int ncounters, cudaStream_t stream)
 {
     const size_t nkeys = (size_t)v.H * (size_t)(v.x1 - v.x0);
     size_t blocks = (nkeys / 2 + 255) / 256;
     if(blocks < (size_t)(v.N + 255) / 256) blocks = (v.N + 255) / 256;
     if(blocks > 148 * 16) blocks = 148 * 16;
     if(blocks < 1) blocks = 1;
-    k_prepare<<<(unsigned)blocks, 256, 0, stream>>>(v);
+    k_prepare<<<(unsigned)blocks, 256, 0, stream>>>(v, counters, ncounters);
     return cudaGetLastError();
 }
 
@@ -211,6 +216,7 @@ struct HzTri
     float xw0, yw0, xw1, yw1, xw2, yw2;
     // attribute planes through the unsnapped float vertices, anchored at vertex 0 (oracle rule F6)
     float z0w, r0, dzdx, dzdy, drdx, drdy;
+    float zw_lo, zw_hi;              // F6: the interpolated depth stays within the vertex depths widened 4x
     unsigned int id;
 };
 
@@ -280,6 +286,9 @@ hz_tri_planes(const HzView& P, HzTri& T,
     T.drdx = (ar * by - br * ay) * inv;
     T.drdy = (br * ax - ar * bx) * inv;
     T.z0w = zw0; T.r0 = r0;
+    const float zw_min = fminf(fminf(zw0, zw1), zw2), zw_max = fmaxf(fmaxf(zw0, zw1), zw2);
+    T.zw_lo = zw_min - 4.0f * (zw_max - zw_min);
+    T.zw_hi = zw_max + 4.0f * (zw_max - zw_min);
 }
 
 // complete set-up of triangle `id` from the mosaic; false if it produces nothing
@@ -299,7 +308,13 @@ __device__ __forceinline__ bool hz_tri_setup(const HzView& P, unsigned int id, H
     }
     if(!hz_tri_bounds(P, v[0], v[1], v[2], T)) return false;
     T.id = id;
-    if(with_planes) hz_tri_planes(P, T, e[0], n[0], v[0].z, e[1], n[1], v[1].z, e[2], n[2], v[2].z);
+    if(with_planes)
+    {
+        hz_tri_planes(P, T, e[0], n[0], v[0].z, e[1], n[1], v[1].z, e[2], n[2], v[2].z);
+        // every fragment's depth lies in [zw_lo, zw_hi] (F6): entirely in front of the near plane or behind the far
+        // plane means every fragment is clipped (F5).  This removes the giants right under the eye.
+        if(T.zw_hi < 0.0f || T.zw_lo > 1.0f) return false;
+    }
     return true;
 }
 
@@ -308,7 +323,8 @@ __device__ __forceinline__ void hz_fragment(const HzView& P, const HzTri& T, int
 {
     const float cx = (float)px + 0.5f, cy = (float)py + 0.5f;
     const float ddx = cx - T.xw0, ddy = cy - T.yw0;
-    const float zw = T.z0w + (T.dzdx * ddx + T.dzdy * ddy);
+    float zw = T.z0w + (T.dzdx * ddx + T.dzdy * ddy);
+    zw = fminf(fmaxf(zw, T.zw_lo), T.zw_hi);                                 // F6
     if(!(zw >= 0.0f && zw <= 1.0f)) return;                                  // F5: view-volume clip per fragment
     const unsigned int q = (unsigned int)((double)zw * 16777215.0 + 0.5);   // F7
     if(q >= HZ_Q_MAX) return;                                                // cannot pass GL_LESS against 1.0
@@ -344,6 +360,17 @@ struct HzEdges
         const I E2 = dx2 * (Py - T.Y2) - dy2 * (Px - T.X2);
         return E0 >= b0 && E1 >= b1 && E2 >= b2;
     }
+    // true if no pixel centre of the box [px0,px1] x [py0,py1] can be inside: some edge function is below its
+    // threshold even at the corner of the box where it is largest
+    __device__ __forceinline__ bool box_outside(const HzTri& T, int px0, int px1, int py0, int py1) const
+    {
+        const I Xa = (I)px0 * 256 + 128, Xb = (I)px1 * 256 + 128;
+        const I Ya = (I)py0 * 256 + 128, Yb = (I)py1 * 256 + 128;
+        const I M0 = dx0 * ((dx0 > 0 ? Yb : Ya) - T.Y0) - dy0 * ((dy0 > 0 ? Xa : Xb) - T.X0);
+        const I M1 = dx1 * ((dx1 > 0 ? Yb : Ya) - T.Y1) - dy1 * ((dy1 > 0 ? Xa : Xb) - T.X1);
+        const I M2 = dx2 * ((dx2 > 0 ? Yb : Ya) - T.Y2) - dy2 * ((dy2 > 0 ? Xa : Xb) - T.X2);
+        return M0 < b0 || M1 < b1 || M2 < b2;
+    }
 };
 
 __device__ __forceinline__ bool hz_tri_is_small(const HzTri& T)
@@ -354,27 +381,148 @@ __device__ __forceinline__ bool hz_tri_is_small(const HzTri& T)
 }
 
 // ================================================================================================
-// k_march: mesh generation + projection + conservative-exact triangle filter
+// culling pyramid (init)
+// ================================================================================================
+
+__global__ void __launch_bounds__(256)
+k_minmax_blocks(const int16_t* __restrict__ mosaic, int N, int pitch, short2* __restrict__ mm, int nb)
+{
+    const int bi = blockIdx.x * blockDim.x + threadIdx.x, bj = blockIdx.y;
+    if(bi >= nb) return;
+    const int c0 = bi * HZ_BLOCK_CELLS, r0 = bj * HZ_BLOCK_CELLS;
+    int lo = 32767, hi = -32768;
+    for(int r = r0; r <= min(r0 + HZ_BLOCK_CELLS, N - 1); r++)
+        for(int c = c0; c <= min(c0 + HZ_BLOCK_CELLS, N - 1); c++)
+        {
+            const int z = mosaic[(size_t)r * pitch + c];
+            lo = min(lo, z); hi = max(hi, z);
+        }
+    mm[(size_t)bj * nb + bi] = make_short2((short)lo, (short)hi);
+}
+
+__global__ void __launch_bounds__(256)
+k_minmax_tiles(const short2* __restrict__ mm, int nb, short2* __restrict__ mt, int nt)
+{
+    const int ti = blockIdx.x * blockDim.x + threadIdx.x, tj = blockIdx.y;
+    if(ti >= nt) return;
+    int lo = 32767, hi = -32768;
+    for(int r = tj * HZ_TILE_BLOCKS; r < min((tj + 1) * HZ_TILE_BLOCKS, nb); r++)
+        for(int c = ti * HZ_TILE_BLOCKS; c < min((ti + 1) * HZ_TILE_BLOCKS, nb); c++)
+        {
+            const short2 v = mm[(size_t)r * nb + c];
+            lo = min(lo, (int)v.x); hi = max(hi, (int)v.y);
+        }
+    mt[(size_t)tj * nt + ti] = make_short2((short)lo, (short)hi);
+}
+
+cudaError_t hz_launch_pyramid(const int16_t* mosaic, int N, int pitch, short2* mm_block, int nb,
+                              short2* mm_tile, int nt, cudaStream_t stream)
+{
+    k_minmax_blocks<<<dim3((nb + 255) / 256, nb), 256, 0, stream>>>(mosaic, N, pitch, mm_block, nb);
+    k_minmax_tiles<<<dim3((nt + 255) / 256, nt), 256, 0, stream>>>(mm_block, nb, mm_tile, nt);
+    return cudaGetLastError();
+}
+
+// ================================================================================================
+// conservative tests on rectangles of the mesh
 // ================================================================================================
 //
-// One warp walks a strip of the mosaic northwards.  Lane l owns vertex columns c0+2l and c0+2l+1 (one aligned
-// 32-bit load per row) and the two cells to their right; the right-hand neighbour's column arrives by
-// shuffle, the previous row stays in registers, so every vertex is projected once per strip (plus one shared
-// column between strips and one shared row between segments).  Only the snapped window position of a vertex
-// is kept.  A cell whose snapped bounding box holds no pixel centre of the target is finished after a few
-// integer instructions -- about 90% of them.  For the others both triangles get the same integer tests the
-// rasteriser will apply (pixel centre inside the bounding box, inside the target, counter-clockwise), and
-// the numbers of the survivors are appended to a global list through a per-warp shared-memory stage (one
-// global atomic per ~64 survivors).  k_raster then sets those triangles up and draws them with every lane busy.
+// A rectangle of vertices (columns c_lo..c_hi, rows r_lo..r_hi, heights within [zmin,zmax]) is dropped when no
+// triangle inside it can produce a fragment that survives:
+//   * every vertex is horizontally farther than zfar   -> every fragment fails the far clip
+//   * the screen-space box of its vertices holds no pixel centre of the target
+//   * every pixel of that box already holds a key with a smaller depth than anything inside can produce
+// All three only ever remove work, never a winning fragment, so the image does not depend on them (nor on the
+// order in which the visibility buffer fills up).
 //
-// Work items (strip x 64-row segment) are handed out through an atomic counter, ordered outwards from the
-// eye: the expensive items next to the eye start first and the cheap far field fills in behind them.
+// Screen box.  Inside one quadrant around the eye the azimuth atan2(e,n) is monotonic in e and in n, so its
+// extremes over the rectangle sit on two known corners; the elevation atan(h/d) is bounded by the extreme heights
+// over the nearest/farthest horizontal distance.  The same device functions as for real vertices are used and
+// HZ_BOX_MARGIN pixels are added all around, which covers their few-ulp non-monotonicity and the 1/512 pixel of
+// snapping.
+// Depth.  A vertex depth is a monotonic float function of its slant range >= its horizontal distance >= the
+// rectangle's nearest horizontal distance.  A fragment's depth stays within its triangle's vertex depths widened
+// by 4x their extent (F6), and the slant ranges of one triangle's vertices differ by at most their 3-D distance
+// <= sqrt(cell diagonal^2 + (zmax-zmin)^2).  That gives a lower bound for the depth of every fragment.
+
+#define HZ_BOX_MARGIN 0.0625f
+
+struct HzBox { int px0, px1, py0, py1; unsigned int qmin; };
+enum { HZ_RECT_DEAD_FAR = 0, HZ_RECT_DEAD_WINDOW = 1, HZ_RECT_ALIVE = 2, HZ_RECT_BOXED = 3 };
+
+__device__ __forceinline__ float hz_window_x(const HzView& P, float e, float n, float halfW)
+{
+    float az = hz_atan2_az(e, n);
+    const float t = (az - P.az_center) * 0.15915494309189535f;
+    az = (t - rintf(t)) * 2.f * HZ_PI_F + P.az_center;
+    return (az - P.az_center) * P.az_ndc_per_rad * halfW + halfW;
+}
+
+__device__ __forceinline__ int
+hz_rect_test(const HzView& P, int c_lo, int c_hi, int r_lo, int r_hi, float zmin, float zmax, HzBox& B)
+{
+    const float e_lo = __ldg(P.e_tab + c_lo), e_hi = __ldg(P.e_tab + c_hi);
+    const float n_lo = __ldg(P.n_tab + r_lo), n_hi = __ldg(P.n_tab + r_hi);
+    const bool  e_in = (e_lo <= 0.f && e_hi >= 0.f), n_in = (n_lo <= 0.f && n_hi >= 0.f);
+    const float e_near = e_in ? 0.f : fminf(fabsf(e_lo), fabsf(e_hi));
+    const float n_near = n_in ? 0.f : fminf(fabsf(n_lo), fabsf(n_hi));
+    const float d2min = e_near * e_near + n_near * n_near;
+
+    // lower bound of the window depth of any fragment: the nearest corner evaluated like a vertex on the eye's
+    // ground plane (hz_depth_shade), minus the extrapolation allowance, minus rounding
+    {
+        const float len = sqrtf(d2min);
+        const float zn  = (len - P.znear) / (P.zfar - P.znear) * 2.f - 1.f;
+        const float zw  = zn * 0.5f + 0.5f;
+        const float dz  = zmax - zmin;
+        const float sep = sqrtf(P.cell_diag2 + dz * dz);
+        const float lo  = zw - (4.004f * sep / (P.zfar - P.znear) + 2e-6f);
+        if(lo > 1.0f) return HZ_RECT_DEAD_FAR;             // every fragment fails the far clip
+        B.qmin = (lo <= 0.0f) ? 0u : (unsigned int)((double)lo * 16777215.0);
+    }
+    if(e_in || n_in) return HZ_RECT_ALIVE;                 // touches an axis through the eye: not worth a box
+
+    const float halfW = 0.5f * (float)P.W, halfH = 0.5f * (float)P.H;
+    const bool east = e_lo > 0.f, north = n_lo > 0.f;
+    // d(az)/de = n/d^2, d(az)/dn = -e/d^2
+    const float x_hi = hz_window_x(P, north ? e_hi : e_lo, east ? n_lo : n_hi, halfW);
+    const float x_lo = hz_window_x(P, north ? e_lo : e_hi, east ? n_hi : n_lo, halfW);
+    if(!(x_lo <= x_hi)) return HZ_RECT_ALIVE;              // the +-pi seam of the window runs through it
+
+    const float e_far = fmaxf(fabsf(e_lo), fabsf(e_hi)), n_far = fmaxf(fabsf(n_lo), fabsf(n_hi));
+    const float d2max = e_far * e_far + n_far * n_far;
+    const float hmax = zmax - P.viewer_z, hmin = zmin - P.viewer_z;
+    const float el_hi = hz_atan_el(hmax, hmax > 0.f ? d2min : d2max);
+    const float el_lo = hz_atan_el(hmin, hmin > 0.f ? d2max : d2min);
+    const float y_hi = el_hi * P.aspect * P.az_ndc_per_rad * halfH + halfH;
+    const float y_lo = el_lo * P.aspect * P.az_ndc_per_rad * halfH + halfH;
+
+    // pixel centres p + 0.5 inside [lo - margin, hi + margin]; the float->int conversions saturate
+    const float fx0 = ceilf(x_lo - 0.5f - HZ_BOX_MARGIN), fx1 = floorf(x_hi - 0.5f + HZ_BOX_MARGIN);
+    const float fy0 = ceilf(y_lo - 0.5f - HZ_BOX_MARGIN), fy1 = floorf(y_hi - 0.5f + HZ_BOX_MARGIN);
+    if(!(fx0 <= fx1 && fy0 <= fy1)) return HZ_RECT_DEAD_WINDOW;
+    if(fx1 < (float)P.x0 || fx0 > (float)(P.x1 - 1) || fy1 < 0.f || fy0 > (float)(P.H - 1)) return HZ_RECT_DEAD_WINDOW;
+    B.px0 = max((int)fx0, P.x0); B.px1 = min((int)fx1, P.x1 - 1);
+    B.py0 = max((int)fy0, 0);    B.py1 = min((int)fy1, P.H - 1);
+    return HZ_RECT_BOXED;
+}
+
+// the visibility buffer is being written by other warps: read through to L2; a stale (older, larger) key only
+// makes the test more cautious
+__device__ __forceinline__ unsigned int hz_vis_depth(const HzView& P, int px, int py)
+{
+    return (unsigned int)(__ldcg(P.vis + (size_t)py * (size_t)(P.x1 - P.x0) + (size_t)(px - P.x0)) >> 40);
+}
+
+// ================================================================================================
+// exact stages for one block of 4x4 cells: projection, integer cull, set-up, rasterisation
+// ================================================================================================
 
 #define HZ_WARPS_PER_CTA 8
-#define HZ_STAGE_SLOTS   192       /* < 64 pending + at most 4*32 new per row */
-#define HZ_STAGE_FLUSH   64
-#define HZ_SMALL_MAX_PIX 8         /* k_raster draws bounding boxes up to this many pixels itself */
-#define HZ_BAND_ROWS     8         /* bigger ones are cut into bands of rows for k_big */
+#define HZ_STAGE_SLOTS   64        /* < 32 pending + at most 32 new per block */
+#define HZ_SMALL_MAX_PIX 8         /* a lane draws bounding boxes up to this many pixels itself */
+#define HZ_BIG_ROWS      8         /* bigger ones are cut into sub-boxes for k_big */
+#define HZ_BIG_COLS      64
 
 struct HzLaneVtx { int X, Y; };
 
@@ -388,27 +536,8 @@ __device__ __forceinline__ HzLaneVtx hz_lane_vertex(const HzView& P, float e, fl
     return o;
 }
 
-__device__ __forceinline__ HzLaneVtx hz_shfl_down1(const HzLaneVtx& v)
-{
-    HzLaneVtx o;
-    o.X = __shfl_down_sync(0xffffffffu, v.X, 1);
-    o.Y = __shfl_down_sync(0xffffffffu, v.Y, 1);
-    return o;
-}
-
-// does the snapped bounding box of the four corners hold a pixel centre of the target?
-__device__ __forceinline__ bool
-hz_cell_alive(const HzView& P, const HzLaneVtx& a, const HzLaneVtx& b, const HzLaneVtx& c, const HzLaneVtx& d)
-{
-    const int bx0 = min(min(a.X, b.X), min(c.X, d.X)), bx1 = max(max(a.X, b.X), max(c.X, d.X));
-    const int by0 = min(min(a.Y, b.Y), min(c.Y, d.Y)), by1 = max(max(a.Y, b.Y), max(c.Y, d.Y));
-    const int px0 = (bx0 + 127) >> 8, px1 = (bx1 - 128) >> 8;
-    const int py0 = (by0 + 127) >> 8, py1 = (by1 - 128) >> 8;
-    return px0 <= px1 && py0 <= py1 && px1 >= P.x0 && px0 < P.x1 && py1 >= 0 && py0 < P.H;
-}
-
 // the rasteriser's integer tests for one triangle (hz_tri_bounds without the float-only seam/guard tests,
-// which k_raster applies; a triangle that fails here cannot produce a fragment there)
+// which set-up applies; a triangle that fails here cannot produce a fragment there)
 __device__ __forceinline__ bool
 hz_tri_alive(const HzView& P, const HzLaneVtx& a, const HzLaneVtx& b, const HzLaneVtx& c)
 {
@@ -421,181 +550,6 @@ hz_tri_alive(const HzView& P, const HzLaneVtx& a, const HzLaneVtx& b, const HzLa
     return area > 0;
 }
 
-// conservative test: can any triangle of the block [c_lo..c_hi] x [r_lo..r_hi] (vertex indices) reach the target?
-__device__ __forceinline__ bool hz_block_dead(const HzView& P, int c_lo, int c_hi, int r_lo, int r_hi)
-{
-    const float e_lo = __ldg(P.e_tab + c_lo), e_hi = __ldg(P.e_tab + c_hi);
-    const float n_lo = __ldg(P.n_tab + r_lo), n_hi = __ldg(P.n_tab + r_hi);
-    // nearest point of the rectangle to the eye
-    const float ne = (e_lo > 0.f) ? e_lo : ((e_hi < 0.f) ? e_hi : 0.f);
-    const float nn = (n_lo > 0.f) ? n_lo : ((n_hi < 0.f) ? n_hi : 0.f);
-    const float d2min = ne * ne + nn * nn;
-    // farther than zfar horizontally => slant range > zfar => window depth > 1 for every fragment
-    if(d2min > P.cull_d2_far) return true;
-
-    if(P.cull_az_half < 3.2f && (ne != 0.f || nn != 0.f))
-    {
-        // the rectangle does not contain the eye: its azimuths form an interval bounded by corner azimuths.
-        // Measure every corner relative to the first one (the fan is < pi wide, so no wrap inside it) and the
-        // first one relative to the middle of the interval of interest.
-        const float ce[4] = { e_lo, e_hi, e_lo, e_hi };
-        const float cn[4] = { n_lo, n_lo, n_hi, n_hi };
-        const float a0 = atan2f(ce[0], cn[0]);
-        float lo = 0.f, hi = 0.f;
-        #pragma unroll
-        for(int k = 1; k < 4; k++)
-        {
-            float d = atan2f(ce[k], cn[k]) - a0;
-            d -= 6.28318530717958648f * rintf(d * 0.15915494309189535f);
-            lo = fminf(lo, d); hi = fmaxf(hi, d);
-        }
-        float m = a0 - P.cull_az_mid;
-        m -= 6.28318530717958648f * rintf(m * 0.15915494309189535f);
-        const float margin = 1e-3f;
-        const float blo = m + lo - margin, bhi = m + hi + margin;
-        bool alive = false;
-        #pragma unroll
-        for(int turn = -1; turn <= 1; turn++)
-        {
-            const float s = 6.28318530717958648f * (float)turn;
-            alive = alive || (blo + s <= P.cull_az_half && bhi + s >= -P.cull_az_half);
-        }
-        if(!alive) return true;
-    }
-    return false;
-}
-
-// k-th element of the sequence c, c+1, c-1, c+2, c-2, ... restricted to [0, n)
-__device__ __forceinline__ int hz_outward(int c, int k, int n)
-{
-    const int m = min(c, n - 1 - c);
-    if(k <= 2 * m) return (k & 1) ? c + (k + 1) / 2 : c - k / 2;
-    return (n - 1 - c > c) ? c + (k - m) : c - (k - m);
-}
-
-__device__ __forceinline__ void hz_stage_flush(const HzView& P, unsigned int* stage, int& count, int lane)
-{
-    __syncwarp();
-    if(count > 0)
-    {
-        unsigned int base = 0;
-        if(lane == 0) base = atomicAdd(P.tri_count, (unsigned int)count);
-        base = __shfl_sync(0xffffffffu, base, 0);
-        for(int k = lane; k < count; k += 32) P.tri_queue[base + k] = stage[k];
-        count = 0;
-    }
-    __syncwarp();
-}
-
-__global__ void __launch_bounds__(HZ_WARPS_PER_CTA * 32, 4)
-k_march(const __grid_constant__ HzView P)
-{
-    __shared__ unsigned int s_stage[HZ_WARPS_PER_CTA][HZ_STAGE_SLOTS];
-
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const int N = P.N;
-    const int n_strips = (N - 1 + HZ_STRIP_CELLS - 1) / HZ_STRIP_CELLS;
-    const int n_segs   = (N - 1 + HZ_SEG_ROWS - 1) / HZ_SEG_ROWS;
-    const unsigned int n_items = (unsigned int)n_strips * (unsigned int)n_segs;
-    const int strip_eye = min(max((int)P.viewer_cell_i / HZ_STRIP_CELLS, 0), n_strips - 1);
-    const int seg_eye   = min(max((int)P.viewer_cell_j / HZ_SEG_ROWS, 0), n_segs - 1);
-
-    unsigned int* stage = s_stage[wib];
-    int count = 0;
-    const float halfW = 0.5f * (float)P.W, halfH = 0.5f * (float)P.H;
-
-    for(;;)
-    {
-        unsigned int item = 0;
-        if(lane == 0) item = atomicAdd(P.work_count, 1u);
-        item = __shfl_sync(0xffffffffu, item, 0);
-        if(item >= n_items) break;
-        const int seg   = hz_outward(seg_eye,   (int)(item / (unsigned int)n_strips), n_segs);
-        const int strip = hz_outward(strip_eye, (int)(item % (unsigned int)n_strips), n_strips);
-
-        const int c0 = strip * HZ_STRIP_CELLS;                   // first vertex column of the strip (even)
-        const int r0 = seg * HZ_SEG_ROWS;                        // first vertex row
-        const int r1 = min(r0 + HZ_SEG_ROWS, N - 1);             // last vertex row (inclusive)
-        const int c_last = min(c0 + HZ_STRIP_CELLS, N - 1);      // last vertex column any cell of the strip touches
-        if(hz_block_dead(P, c0, c_last, r0, r1)) continue;
-
-        // this lane's two vertex columns (clamped for loads; cells beyond the mesh are masked below)
-        const int colA = c0 + 2 * lane, colB = colA + 1;
-        const float eA = __ldg(P.e_tab + min(colA, N - 1)), eB = __ldg(P.e_tab + min(colB, N - 1));
-        // cell 0 spans columns colA..colB, cell 1 spans colB..colA+2 (the neighbour lane's first column)
-        const bool cell0_ok = (lane < 31) && (colB <= N - 1);
-        const bool cell1_ok = (lane < 31) && (colA + 2 <= N - 1);
-
-        // mosaic rows are pitch-aligned and colA is even: one 32-bit load fetches both heights
-        const int16_t* mrow = P.mosaic + (size_t)r0 * P.pitch + min(colA, P.pitch - 2);
-
-        HzLaneVtx pA, pB, pC;   // previous row
-        {
-            const unsigned int zz = __ldg((const unsigned int*)mrow);
-            const float n = __ldg(P.n_tab + r0);
-            pA = hz_lane_vertex(P, eA, n, (float)(short)(zz & 0xFFFFu), halfW, halfH);
-            pB = hz_lane_vertex(P, eB, n, (float)(short)(zz >> 16),     halfW, halfH);
-            pC = hz_shfl_down1(pA);
-        }
-
-        unsigned int zz_next = (r0 + 1 <= r1) ? __ldg((const unsigned int*)(mrow + P.pitch)) : 0u;
-        float n_next = (r0 + 1 <= r1) ? __ldg(P.n_tab + r0 + 1) : 0.f;
-        for(int j = r0 + 1; j <= r1; j++)
-        {
-            const unsigned int zz = zz_next;
-            const float n = n_next;
-            if(j + 1 <= r1)
-            {
-                zz_next = __ldg((const unsigned int*)(mrow + (size_t)(j + 1 - r0) * P.pitch));
-                n_next  = __ldg(P.n_tab + j + 1);
-            }
-            const HzLaneVtx cA = hz_lane_vertex(P, eA, n, (float)(short)(zz & 0xFFFFu), halfW, halfH);
-            const HzLaneVtx cB = hz_lane_vertex(P, eB, n, (float)(short)(zz >> 16),     halfW, halfH);
-            const HzLaneVtx cC = hz_shfl_down1(cA);
-
-            // cell (j-1, colA): corners pA pB / cA cB ; cell (j-1, colB): corners pB pC / cB cC
-            unsigned int m = 0;
-            if(cell0_ok && hz_cell_alive(P, pA, pB, cA, cB))
-            {
-                if(hz_tri_alive(P, pA, cB, cA)) m |= 1u;     // (j-1,i), (j,i+1), (j,i)
-                if(hz_tri_alive(P, pA, pB, cB)) m |= 2u;     // (j-1,i), (j-1,i+1), (j,i+1)
-            }
-            if(cell1_ok && hz_cell_alive(P, pB, pC, cB, cC))
-            {
-                if(hz_tri_alive(P, pB, cC, cB)) m |= 4u;
-                if(hz_tri_alive(P, pB, pC, cC)) m |= 8u;
-            }
-            if(__any_sync(0xffffffffu, m != 0))
-            {
-                const unsigned int id0 = 2u * ((unsigned int)(j - 1) * (unsigned int)(N - 1) + (unsigned int)colA);
-                const unsigned int lt = (1u << lane) - 1u;
-                #pragma unroll
-                for(int b = 0; b < 4; b++)
-                {
-                    const bool on = (m >> b) & 1u;
-                    const unsigned int ballot = __ballot_sync(0xffffffffu, on);
-                    if(on) stage[count + __popc(ballot & lt)] = id0 + (unsigned int)b;
-                    count += __popc(ballot);
-                }
-                if(count >= HZ_STAGE_FLUSH) hz_stage_flush(P, stage, count, lane);
-            }
-            pA = cA; pB = cB; pC = cC;
-        }
-    }
-    hz_stage_flush(P, stage, count, lane);
-}
-
-cudaError_t hz_launch_march(const HzView& v, cudaStream_t stream)
-{
-    // persistent: 4 CTAs of 8 warps per SM, the warps pull (strip, segment) items until none are left
-    k_march<<<148 * 4, HZ_WARPS_PER_CTA * 32, 0, stream>>>(v);
-    return cudaGetLastError();
-}
-
-// ================================================================================================
-// k_raster: one thread per surviving triangle
-// ================================================================================================
-
 template <typename I>
 __device__ __forceinline__ void hz_draw_box(const HzView& P, const HzTri& T)
 {
@@ -605,83 +559,392 @@ __device__ __forceinline__ void hz_draw_box(const HzView& P, const HzTri& T)
             if(E.inside(T, px, py)) hz_fragment(P, T, px, py);
 }
 
-__global__ void __launch_bounds__(256)
-k_raster(const __grid_constant__ HzView P)
+// set-up + rasterisation of one triangle per lane (GL primitive assembly .. depth test).  Large bounding boxes are
+// cut into HZ_BIG_ROWS x HZ_BIG_COLS sub-boxes and queued for k_big.  Returns the number of queue entries made.
+__device__ __noinline__ unsigned int hz_raster_one(const HzView& P, unsigned int id)
 {
-    const unsigned int count = *P.tri_count;
-    const unsigned int nth = gridDim.x * blockDim.x;
-    for(unsigned int t = blockIdx.x * blockDim.x + threadIdx.x; t < count; t += nth)
+    HzTri T;
+    if(!hz_tri_setup(P, id, T, true)) return 0;
+    const int bw = T.px1 - T.px0 + 1, bh = T.py1 - T.py0 + 1;
+    if(bw * bh > HZ_SMALL_MAX_PIX)
     {
-        HzTri T;
-        const unsigned int id = P.tri_queue[t];
-        if(!hz_tri_setup(P, id, T, true)) continue;
-        const int bw = T.px1 - T.px0 + 1, bh = T.py1 - T.py0 + 1;
-        if((long long)bw * bh > HZ_SMALL_MAX_PIX)
+        const unsigned int ny = (unsigned int)((bh + HZ_BIG_ROWS - 1) / HZ_BIG_ROWS);
+        const unsigned int nx = (unsigned int)((bw + HZ_BIG_COLS - 1) / HZ_BIG_COLS);
+        const unsigned int slot = atomicAdd(P.big_count, nx * ny);
+        if(slot + nx * ny <= P.big_capacity)
         {
-            const unsigned int bands = (unsigned int)((bh + HZ_BAND_ROWS - 1) / HZ_BAND_ROWS);
-            const unsigned int slot = atomicAdd(P.big_count, bands);
-            if(slot + bands <= P.big_capacity)
-            {
-                for(unsigned int b = 0; b < bands; b++) P.big_queue[slot + b] = make_uint2(id, b);
-                continue;
-            }
-            // queue full: draw it here (slow but correct)
+            for(unsigned int by = 0; by < ny; by++)
+                for(unsigned int bx = 0; bx < nx; bx++)
+                    P.big_queue[slot + by * nx + bx] = make_uint2(id, by | (bx << 16));
+            return nx * ny;
         }
-        if(hz_tri_is_small(T)) hz_draw_box<int>(P, T);
-        else                   hz_draw_box<long long>(P, T);
+        // queue full: draw it here (slow but correct)
+    }
+    if(hz_tri_is_small(T)) hz_draw_box<int>(P, T);
+    else                   hz_draw_box<long long>(P, T);
+    return 0;
+}
+
+struct HzWarpState
+{
+    unsigned int* stage;     // [HZ_STAGE_SLOTS] triangle numbers waiting for set-up
+    HzLaneVtx*    verts;     // [25] snapped vertices of the block being meshed
+    int count;
+    unsigned int n_meshed, n_tris, n_big;
+};
+
+__device__ __forceinline__ void hz_stage_drain(const HzView& P, HzWarpState& S, int lane, bool all)
+{
+    __syncwarp();
+    while(S.count >= 32 || (all && S.count > 0))
+    {
+        const int take = min(S.count, 32);
+        const int base = S.count - take;
+        unsigned int nb = 0;
+        if(lane < take) nb = hz_raster_one(P, S.stage[base + lane]);
+        S.n_big += nb;            // per lane; summed over the warp at the end
+        S.count = base;
+        __syncwarp();
     }
 }
 
-cudaError_t hz_launch_raster(const HzView& v, cudaStream_t stream)
+// the 32 triangles of block (bj,bi): lane = triangle
+__device__ __forceinline__ void hz_mesh_block(const HzView& P, int bj, int bi, int lane, HzWarpState& S)
 {
-    k_raster<<<148 * 8, 256, 0, stream>>>(v);
+    const int N = P.N;
+    const float halfW = 0.5f * (float)P.W, halfH = 0.5f * (float)P.H;
+    if(lane < 25)
+    {
+        const int r = lane / 5, c = lane - 5 * r;
+        const int vj = min(bj * HZ_BLOCK_CELLS + r, N - 1), vi = min(bi * HZ_BLOCK_CELLS + c, N - 1);
+        const float z = (float)__ldg(P.mosaic + (size_t)vj * P.pitch + vi);
+        S.verts[lane] = hz_lane_vertex(P, __ldg(P.e_tab + vi), __ldg(P.n_tab + vj), z, halfW, halfH);
+    }
+    __syncwarp();
+    const int cell = lane >> 1, cr = cell >> 2, cc = cell & 3;
+    const int j = bj * HZ_BLOCK_CELLS + cr, i = bi * HZ_BLOCK_CELLS + cc;
+    bool on = false;
+    if(j < N - 1 && i < N - 1)
+    {
+        // lib:496-508: even triangle (j,i),(j+1,i+1),(j+1,i) ; odd triangle (j,i),(j,i+1),(j+1,i+1)
+        const HzLaneVtx a = S.verts[cr * 5 + cc];
+        const HzLaneVtx d = S.verts[(cr + 1) * 5 + cc + 1];
+        if((lane & 1) == 0) on = hz_tri_alive(P, a, d, S.verts[(cr + 1) * 5 + cc]);
+        else                on = hz_tri_alive(P, a, S.verts[cr * 5 + cc + 1], d);
+    }
+    const unsigned int ballot = __ballot_sync(0xffffffffu, on);
+    if(on) S.stage[S.count + __popc(ballot & ((1u << lane) - 1u))] =
+               2u * ((unsigned int)j * (unsigned int)(N - 1) + (unsigned int)i) + (unsigned int)(lane & 1);
+    S.count += __popc(ballot);
+    S.n_meshed += 1;
+    S.n_tris += __popc(ballot);
+    if(S.count >= 32) hz_stage_drain(P, S, lane, false);
+    else __syncwarp();
+}
+
+__device__ __forceinline__ unsigned int hz_warp_sum(unsigned int v)
+{
+    #pragma unroll
+    for(int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// ================================================================================================
+// k_near: the tiles around the eye, one warp per block, no pyramid and no occlusion tests
+// ================================================================================================
+
+__device__ __forceinline__ void hz_near_tiles(const HzView& P, int& ti0, int& ti1, int& tj0, int& tj1)
+{
+    ti0 = max(P.eye_ti - P.near_rings, 0); ti1 = min(P.eye_ti + P.near_rings, P.nt - 1);
+    tj0 = max(P.eye_tj - P.near_rings, 0); tj1 = min(P.eye_tj + P.near_rings, P.nt - 1);
+}
+
+__global__ void __launch_bounds__(HZ_WARPS_PER_CTA * 32)
+k_near(const __grid_constant__ HzView P)
+{
+    __shared__ unsigned int s_stage[HZ_WARPS_PER_CTA][HZ_STAGE_SLOTS];
+    __shared__ HzLaneVtx    s_verts[HZ_WARPS_PER_CTA][25];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    HzWarpState S = { s_stage[wib], s_verts[wib], 0, 0u, 0u, 0u };
+
+    int ti0, ti1, tj0, tj1;
+    hz_near_tiles(P, ti0, ti1, tj0, tj1);
+    const int bi0 = ti0 * HZ_TILE_BLOCKS, bi1 = min((ti1 + 1) * HZ_TILE_BLOCKS, P.nb);
+    const int bj0 = tj0 * HZ_TILE_BLOCKS, bj1 = min((tj1 + 1) * HZ_TILE_BLOCKS, P.nb);
+    const int nbi = bi1 - bi0, nblocks = nbi * (bj1 - bj0);
+    const int nwarps = gridDim.x * HZ_WARPS_PER_CTA;
+    unsigned int n_blocks = 0, n_far = 0, n_window = 0;
+    for(int b = blockIdx.x * HZ_WARPS_PER_CTA + wib; b < nblocks; b += nwarps)
+    {
+        const int bj = bj0 + b / nbi, bi = bi0 + b % nbi;
+        const short2 mm = __ldg(P.mm_block + (size_t)bj * P.nb + bi);
+        HzBox B;
+        const int r = hz_rect_test(P, bi * HZ_BLOCK_CELLS, min(bi * HZ_BLOCK_CELLS + HZ_BLOCK_CELLS, P.N - 1),
+                                   bj * HZ_BLOCK_CELLS, min(bj * HZ_BLOCK_CELLS + HZ_BLOCK_CELLS, P.N - 1),
+                                   (float)mm.x, (float)mm.y, B);
+        n_blocks++;
+        if(r == HZ_RECT_DEAD_FAR)    { n_far++;    continue; }
+        if(r == HZ_RECT_DEAD_WINDOW) { n_window++; continue; }
+        hz_mesh_block(P, bj, bi, lane, S);
+    }
+    hz_stage_drain(P, S, lane, true);
+    const unsigned int n_big = hz_warp_sum(S.n_big);
+    if(lane == 0)
+    {
+        atomicAdd(P.stats + HZ_STAT_BLOCKS, n_blocks);
+        atomicAdd(P.stats + HZ_STAT_BLOCKS_FAR, n_far);
+        atomicAdd(P.stats + HZ_STAT_BLOCKS_WINDOW, n_window);
+        atomicAdd(P.stats + HZ_STAT_BLOCKS_MESHED, S.n_meshed);
+        atomicAdd(P.stats + HZ_STAT_TRIANGLES, S.n_tris);
+        atomicAdd(P.stats + HZ_STAT_BIG_ENTRIES, n_big);
+    }
+}
+
+cudaError_t hz_launch_near(const HzView& v, cudaStream_t stream)
+{
+    const int side = min(2 * v.near_rings + 1, v.nt) * HZ_TILE_BLOCKS;
+    const int nblocks = side * side;
+    int ctas = (nblocks + HZ_WARPS_PER_CTA - 1) / HZ_WARPS_PER_CTA;
+    if(ctas > 148 * 8) ctas = 148 * 8;
+    if(ctas < 1) ctas = 1;
+    k_near<<<ctas, HZ_WARPS_PER_CTA * 32, 0, stream>>>(v);
     return cudaGetLastError();
 }
 
 // ================================================================================================
-// k_big: one warp per (triangle, band of rows), lanes spread over the band's pixels
+// k_tiles / k_blocks / k_mesh: everything beyond the near tiles, hierarchically culled, band by band
 // ================================================================================================
+//
+// The rest of the mesh is walked in a few bands of growing Chebyshev distance (in tiles) around the eye's tile.
+// Per band three kernels run back to back, each with one unit of work per thread or warp so that no warp ever
+// carries a long serial chain:
+//   k_tiles   thread = tile (32x32 cells): conservative test of the whole tile        -> queue of live tiles
+//   k_blocks  thread = block (4x4 cells) of a live tile: the same test on the block   -> queue of live blocks
+//   k_mesh    warp   = live block: projection, exact integer cull, set-up, rasterisation (lane = triangle)
+// Everything a band draws is in the visibility buffer before the next band is tested against it, and within a
+// band whatever has already been drawn helps too.
+
+// k-th tile of the ring walk around (0,0): k = 0 is the centre, ring r >= 1 holds the 8r tiles k in [(2r-1)^2, (2r+1)^2)
+__device__ __forceinline__ void hz_ring_walk(unsigned int k, int& dx, int& dy)
+{
+    if(k == 0) { dx = 0; dy = 0; return; }
+    int r = (int)ceilf((sqrtf((float)k + 1.0f) - 1.0f) * 0.5f);
+    while((unsigned int)((2 * r + 1) * (2 * r + 1)) <= k) r++;
+    while(r > 1 && (unsigned int)((2 * r - 1) * (2 * r - 1)) > k) r--;
+    const unsigned int off = k - (unsigned int)((2 * r - 1) * (2 * r - 1));
+    const int side = (int)(off / (unsigned int)(2 * r)), pos = (int)(off % (unsigned int)(2 * r));
+    switch(side)
+    {
+    case 0:  dx = -r + pos; dy = -r;       break;
+    case 1:  dx =  r;       dy = -r + pos; break;
+    case 2:  dx =  r - pos; dy =  r;       break;
+    default: dx = -r;       dy =  r - pos; break;
+    }
+}
+
+// Eight keys are fetched per round so that the L2 round trips overlap; the loop ends at the first round that
+// shows something not nearer.
+__device__ __forceinline__ bool hz_box_occluded_thread(const HzView& P, const HzBox& B, int max_pix)
+{
+    const int w = B.px1 - B.px0 + 1, h = B.py1 - B.py0 + 1;
+    const int npix = w * h;
+    if(npix > max_pix) return false;
+    const size_t Wt = (size_t)(P.x1 - P.x0);
+    const unsigned long long* base = P.vis + (size_t)B.py0 * Wt + (size_t)(B.px0 - P.x0);
+    for(int p = 0; p < npix; p += 8)
+    {
+        unsigned int farthest = 0;
+        #pragma unroll
+        for(int u = 0; u < 8; u++)
+        {
+            const int idx = min(p + u, npix - 1);
+            const int y = idx / w, x = idx - y * w;
+            farthest = max(farthest, (unsigned int)(__ldcg(base + (size_t)y * Wt + x) >> 40));
+        }
+        if(farthest >= B.qmin) return false;
+    }
+    return true;
+}
+
+// appends `value` of every lane with `on` to queue[*count...] with one atomic per warp; all 32 lanes must call
+__device__ __forceinline__ void hz_warp_append(bool on, unsigned int value, unsigned int* queue, unsigned int* count, int lane)
+{
+    const unsigned int ballot = __ballot_sync(0xffffffffu, on);
+    if(ballot == 0) return;
+    unsigned int base = 0;
+    if(lane == 0) base = atomicAdd(count, (unsigned int)__popc(ballot));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if(on) queue[base + __popc(ballot & ((1u << lane) - 1u))] = value;
+}
+
+__global__ void __launch_bounds__(256)
+k_tiles(const __grid_constant__ HzView P)
+{
+    const int lane = threadIdx.x & 31;
+    const int nt = P.nt, N = P.N;
+    const int rmax = max(max(P.eye_ti, nt - 1 - P.eye_ti), max(P.eye_tj, nt - 1 - P.eye_tj));
+    const int ring_hi = min(P.ring_hi, rmax + 1);
+    if(P.ring_lo >= ring_hi) return;
+    const unsigned int first = (unsigned int)((2 * P.ring_lo - 1) * (2 * P.ring_lo - 1));
+    const unsigned int last  = (unsigned int)((2 * ring_hi - 1) * (2 * ring_hi - 1));
+    const unsigned int nth = gridDim.x * blockDim.x;
+    unsigned int n_all = 0, n_far = 0, n_window = 0, n_occl = 0;
+    for(unsigned int k0 = first + (blockIdx.x * blockDim.x + threadIdx.x - lane); k0 < last; k0 += nth)
+    {
+        const unsigned int k = k0 + lane;
+        bool on = false;
+        unsigned int id = 0;
+        if(k < last)
+        {
+            int dx, dy;
+            hz_ring_walk(k, dx, dy);
+            const int ti = P.eye_ti + dx, tj = P.eye_tj + dy;
+            if(ti >= 0 && ti < nt && tj >= 0 && tj < nt)
+            {
+                n_all++;
+                const int tc0 = ti * HZ_TILE_CELLS, tr0 = tj * HZ_TILE_CELLS;
+                const short2 mt = __ldg(P.mm_tile + (size_t)tj * nt + ti);
+                HzBox B;
+                const int r = hz_rect_test(P, tc0, min(tc0 + HZ_TILE_CELLS, N - 1), tr0, min(tr0 + HZ_TILE_CELLS, N - 1),
+                                           (float)mt.x, (float)mt.y, B);
+                if(r == HZ_RECT_DEAD_FAR)         n_far++;
+                else if(r == HZ_RECT_DEAD_WINDOW) n_window++;
+                else if(r == HZ_RECT_BOXED && hz_box_occluded_thread(P, B, P.occl_tile_max_pix)) n_occl++;
+                else { on = true; id = (unsigned int)(tj * nt + ti); }
+            }
+        }
+        hz_warp_append(on, id, P.tile_queue, P.tile_count, lane);
+    }
+    n_all = hz_warp_sum(n_all); n_far = hz_warp_sum(n_far); n_window = hz_warp_sum(n_window); n_occl = hz_warp_sum(n_occl);
+    if(lane == 0 && n_all)
+    {
+        atomicAdd(P.stats + HZ_STAT_TILES, n_all);
+        atomicAdd(P.stats + HZ_STAT_TILES_FAR, n_far);
+        atomicAdd(P.stats + HZ_STAT_TILES_WINDOW, n_window);
+        atomicAdd(P.stats + HZ_STAT_TILES_OCCLUDED, n_occl);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_blocks(const __grid_constant__ HzView P)
+{
+    const int lane = threadIdx.x & 31;
+    const int nt = P.nt, nb = P.nb, N = P.N;
+    const unsigned int total = *P.tile_count * (unsigned int)(HZ_TILE_BLOCKS * HZ_TILE_BLOCKS);
+    const unsigned int nth = gridDim.x * blockDim.x;
+    unsigned int n_all = 0, n_far = 0, n_window = 0, n_occl = 0;
+    for(unsigned int t0 = blockIdx.x * blockDim.x + threadIdx.x - lane; t0 < total; t0 += nth)
+    {
+        const unsigned int t = t0 + lane;          // total is a multiple of 64: every lane has an entry
+        const unsigned int tile = P.tile_queue[t >> 6];
+        const int tj = (int)(tile / (unsigned int)nt), ti = (int)(tile % (unsigned int)nt);
+        const int bj = tj * HZ_TILE_BLOCKS + (int)((t >> 3) & 7u), bi = ti * HZ_TILE_BLOCKS + (int)(t & 7u);
+        bool on = false;
+        if(bj < nb && bi < nb)
+        {
+            const short2 mm = __ldg(P.mm_block + (size_t)bj * nb + bi);
+            HzBox B;
+            const int c0 = bi * HZ_BLOCK_CELLS, r0 = bj * HZ_BLOCK_CELLS;
+            const int r = hz_rect_test(P, c0, min(c0 + HZ_BLOCK_CELLS, N - 1), r0, min(r0 + HZ_BLOCK_CELLS, N - 1),
+                                       (float)mm.x, (float)mm.y, B);
+            n_all++;
+            if(r == HZ_RECT_DEAD_FAR)         n_far++;
+            else if(r == HZ_RECT_DEAD_WINDOW) n_window++;
+            else if(r == HZ_RECT_BOXED && hz_box_occluded_thread(P, B, P.occl_block_max_pix)) n_occl++;
+            else on = true;
+        }
+        hz_warp_append(on, (unsigned int)(bj * nb + bi), P.block_queue, P.block_count, lane);
+    }
+    n_all = hz_warp_sum(n_all); n_far = hz_warp_sum(n_far); n_window = hz_warp_sum(n_window); n_occl = hz_warp_sum(n_occl);
+    if(lane == 0 && n_all)
+    {
+        atomicAdd(P.stats + HZ_STAT_BLOCKS, n_all);
+        atomicAdd(P.stats + HZ_STAT_BLOCKS_FAR, n_far);
+        atomicAdd(P.stats + HZ_STAT_BLOCKS_WINDOW, n_window);
+        atomicAdd(P.stats + HZ_STAT_BLOCKS_OCCLUDED, n_occl);
+    }
+}
+
+__global__ void __launch_bounds__(HZ_WARPS_PER_CTA * 32)
+k_mesh(const __grid_constant__ HzView P)
+{
+    __shared__ unsigned int s_stage[HZ_WARPS_PER_CTA][HZ_STAGE_SLOTS];
+    __shared__ HzLaneVtx    s_verts[HZ_WARPS_PER_CTA][25];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    HzWarpState S = { s_stage[wib], s_verts[wib], 0, 0u, 0u, 0u };
+    const unsigned int n = *P.block_count;
+    const unsigned int nwarps = gridDim.x * HZ_WARPS_PER_CTA;
+    for(unsigned int b = blockIdx.x * HZ_WARPS_PER_CTA + wib; b < n; b += nwarps)
+    {
+        const unsigned int id = P.block_queue[b];
+        hz_mesh_block(P, (int)(id / (unsigned int)P.nb), (int)(id % (unsigned int)P.nb), lane, S);
+    }
+    hz_stage_drain(P, S, lane, true);
+    const unsigned int n_big = hz_warp_sum(S.n_big);
+    if(lane == 0 && S.n_meshed)
+    {
+        atomicAdd(P.stats + HZ_STAT_BLOCKS_MESHED, S.n_meshed);
+        atomicAdd(P.stats + HZ_STAT_TRIANGLES, S.n_tris);
+        atomicAdd(P.stats + HZ_STAT_BIG_ENTRIES, n_big);
+    }
+}
+
+cudaError_t hz_launch_band(const HzView& v, cudaStream_t stream, int* launches)
+{
+    *launches = 0;
+    const int rmax = max(max(v.eye_ti, v.nt - 1 - v.eye_ti), max(v.eye_tj, v.nt - 1 - v.eye_tj));
+    const int ring_hi = min(v.ring_hi, rmax + 1);
+    if(v.ring_lo >= ring_hi) return cudaSuccess;
+    const long long ntiles = (long long)(2 * ring_hi - 1) * (2 * ring_hi - 1) - (long long)(2 * v.ring_lo - 1) * (2 * v.ring_lo - 1);
+    long long ctas = (ntiles + 255) / 256;
+    if(ctas > 148 * 8) ctas = 148 * 8;
+    k_tiles<<<(unsigned)ctas, 256, 0, stream>>>(v);
+    k_blocks<<<148 * 8, 256, 0, stream>>>(v);
+    k_mesh<<<148 * 4, HZ_WARPS_PER_CTA * 32, 0, stream>>>(v);
+    *launches = 3;
+    return cudaGetLastError();
+}
+
+// ================================================================================================
+// k_big: one warp per (triangle, sub-box), lanes spread over the sub-box's pixels
+// ================================================================================================
+
+template <typename I>
+__device__ __forceinline__ void hz_draw_subbox(const HzView& P, const HzTri& T, int x0, int x1, int y0, int y1, int lane)
+{
+    const HzEdges<I> E(T);
+    if(E.box_outside(T, x0, x1, y0, y1)) return;
+    const int bw = x1 - x0 + 1;
+    const int npix = bw * (y1 - y0 + 1);
+    for(int p = lane; p < npix; p += 32)
+    {
+        const int py = y0 + p / bw, px = x0 + p % bw;
+        if(E.inside(T, px, py)) hz_fragment(P, T, px, py);
+    }
+}
 
 __global__ void __launch_bounds__(256)
 k_big(const __grid_constant__ HzView P)
 {
     unsigned int count = *P.big_count;
     if(count > P.big_capacity) count = P.big_capacity;
-    const unsigned int lane = threadIdx.x & 31;
+    const int lane = threadIdx.x & 31;
     const unsigned int nwarps = gridDim.x * (blockDim.x >> 5);
     for(unsigned int t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); t < count; t += nwarps)
     {
         const uint2 entry = P.big_queue[t];
         HzTri T;
-        if(!hz_tri_setup(P, entry.x, T, true)) continue;      // cannot happen: k_raster accepted it
-        const int y0 = T.py0 + (int)entry.y * HZ_BAND_ROWS;
-        const int y1 = min(y0 + HZ_BAND_ROWS - 1, T.py1);
-        const int bw = T.px1 - T.px0 + 1;
-        const int npix = bw * (y1 - y0 + 1);
-        if(hz_tri_is_small(T))
-        {
-            const HzEdges<int> E(T);
-            for(int p = (int)lane; p < npix; p += 32)
-            {
-                const int py = y0 + p / bw, px = T.px0 + p % bw;
-                if(E.inside(T, px, py)) hz_fragment(P, T, px, py);
-            }
-        }
-        else
-        {
-            const HzEdges<long long> E(T);
-            for(int p = (int)lane; p < npix; p += 32)
-            {
-                const int py = y0 + p / bw, px = T.px0 + p % bw;
-                if(E.inside(T, px, py)) hz_fragment(P, T, px, py);
-            }
-        }
+        if(!hz_tri_setup(P, entry.x, T, true)) continue;      // cannot happen: it was accepted when queued
+        const int y0 = T.py0 + (int)(entry.y & 0xFFFFu) * HZ_BIG_ROWS, y1 = min(y0 + HZ_BIG_ROWS - 1, T.py1);
+        const int x0 = T.px0 + (int)(entry.y >> 16) * HZ_BIG_COLS,     x1 = min(x0 + HZ_BIG_COLS - 1, T.px1);
+        if(hz_tri_is_small(T)) hz_draw_subbox<int>(P, T, x0, x1, y0, y1, lane);
+        else                   hz_draw_subbox<long long>(P, T, x0, x1, y0, y1, lane);
     }
 }
 
 cudaError_t hz_launch_big(const HzView& v, cudaStream_t stream)
 {
-    k_big<<<148 * 4, 256, 0, stream>>>(v);
+    k_big<<<148 * 8, 256, 0, stream>>>(v);
     return cudaGetLastError();
 }
 
@@ -778,5 +1041,33 @@ cudaError_t hz_launch_resolve(const HzResolve& r, cudaStream_t stream)
         const long long n = (long long)r.Wt * r.H;
         k_resolve1<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(r);
     }
+    return cudaGetLastError();
+}
+
+// ================================================================================================
+// k_horizon: per image column, the topmost terrain pixel (row, range); -1 / -1.0f if the column is all sky
+// ================================================================================================
+
+__global__ void __launch_bounds__(256)
+k_horizon(const float* __restrict__ ranges, int n, int W, int H, int* __restrict__ rows, float* __restrict__ range)
+{
+    const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if(g >= (long long)n * W) return;
+    const int img = (int)(g / W), x = (int)(g % W);
+    const float* col = ranges + (size_t)img * W * H + x;
+    int row = -1; float r = -1.0f;
+    for(int y = 0; y < H; y++)
+    {
+        const float v = col[(size_t)y * W];
+        if(v > 0.0f) { row = y; r = v; break; }
+    }
+    rows[g] = row; range[g] = r;
+}
+
+cudaError_t hz_launch_horizon(const float* ranges, int n, int W, int H, int* rows, float* range, cudaStream_t stream)
+{
+    const long long total = (long long)n * W;
+    if(total <= 0) return cudaSuccess;
+    k_horizon<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(ranges, n, W, H, rows, range);
     return cudaGetLastError();
 }

@@ -67,20 +67,37 @@ bool horizonator_download_mosaic(const horizonator_context_t* ctx, int16_t* mosa
  * milliseconds (CUDA events on the context's stream).  For benchmarks of the init path. */
 bool horizonator_time_mosaic(const horizonator_context_t* ctx, int reps, float* ms_per_run);
 
+/* Per-column horizon of n range images (device memory, n*H*W floats as the render calls
+ * write them): d_rows[n*W] = row (0 = top) of the topmost terrain pixel of each column or -1,
+ * d_range[n*W] = the range there or -1.  The reduced product of a viewpoint batch: a few
+ * bytes per column instead of a full image. */
+bool horizonator_horizon_profile_device(const horizonator_context_t* ctx,
+                                        const void* d_ranges, int n,
+                                        void* d_rows, void* d_range,
+                                        void* stream);
+
 /* Per-kernel device times.  While enabled, every render records CUDA events around each of
  * its kernels on the stream it runs on.  horizonator_profile_read() waits for them and reports
  * the MEAN duration in milliseconds per render of: out_ms[0] k_prepare (clear + axis tables),
- * [1] k_march (mesh + projection + cull -> triangle list), [2] k_raster (set-up + rasterise
- * the list), [3] k_big (large triangles), [4] k_resolve (keys -> image + ranges), over the
- * *renders recorded since the last read. */
+ * [1] k_near (foreground tiles: mesh, projection, cull, rasterise), [2] k_big of the
+ * foreground, [3] k_march (the rest of the mesh, hierarchically culled), [4] k_big of the
+ * rest, [5] k_resolve (keys -> image + ranges), over the *renders recorded since the last
+ * read. */
 bool horizonator_profile_enable(const horizonator_context_t* ctx, bool on);
-bool horizonator_profile_read(const horizonator_context_t* ctx, float out_ms[5], int* renders);
+bool horizonator_profile_read(const horizonator_context_t* ctx, float out_ms[6], int* renders);
 
-/* Counters of the most recent render on this context: out[0] = (triangle, row band) pairs
+/* Counters of the most recent render on this context: out[0] = (triangle, sub-box) pairs
  * queued for the large-triangle kernel, out[1] = that queue's capacity, out[2] = kernel
  * launches the render issued, out[3] = CUDA device ordinal, out[4] = triangles that passed
- * the cull and were rasterised. */
+ * the cull and were set up for rasterisation. */
 bool horizonator_last_render_stats(const horizonator_context_t* ctx, unsigned int out[5]);
+
+/* Culling counters of the most recent render: out[0..3] far-pass tiles looked at / dropped
+ * beyond zfar / dropped without a pixel centre in their screen box / dropped as occluded,
+ * out[4..7] the same for 4x4-cell blocks (both passes), out[8] blocks whose 32 triangles were
+ * projected and tested exactly, out[9] triangles set up, out[10] large-triangle queue entries;
+ * out[11..15] reserved (0). */
+bool horizonator_render_counters(const horizonator_context_t* ctx, unsigned int out[16]);
 
 #ifdef __cplusplus
 }

@@ -21,6 +21,11 @@
  *       (keeps the 64-bit edge functions on 1/256-pixel coordinates free of overflow).
  *   F6  zw and the red channel are interpolated as planes through the UNSNAPPED float
  *       vertices, anchored at the triangle's first vertex, evaluated at the pixel centre.
+ *       The pixel centre can lie up to 1/256 pixel outside the unsnapped triangle, so the
+ *       plane is extrapolated a little; across a sliver thinner than that the extrapolation
+ *       is unbounded.  The interpolated zw is therefore limited to the range of the three
+ *       vertex values widened by 4x its own extent on either side (reached only by slivers
+ *       thinner than about 1/1000 pixel, where the value is an artefact anyway).
  *   F7  GL_DEPTH_COMPONENT renderbuffer = 24-bit unsigned normalised: q = floor(zw*(2^24-1)+.5);
  *       test GL_LESS on q against the stored q, cleared to 2^24-1; read back as float(q/(2^24-1)).
  *   F8  GL_RGB renderbuffer = 8-bit unsigned normalised: c8 = floor(clamp(c,0,1)*255 + .5).
@@ -193,6 +198,10 @@ draw_one(uint32_t* zr, int W, int H, const glp_vtx_t* v0, const glp_vtx_t* v1, c
     const float dzdy = (bz * ax - az * bx) * inv;
     const float drdx = (ar * by - br * ay) * inv;
     const float drdy = (br * ax - ar * bx) * inv;
+    const float zw_min = fminf(fminf(v0->zw, v1->zw), v2->zw);
+    const float zw_max = fmaxf(fmaxf(v0->zw, v1->zw), v2->zw);
+    const float zw_lo = zw_min - 4.0f * (zw_max - zw_min);
+    const float zw_hi = zw_max + 4.0f * (zw_max - zw_min);
 
     /* F4: edge a->b owns its boundary iff dy<0 or (dy==0 and dx<0) */
     const int64_t e0dx = X1 - X0, e0dy = Y1 - Y0;
@@ -215,7 +224,8 @@ draw_one(uint32_t* zr, int W, int H, const glp_vtx_t* v0, const glp_vtx_t* v1, c
 
             const float cx = (float)px + 0.5f, cy = (float)py + 0.5f;
             const float ddx = cx - v0->xw, ddy = cy - v0->yw;
-            const float zw = v0->zw + (dzdx * ddx + dzdy * ddy);
+            float zw = v0->zw + (dzdx * ddx + dzdy * ddy);
+            zw = fminf(fmaxf(zw, zw_lo), zw_hi);                            /* F6 */
             if(!(zw >= 0.0f && zw <= 1.0f)) continue;                       /* F5 */
 
             const uint32_t q = (uint32_t)((double)zw * (double)GLP_Z24_MAX + 0.5);   /* F7 */

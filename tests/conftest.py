@@ -8,6 +8,15 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 
+def load_build_module():
+    """horizonator_b200/build.py loaded by path: importing the package itself needs an up-to-date library."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("hz_build", os.path.join(ROOT, "horizonator_b200", "build.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 
@@ -15,7 +24,7 @@ def pytest_configure(config):
 @pytest.fixture(scope="session", autouse=True)
 def _native_built():
     """Build what is missing: the product library (nvcc), the synthetic-tile generator and the oracle (gcc)."""
-    from horizonator_b200 import build as hb
+    hb = load_build_module()
     hb.build_library()
     hb.build_synth()
     from oracle import binding
