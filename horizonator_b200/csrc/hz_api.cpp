@@ -33,10 +33,13 @@ namespace {
 constexpr int   TANEL_SLOTS     = 8;
 constexpr float PI_F            = 3.14159265358979f;       // vertex.glsl:31
 constexpr unsigned BIG_CAPACITY = 1u << 21;      // (triangle, sub-box) pairs per pass; overflow is drawn inline
+constexpr unsigned TRI_CAPACITY = 1u << 23;      // triangles per stage awaiting set-up; overflow is drawn inline
+constexpr unsigned BIGTRI_CAPACITY = 1u << 18;   // set-up records of triangles queued for the large-triangle kernel
 constexpr int   PROF_EVENTS     = 7;            // 6 stages per render
 constexpr int   MAX_BANDS       = 6;
-// [0] big_count near, [1] big_count bands, [2+2b] tile_count, [3+2b] block_count of band b, then the stats
-constexpr int   STATS_AT        = 2 + 2 * MAX_BANDS;
+// [0] big_count near, [1] big_count bands, [2] tri_count near, [3] big-triangle records, [4+3b] tile_count,
+// [5+3b] block_count, [6+3b] tri_count of band b, then the stats
+constexpr int   STATS_AT        = 4 + 3 * MAX_BANDS;
 constexpr int   N_COUNTERS      = STATS_AT + HZ_STAT_COUNT;
 
 // what the reference keeps in GL uniforms
@@ -53,8 +56,9 @@ struct Scratch
     cudaEvent_t  done = nullptr;       // lanes only
     unsigned long long* d_vis = nullptr;
     float *d_e = nullptr, *d_n = nullptr;
-    uint32_t *d_tile_queue = nullptr, *d_block_queue = nullptr;
+    uint32_t *d_tile_queue = nullptr, *d_block_queue = nullptr, *d_tri_queue = nullptr;
     uint2*    d_big_queue = nullptr;   // [2][BIG_CAPACITY]: near pass, bands
+    uint4*    d_bigtri = nullptr;      // [BIGTRI_CAPACITY][6]
     uint32_t* d_counters  = nullptr;   // [N_COUNTERS]
     uint8_t*  d_image  = nullptr;      // lanes only: staging of one view's outputs for the host-pointer batch call
     float*    d_ranges = nullptr;
@@ -72,9 +76,9 @@ struct Slot
     short2 *d_mm_block = nullptr, *d_mm_tile = nullptr;   // culling pyramid
     int nb = 0, nt = 0;
     int near_rings = 2;
-    int n_bands = 3;
-    int occl_tile_max_pix = 128, occl_block_max_pix = 32;
-    int band_end[MAX_BANDS] = { 12, 48, 1 << 20, 0, 0, 0 };   // ring at which each band ends (exclusive)
+    int n_bands = 2;
+    int occl_tile_max_pix = 64, occl_block_max_pix = 16, small_max_pix = 16;
+    int band_end[MAX_BANDS] = { 24, 1 << 20, 0, 0, 0, 0 };   // ring at which each band ends (exclusive)
     int n_lanes_max = 8;
 
     // target
@@ -105,6 +109,7 @@ struct Slot
 
     // optional per-kernel timing: PROF_EVENTS events per recorded render
     bool profiling = false;
+    bool collect_stats = false;      // culling counters (horizonator_render_counters); off: the kernels skip them
     std::vector<cudaEvent_t> prof_events;
     size_t prof_used = 0;
 };
@@ -171,7 +176,8 @@ bool alloc_target(Slot& s, int W, int H)
 void free_scratch(Scratch& c)
 {
     cudaFree(c.d_vis); cudaFree(c.d_e); cudaFree(c.d_n);
-    cudaFree(c.d_tile_queue); cudaFree(c.d_block_queue); cudaFree(c.d_big_queue); cudaFree(c.d_counters);
+    cudaFree(c.d_tile_queue); cudaFree(c.d_block_queue); cudaFree(c.d_tri_queue); cudaFree(c.d_big_queue);
+    cudaFree(c.d_counters); cudaFree(c.d_bigtri);
     cudaFree(c.d_image); cudaFree(c.d_ranges);
     if(c.done) cudaEventDestroy(c.done);
     if(c.stream) cudaStreamDestroy(c.stream);
@@ -185,7 +191,9 @@ bool alloc_scratch(const Slot& s, Scratch& c, bool own_stream)
     CUDA_TRY(cudaMalloc(&c.d_n, (size_t)s.N * sizeof(float)));
     CUDA_TRY(cudaMalloc(&c.d_tile_queue, (size_t)s.nt * s.nt * sizeof(uint32_t)));
     CUDA_TRY(cudaMalloc(&c.d_block_queue, (size_t)s.nb * s.nb * sizeof(uint32_t)));
+    CUDA_TRY(cudaMalloc(&c.d_tri_queue, (size_t)TRI_CAPACITY * sizeof(uint32_t)));
     CUDA_TRY(cudaMalloc(&c.d_big_queue, 2 * (size_t)BIG_CAPACITY * sizeof(uint2)));
+    CUDA_TRY(cudaMalloc(&c.d_bigtri, (size_t)BIGTRI_CAPACITY * 6 * sizeof(uint4)));
     CUDA_TRY(cudaMalloc(&c.d_counters, N_COUNTERS * sizeof(uint32_t)));
     if(own_stream)
     {
@@ -305,9 +313,12 @@ bool enqueue_render(Slot& s, Scratch& sc, const ViewState& vs, int x0, int x1,
     v.znear = s.znear; v.zfar = s.zfar; v.znear_color = s.znear_color; v.zfar_color = s.zfar_color;
     v.W = s.W; v.H = s.H; v.x0 = x0; v.x1 = x1;
     v.vis = sc.d_vis;
-    v.stats      = sc.d_counters + STATS_AT;
+    v.stats      = s.collect_stats ? sc.d_counters + STATS_AT : nullptr;
     v.tile_queue = sc.d_tile_queue; v.block_queue = sc.d_block_queue;
+    v.tri_queue = sc.d_tri_queue; v.tri_capacity = TRI_CAPACITY;
+    v.bigtri = sc.d_bigtri; v.bigtri_count = sc.d_counters + 3; v.bigtri_capacity = BIGTRI_CAPACITY;
     v.occl_tile_max_pix = s.occl_tile_max_pix; v.occl_block_max_pix = s.occl_block_max_pix;
+    v.small_max_pix = s.small_max_pix;
     v.big_capacity = BIG_CAPACITY;
 
     // the eye's tile, and how many rings of tiles around it form the foreground pass
@@ -340,6 +351,7 @@ bool enqueue_render(Slot& s, Scratch& sc, const ViewState& vs, int x0, int x1,
         s.prof_used += PROF_EVENTS;
     }
     HzView v_near = v, v_far = v;
+    v_near.tri_count = sc.d_counters + 2;
     v_near.big_queue = sc.d_big_queue;                 v_near.big_count = sc.d_counters + 0;
     v_far.big_queue  = sc.d_big_queue + BIG_CAPACITY;  v_far.big_count  = sc.d_counters + 1;
 
@@ -347,6 +359,7 @@ bool enqueue_render(Slot& s, Scratch& sc, const ViewState& vs, int x0, int x1,
     CUDA_TRY(hz_launch_prepare(v, sc.d_counters, N_COUNTERS, st));
     if(ev) CUDA_TRY(cudaEventRecord(ev[1], st));
     CUDA_TRY(hz_launch_near(v_near, st));
+    CUDA_TRY(hz_launch_raster(v_near, st));
     if(ev) CUDA_TRY(cudaEventRecord(ev[2], st));
     CUDA_TRY(hz_launch_big(v_near, st));
     if(ev) CUDA_TRY(cudaEventRecord(ev[3], st));
@@ -357,7 +370,8 @@ bool enqueue_render(Slot& s, Scratch& sc, const ViewState& vs, int x0, int x1,
         {
             HzView vb = v_far;
             vb.ring_lo = lo; vb.ring_hi = s.band_end[b] > lo ? s.band_end[b] : lo;
-            vb.tile_count = sc.d_counters + 2 + 2 * b; vb.block_count = sc.d_counters + 3 + 2 * b;
+            vb.tile_count = sc.d_counters + 4 + 3 * b; vb.block_count = sc.d_counters + 5 + 3 * b;
+            vb.tri_count  = sc.d_counters + 6 + 3 * b;
             int n = 0;
             CUDA_TRY(hz_launch_band(vb, st, &n));
             band_launches += n;
@@ -367,7 +381,7 @@ bool enqueue_render(Slot& s, Scratch& sc, const ViewState& vs, int x0, int x1,
     if(ev) CUDA_TRY(cudaEventRecord(ev[4], st));
     CUDA_TRY(hz_launch_big(v_far, st));
     if(ev) CUDA_TRY(cudaEventRecord(ev[5], st));
-    s.launches_last = 4 + band_launches;
+    s.launches_last = 5 + band_launches;
     if(d_image || d_ranges)
     {
         HzResolve r{};
@@ -503,6 +517,7 @@ bool horizonator_init(horizonator_context_t* ctx,
         if(const char* env = getenv("HORIZONATOR_NEAR_RINGS")) s->near_rings = atoi(env) < 0 ? 0 : atoi(env);
         if(const char* env = getenv("HORIZONATOR_OCCL_TILE_PIX"))  s->occl_tile_max_pix  = atoi(env);
         if(const char* env = getenv("HORIZONATOR_OCCL_BLOCK_PIX")) s->occl_block_max_pix = atoi(env);
+        if(const char* env = getenv("HORIZONATOR_SMALL_PIX"))      s->small_max_pix = atoi(env);
         if(const char* env = getenv("HORIZONATOR_BANDS"))
         {
             // comma-separated rings at which the bands end; the last band always runs to the edge of the mesh
@@ -918,6 +933,7 @@ bool horizonator_profile_enable(const horizonator_context_t* ctx, bool on)
     Slot* s = slot_of(ctx);
     if(s == nullptr) return false;
     s->profiling = on;
+    s->collect_stats = on;
     return true;
 }
 
@@ -954,7 +970,8 @@ bool horizonator_last_render_stats(const horizonator_context_t* ctx, unsigned in
     unsigned int counters[N_COUNTERS] = {};
     CUDA_TRY(cudaMemcpy(counters, s->main.d_counters, sizeof(counters), cudaMemcpyDeviceToHost));
     out[0] = counters[0] + counters[1]; out[1] = 2 * BIG_CAPACITY; out[2] = s->launches_last; out[3] = (unsigned)s->device;
-    out[4] = counters[STATS_AT + HZ_STAT_TRIANGLES];
+    out[4] = counters[2];
+    for(int b = 0; b < MAX_BANDS; b++) out[4] += counters[6 + 3 * b];     // triangle lists of the near pass and the bands
     return true;
 }
 

@@ -89,12 +89,21 @@ struct HzView
     uint32_t* tile_count;
     uint32_t* block_queue;       // live blocks of the band (bj*nb+bi)
     uint32_t* block_count;
+    uint32_t* tri_queue;         // triangles of the stage that passed the exact integer tests
+    uint32_t* tri_count;
+    uint32_t  tri_capacity;
     int occl_tile_max_pix, occl_block_max_pix;   // largest screen box one thread checks against the visibility buffer
+    int small_max_pix;           // a lane rasterises bounding boxes up to this many pixels itself; larger ones go to k_big
 
-    // (triangle, sub-box) pairs too big for one thread; one queue for the near pass, one for all bands
+    // triangles too big for one thread: the set-up triangle goes to the record pool (6 x 16 bytes each), and one
+    // (record, sub-box) entry per sub-box of its bounding box to a queue -- one queue for the near pass, one for all
+    // the bands, one pool for both
     uint2*    big_queue;
     uint32_t* big_count;
     uint32_t  big_capacity;
+    uint4*    bigtri;
+    uint32_t* bigtri_count;
+    uint32_t  bigtri_capacity;
     uint32_t* stats;             // [HZ_STAT_COUNT]
 
     float cell_diag2;            // (east cell size)^2 + (north cell size)^2 in metres^2, rounded up
@@ -115,8 +124,9 @@ cudaError_t hz_launch_mosaic (const HzTiles& t, int16_t* mosaic, int N, int pitc
 cudaError_t hz_launch_pyramid(const int16_t* mosaic, int N, int pitch, short2* mm_block, int nb,
                               short2* mm_tile, int nt, cudaStream_t stream);
 cudaError_t hz_launch_prepare(const HzView& v, uint32_t* counters, int ncounters, cudaStream_t stream);
-cudaError_t hz_launch_near   (const HzView& v, cudaStream_t stream);   // foreground tiles, no occlusion tests
-cudaError_t hz_launch_band   (const HzView& v, cudaStream_t stream, int* launches);   // one band of the rest: k_tiles, k_blocks, k_mesh
+cudaError_t hz_launch_near   (const HzView& v, cudaStream_t stream);   // foreground tiles -> triangle list
+cudaError_t hz_launch_raster (const HzView& v, cudaStream_t stream);   // set-up + rasterise a triangle list
+cudaError_t hz_launch_band   (const HzView& v, cudaStream_t stream, int* launches);   // one band of the rest: k_tiles, k_blocks, k_mesh, k_raster
 cudaError_t hz_launch_big    (const HzView& v, cudaStream_t stream);   // queued large triangles of one pass
 cudaError_t hz_launch_resolve(const HzResolve& r, cudaStream_t stream);
 cudaError_t hz_launch_horizon(const float* ranges, int n, int W, int H, int* rows, float* range, cudaStream_t stream);

@@ -5,12 +5,14 @@
 //   k_minmax_* (init)    (min,max) height per 4x4-cell block and per 32x32-cell tile: the culling pyramid
 //   k_prepare  (render)  clear visibility keys, per-column/row metre tables    glClear, lib:896; vertex.glsl:128-130
 //   k_near     (render)  the tiles around the eye: mesh generation, projection,  lib:496-508 (index pattern), vertex.glsl,
-//                        exact integer cull, set-up and rasterisation             geometry.glsl, GL cull/clip/raster/depth
+//                        exact integer cull -> list of triangles                  GL cull/clip
 //   k_tiles, k_blocks, k_mesh (render)
 //                        the rest of the mesh in bands outwards from the eye: whole tiles, then blocks, are dropped
 //                        by conservative tests (beyond zfar, no pixel centre of the target inside their screen box,
 //                        everything in that box already nearer in the visibility buffer); what is left goes
-//                        through the same exact stages as in k_near
+//                        through the same exact stages as in k_near -> list of triangles
+//   k_raster   (render)  set-up, rasterisation and depth test of a list,          vertex.glsl, geometry.glsl, GL raster,
+//                        one thread per triangle                                  depth test, fragment.glsl
 //   k_big      (render)  the few triangles with large bounding boxes, one warp per 8x64-pixel sub-box
 //   k_resolve  (render)  keys -> BGR8 image + float range image, top row first lib:936-1048
 //   k_horizon  (extra)   range image -> per-column topmost terrain row and its range
@@ -23,6 +25,29 @@
 #include "hz_math.cuh"
 
 #include <cstdint>
+
+// ---- launches ----------------------------------------------------------------------------------
+// A render is a chain of a dozen short kernels on one stream.  Each is launched with programmatic stream
+// serialisation (PDL): its CTAs may be placed on the SMs while the previous kernel is still draining, and wait at
+// hz_wait_for_previous_kernel() -- the first statement of every render kernel -- until that kernel has completed and
+// its writes are visible.  That hides most of the launch latency between the kernels; the ordering is unchanged.
+__device__ __forceinline__ void hz_wait_for_previous_kernel()
+{
+    cudaGridDependencySynchronize();
+    cudaTriggerProgrammaticLaunchCompletion();
+}
+
+template <typename... KArgs, typename... Args>
+static cudaError_t hz_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, cudaStream_t stream, Args&&... args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = 0; cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
 
 // ================================================================================================
 // k_mosaic
@@ -129,6 +154,7 @@ cudaError_t hz_launch_mosaic(const HzTiles& t, int16_t* mosaic, int N, int pitch
 __global__ void __launch_bounds__(256)
 k_prepare(const __grid_constant__ HzView P, uint32_t* counters, int ncounters)
 {
+    hz_wait_for_previous_kernel();
     const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const size_t nth = (size_t)gridDim.x * blockDim.x;
 
@@ -157,8 +183,7 @@ cudaError_t hz_launch_prepare(const HzView& v, uint32_t* counters, int ncounters
     if(blocks < (size_t)(v.N + 255) / 256) blocks = (v.N + 255) / 256;
     if(blocks > 148 * 16) blocks = 148 * 16;
     if(blocks < 1) blocks = 1;
-    k_prepare<<<(unsigned)blocks, 256, 0, stream>>>(v, counters, ncounters);
-    return cudaGetLastError();
+    return hz_launch(k_prepare, dim3((unsigned)blocks), dim3(256), stream, v, counters, ncounters);
 }
 
 // ================================================================================================
@@ -318,6 +343,19 @@ __device__ __forceinline__ bool hz_tri_setup(const HzView& P, unsigned int id, H
     return true;
 }
 
+// F7: floor(zw * (2^24-1) + 0.5) for 0 <= zw <= 1, exactly as the double-precision expression of the oracle gives it
+// (the product of two 24-bit numbers and the added half are exact in double), in integer arithmetic: B200 has next
+// to no FP64 throughput, and this runs once per fragment.
+__device__ __forceinline__ unsigned int hz_quantise24(float zw)
+{
+    const unsigned int bits = __float_as_uint(zw);
+    const unsigned int ex = bits >> 23;                      // zw >= 0: no sign bit
+    if(ex < 127u - 40u) return 0u;                           // zw < 2^-40: rounds to 0 (also zero and denormals)
+    const unsigned long long mant = (unsigned long long)((bits & 0x7FFFFFu) | 0x800000u);
+    const unsigned int shift = 150u - ex;                    // zw = mant * 2^-shift, 23 <= shift <= 63
+    return (unsigned int)((mant * 16777215ull + (1ull << (shift - 1u))) >> shift);
+}
+
 // depth test + colour write for one covered pixel centre
 __device__ __forceinline__ void hz_fragment(const HzView& P, const HzTri& T, int px, int py)
 {
@@ -326,7 +364,7 @@ __device__ __forceinline__ void hz_fragment(const HzView& P, const HzTri& T, int
     float zw = T.z0w + (T.dzdx * ddx + T.dzdy * ddy);
     zw = fminf(fmaxf(zw, T.zw_lo), T.zw_hi);                                 // F6
     if(!(zw >= 0.0f && zw <= 1.0f)) return;                                  // F5: view-volume clip per fragment
-    const unsigned int q = (unsigned int)((double)zw * 16777215.0 + 0.5);   // F7
+    const unsigned int q = hz_quantise24(zw);                                // F7
     if(q >= HZ_Q_MAX) return;                                                // cannot pass GL_LESS against 1.0
     float r = T.r0 + (T.drdx * ddx + T.drdy * ddy);
     r = fmaxf(fminf(r, 1.0f), 0.0f);
@@ -337,7 +375,7 @@ __device__ __forceinline__ void hz_fragment(const HzView& P, const HzTri& T, int
 
 // Edge functions E_k(P) = dx_k*(Py - Y_k) - dy_k*(Px - X_k) on the snapped positions (F3); an edge owns its
 // boundary iff it runs downwards, or is horizontal running leftwards (F4).  I = int when every term fits in
-// 32 bits (triangle smaller than 128 pixels), long long otherwise.
+// 32 bits (triangle smaller than 64 pixels), long long otherwise.
 template <typename I>
 struct HzEdges
 {
@@ -377,7 +415,7 @@ __device__ __forceinline__ bool hz_tri_is_small(const HzTri& T)
 {
     const int bx0 = min(min(T.X0, T.X1), T.X2), bx1 = max(max(T.X0, T.X1), T.X2);
     const int by0 = min(min(T.Y0, T.Y1), T.Y2), by1 = max(max(T.Y0, T.Y1), T.Y2);
-    return (bx1 - bx0) < 32768 && (by1 - by0) < 32768;      // every difference < 2^15 => products < 2^30
+    return (bx1 - bx0) < 16384 && (by1 - by0) < 16384;      // every difference < 2^14 => products < 2^28, sums and steps far from 2^31
 }
 
 // ================================================================================================
@@ -438,14 +476,14 @@ cudaError_t hz_launch_pyramid(const int16_t* mosaic, int N, int pitch, short2* m
 // Screen box.  Inside one quadrant around the eye the azimuth atan2(e,n) is monotonic in e and in n, so its
 // extremes over the rectangle sit on two known corners; the elevation atan(h/d) is bounded by the extreme heights
 // over the nearest/farthest horizontal distance.  The same device functions as for real vertices are used and
-// HZ_BOX_MARGIN pixels are added all around, which covers their few-ulp non-monotonicity and the 1/512 pixel of
-// snapping.
+// HZ_BOX_MARGIN (1/64) pixel is added all around, which covers their few-ulp non-monotonicity (< 1/1000 pixel) and
+// the 1/512 pixel of snapping.
 // Depth.  A vertex depth is a monotonic float function of its slant range >= its horizontal distance >= the
 // rectangle's nearest horizontal distance.  A fragment's depth stays within its triangle's vertex depths widened
 // by 4x their extent (F6), and the slant ranges of one triangle's vertices differ by at most their 3-D distance
 // <= sqrt(cell diagonal^2 + (zmax-zmin)^2).  That gives a lower bound for the depth of every fragment.
 
-#define HZ_BOX_MARGIN 0.0625f
+#define HZ_BOX_MARGIN 0.015625f
 
 struct HzBox { int px0, px1, py0, py1; unsigned int qmin; };
 enum { HZ_RECT_DEAD_FAR = 0, HZ_RECT_DEAD_WINDOW = 1, HZ_RECT_ALIVE = 2, HZ_RECT_BOXED = 3 };
@@ -519,10 +557,8 @@ __device__ __forceinline__ unsigned int hz_vis_depth(const HzView& P, int px, in
 // ================================================================================================
 
 #define HZ_WARPS_PER_CTA 8
-#define HZ_STAGE_SLOTS   64        /* < 32 pending + at most 32 new per block */
-#define HZ_SMALL_MAX_PIX 8         /* a lane draws bounding boxes up to this many pixels itself */
-#define HZ_BIG_ROWS      8         /* bigger ones are cut into sub-boxes for k_big */
-#define HZ_BIG_COLS      64
+#define HZ_BIG_ROWS      4         /* large bounding boxes are cut into sub-boxes of this size for k_big: */
+#define HZ_BIG_COLS      32        /* lane = column, a few rows each */
 
 struct HzLaneVtx { int X, Y; };
 
@@ -550,66 +586,141 @@ hz_tri_alive(const HzView& P, const HzLaneVtx& a, const HzLaneVtx& b, const HzLa
     return area > 0;
 }
 
+// one thread walks the whole bounding box; the edge functions are stepped (E(x+1) = E(x) - 256*dy, E(y+1) = E(y) + 256*dx)
 template <typename I>
 __device__ __forceinline__ void hz_draw_box(const HzView& P, const HzTri& T)
 {
     const HzEdges<I> E(T);
+    const I Px = (I)T.px0 * 256 + 128, Py = (I)T.py0 * 256 + 128;
+    I r0 = E.dx0 * (Py - T.Y0) - E.dy0 * (Px - T.X0) - E.b0;      // >= 0 <=> inside, per edge
+    I r1 = E.dx1 * (Py - T.Y1) - E.dy1 * (Px - T.X1) - E.b1;
+    I r2 = E.dx2 * (Py - T.Y2) - E.dy2 * (Px - T.X2) - E.b2;
+    const I sx0 = E.dy0 * 256, sx1 = E.dy1 * 256, sx2 = E.dy2 * 256;
+    const I sy0 = E.dx0 * 256, sy1 = E.dx1 * 256, sy2 = E.dx2 * 256;
     for(int py = T.py0; py <= T.py1; py++)
+    {
+        I e0 = r0, e1 = r1, e2 = r2;
         for(int px = T.px0; px <= T.px1; px++)
-            if(E.inside(T, px, py)) hz_fragment(P, T, px, py);
+        {
+            if((e0 | e1 | e2) >= 0) hz_fragment(P, T, px, py);
+            e0 -= sx0; e1 -= sx1; e2 -= sx2;
+        }
+        r0 += sy0; r1 += sy1; r2 += sy2;
+    }
 }
 
-// set-up + rasterisation of one triangle per lane (GL primitive assembly .. depth test).  Large bounding boxes are
-// cut into HZ_BIG_ROWS x HZ_BIG_COLS sub-boxes and queued for k_big.  Returns the number of queue entries made.
-__device__ __noinline__ unsigned int hz_raster_one(const HzView& P, unsigned int id)
+// Never on the normal path: draws one triangle completely, whatever its size, in the calling thread.  Used when a
+// queue is full.  Kept out of line so that its registers (64-bit edge functions) spill here instead of inflating
+// the kernels that merely might call it.
+__device__ __noinline__ void hz_draw_slow(const HzView& P, unsigned int id)
+{
+    HzTri T;
+    if(!hz_tri_setup(P, id, T, true)) return;
+    if(hz_tri_is_small(T)) hz_draw_box<int>(P, T);
+    else                   hz_draw_box<long long>(P, T);
+}
+
+// What k_big needs of a set-up triangle, as 6 x 16 bytes in the record pool (set-up is ~500 instructions per
+// triangle; k_big has one warp per sub-box and would repeat it for each).
+#define HZ_TRI_RECORD_VEC 6
+__device__ __forceinline__ void hz_tri_store(uint4* rec, const HzTri& T)
+{
+    rec[0] = make_uint4((unsigned)T.X0, (unsigned)T.Y0, (unsigned)T.X1, (unsigned)T.Y1);
+    rec[1] = make_uint4((unsigned)T.X2, (unsigned)T.Y2, (unsigned)T.px0, (unsigned)T.px1);
+    rec[2] = make_uint4((unsigned)T.py0, (unsigned)T.py1, __float_as_uint(T.xw0), __float_as_uint(T.yw0));
+    rec[3] = make_uint4(__float_as_uint(T.z0w), __float_as_uint(T.r0), __float_as_uint(T.dzdx), __float_as_uint(T.dzdy));
+    rec[4] = make_uint4(__float_as_uint(T.drdx), __float_as_uint(T.drdy), __float_as_uint(T.zw_lo), __float_as_uint(T.zw_hi));
+    rec[5] = make_uint4(T.id, 0u, 0u, 0u);
+}
+__device__ __forceinline__ void hz_tri_load(const uint4* rec, HzTri& T)
+{
+    const uint4 a = __ldcg(rec + 0), b = __ldcg(rec + 1), c = __ldcg(rec + 2), d = __ldcg(rec + 3), e = __ldcg(rec + 4),
+                f = __ldcg(rec + 5);
+    T.X0 = (int)a.x; T.Y0 = (int)a.y; T.X1 = (int)a.z; T.Y1 = (int)a.w;
+    T.X2 = (int)b.x; T.Y2 = (int)b.y; T.px0 = (int)b.z; T.px1 = (int)b.w;
+    T.py0 = (int)c.x; T.py1 = (int)c.y; T.xw0 = __uint_as_float(c.z); T.yw0 = __uint_as_float(c.w);
+    T.z0w = __uint_as_float(d.x); T.r0 = __uint_as_float(d.y); T.dzdx = __uint_as_float(d.z); T.dzdy = __uint_as_float(d.w);
+    T.drdx = __uint_as_float(e.x); T.drdy = __uint_as_float(e.y); T.zw_lo = __uint_as_float(e.z); T.zw_hi = __uint_as_float(e.w);
+    T.id = f.x;
+}
+
+// set-up + rasterisation of one triangle by one thread (GL primitive assembly .. depth test).  Bounding boxes above
+// P.small_max_pix pixels, and triangles too large for 32-bit edge functions, go to k_big instead: the set-up
+// triangle into the record pool and one queue entry per HZ_BIG_ROWS x HZ_BIG_COLS sub-box of its bounding box.
+// Returns the number of queue entries made.
+__device__ __forceinline__ unsigned int hz_raster_one(const HzView& P, unsigned int id)
 {
     HzTri T;
     if(!hz_tri_setup(P, id, T, true)) return 0;
     const int bw = T.px1 - T.px0 + 1, bh = T.py1 - T.py0 + 1;
-    if(bw * bh > HZ_SMALL_MAX_PIX)
+    if(bw * bh <= P.small_max_pix && hz_tri_is_small(T))
     {
-        const unsigned int ny = (unsigned int)((bh + HZ_BIG_ROWS - 1) / HZ_BIG_ROWS);
-        const unsigned int nx = (unsigned int)((bw + HZ_BIG_COLS - 1) / HZ_BIG_COLS);
-        const unsigned int slot = atomicAdd(P.big_count, nx * ny);
-        if(slot + nx * ny <= P.big_capacity)
-        {
-            for(unsigned int by = 0; by < ny; by++)
-                for(unsigned int bx = 0; bx < nx; bx++)
-                    P.big_queue[slot + by * nx + bx] = make_uint2(id, by | (bx << 16));
-            return nx * ny;
-        }
-        // queue full: draw it here (slow but correct)
+        hz_draw_box<int>(P, T);
+        return 0;
     }
-    if(hz_tri_is_small(T)) hz_draw_box<int>(P, T);
-    else                   hz_draw_box<long long>(P, T);
-    return 0;
+    const unsigned int ny = (unsigned int)((bh + HZ_BIG_ROWS - 1) / HZ_BIG_ROWS);
+    const unsigned int nx = (unsigned int)((bw + HZ_BIG_COLS - 1) / HZ_BIG_COLS);
+    const unsigned int rec  = atomicAdd(P.bigtri_count, 1u);
+    const unsigned int slot = atomicAdd(P.big_count, nx * ny);
+    if(rec >= P.bigtri_capacity || slot + nx * ny > P.big_capacity)
+    {
+        // pool or queue full: draw it here, and poison the queue slots it reserved (k_big skips those)
+        for(unsigned int k = slot; k < min(slot + nx * ny, P.big_capacity); k++) P.big_queue[k] = make_uint2(0xFFFFFFFFu, 0u);
+        hz_draw_slow(P, id);
+        return 0;
+    }
+    hz_tri_store(P.bigtri + (size_t)rec * HZ_TRI_RECORD_VEC, T);
+    for(unsigned int by = 0; by < ny; by++)
+        for(unsigned int bx = 0; bx < nx; bx++)
+            P.big_queue[slot + by * nx + bx] = make_uint2(rec, by | (bx << 16));
+    return nx * ny;
 }
 
-struct HzWarpState
+__device__ __forceinline__ unsigned int hz_warp_sum(unsigned int v)
 {
-    unsigned int* stage;     // [HZ_STAGE_SLOTS] triangle numbers waiting for set-up
-    HzLaneVtx*    verts;     // [25] snapped vertices of the block being meshed
-    int count;
-    unsigned int n_meshed, n_tris, n_big;
+    #pragma unroll
+    for(int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// height of the vertex lane `lane` (< 25) projects for block (bj,bi): fetched apart from the meshing so that the
+// caller can have the next block's DRAM reads in flight while it works on the current one
+__device__ __forceinline__ float hz_block_vertex_z(const HzView& P, int bj, int bi, int lane)
+{
+    if(lane >= 25) return 0.f;
+    const int r = lane / 5, c = lane - 5 * r;
+    const int vj = min(bj * HZ_BLOCK_CELLS + r, P.N - 1), vi = min(bi * HZ_BLOCK_CELLS + c, P.N - 1);
+    return (float)__ldg(P.mosaic + (size_t)vj * P.pitch + vi);
+}
+
+// What a warp carries while it meshes blocks: 25 snapped vertices of the current block and the numbers of the
+// triangles that passed the exact tests but have not been written to the stage's triangle list yet.
+#define HZ_STAGE_SLOTS 64          /* < 32 pending + at most 32 new per block */
+struct HzMeshWarp
+{
+    HzLaneVtx    verts[25];
+    unsigned int stage[HZ_STAGE_SLOTS];
 };
 
-__device__ __forceinline__ void hz_stage_drain(const HzView& P, HzWarpState& S, int lane, bool all)
+// writes stage[0..count) to the triangle list with one atomic; all lanes call
+__device__ __forceinline__ void hz_stage_flush(const HzView& P, const unsigned int* stage, int count, int lane)
 {
-    __syncwarp();
-    while(S.count >= 32 || (all && S.count > 0))
+    if(count == 0) return;
+    unsigned int base = 0;
+    if(lane == 0) base = atomicAdd(P.tri_count, (unsigned int)count);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    for(int k = lane; k < count; k += 32)
     {
-        const int take = min(S.count, 32);
-        const int base = S.count - take;
-        unsigned int nb = 0;
-        if(lane < take) nb = hz_raster_one(P, S.stage[base + lane]);
-        S.n_big += nb;            // per lane; summed over the warp at the end
-        S.count = base;
-        __syncwarp();
+        if(base + k < P.tri_capacity) P.tri_queue[base + k] = stage[k];
+        else                          hz_draw_slow(P, stage[k]);      // list full
     }
 }
 
-// the 32 triangles of block (bj,bi): lane = triangle
-__device__ __forceinline__ void hz_mesh_block(const HzView& P, int bj, int bi, int lane, HzWarpState& S)
+// The 32 triangles of block (bj,bi): lanes 0..24 project one vertex each (height z), then lane = triangle; the
+// numbers of the triangles that pass the exact integer tests go to the warp's stage, which is written out whenever
+// it holds 32 or more.  `count` is the stage's fill (the same in all lanes).  Returns how many passed.
+__device__ __forceinline__ unsigned int
+hz_mesh_block(const HzView& P, int bj, int bi, int lane, float z, HzMeshWarp& M, int& count)
 {
     const int N = P.N;
     const float halfW = 0.5f * (float)P.W, halfH = 0.5f * (float)P.H;
@@ -617,8 +728,7 @@ __device__ __forceinline__ void hz_mesh_block(const HzView& P, int bj, int bi, i
     {
         const int r = lane / 5, c = lane - 5 * r;
         const int vj = min(bj * HZ_BLOCK_CELLS + r, N - 1), vi = min(bi * HZ_BLOCK_CELLS + c, N - 1);
-        const float z = (float)__ldg(P.mosaic + (size_t)vj * P.pitch + vi);
-        S.verts[lane] = hz_lane_vertex(P, __ldg(P.e_tab + vi), __ldg(P.n_tab + vj), z, halfW, halfH);
+        M.verts[lane] = hz_lane_vertex(P, __ldg(P.e_tab + vi), __ldg(P.n_tab + vj), z, halfW, halfH);
     }
     __syncwarp();
     const int cell = lane >> 1, cr = cell >> 2, cc = cell & 3;
@@ -627,26 +737,47 @@ __device__ __forceinline__ void hz_mesh_block(const HzView& P, int bj, int bi, i
     if(j < N - 1 && i < N - 1)
     {
         // lib:496-508: even triangle (j,i),(j+1,i+1),(j+1,i) ; odd triangle (j,i),(j,i+1),(j+1,i+1)
-        const HzLaneVtx a = S.verts[cr * 5 + cc];
-        const HzLaneVtx d = S.verts[(cr + 1) * 5 + cc + 1];
-        if((lane & 1) == 0) on = hz_tri_alive(P, a, d, S.verts[(cr + 1) * 5 + cc]);
-        else                on = hz_tri_alive(P, a, S.verts[cr * 5 + cc + 1], d);
+        const HzLaneVtx a = M.verts[cr * 5 + cc];
+        const HzLaneVtx d = M.verts[(cr + 1) * 5 + cc + 1];
+        if((lane & 1) == 0) on = hz_tri_alive(P, a, d, M.verts[(cr + 1) * 5 + cc]);
+        else                on = hz_tri_alive(P, a, M.verts[cr * 5 + cc + 1], d);
     }
-    const unsigned int ballot = __ballot_sync(0xffffffffu, on);
-    if(on) S.stage[S.count + __popc(ballot & ((1u << lane) - 1u))] =
+    const unsigned int ballot = __ballot_sync(0xffffffffu, on);     // also orders the reads of verts before the next block
+    if(ballot == 0) return 0;
+    if(on) M.stage[count + __popc(ballot & ((1u << lane) - 1u))] =
                2u * ((unsigned int)j * (unsigned int)(N - 1) + (unsigned int)i) + (unsigned int)(lane & 1);
-    S.count += __popc(ballot);
-    S.n_meshed += 1;
-    S.n_tris += __popc(ballot);
-    if(S.count >= 32) hz_stage_drain(P, S, lane, false);
-    else __syncwarp();
+    count += __popc(ballot);
+    __syncwarp();
+    if(count >= 32)
+    {
+        hz_stage_flush(P, M.stage, count, lane);
+        count = 0;
+        __syncwarp();
+    }
+    return (unsigned int)__popc(ballot);
 }
 
-__device__ __forceinline__ unsigned int hz_warp_sum(unsigned int v)
+// end of a meshing kernel: the leftovers of all warps of the CTA go out with one atomic.  Every thread calls.
+__device__ __forceinline__ void
+hz_stage_flush_cta(const HzView& P, const HzMeshWarp& M, int count, unsigned int* s_total, unsigned int* s_base)
 {
-    #pragma unroll
-    for(int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
+    const int lane = threadIdx.x & 31;
+    if(threadIdx.x == 0) *s_total = 0;
+    __syncthreads();
+    unsigned int off = 0;
+    if(lane == 0 && count) off = atomicAdd(s_total, (unsigned int)count);
+    off = __shfl_sync(0xffffffffu, off, 0);
+    __syncthreads();
+    const unsigned int total = *s_total;
+    if(total == 0) return;
+    if(threadIdx.x == 0) *s_base = atomicAdd(P.tri_count, total);
+    __syncthreads();
+    const unsigned int base = *s_base + off;
+    for(int k = lane; k < count; k += 32)
+    {
+        if(base + k < P.tri_capacity) P.tri_queue[base + k] = M.stage[k];
+        else                          hz_draw_slow(P, M.stage[k]);
+    }
 }
 
 // ================================================================================================
@@ -659,13 +790,13 @@ __device__ __forceinline__ void hz_near_tiles(const HzView& P, int& ti0, int& ti
     tj0 = max(P.eye_tj - P.near_rings, 0); tj1 = min(P.eye_tj + P.near_rings, P.nt - 1);
 }
 
-__global__ void __launch_bounds__(HZ_WARPS_PER_CTA * 32)
+__global__ void __launch_bounds__(HZ_WARPS_PER_CTA * 32, 4)
 k_near(const __grid_constant__ HzView P)
 {
-    __shared__ unsigned int s_stage[HZ_WARPS_PER_CTA][HZ_STAGE_SLOTS];
-    __shared__ HzLaneVtx    s_verts[HZ_WARPS_PER_CTA][25];
+    hz_wait_for_previous_kernel();
+    __shared__ HzMeshWarp s_warp[HZ_WARPS_PER_CTA];
+    __shared__ unsigned int s_total, s_base;
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    HzWarpState S = { s_stage[wib], s_verts[wib], 0, 0u, 0u, 0u };
 
     int ti0, ti1, tj0, tj1;
     hz_near_tiles(P, ti0, ti1, tj0, tj1);
@@ -673,30 +804,22 @@ k_near(const __grid_constant__ HzView P)
     const int bj0 = tj0 * HZ_TILE_BLOCKS, bj1 = min((tj1 + 1) * HZ_TILE_BLOCKS, P.nb);
     const int nbi = bi1 - bi0, nblocks = nbi * (bj1 - bj0);
     const int nwarps = gridDim.x * HZ_WARPS_PER_CTA;
-    unsigned int n_blocks = 0, n_far = 0, n_window = 0;
+    // no conservative tests here: next to the eye nearly every block shows, and what does not falls to the exact
+    // integer tests of hz_mesh_block anyway
+    unsigned int n_blocks = 0, n_tris = 0;
+    int count = 0;
     for(int b = blockIdx.x * HZ_WARPS_PER_CTA + wib; b < nblocks; b += nwarps)
     {
-        const int bj = bj0 + b / nbi, bi = bi0 + b % nbi;
-        const short2 mm = __ldg(P.mm_block + (size_t)bj * P.nb + bi);
-        HzBox B;
-        const int r = hz_rect_test(P, bi * HZ_BLOCK_CELLS, min(bi * HZ_BLOCK_CELLS + HZ_BLOCK_CELLS, P.N - 1),
-                                   bj * HZ_BLOCK_CELLS, min(bj * HZ_BLOCK_CELLS + HZ_BLOCK_CELLS, P.N - 1),
-                                   (float)mm.x, (float)mm.y, B);
         n_blocks++;
-        if(r == HZ_RECT_DEAD_FAR)    { n_far++;    continue; }
-        if(r == HZ_RECT_DEAD_WINDOW) { n_window++; continue; }
-        hz_mesh_block(P, bj, bi, lane, S);
+        const int bj = bj0 + b / nbi, bi = bi0 + b % nbi;
+        n_tris += hz_mesh_block(P, bj, bi, lane, hz_block_vertex_z(P, bj, bi, lane), s_warp[wib], count);
     }
-    hz_stage_drain(P, S, lane, true);
-    const unsigned int n_big = hz_warp_sum(S.n_big);
-    if(lane == 0)
+    hz_stage_flush_cta(P, s_warp[wib], count, &s_total, &s_base);
+    if(P.stats && lane == 0 && n_blocks)
     {
         atomicAdd(P.stats + HZ_STAT_BLOCKS, n_blocks);
-        atomicAdd(P.stats + HZ_STAT_BLOCKS_FAR, n_far);
-        atomicAdd(P.stats + HZ_STAT_BLOCKS_WINDOW, n_window);
-        atomicAdd(P.stats + HZ_STAT_BLOCKS_MESHED, S.n_meshed);
-        atomicAdd(P.stats + HZ_STAT_TRIANGLES, S.n_tris);
-        atomicAdd(P.stats + HZ_STAT_BIG_ENTRIES, n_big);
+        atomicAdd(P.stats + HZ_STAT_BLOCKS_MESHED, n_blocks);
+        atomicAdd(P.stats + HZ_STAT_TRIANGLES, n_tris);
     }
 }
 
@@ -707,8 +830,7 @@ cudaError_t hz_launch_near(const HzView& v, cudaStream_t stream)
     int ctas = (nblocks + HZ_WARPS_PER_CTA - 1) / HZ_WARPS_PER_CTA;
     if(ctas > 148 * 8) ctas = 148 * 8;
     if(ctas < 1) ctas = 1;
-    k_near<<<ctas, HZ_WARPS_PER_CTA * 32, 0, stream>>>(v);
-    return cudaGetLastError();
+    return hz_launch(k_near, dim3(ctas), dim3(HZ_WARPS_PER_CTA * 32), stream, v);
 }
 
 // ================================================================================================
@@ -716,11 +838,12 @@ cudaError_t hz_launch_near(const HzView& v, cudaStream_t stream)
 // ================================================================================================
 //
 // The rest of the mesh is walked in a few bands of growing Chebyshev distance (in tiles) around the eye's tile.
-// Per band three kernels run back to back, each with one unit of work per thread or warp so that no warp ever
+// Per band four kernels run back to back, each with one unit of work per thread or warp so that no warp ever
 // carries a long serial chain:
 //   k_tiles   thread = tile (32x32 cells): conservative test of the whole tile        -> queue of live tiles
 //   k_blocks  thread = block (4x4 cells) of a live tile: the same test on the block   -> queue of live blocks
-//   k_mesh    warp   = live block: projection, exact integer cull, set-up, rasterisation (lane = triangle)
+//   k_mesh    warp   = live block: projection, exact integer cull (lane = triangle)   -> list of triangles
+//   k_raster  thread = triangle: set-up, rasterisation, depth test
 // Everything a band draws is in the visibility buffer before the next band is tested against it, and within a
 // band whatever has already been drawn helps too.
 
@@ -742,45 +865,79 @@ __device__ __forceinline__ void hz_ring_walk(unsigned int k, int& dx, int& dy)
     }
 }
 
-// Eight keys are fetched per round so that the L2 round trips overlap; the loop ends at the first round that
-// shows something not nearer.
+// Eight keys are fetched per round, walking the box row by row, so that the L2 round trips overlap whatever the
+// shape of the box; the walk ends at the first round that shows something not nearer.
 __device__ __forceinline__ bool hz_box_occluded_thread(const HzView& P, const HzBox& B, int max_pix)
 {
     const int w = B.px1 - B.px0 + 1, h = B.py1 - B.py0 + 1;
     const int npix = w * h;
     if(npix > max_pix) return false;
     const size_t Wt = (size_t)(P.x1 - P.x0);
-    const unsigned long long* base = P.vis + (size_t)B.py0 * Wt + (size_t)(B.px0 - P.x0);
+    const unsigned long long* row = P.vis + (size_t)B.py0 * Wt + (size_t)(B.px0 - P.x0);
+    int x = 0;
     for(int p = 0; p < npix; p += 8)
     {
         unsigned int farthest = 0;
         #pragma unroll
         for(int u = 0; u < 8; u++)
         {
-            const int idx = min(p + u, npix - 1);
-            const int y = idx / w, x = idx - y * w;
-            farthest = max(farthest, (unsigned int)(__ldcg(base + (size_t)y * Wt + x) >> 40));
+            if(p + u < npix)
+            {
+                farthest = max(farthest, (unsigned int)(__ldcg(row + x) >> 40));
+                if(++x == w) { x = 0; row += Wt; }
+            }
         }
         if(farthest >= B.qmin) return false;
     }
     return true;
 }
 
-// appends `value` of every lane with `on` to queue[*count...] with one atomic per warp; all 32 lanes must call
-__device__ __forceinline__ void hz_warp_append(bool on, unsigned int value, unsigned int* queue, unsigned int* count, int lane)
+// Appends `value` of every thread with `on` to queue[*count...] with ONE global atomic per CTA: thousands of warps
+// bumping the same counter serialise in one L2 slice, which is what these short kernels would otherwise wait on.
+// Every thread of the CTA must call it (it synchronises the CTA), with `on` false where there is nothing to add.
+struct HzCtaAppend
 {
+    unsigned int count, base;
+    unsigned int buf[256];
+};
+
+__device__ __forceinline__ void
+hz_cta_append(HzCtaAppend& A, bool on, unsigned int value, unsigned int* queue, unsigned int* count)
+{
+    const int lane = threadIdx.x & 31;
+    if(threadIdx.x == 0) A.count = 0;
+    __syncthreads();
     const unsigned int ballot = __ballot_sync(0xffffffffu, on);
-    if(ballot == 0) return;
-    unsigned int base = 0;
-    if(lane == 0) base = atomicAdd(count, (unsigned int)__popc(ballot));
-    base = __shfl_sync(0xffffffffu, base, 0);
-    if(on) queue[base + __popc(ballot & ((1u << lane) - 1u))] = value;
+    unsigned int wbase = 0;
+    if(lane == 0 && ballot) wbase = atomicAdd(&A.count, (unsigned int)__popc(ballot));
+    wbase = __shfl_sync(0xffffffffu, wbase, 0);
+    if(on) A.buf[wbase + __popc(ballot & ((1u << lane) - 1u))] = value;
+    __syncthreads();
+    const unsigned int n = A.count;
+    if(n == 0) return;                                   // the same for the whole CTA
+    if(threadIdx.x == 0) A.base = atomicAdd(count, n);
+    __syncthreads();
+    if(threadIdx.x < n) queue[A.base + threadIdx.x] = A.buf[threadIdx.x];
+}
+
+// diagnostics: per-CTA sums in shared memory, then one global atomic per counter and CTA (only when P.stats is set)
+__device__ __forceinline__ void hz_cta_stats4(unsigned int* s4, unsigned int* global4, unsigned int a, unsigned int b,
+                                              unsigned int c, unsigned int d)
+{
+    if(threadIdx.x < 4) s4[threadIdx.x] = 0;
+    __syncthreads();
+    a = hz_warp_sum(a); b = hz_warp_sum(b); c = hz_warp_sum(c); d = hz_warp_sum(d);
+    if((threadIdx.x & 31) == 0) { atomicAdd(s4 + 0, a); atomicAdd(s4 + 1, b); atomicAdd(s4 + 2, c); atomicAdd(s4 + 3, d); }
+    __syncthreads();
+    if(threadIdx.x < 4 && s4[threadIdx.x]) atomicAdd(global4 + threadIdx.x, s4[threadIdx.x]);
 }
 
 __global__ void __launch_bounds__(256)
 k_tiles(const __grid_constant__ HzView P)
 {
-    const int lane = threadIdx.x & 31;
+    hz_wait_for_previous_kernel();
+    __shared__ HzCtaAppend s_app;
+    __shared__ unsigned int s_stats[4];
     const int nt = P.nt, N = P.N;
     const int rmax = max(max(P.eye_ti, nt - 1 - P.eye_ti), max(P.eye_tj, nt - 1 - P.eye_tj));
     const int ring_hi = min(P.ring_hi, rmax + 1);
@@ -789,9 +946,9 @@ k_tiles(const __grid_constant__ HzView P)
     const unsigned int last  = (unsigned int)((2 * ring_hi - 1) * (2 * ring_hi - 1));
     const unsigned int nth = gridDim.x * blockDim.x;
     unsigned int n_all = 0, n_far = 0, n_window = 0, n_occl = 0;
-    for(unsigned int k0 = first + (blockIdx.x * blockDim.x + threadIdx.x - lane); k0 < last; k0 += nth)
+    for(unsigned int k0 = first + blockIdx.x * blockDim.x; k0 < last; k0 += nth)      // the same trip count CTA-wide
     {
-        const unsigned int k = k0 + lane;
+        const unsigned int k = k0 + threadIdx.x;
         bool on = false;
         unsigned int id = 0;
         if(k < last)
@@ -813,80 +970,112 @@ k_tiles(const __grid_constant__ HzView P)
                 else { on = true; id = (unsigned int)(tj * nt + ti); }
             }
         }
-        hz_warp_append(on, id, P.tile_queue, P.tile_count, lane);
+        hz_cta_append(s_app, on, id, P.tile_queue, P.tile_count);
     }
-    n_all = hz_warp_sum(n_all); n_far = hz_warp_sum(n_far); n_window = hz_warp_sum(n_window); n_occl = hz_warp_sum(n_occl);
-    if(lane == 0 && n_all)
-    {
-        atomicAdd(P.stats + HZ_STAT_TILES, n_all);
-        atomicAdd(P.stats + HZ_STAT_TILES_FAR, n_far);
-        atomicAdd(P.stats + HZ_STAT_TILES_WINDOW, n_window);
-        atomicAdd(P.stats + HZ_STAT_TILES_OCCLUDED, n_occl);
-    }
+    if(P.stats) hz_cta_stats4(s_stats, P.stats + HZ_STAT_TILES, n_all, n_far, n_window, n_occl);
 }
 
 __global__ void __launch_bounds__(256)
 k_blocks(const __grid_constant__ HzView P)
 {
-    const int lane = threadIdx.x & 31;
+    hz_wait_for_previous_kernel();
+    __shared__ HzCtaAppend s_app;
+    __shared__ unsigned int s_stats[4];
     const int nt = P.nt, nb = P.nb, N = P.N;
     const unsigned int total = *P.tile_count * (unsigned int)(HZ_TILE_BLOCKS * HZ_TILE_BLOCKS);
     const unsigned int nth = gridDim.x * blockDim.x;
     unsigned int n_all = 0, n_far = 0, n_window = 0, n_occl = 0;
-    for(unsigned int t0 = blockIdx.x * blockDim.x + threadIdx.x - lane; t0 < total; t0 += nth)
+    for(unsigned int t0 = blockIdx.x * blockDim.x; t0 < total; t0 += nth)     // total is a multiple of 64: no ragged end
     {
-        const unsigned int t = t0 + lane;          // total is a multiple of 64: every lane has an entry
-        const unsigned int tile = P.tile_queue[t >> 6];
-        const int tj = (int)(tile / (unsigned int)nt), ti = (int)(tile % (unsigned int)nt);
-        const int bj = tj * HZ_TILE_BLOCKS + (int)((t >> 3) & 7u), bi = ti * HZ_TILE_BLOCKS + (int)(t & 7u);
+        const unsigned int t = t0 + threadIdx.x;
         bool on = false;
-        if(bj < nb && bi < nb)
+        unsigned int id = 0;
+        if(t < total)
         {
-            const short2 mm = __ldg(P.mm_block + (size_t)bj * nb + bi);
-            HzBox B;
-            const int c0 = bi * HZ_BLOCK_CELLS, r0 = bj * HZ_BLOCK_CELLS;
-            const int r = hz_rect_test(P, c0, min(c0 + HZ_BLOCK_CELLS, N - 1), r0, min(r0 + HZ_BLOCK_CELLS, N - 1),
-                                       (float)mm.x, (float)mm.y, B);
-            n_all++;
-            if(r == HZ_RECT_DEAD_FAR)         n_far++;
-            else if(r == HZ_RECT_DEAD_WINDOW) n_window++;
-            else if(r == HZ_RECT_BOXED && hz_box_occluded_thread(P, B, P.occl_block_max_pix)) n_occl++;
-            else on = true;
+            const unsigned int tile = P.tile_queue[t >> 6];
+            const int tj = (int)(tile / (unsigned int)nt), ti = (int)(tile % (unsigned int)nt);
+            const int bj = tj * HZ_TILE_BLOCKS + (int)((t >> 3) & 7u), bi = ti * HZ_TILE_BLOCKS + (int)(t & 7u);
+            if(bj < nb && bi < nb)
+            {
+                const short2 mm = __ldg(P.mm_block + (size_t)bj * nb + bi);
+                HzBox B;
+                const int c0 = bi * HZ_BLOCK_CELLS, r0 = bj * HZ_BLOCK_CELLS;
+                const int r = hz_rect_test(P, c0, min(c0 + HZ_BLOCK_CELLS, N - 1), r0, min(r0 + HZ_BLOCK_CELLS, N - 1),
+                                           (float)mm.x, (float)mm.y, B);
+                n_all++;
+                if(r == HZ_RECT_DEAD_FAR)         n_far++;
+                else if(r == HZ_RECT_DEAD_WINDOW) n_window++;
+                else if(r == HZ_RECT_BOXED && hz_box_occluded_thread(P, B, P.occl_block_max_pix)) n_occl++;
+                else { on = true; id = (unsigned int)(bj * nb + bi); }
+            }
         }
-        hz_warp_append(on, (unsigned int)(bj * nb + bi), P.block_queue, P.block_count, lane);
+        hz_cta_append(s_app, on, id, P.block_queue, P.block_count);
     }
-    n_all = hz_warp_sum(n_all); n_far = hz_warp_sum(n_far); n_window = hz_warp_sum(n_window); n_occl = hz_warp_sum(n_occl);
-    if(lane == 0 && n_all)
+    if(P.stats) hz_cta_stats4(s_stats, P.stats + HZ_STAT_BLOCKS, n_all, n_far, n_window, n_occl);
+}
+
+__global__ void __launch_bounds__(HZ_WARPS_PER_CTA * 32, 4)
+k_mesh(const __grid_constant__ HzView P)
+{
+    hz_wait_for_previous_kernel();
+    __shared__ HzMeshWarp s_warp[HZ_WARPS_PER_CTA];
+    __shared__ unsigned int s_total, s_base;
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const unsigned int n = *P.block_count;
+    const unsigned int nwarps = gridDim.x * HZ_WARPS_PER_CTA;
+    unsigned int b = blockIdx.x * HZ_WARPS_PER_CTA + wib;
+    int bj = 0, bi = 0;
+    float z = 0.f;
+    if(b < n)
     {
-        atomicAdd(P.stats + HZ_STAT_BLOCKS, n_all);
-        atomicAdd(P.stats + HZ_STAT_BLOCKS_FAR, n_far);
-        atomicAdd(P.stats + HZ_STAT_BLOCKS_WINDOW, n_window);
-        atomicAdd(P.stats + HZ_STAT_BLOCKS_OCCLUDED, n_occl);
+        const unsigned int id = P.block_queue[b];
+        bj = (int)(id / (unsigned int)P.nb); bi = (int)(id % (unsigned int)P.nb);
+        z = hz_block_vertex_z(P, bj, bi, lane);
+    }
+    unsigned int n_meshed = 0, n_tris = 0;
+    int count = 0;
+    while(b < n)
+    {
+        // next block's queue entry and heights first: their latency hides behind this block's arithmetic
+        const unsigned int b_next = b + nwarps;
+        int bj_next = 0, bi_next = 0;
+        float z_next = 0.f;
+        if(b_next < n)
+        {
+            const unsigned int id = P.block_queue[b_next];
+            bj_next = (int)(id / (unsigned int)P.nb); bi_next = (int)(id % (unsigned int)P.nb);
+            z_next = hz_block_vertex_z(P, bj_next, bi_next, lane);
+        }
+        n_tris += hz_mesh_block(P, bj, bi, lane, z, s_warp[wib], count);
+        n_meshed++;
+        b = b_next; bj = bj_next; bi = bi_next; z = z_next;
+    }
+    hz_stage_flush_cta(P, s_warp[wib], count, &s_total, &s_base);
+    if(P.stats && lane == 0 && n_meshed)
+    {
+        atomicAdd(P.stats + HZ_STAT_BLOCKS_MESHED, n_meshed);
+        atomicAdd(P.stats + HZ_STAT_TRIANGLES, n_tris);
     }
 }
 
-__global__ void __launch_bounds__(HZ_WARPS_PER_CTA * 32)
-k_mesh(const __grid_constant__ HzView P)
+// ---- k_raster: one thread per triangle of a stage's list
+
+__global__ void __launch_bounds__(256, 3)
+k_raster(const __grid_constant__ HzView P)
 {
-    __shared__ unsigned int s_stage[HZ_WARPS_PER_CTA][HZ_STAGE_SLOTS];
-    __shared__ HzLaneVtx    s_verts[HZ_WARPS_PER_CTA][25];
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    HzWarpState S = { s_stage[wib], s_verts[wib], 0, 0u, 0u, 0u };
-    const unsigned int n = *P.block_count;
-    const unsigned int nwarps = gridDim.x * HZ_WARPS_PER_CTA;
-    for(unsigned int b = blockIdx.x * HZ_WARPS_PER_CTA + wib; b < n; b += nwarps)
-    {
-        const unsigned int id = P.block_queue[b];
-        hz_mesh_block(P, (int)(id / (unsigned int)P.nb), (int)(id % (unsigned int)P.nb), lane, S);
-    }
-    hz_stage_drain(P, S, lane, true);
-    const unsigned int n_big = hz_warp_sum(S.n_big);
-    if(lane == 0 && S.n_meshed)
-    {
-        atomicAdd(P.stats + HZ_STAT_BLOCKS_MESHED, S.n_meshed);
-        atomicAdd(P.stats + HZ_STAT_TRIANGLES, S.n_tris);
-        atomicAdd(P.stats + HZ_STAT_BIG_ENTRIES, n_big);
-    }
+    hz_wait_for_previous_kernel();
+    const unsigned int n = min(*P.tri_count, P.tri_capacity);
+    const unsigned int nth = gridDim.x * blockDim.x;
+    unsigned int n_big = 0;
+    for(unsigned int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += nth)
+        n_big += hz_raster_one(P, P.tri_queue[t]);
+    n_big = hz_warp_sum(n_big);
+    if(P.stats && (threadIdx.x & 31) == 0 && n_big) atomicAdd(P.stats + HZ_STAT_BIG_ENTRIES, n_big);
+}
+
+cudaError_t hz_launch_raster(const HzView& v, cudaStream_t stream)
+{
+    return hz_launch(k_raster, dim3(148 * 6), dim3(256), stream, v);
 }
 
 cudaError_t hz_launch_band(const HzView& v, cudaStream_t stream, int* launches)
@@ -898,43 +1087,55 @@ cudaError_t hz_launch_band(const HzView& v, cudaStream_t stream, int* launches)
     const long long ntiles = (long long)(2 * ring_hi - 1) * (2 * ring_hi - 1) - (long long)(2 * v.ring_lo - 1) * (2 * v.ring_lo - 1);
     long long ctas = (ntiles + 255) / 256;
     if(ctas > 148 * 8) ctas = 148 * 8;
-    k_tiles<<<(unsigned)ctas, 256, 0, stream>>>(v);
-    k_blocks<<<148 * 8, 256, 0, stream>>>(v);
-    k_mesh<<<148 * 4, HZ_WARPS_PER_CTA * 32, 0, stream>>>(v);
-    *launches = 3;
-    return cudaGetLastError();
+    cudaError_t e;
+    if((e = hz_launch(k_tiles,  dim3((unsigned)ctas), dim3(256), stream, v)) != cudaSuccess) return e;
+    if((e = hz_launch(k_blocks, dim3(148 * 8), dim3(256), stream, v)) != cudaSuccess) return e;
+    if((e = hz_launch(k_mesh,   dim3(148 * 4), dim3(HZ_WARPS_PER_CTA * 32), stream, v)) != cudaSuccess) return e;
+    if((e = hz_launch(k_raster, dim3(148 * 6), dim3(256), stream, v)) != cudaSuccess) return e;
+    *launches = 4;
+    return cudaSuccess;
 }
 
 // ================================================================================================
 // k_big: one warp per (triangle, sub-box), lanes spread over the sub-box's pixels
 // ================================================================================================
 
+// lane = column of the sub-box; each lane steps its edge functions down the rows
 template <typename I>
 __device__ __forceinline__ void hz_draw_subbox(const HzView& P, const HzTri& T, int x0, int x1, int y0, int y1, int lane)
 {
     const HzEdges<I> E(T);
     if(E.box_outside(T, x0, x1, y0, y1)) return;
-    const int bw = x1 - x0 + 1;
-    const int npix = bw * (y1 - y0 + 1);
-    for(int p = lane; p < npix; p += 32)
+    const int px = x0 + lane;
+    if(px > x1) return;
+    const I Px = (I)px * 256 + 128, Py = (I)y0 * 256 + 128;
+    I e0 = E.dx0 * (Py - T.Y0) - E.dy0 * (Px - T.X0) - E.b0;      // >= 0 <=> inside, per edge
+    I e1 = E.dx1 * (Py - T.Y1) - E.dy1 * (Px - T.X1) - E.b1;
+    I e2 = E.dx2 * (Py - T.Y2) - E.dy2 * (Px - T.X2) - E.b2;
+    const I sy0 = E.dx0 * 256, sy1 = E.dx1 * 256, sy2 = E.dx2 * 256;
+    for(int py = y0; py <= y1; py++)
     {
-        const int py = y0 + p / bw, px = x0 + p % bw;
-        if(E.inside(T, px, py)) hz_fragment(P, T, px, py);
+        if((e0 | e1 | e2) >= 0) hz_fragment(P, T, px, py);
+        e0 += sy0; e1 += sy1; e2 += sy2;
     }
 }
 
 __global__ void __launch_bounds__(256)
 k_big(const __grid_constant__ HzView P)
 {
+    hz_wait_for_previous_kernel();
+    // every slot below min(count, capacity) was written: with a record index, or poisoned by a triangle that found
+    // the record pool or the queue exhausted and drew itself (hz_raster_one)
     unsigned int count = *P.big_count;
     if(count > P.big_capacity) count = P.big_capacity;
     const int lane = threadIdx.x & 31;
     const unsigned int nwarps = gridDim.x * (blockDim.x >> 5);
     for(unsigned int t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); t < count; t += nwarps)
     {
-        const uint2 entry = P.big_queue[t];
+        const uint2 entry = __ldcg(P.big_queue + t);
+        if(entry.x >= P.bigtri_capacity) continue;
         HzTri T;
-        if(!hz_tri_setup(P, entry.x, T, true)) continue;      // cannot happen: it was accepted when queued
+        hz_tri_load(P.bigtri + (size_t)entry.x * HZ_TRI_RECORD_VEC, T);
         const int y0 = T.py0 + (int)(entry.y & 0xFFFFu) * HZ_BIG_ROWS, y1 = min(y0 + HZ_BIG_ROWS - 1, T.py1);
         const int x0 = T.px0 + (int)(entry.y >> 16) * HZ_BIG_COLS,     x1 = min(x0 + HZ_BIG_COLS - 1, T.px1);
         if(hz_tri_is_small(T)) hz_draw_subbox<int>(P, T, x0, x1, y0, y1, lane);
@@ -944,8 +1145,7 @@ k_big(const __grid_constant__ HzView P)
 
 cudaError_t hz_launch_big(const HzView& v, cudaStream_t stream)
 {
-    k_big<<<148 * 8, 256, 0, stream>>>(v);
-    return cudaGetLastError();
+    return hz_launch(k_big, dim3(148 * 8), dim3(256), stream, v);
 }
 
 // ================================================================================================
@@ -968,6 +1168,7 @@ __device__ __forceinline__ float hz_range_of_key(unsigned long long key, float t
 __global__ void __launch_bounds__(256)
 k_resolve4(const HzResolve R)
 {
+    hz_wait_for_previous_kernel();
     const int groups_per_row = R.Wt >> 2;
     const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if(g >= (long long)groups_per_row * R.H) return;
@@ -1013,6 +1214,7 @@ k_resolve4(const HzResolve R)
 __global__ void __launch_bounds__(256)
 k_resolve1(const HzResolve R)
 {
+    hz_wait_for_previous_kernel();
     const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if(g >= (long long)R.Wt * R.H) return;
     const int y = (int)(g / R.Wt), x = (int)(g % R.Wt);
@@ -1034,14 +1236,13 @@ cudaError_t hz_launch_resolve(const HzResolve& r, cudaStream_t stream)
     if(aligned)
     {
         const long long n = (long long)(r.Wt / 4) * r.H;
-        k_resolve4<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(r);
+        return hz_launch(k_resolve4, dim3((unsigned)((n + 255) / 256)), dim3(256), stream, r);
     }
     else
     {
         const long long n = (long long)r.Wt * r.H;
-        k_resolve1<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(r);
+        return hz_launch(k_resolve1, dim3((unsigned)((n + 255) / 256)), dim3(256), stream, r);
     }
-    return cudaGetLastError();
 }
 
 // ================================================================================================

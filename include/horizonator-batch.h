@@ -92,7 +92,8 @@ bool horizonator_profile_read(const horizonator_context_t* ctx, float out_ms[6],
  * the cull and were set up for rasterisation. */
 bool horizonator_last_render_stats(const horizonator_context_t* ctx, unsigned int out[5]);
 
-/* Culling counters of the most recent render: out[0..3] far-pass tiles looked at / dropped
+/* Culling counters of the most recent render, collected only while horizonator_profile_enable()
+ * is on (all zero otherwise): out[0..3] far-pass tiles looked at / dropped
  * beyond zfar / dropped without a pixel centre in their screen box / dropped as occluded,
  * out[4..7] the same for 4x4-cell blocks (both passes), out[8] blocks whose 32 triangles were
  * projected and tested exactly, out[9] triangles set up, out[10] large-triangle queue entries;

@@ -2,8 +2,8 @@
 # parameter sweep of the band structure / occlusion-box limits / lanes on the C2 benchmark (GPU box)
 # each config: near_rings|bands|tile_pix|block_pix|batch
 for cfg in "$@"; do
-  IFS='|' read nr bands tp bp batch <<< "$cfg"
-  HORIZONATOR_NEAR_RINGS=$nr HORIZONATOR_BANDS=$bands HORIZONATOR_OCCL_TILE_PIX=$tp HORIZONATOR_OCCL_BLOCK_PIX=$bp HORIZONATOR_LANES=$batch \
+  IFS="|" read nr bands tp bp batch sp <<< "$cfg"
+  HORIZONATOR_NEAR_RINGS=$nr HORIZONATOR_BANDS=$bands HORIZONATOR_OCCL_TILE_PIX=$tp HORIZONATOR_OCCL_BLOCK_PIX=$bp HORIZONATOR_LANES=$batch HORIZONATOR_SMALL_PIX=${sp:-64} \
     python bench.py --no-cpu-baseline --steps 40 --batch $batch 2>/dev/null | python -c "
 import json,sys
 d=json.loads(sys.stdin.read()); r=d['roofline']; k=r['kernel_ms_single_panorama']; c=d['aux']['culling']
