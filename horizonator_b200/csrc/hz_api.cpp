@@ -36,7 +36,7 @@ constexpr unsigned BIG_CAPACITY = 1u << 21;      // (triangle, sub-box) pairs pe
 constexpr unsigned TRI_CAPACITY = 1u << 23;      // triangles per stage awaiting set-up; overflow is drawn inline
 constexpr unsigned BIGTRI_CAPACITY = 1u << 18;   // set-up records of triangles queued for the large-triangle kernel
 constexpr int   PROF_EVENTS     = 7;            // 6 stages per render
-constexpr int   MAX_BANDS       = 6;
+constexpr int   MAX_BANDS       = HZ_MAX_BANDS;
 // [0] big_count near, [1] big_count bands, [2] tri_count near, [3] big-triangle records, [4+3b] tile_count,
 // [5+3b] block_count, [6+3b] tri_count of band b, then the stats
 constexpr int   STATS_AT        = 4 + 3 * MAX_BANDS;
@@ -48,6 +48,8 @@ struct ViewState
     float viewer_cell_i = 0, viewer_cell_j = 0, viewer_z = 0, cos_viewer_lat = 1;
     float az_deg0 = -45.f, az_deg1 = 45.f;
 };
+
+constexpr int PARAM_RING = 16;
 
 // everything one render writes besides its outputs
 struct Scratch
@@ -62,6 +64,16 @@ struct Scratch
     uint32_t* d_counters  = nullptr;   // [N_COUNTERS]
     uint8_t*  d_image  = nullptr;      // lanes only: staging of one view's outputs for the host-pointer batch call
     float*    d_ranges = nullptr;
+
+    // parameters of the render in flight: the kernels read d_views; the host fills a slot of the pinned ring and
+    // copies it over (the ring lets several renders be queued without waiting)
+    HzView* d_views = nullptr;         // [HZ_V_COUNT]
+    HzView* h_views = nullptr;         // pinned [PARAM_RING][HZ_V_COUNT]
+    cudaEvent_t ring_ev[PARAM_RING] = {};
+    int ring_next = 0;
+    cudaGraphExec_t graph = nullptr;   // the standard chain, captured on first use
+    int  graph_launches = 0;
+    bool graph_failed = false;
 };
 
 struct Slot
@@ -109,6 +121,7 @@ struct Slot
 
     // optional per-kernel timing: PROF_EVENTS events per recorded render
     bool profiling = false;
+    bool use_graphs = true;
     bool collect_stats = false;      // culling counters (horizonator_render_counters); off: the kernels skip them
     std::vector<cudaEvent_t> prof_events;
     size_t prof_used = 0;
@@ -137,8 +150,16 @@ struct DeviceGuard
     ~DeviceGuard() { if(prev >= 0) cudaSetDevice(prev); }
 };
 
+void drop_graph(Scratch& c)
+{
+    if(c.graph) cudaGraphExecDestroy(c.graph);
+    c.graph = nullptr; c.graph_failed = false;
+}
+
 void free_target(Slot& s)
 {
+    drop_graph(s.main);
+    for(Scratch& l : s.lanes) drop_graph(l);
     cudaFree(s.main.d_vis); s.main.d_vis = nullptr;
     for(Scratch& l : s.lanes)
     {
@@ -178,6 +199,9 @@ void free_scratch(Scratch& c)
     cudaFree(c.d_vis); cudaFree(c.d_e); cudaFree(c.d_n);
     cudaFree(c.d_tile_queue); cudaFree(c.d_block_queue); cudaFree(c.d_tri_queue); cudaFree(c.d_big_queue);
     cudaFree(c.d_counters); cudaFree(c.d_bigtri);
+    cudaFree(c.d_views); cudaFreeHost(c.h_views);
+    for(cudaEvent_t e : c.ring_ev) if(e) cudaEventDestroy(e);
+    if(c.graph) cudaGraphExecDestroy(c.graph);
     cudaFree(c.d_image); cudaFree(c.d_ranges);
     if(c.done) cudaEventDestroy(c.done);
     if(c.stream) cudaStreamDestroy(c.stream);
@@ -195,6 +219,9 @@ bool alloc_scratch(const Slot& s, Scratch& c, bool own_stream)
     CUDA_TRY(cudaMalloc(&c.d_big_queue, 2 * (size_t)BIG_CAPACITY * sizeof(uint2)));
     CUDA_TRY(cudaMalloc(&c.d_bigtri, (size_t)BIGTRI_CAPACITY * 6 * sizeof(uint4)));
     CUDA_TRY(cudaMalloc(&c.d_counters, N_COUNTERS * sizeof(uint32_t)));
+    CUDA_TRY(cudaMalloc(&c.d_views, HZ_V_COUNT * sizeof(HzView)));
+    CUDA_TRY(cudaMallocHost(&c.h_views, (size_t)PARAM_RING * HZ_V_COUNT * sizeof(HzView)));
+    for(cudaEvent_t& e : c.ring_ev) CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     if(own_stream)
     {
         CUDA_TRY(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
@@ -289,6 +316,63 @@ bool tanel_for(Slot& s, float az_deg0, float az_deg1, cudaStream_t st, const flo
     return true;
 }
 
+// the kernels of one render, in order, reading their parameters from sc.d_views; hv = the host copy of those
+bool launch_chain(Slot& s, Scratch& sc, const HzView* hv, bool worst_case, bool resolve, cudaStream_t st,
+                  cudaEvent_t* ev, int* launches)
+{
+    const HzView* dv = sc.d_views;
+    int n = 0;
+    if(ev) CUDA_TRY(cudaEventRecord(ev[0], st));
+    CUDA_TRY(hz_launch_prepare(hv[HZ_V_NEAR], dv + HZ_V_NEAR, st)); n++;
+    if(ev) CUDA_TRY(cudaEventRecord(ev[1], st));
+    CUDA_TRY(hz_launch_near(hv[HZ_V_NEAR], dv + HZ_V_NEAR, st)); n++;
+    CUDA_TRY(hz_launch_raster(dv + HZ_V_NEAR, st)); n++;
+    if(ev) CUDA_TRY(cudaEventRecord(ev[2], st));
+    CUDA_TRY(hz_launch_big(dv + HZ_V_NEAR, st)); n++;
+    if(ev) CUDA_TRY(cudaEventRecord(ev[3], st));
+    for(int b = 0; b < s.n_bands; b++)
+    {
+        int k = 0;
+        CUDA_TRY(hz_launch_band(hv[HZ_V_BAND0 + b], dv + HZ_V_BAND0 + b, worst_case, st, &k));
+        n += k;
+    }
+    if(ev) CUDA_TRY(cudaEventRecord(ev[4], st));
+    CUDA_TRY(hz_launch_big(dv + HZ_V_FAR, st)); n++;
+    if(ev) CUDA_TRY(cudaEventRecord(ev[5], st));
+    if(resolve) { CUDA_TRY(hz_launch_resolve(hv[HZ_V_NEAR], dv + HZ_V_NEAR, st)); n++; }
+    if(ev) CUDA_TRY(cudaEventRecord(ev[6], st));
+    *launches = n;
+    return true;
+}
+
+// Captures the standard chain (full width, vectorised resolve, grids sized for any eye position) once per scratch
+// set; every later standard render is one cudaGraphLaunch after the parameter copy.  A dozen separate launches cost
+// more host time than the GPU needs for the render.
+bool capture_graph(Slot& s, Scratch& sc, const HzView* hv)
+{
+    cudaStream_t cs = nullptr;
+    if(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); return false; }
+    cudaGraph_t g = nullptr;
+    bool ok = cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+    int launches = 0;
+    if(ok)
+    {
+        ok = launch_chain(s, sc, hv, true, true, cs, nullptr, &launches);
+        if(cudaStreamEndCapture(cs, &g) != cudaSuccess) ok = false;
+    }
+    if(ok && cudaGraphInstantiate(&sc.graph, g, 0) != cudaSuccess) { ok = false; sc.graph = nullptr; }
+    if(g) cudaGraphDestroy(g);
+    cudaStreamDestroy(cs);
+    if(!ok)
+    {
+        cudaGetLastError();
+        MSG("CUDA graph capture of the render chain failed; launching the kernels one by one instead");
+        return false;
+    }
+    sc.graph_launches = launches;
+    return true;
+}
+
 // enqueue one render of columns [x0,x1) into d_image / d_ranges (device, either may be null)
 bool enqueue_render(Slot& s, Scratch& sc, const ViewState& vs, int x0, int x1,
                     uint8_t* d_image, float* d_ranges, cudaStream_t st)
@@ -338,6 +422,51 @@ bool enqueue_render(Slot& s, Scratch& sc, const ViewState& vs, int x0, int x1,
     const float* d_tanel = nullptr;
     if(d_ranges && !tanel_for(s, vs.az_deg0, vs.az_deg1, st, &d_tanel)) return false;
 
+    v.counters = sc.d_counters; v.ncounters = N_COUNTERS;
+    v.tanel = d_tanel; v.out_image = d_image; v.out_ranges = d_ranges;
+
+    // ---- the parameter block: variants of v for the near pass, the far queue and each band, into a slot of the
+    // pinned ring, then one small copy to the device
+    const int slot = sc.ring_next;
+    sc.ring_next = (sc.ring_next + 1) % PARAM_RING;
+    CUDA_TRY(cudaEventSynchronize(sc.ring_ev[slot]));             // the copy that last used this slot is done
+    HzView* hv = sc.h_views + (size_t)slot * HZ_V_COUNT;
+    for(int k = 0; k < HZ_V_COUNT; k++) hv[k] = v;
+    hv[HZ_V_NEAR].tri_count = sc.d_counters + 2;
+    hv[HZ_V_NEAR].big_queue = sc.d_big_queue;                 hv[HZ_V_NEAR].big_count = sc.d_counters + 0;
+    for(int k = HZ_V_FAR; k < HZ_V_COUNT; k++)
+    {
+        hv[k].big_queue = sc.d_big_queue + BIG_CAPACITY;      hv[k].big_count = sc.d_counters + 1;
+    }
+    {
+        int lo = s.near_rings + 1;
+        for(int b = 0; b < s.n_bands; b++)
+        {
+            HzView& vb = hv[HZ_V_BAND0 + b];
+            vb.ring_lo = lo; vb.ring_hi = s.band_end[b] > lo ? s.band_end[b] : lo;
+            vb.tile_count = sc.d_counters + 4 + 3 * b; vb.block_count = sc.d_counters + 5 + 3 * b;
+            vb.tri_count  = sc.d_counters + 6 + 3 * b;
+            lo = vb.ring_hi;
+        }
+    }
+    CUDA_TRY(cudaMemcpyAsync(sc.d_views, hv, HZ_V_COUNT * sizeof(HzView), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaEventRecord(sc.ring_ev[slot], st));
+
+    // ---- the kernels: a replay of the captured graph where the chain has its standard shape, one by one otherwise
+    const bool standard = !s.profiling && s.use_graphs && x0 == 0 && x1 == s.W && (d_image || d_ranges) &&
+                          hz_resolve_is_vectorisable(v);
+    if(standard && !sc.graph_failed)
+    {
+        if(sc.graph == nullptr && !capture_graph(s, sc, hv)) sc.graph_failed = true;
+        if(sc.graph != nullptr)
+        {
+            CUDA_TRY(cudaGraphLaunch(sc.graph, st));
+            s.launches_last = sc.graph_launches;
+            if(&sc == &s.main) s.have_render = true;
+            return true;
+        }
+    }
+
     cudaEvent_t* ev = nullptr;
     if(s.profiling)
     {
@@ -350,48 +479,9 @@ bool enqueue_render(Slot& s, Scratch& sc, const ViewState& vs, int x0, int x1,
         ev = &s.prof_events[s.prof_used];
         s.prof_used += PROF_EVENTS;
     }
-    HzView v_near = v, v_far = v;
-    v_near.tri_count = sc.d_counters + 2;
-    v_near.big_queue = sc.d_big_queue;                 v_near.big_count = sc.d_counters + 0;
-    v_far.big_queue  = sc.d_big_queue + BIG_CAPACITY;  v_far.big_count  = sc.d_counters + 1;
-
-    if(ev) CUDA_TRY(cudaEventRecord(ev[0], st));
-    CUDA_TRY(hz_launch_prepare(v, sc.d_counters, N_COUNTERS, st));
-    if(ev) CUDA_TRY(cudaEventRecord(ev[1], st));
-    CUDA_TRY(hz_launch_near(v_near, st));
-    CUDA_TRY(hz_launch_raster(v_near, st));
-    if(ev) CUDA_TRY(cudaEventRecord(ev[2], st));
-    CUDA_TRY(hz_launch_big(v_near, st));
-    if(ev) CUDA_TRY(cudaEventRecord(ev[3], st));
-    int band_launches = 0;
-    {
-        int lo = s.near_rings + 1;
-        for(int b = 0; b < s.n_bands; b++)
-        {
-            HzView vb = v_far;
-            vb.ring_lo = lo; vb.ring_hi = s.band_end[b] > lo ? s.band_end[b] : lo;
-            vb.tile_count = sc.d_counters + 4 + 3 * b; vb.block_count = sc.d_counters + 5 + 3 * b;
-            vb.tri_count  = sc.d_counters + 6 + 3 * b;
-            int n = 0;
-            CUDA_TRY(hz_launch_band(vb, st, &n));
-            band_launches += n;
-            lo = vb.ring_hi;
-        }
-    }
-    if(ev) CUDA_TRY(cudaEventRecord(ev[4], st));
-    CUDA_TRY(hz_launch_big(v_far, st));
-    if(ev) CUDA_TRY(cudaEventRecord(ev[5], st));
-    s.launches_last = 5 + band_launches;
-    if(d_image || d_ranges)
-    {
-        HzResolve r{};
-        r.vis = sc.d_vis; r.Wt = x1 - x0; r.H = s.H;
-        r.tanel = d_tanel; r.znear = s.znear; r.zfar = s.zfar;
-        r.image = d_image; r.ranges = d_ranges;
-        CUDA_TRY(hz_launch_resolve(r, st));
-        s.launches_last++;
-    }
-    if(ev) CUDA_TRY(cudaEventRecord(ev[6], st));
+    int launches = 0;
+    if(!launch_chain(s, sc, hv, false, d_image || d_ranges, st, ev, &launches)) return false;
+    s.launches_last = launches;
     if(&sc == &s.main) s.have_render = (x0 == 0 && x1 == s.W);
     return true;
 }
@@ -532,6 +622,7 @@ bool horizonator_init(horizonator_context_t* ctx,
             s->band_end[n++] = 1 << 20;
             s->n_bands = n;
         }
+        if(const char* env = getenv("HORIZONATOR_GRAPHS")) s->use_graphs = atoi(env) != 0;
         if(const char* env = getenv("HORIZONATOR_LANES")) s->n_lanes_max = atoi(env) < 1 ? 1 : (atoi(env) > 32 ? 32 : atoi(env));
         if(fail(cudaMalloc(&s->d_mm_block, (size_t)s->nb * s->nb * sizeof(short2)), "cudaMalloc(pyramid)")) break;
         if(fail(cudaMalloc(&s->d_mm_tile, (size_t)s->nt * s->nt * sizeof(short2)), "cudaMalloc(pyramid)")) break;

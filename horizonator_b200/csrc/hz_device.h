@@ -107,26 +107,32 @@ struct HzView
     uint32_t* stats;             // [HZ_STAT_COUNT]
 
     float cell_diag2;            // (east cell size)^2 + (north cell size)^2 in metres^2, rounded up
-};
 
-struct HzResolve
-{
-    const unsigned long long* vis;
-    int   Wt, H;                 // target width (x1-x0), height
+    // k_prepare zeroes these; k_resolve turns the visibility keys into the outputs
+    uint32_t* counters;
+    int       ncounters;
     const float* tanel;          // [H] tan(elevation) per GL row, host-computed (lib:1007-1012)
-    float znear, zfar;
-    uint8_t* image;              // [H][Wt][3] B,G,R top row first, or nullptr
-    float*   ranges;             // [H][Wt] top row first, or nullptr
+    uint8_t*  out_image;         // [H][x1-x0][3] B,G,R top row first, or nullptr
+    float*    out_ranges;        // [H][x1-x0] top row first, or nullptr
 };
 
-// All launches are asynchronous on `stream`.
+// A render's parameters live in device memory as a small array of HzView variants that differ only in the
+// queue/counter/band fields: the kernels take a pointer to their variant, so that the same captured CUDA graph can
+// be replayed for every view after one small host->device copy.
+enum { HZ_V_NEAR = 0, HZ_V_FAR = 1, HZ_V_BAND0 = 2 };
+constexpr int HZ_MAX_BANDS = 6;
+constexpr int HZ_V_COUNT   = HZ_V_BAND0 + HZ_MAX_BANDS;
+
+// All launches are asynchronous on `stream`.  `v` is the host copy of the variant (for grid sizing), `d_v` the device
+// copy the kernel reads.
 cudaError_t hz_launch_mosaic (const HzTiles& t, int16_t* mosaic, int N, int pitch, cudaStream_t stream);
 cudaError_t hz_launch_pyramid(const int16_t* mosaic, int N, int pitch, short2* mm_block, int nb,
                               short2* mm_tile, int nt, cudaStream_t stream);
-cudaError_t hz_launch_prepare(const HzView& v, uint32_t* counters, int ncounters, cudaStream_t stream);
-cudaError_t hz_launch_near   (const HzView& v, cudaStream_t stream);   // foreground tiles -> triangle list
-cudaError_t hz_launch_raster (const HzView& v, cudaStream_t stream);   // set-up + rasterise a triangle list
-cudaError_t hz_launch_band   (const HzView& v, cudaStream_t stream, int* launches);   // one band of the rest: k_tiles, k_blocks, k_mesh, k_raster
-cudaError_t hz_launch_big    (const HzView& v, cudaStream_t stream);   // queued large triangles of one pass
-cudaError_t hz_launch_resolve(const HzResolve& r, cudaStream_t stream);
+cudaError_t hz_launch_prepare(const HzView& v, const HzView* d_v, cudaStream_t stream);  // clear keys, axis tables, counters
+cudaError_t hz_launch_near   (const HzView& v, const HzView* d_v, cudaStream_t stream);  // foreground tiles -> triangle list
+cudaError_t hz_launch_raster (const HzView* d_v, cudaStream_t stream);                   // set-up + rasterise a triangle list
+cudaError_t hz_launch_band   (const HzView& v, const HzView* d_v, bool worst_case, cudaStream_t stream, int* launches);
+cudaError_t hz_launch_big    (const HzView* d_v, cudaStream_t stream);                   // queued large triangles of one pass
+cudaError_t hz_launch_resolve(const HzView& v, const HzView* d_v, cudaStream_t stream);
+bool        hz_resolve_is_vectorisable(const HzView& v);
 cudaError_t hz_launch_horizon(const float* ranges, int n, int W, int H, int* rows, float* range, cudaStream_t stream);

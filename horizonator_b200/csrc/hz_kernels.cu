@@ -152,9 +152,10 @@ cudaError_t hz_launch_mosaic(const HzTiles& t, int16_t* mosaic, int N, int pitch
 // ================================================================================================
 
 __global__ void __launch_bounds__(256)
-k_prepare(const __grid_constant__ HzView P, uint32_t* counters, int ncounters)
+k_prepare(const HzView* __restrict__ V)
 {
     hz_wait_for_previous_kernel();
+    const HzView& P = *V;
     const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const size_t nth = (size_t)gridDim.x * blockDim.x;
 
@@ -173,17 +174,17 @@ k_prepare(const __grid_constant__ HzView P, uint32_t* counters, int ncounters)
         P.e_tab[k] = (f - P.viewer_cell_i) * P.deg_per_cell * HZ_REARTH_F * HZ_PI_F / 180.f * P.cos_viewer_lat;
         P.n_tab[k] = (f - P.viewer_cell_j) * P.deg_per_cell * HZ_REARTH_F * HZ_PI_F / 180.f;
     }
-    if(tid < (size_t)ncounters) counters[tid] = 0;
+    if(tid < (size_t)P.ncounters) P.counters[tid] = 0;
 }
 
-cudaError_t hz_launch_prepare(const HzView& v, uint32_t* counters, int ncounters, cudaStream_t stream)
+cudaError_t hz_launch_prepare(const HzView& v, const HzView* d_v, cudaStream_t stream)
 {
     const size_t nkeys = (size_t)v.H * (size_t)(v.x1 - v.x0);
     size_t blocks = (nkeys / 2 + 255) / 256;
     if(blocks < (size_t)(v.N + 255) / 256) blocks = (v.N + 255) / 256;
     if(blocks > 148 * 16) blocks = 148 * 16;
     if(blocks < 1) blocks = 1;
-    return hz_launch(k_prepare, dim3((unsigned)blocks), dim3(256), stream, v, counters, ncounters);
+    return hz_launch(k_prepare, dim3((unsigned)blocks), dim3(256), stream, d_v);
 }
 
 // ================================================================================================
@@ -791,9 +792,10 @@ __device__ __forceinline__ void hz_near_tiles(const HzView& P, int& ti0, int& ti
 }
 
 __global__ void __launch_bounds__(HZ_WARPS_PER_CTA * 32, 4)
-k_near(const __grid_constant__ HzView P)
+k_near(const HzView* __restrict__ V)
 {
     hz_wait_for_previous_kernel();
+    const HzView& P = *V;
     __shared__ HzMeshWarp s_warp[HZ_WARPS_PER_CTA];
     __shared__ unsigned int s_total, s_base;
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -823,14 +825,14 @@ k_near(const __grid_constant__ HzView P)
     }
 }
 
-cudaError_t hz_launch_near(const HzView& v, cudaStream_t stream)
+cudaError_t hz_launch_near(const HzView& v, const HzView* d_v, cudaStream_t stream)
 {
     const int side = min(2 * v.near_rings + 1, v.nt) * HZ_TILE_BLOCKS;
     const int nblocks = side * side;
     int ctas = (nblocks + HZ_WARPS_PER_CTA - 1) / HZ_WARPS_PER_CTA;
     if(ctas > 148 * 8) ctas = 148 * 8;
     if(ctas < 1) ctas = 1;
-    return hz_launch(k_near, dim3(ctas), dim3(HZ_WARPS_PER_CTA * 32), stream, v);
+    return hz_launch(k_near, dim3(ctas), dim3(HZ_WARPS_PER_CTA * 32), stream, d_v);
 }
 
 // ================================================================================================
@@ -933,9 +935,10 @@ __device__ __forceinline__ void hz_cta_stats4(unsigned int* s4, unsigned int* gl
 }
 
 __global__ void __launch_bounds__(256)
-k_tiles(const __grid_constant__ HzView P)
+k_tiles(const HzView* __restrict__ V)
 {
     hz_wait_for_previous_kernel();
+    const HzView& P = *V;
     __shared__ HzCtaAppend s_app;
     __shared__ unsigned int s_stats[4];
     const int nt = P.nt, N = P.N;
@@ -976,9 +979,10 @@ k_tiles(const __grid_constant__ HzView P)
 }
 
 __global__ void __launch_bounds__(256)
-k_blocks(const __grid_constant__ HzView P)
+k_blocks(const HzView* __restrict__ V)
 {
     hz_wait_for_previous_kernel();
+    const HzView& P = *V;
     __shared__ HzCtaAppend s_app;
     __shared__ unsigned int s_stats[4];
     const int nt = P.nt, nb = P.nb, N = P.N;
@@ -1015,9 +1019,10 @@ k_blocks(const __grid_constant__ HzView P)
 }
 
 __global__ void __launch_bounds__(HZ_WARPS_PER_CTA * 32, 4)
-k_mesh(const __grid_constant__ HzView P)
+k_mesh(const HzView* __restrict__ V)
 {
     hz_wait_for_previous_kernel();
+    const HzView& P = *V;
     __shared__ HzMeshWarp s_warp[HZ_WARPS_PER_CTA];
     __shared__ unsigned int s_total, s_base;
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -1061,9 +1066,10 @@ k_mesh(const __grid_constant__ HzView P)
 // ---- k_raster: one thread per triangle of a stage's list
 
 __global__ void __launch_bounds__(256, 3)
-k_raster(const __grid_constant__ HzView P)
+k_raster(const HzView* __restrict__ V)
 {
     hz_wait_for_previous_kernel();
+    const HzView& P = *V;
     const unsigned int n = min(*P.tri_count, P.tri_capacity);
     const unsigned int nth = gridDim.x * blockDim.x;
     unsigned int n_big = 0;
@@ -1073,25 +1079,28 @@ k_raster(const __grid_constant__ HzView P)
     if(P.stats && (threadIdx.x & 31) == 0 && n_big) atomicAdd(P.stats + HZ_STAT_BIG_ENTRIES, n_big);
 }
 
-cudaError_t hz_launch_raster(const HzView& v, cudaStream_t stream)
+cudaError_t hz_launch_raster(const HzView* d_v, cudaStream_t stream)
 {
-    return hz_launch(k_raster, dim3(148 * 6), dim3(256), stream, v);
+    return hz_launch(k_raster, dim3(148 * 6), dim3(256), stream, d_v);
 }
 
-cudaError_t hz_launch_band(const HzView& v, cudaStream_t stream, int* launches)
+// `worst_case`: size the tile kernel for any eye position (a CUDA graph is captured once per context and replayed
+// for every view); otherwise for this view's eye tile, and nothing is launched if the band is empty.
+cudaError_t hz_launch_band(const HzView& v, const HzView* d_v, bool worst_case, cudaStream_t stream, int* launches)
 {
     *launches = 0;
-    const int rmax = max(max(v.eye_ti, v.nt - 1 - v.eye_ti), max(v.eye_tj, v.nt - 1 - v.eye_tj));
+    const int rmax = worst_case ? v.nt - 1
+                                : max(max(v.eye_ti, v.nt - 1 - v.eye_ti), max(v.eye_tj, v.nt - 1 - v.eye_tj));
     const int ring_hi = min(v.ring_hi, rmax + 1);
     if(v.ring_lo >= ring_hi) return cudaSuccess;
     const long long ntiles = (long long)(2 * ring_hi - 1) * (2 * ring_hi - 1) - (long long)(2 * v.ring_lo - 1) * (2 * v.ring_lo - 1);
     long long ctas = (ntiles + 255) / 256;
     if(ctas > 148 * 8) ctas = 148 * 8;
     cudaError_t e;
-    if((e = hz_launch(k_tiles,  dim3((unsigned)ctas), dim3(256), stream, v)) != cudaSuccess) return e;
-    if((e = hz_launch(k_blocks, dim3(148 * 8), dim3(256), stream, v)) != cudaSuccess) return e;
-    if((e = hz_launch(k_mesh,   dim3(148 * 4), dim3(HZ_WARPS_PER_CTA * 32), stream, v)) != cudaSuccess) return e;
-    if((e = hz_launch(k_raster, dim3(148 * 6), dim3(256), stream, v)) != cudaSuccess) return e;
+    if((e = hz_launch(k_tiles,  dim3((unsigned)ctas), dim3(256), stream, d_v)) != cudaSuccess) return e;
+    if((e = hz_launch(k_blocks, dim3(148 * 8), dim3(256), stream, d_v)) != cudaSuccess) return e;
+    if((e = hz_launch(k_mesh,   dim3(148 * 4), dim3(HZ_WARPS_PER_CTA * 32), stream, d_v)) != cudaSuccess) return e;
+    if((e = hz_launch(k_raster, dim3(148 * 6), dim3(256), stream, d_v)) != cudaSuccess) return e;
     *launches = 4;
     return cudaSuccess;
 }
@@ -1121,9 +1130,10 @@ __device__ __forceinline__ void hz_draw_subbox(const HzView& P, const HzTri& T, 
 }
 
 __global__ void __launch_bounds__(256)
-k_big(const __grid_constant__ HzView P)
+k_big(const HzView* __restrict__ V)
 {
     hz_wait_for_previous_kernel();
+    const HzView& P = *V;
     // every slot below min(count, capacity) was written: with a record index, or poisoned by a triangle that found
     // the record pool or the queue exhausted and drew itself (hz_raster_one)
     unsigned int count = *P.big_count;
@@ -1143,9 +1153,9 @@ k_big(const __grid_constant__ HzView P)
     }
 }
 
-cudaError_t hz_launch_big(const HzView& v, cudaStream_t stream)
+cudaError_t hz_launch_big(const HzView* d_v, cudaStream_t stream)
 {
-    return hz_launch(k_big, dim3(148 * 8), dim3(256), stream, v);
+    return hz_launch(k_big, dim3(148 * 8), dim3(256), stream, d_v);
 }
 
 // ================================================================================================
@@ -1164,11 +1174,30 @@ __device__ __forceinline__ float hz_range_of_key(unsigned long long key, float t
     return (float)sqrt((double)length_en * (double)length_en + (double)z * (double)z);
 }
 
+struct HzResolve
+{
+    const unsigned long long* vis;
+    int   Wt, H;                 // target width (x1-x0), height
+    const float* tanel;          // [H] tan(elevation) per GL row, host-computed (lib:1007-1012)
+    float znear, zfar;
+    uint8_t* image;              // [H][Wt][3] B,G,R top row first, or nullptr
+    float*   ranges;             // [H][Wt] top row first, or nullptr
+};
+
+__device__ __forceinline__ HzResolve hz_resolve_params(const HzView& P)
+{
+    HzResolve R;
+    R.vis = P.vis; R.Wt = P.x1 - P.x0; R.H = P.H; R.tanel = P.tanel; R.znear = P.znear; R.zfar = P.zfar;
+    R.image = P.out_image; R.ranges = P.out_ranges;
+    return R;
+}
+
 // 4 pixels per thread: 2x16 B of keys in, 12 B of BGR and 16 B of range out
 __global__ void __launch_bounds__(256)
-k_resolve4(const HzResolve R)
+k_resolve4(const HzView* __restrict__ V)
 {
     hz_wait_for_previous_kernel();
+    const HzResolve R = hz_resolve_params(*V);
     const int groups_per_row = R.Wt >> 2;
     const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if(g >= (long long)groups_per_row * R.H) return;
@@ -1212,9 +1241,10 @@ k_resolve4(const HzResolve R)
 
 // any width
 __global__ void __launch_bounds__(256)
-k_resolve1(const HzResolve R)
+k_resolve1(const HzView* __restrict__ V)
 {
     hz_wait_for_previous_kernel();
+    const HzResolve R = hz_resolve_params(*V);
     const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if(g >= (long long)R.Wt * R.H) return;
     const int y = (int)(g / R.Wt), x = (int)(g % R.Wt);
@@ -1230,18 +1260,23 @@ k_resolve1(const HzResolve R)
     if(R.ranges) R.ranges[dst] = hz_range_of_key(key, R.tanel[y], R.znear, R.zfar);
 }
 
-cudaError_t hz_launch_resolve(const HzResolve& r, cudaStream_t stream)
+bool hz_resolve_is_vectorisable(const HzView& v)
 {
-    const bool aligned = (r.Wt % 4 == 0) && (((uintptr_t)r.image & 3) == 0) && (((uintptr_t)r.ranges & 15) == 0);
-    if(aligned)
+    return ((v.x1 - v.x0) % 4 == 0) && (((uintptr_t)v.out_image & 3) == 0) && (((uintptr_t)v.out_ranges & 15) == 0);
+}
+
+cudaError_t hz_launch_resolve(const HzView& v, const HzView* d_v, cudaStream_t stream)
+{
+    const int Wt = v.x1 - v.x0;
+    if(hz_resolve_is_vectorisable(v))
     {
-        const long long n = (long long)(r.Wt / 4) * r.H;
-        return hz_launch(k_resolve4, dim3((unsigned)((n + 255) / 256)), dim3(256), stream, r);
+        const long long n = (long long)(Wt / 4) * v.H;
+        return hz_launch(k_resolve4, dim3((unsigned)((n + 255) / 256)), dim3(256), stream, d_v);
     }
     else
     {
-        const long long n = (long long)r.Wt * r.H;
-        return hz_launch(k_resolve1, dim3((unsigned)((n + 255) / 256)), dim3(256), stream, r);
+        const long long n = (long long)Wt * v.H;
+        return hz_launch(k_resolve1, dim3((unsigned)((n + 255) / 256)), dim3(256), stream, d_v);
     }
 }
 
