@@ -89,9 +89,9 @@ struct Slot
     int nb = 0, nt = 0;
     int near_rings = 2;
     int n_bands = 2;
-    int occl_tile_max_pix = 64, occl_block_max_pix = 16, small_max_pix = 16;
-    int band_end[MAX_BANDS] = { 24, 1 << 20, 0, 0, 0, 0 };   // ring at which each band ends (exclusive)
-    int n_lanes_max = 8;
+    int occl_tile_max_pix = 64, occl_block_max_pix = 32, small_max_pix = 16;
+    int band_end[MAX_BANDS] = { 48, 1 << 20, 0, 0, 0, 0 };   // ring at which each band ends (exclusive)
+    int n_lanes_max = 16;
 
     // target
     int W = 0, H = 0;
@@ -417,6 +417,7 @@ bool enqueue_render(Slot& s, Scratch& sc, const ViewState& vs, int x0, int x1,
     {
         const double cn = (double)v.deg_per_cell * 6371000.0 * M_PI / 180.0, ce = cn * fabs((double)vs.cos_viewer_lat);
         v.cell_diag2 = (float)((ce * ce + cn * cn) * 1.01);
+        v.inv_zrange = (s.zfar > s.znear) ? 1.0f / (s.zfar - s.znear) : 0.0f;   // 0: no far/occlusion culling
     }
 
     const float* d_tanel = nullptr;

@@ -107,6 +107,7 @@ struct HzView
     uint32_t* stats;             // [HZ_STAT_COUNT]
 
     float cell_diag2;            // (east cell size)^2 + (north cell size)^2 in metres^2, rounded up
+    float inv_zrange;            // 1/(zfar-znear), for the conservative depth bound only
 
     // k_prepare zeroes these; k_resolve turns the visibility keys into the outputs
     uint32_t* counters;

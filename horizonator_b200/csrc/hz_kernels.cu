@@ -156,35 +156,40 @@ k_prepare(const HzView* __restrict__ V)
 {
     hz_wait_for_previous_kernel();
     const HzView& P = *V;
-    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const size_t nth = (size_t)gridDim.x * blockDim.x;
+    const unsigned int tid = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned int nth = gridDim.x * blockDim.x;
 
-    // glClear: depth 1.0 everywhere.  Keys are cleared two at a time.
+    // glClear: depth 1.0 everywhere.  Keys are cleared two at a time (16-byte stores), four stores per trip.
     const size_t nkeys = (size_t)P.H * (size_t)(P.x1 - P.x0);
+    const unsigned int npairs = (unsigned int)(nkeys / 2);
     ulonglong2* v2 = (ulonglong2*)P.vis;
-    for(size_t k = tid; k < nkeys / 2; k += nth) v2[k] = make_ulonglong2(HZ_KEY_CLEAR, HZ_KEY_CLEAR);
+    const ulonglong2 clear2 = make_ulonglong2(HZ_KEY_CLEAR, HZ_KEY_CLEAR);
+    unsigned int k = tid;
+    for(; k + 3u * nth < npairs; k += 4u * nth)
+    {
+        v2[k] = clear2; v2[k + nth] = clear2; v2[k + 2u * nth] = clear2; v2[k + 3u * nth] = clear2;
+    }
+    for(; k < npairs; k += nth) v2[k] = clear2;
     if(tid == 0 && (nkeys & 1)) P.vis[nkeys - 1] = HZ_KEY_CLEAR;
 
     // vertex.glsl:128-130, operator by operator:
     //   e = (i - viewer_cell_i) * DEG_PER_CELL * Rearth * pi/180. * cos_viewer_lat
     //   n = (j - viewer_cell_j) * DEG_PER_CELL * Rearth * pi/180.
-    for(size_t k = tid; k < (size_t)P.N; k += nth)
+    for(unsigned int c = tid; c < (unsigned int)P.N; c += nth)
     {
-        const float f = (float)(int)k;
-        P.e_tab[k] = (f - P.viewer_cell_i) * P.deg_per_cell * HZ_REARTH_F * HZ_PI_F / 180.f * P.cos_viewer_lat;
-        P.n_tab[k] = (f - P.viewer_cell_j) * P.deg_per_cell * HZ_REARTH_F * HZ_PI_F / 180.f;
+        const float f = (float)(int)c;
+        P.e_tab[c] = (f - P.viewer_cell_i) * P.deg_per_cell * HZ_REARTH_F * HZ_PI_F / 180.f * P.cos_viewer_lat;
+        P.n_tab[c] = (f - P.viewer_cell_j) * P.deg_per_cell * HZ_REARTH_F * HZ_PI_F / 180.f;
     }
-    if(tid < (size_t)P.ncounters) P.counters[tid] = 0;
+    if(tid < (unsigned int)P.ncounters) P.counters[tid] = 0;
 }
 
 cudaError_t hz_launch_prepare(const HzView& v, const HzView* d_v, cudaStream_t stream)
 {
-    const size_t nkeys = (size_t)v.H * (size_t)(v.x1 - v.x0);
-    size_t blocks = (nkeys / 2 + 255) / 256;
-    if(blocks < (size_t)(v.N + 255) / 256) blocks = (v.N + 255) / 256;
-    if(blocks > 148 * 16) blocks = 148 * 16;
-    if(blocks < 1) blocks = 1;
-    return hz_launch(k_prepare, dim3((unsigned)blocks), dim3(256), stream, d_v);
+    // enough threads to cover the axis tables in one trip and to keep the stores of the clear flowing
+    unsigned int blocks = (unsigned int)((v.N + 255) / 256);
+    if(blocks < 148 * 2) blocks = 148 * 2;
+    return hz_launch(k_prepare, dim3(blocks), dim3(256), stream, d_v);
 }
 
 // ================================================================================================
@@ -508,16 +513,17 @@ hz_rect_test(const HzView& P, int c_lo, int c_hi, int r_lo, int r_hi, float zmin
     const float d2min = e_near * e_near + n_near * n_near;
 
     // lower bound of the window depth of any fragment: the nearest corner evaluated like a vertex on the eye's
-    // ground plane (hz_depth_shade), minus the extrapolation allowance, minus rounding
+    // ground plane (hz_depth_shade), minus the extrapolation allowance.  Approximate square roots and a reciprocal
+    // instead of the exact operations of a real vertex: each is within 2 ulp, the 2e-5 below (3 m at 150 km) is
+    // two orders of magnitude more than they and the later float->integer truncation can add up to.
     {
-        const float len = sqrtf(d2min);
-        const float zn  = (len - P.znear) / (P.zfar - P.znear) * 2.f - 1.f;
-        const float zw  = zn * 0.5f + 0.5f;
+        const float len = d2min * rsqrtf(fmaxf(d2min, 1e-30f));
         const float dz  = zmax - zmin;
-        const float sep = sqrtf(P.cell_diag2 + dz * dz);
-        const float lo  = zw - (4.004f * sep / (P.zfar - P.znear) + 2e-6f);
+        const float s2  = P.cell_diag2 + dz * dz;
+        const float sep = s2 * rsqrtf(s2);
+        const float lo  = (len - P.znear - 4.004f * sep) * P.inv_zrange - 2e-5f;
         if(lo > 1.0f) return HZ_RECT_DEAD_FAR;             // every fragment fails the far clip
-        B.qmin = (lo <= 0.0f) ? 0u : (unsigned int)((double)lo * 16777215.0);
+        B.qmin = (lo <= 0.0f) ? 0u : (unsigned int)(lo * 16777215.0f);
     }
     if(e_in || n_in) return HZ_RECT_ALIVE;                 // touches an axis through the eye: not worth a box
 
@@ -1166,8 +1172,11 @@ cudaError_t hz_launch_big(const HzView* d_v, cudaStream_t stream)
 __device__ __forceinline__ float hz_range_of_key(unsigned long long key, float tanel, float znear, float zfar)
 {
     const unsigned int q = (unsigned int)(key >> 40);
+    // lib:1016 "depth == 1.0f -> -1": of the 24-bit values only the cleared one reads back as 1.0f (the next lower
+    // one is 1 - 2^-24, exactly representable).  Checked first: most of a panorama is sky, and the rest of this
+    // function is FP64.
+    if(q == HZ_Q_MAX) return -1.0f;
     const float depth = (float)((double)q * (1.0 / 16777215.0));             // F7 read-back
-    if(depth == 1.0f) return -1.0f;                                          // lib:1016
     const float length_en = depth * (zfar - znear) + znear;                  // lib:1018
     const float z = tanel * length_en;
     // hypotf (lib:1024): glibc evaluates it in double and rounds once
@@ -1229,12 +1238,16 @@ k_resolve4(const HzView* __restrict__ V)
     }
     if(R.ranges)
     {
-        const float t = R.tanel[y];
-        float4 r;
-        r.x = hz_range_of_key(k[0], t, R.znear, R.zfar);
-        r.y = hz_range_of_key(k[1], t, R.znear, R.zfar);
-        r.z = hz_range_of_key(k[2], t, R.znear, R.zfar);
-        r.w = hz_range_of_key(k[3], t, R.znear, R.zfar);
+        float4 r = make_float4(-1.0f, -1.0f, -1.0f, -1.0f);
+        // most groups of four pixels are sky: skip the FP64 conversion for them altogether
+        if(((unsigned int)(k[0] >> 40) & (unsigned int)(k[1] >> 40) & (unsigned int)(k[2] >> 40) & (unsigned int)(k[3] >> 40)) != HZ_Q_MAX)
+        {
+            const float t = R.tanel[y];
+            r.x = hz_range_of_key(k[0], t, R.znear, R.zfar);
+            r.y = hz_range_of_key(k[1], t, R.znear, R.zfar);
+            r.z = hz_range_of_key(k[2], t, R.znear, R.zfar);
+            r.w = hz_range_of_key(k[3], t, R.znear, R.zfar);
+        }
         *(float4*)(R.ranges + dst) = r;
     }
 }
