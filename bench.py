@@ -317,14 +317,13 @@ def run_b200(args):
     # concurrent panoramas overlap, so a single kernel's duration no longer measures the machine)
     achieved = alg * (K * B / (ms_total / 1e3)) / 1e9
     traffic = None
-    tp = os.path.join(ROOT, "profiles", "dominant_kernel_dram_bytes.json")
+    tp = os.path.join(ROOT, "profiles", "dram_bytes_per_panorama.json")
     if os.path.exists(tp):
         try:
-            rec = json.load(open(tp))
-            if rec.get("kernel") == "k_" + dominant:
-                traffic = rec.get("dram_bytes_per_launch")
+            traffic = json.load(open(tp)).get("dram_bytes_per_panorama")
         except Exception:
             traffic = None
+
     mosaic_ms = h.time_mosaic(5)
     out = {
         "metric": "panoramas/sec (SRTM1, 3600x600 px)",
@@ -360,6 +359,9 @@ def run_b200(args):
                      "algorithmic_bytes_per_launch": alg,
                      "kernel_ms_single_panorama": {k: prof[k] for k in kernels},
                      "latency_ms_single_panorama": latency_ms,
+                     "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum summed over the 14 kernels of one "
+                                     "panorama (one CUDA-graph launch), from the ncu capture summarised in "
+                                     "profiles/r01o_kernels_per_panorama.txt",
                      "note": "achieved = algorithmic bytes per panorama (one read of the int16 DEM square + one write of "
                              "image and range, SURVEY 8d) x measured panoramas/s; kernel = the longest stage of a lone "
                              "panorama.  Hierarchical culling makes the kernels read far less DRAM than the "
