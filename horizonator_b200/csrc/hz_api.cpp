@@ -32,9 +32,11 @@ namespace {
 
 constexpr int   TANEL_SLOTS     = 8;
 constexpr float PI_F            = 3.14159265358979f;       // vertex.glsl:31
-constexpr unsigned BIG_CAPACITY = 1u << 21;      // (triangle, sub-box) pairs per pass; overflow is drawn inline
-constexpr unsigned TRI_CAPACITY = 1u << 23;      // triangles per stage awaiting set-up; overflow is drawn inline
-constexpr unsigned BIGTRI_CAPACITY = 1u << 18;   // set-up records of triangles queued for the large-triangle kernel
+// Queue capacities grow with the image (set in alloc_target); whatever does not fit is drawn by a slow in-kernel
+// path, so these only have to be generous, not safe.
+//   triangles of one stage awaiting set-up:                    max(2^22, pixels/2)
+//   (record, sub-box) pairs for the large-triangle kernel:     max(2^20, pixels/8) per pass
+//   set-up records of those triangles:                         max(2^16, pixels/16)
 constexpr int   PROF_EVENTS     = 7;            // 6 stages per render
 constexpr int   MAX_BANDS       = HZ_MAX_BANDS;
 // [0] big_count near, [1] big_count bands, [2] tri_count near, [3] big-triangle records, [4+3b] tile_count,
@@ -98,6 +100,7 @@ struct Slot
     uint8_t* d_image  = nullptr;
     float*   d_ranges = nullptr;
     size_t   target_pixels = 0;      // capacity of the buffers above
+    uint32_t tri_capacity = 0, big_capacity = 0, bigtri_capacity = 0;
 
     // tan(elevation) per row, computed on the host like the reference's read-back does
     float*   d_tanel = nullptr;      // [TANEL_SLOTS][H]
@@ -156,16 +159,35 @@ void drop_graph(Scratch& c)
     c.graph = nullptr; c.graph_failed = false;
 }
 
+// the part of a scratch set whose size depends on the image
+void free_scratch_target(Scratch& c)
+{
+    drop_graph(c);
+    cudaFree(c.d_vis); cudaFree(c.d_image); cudaFree(c.d_ranges);
+    cudaFree(c.d_tri_queue); cudaFree(c.d_big_queue); cudaFree(c.d_bigtri);
+    c.d_vis = nullptr; c.d_image = nullptr; c.d_ranges = nullptr;
+    c.d_tri_queue = nullptr; c.d_big_queue = nullptr; c.d_bigtri = nullptr;
+}
+
+bool alloc_scratch_target(const Slot& s, Scratch& c, bool staging)
+{
+    const size_t px = s.target_pixels;
+    CUDA_TRY(cudaMalloc(&c.d_vis, px * sizeof(unsigned long long)));
+    CUDA_TRY(cudaMalloc(&c.d_tri_queue, (size_t)s.tri_capacity * sizeof(uint32_t)));
+    CUDA_TRY(cudaMalloc(&c.d_big_queue, 2 * (size_t)s.big_capacity * sizeof(uint2)));
+    CUDA_TRY(cudaMalloc(&c.d_bigtri, (size_t)s.bigtri_capacity * 6 * sizeof(uint4)));
+    if(staging)
+    {
+        CUDA_TRY(cudaMalloc(&c.d_image, px * 3));
+        CUDA_TRY(cudaMalloc(&c.d_ranges, px * sizeof(float)));
+    }
+    return true;
+}
+
 void free_target(Slot& s)
 {
-    drop_graph(s.main);
-    for(Scratch& l : s.lanes) drop_graph(l);
-    cudaFree(s.main.d_vis); s.main.d_vis = nullptr;
-    for(Scratch& l : s.lanes)
-    {
-        cudaFree(l.d_vis); cudaFree(l.d_image); cudaFree(l.d_ranges);
-        l.d_vis = nullptr; l.d_image = nullptr; l.d_ranges = nullptr;
-    }
+    free_scratch_target(s.main);
+    for(Scratch& l : s.lanes) free_scratch_target(l);
     cudaFree(s.d_image);  s.d_image = nullptr;
     cudaFree(s.d_ranges); s.d_ranges = nullptr;
     cudaFree(s.d_tanel);  s.d_tanel = nullptr;
@@ -178,13 +200,14 @@ bool alloc_target(Slot& s, int W, int H)
 {
     free_target(s);
     const size_t px = (size_t)W * (size_t)H;
-    CUDA_TRY(cudaMalloc(&s.main.d_vis, px * sizeof(unsigned long long)));
-    for(Scratch& l : s.lanes)
-    {
-        CUDA_TRY(cudaMalloc(&l.d_vis, px * sizeof(unsigned long long)));
-        CUDA_TRY(cudaMalloc(&l.d_image, px * 3));
-        CUDA_TRY(cudaMalloc(&l.d_ranges, px * sizeof(float)));
-    }
+    auto cap = [px](size_t floor_, size_t div) {
+        const size_t c = px / div > floor_ ? px / div : floor_;
+        return (uint32_t)(c > 0x7FFFFFFFu ? 0x7FFFFFFFu : c);
+    };
+    s.target_pixels = px;
+    s.tri_capacity = cap((size_t)1 << 22, 2); s.big_capacity = cap((size_t)1 << 20, 8); s.bigtri_capacity = cap((size_t)1 << 16, 16);
+    if(!alloc_scratch_target(s, s.main, false)) return false;
+    for(Scratch& l : s.lanes) if(!alloc_scratch_target(s, l, true)) return false;
     CUDA_TRY(cudaMalloc(&s.d_image, px * 3));
     CUDA_TRY(cudaMalloc(&s.d_ranges, px * sizeof(float)));
     CUDA_TRY(cudaMalloc(&s.d_tanel, (size_t)TANEL_SLOTS * H * sizeof(float)));
@@ -196,13 +219,12 @@ bool alloc_target(Slot& s, int W, int H)
 
 void free_scratch(Scratch& c)
 {
-    cudaFree(c.d_vis); cudaFree(c.d_e); cudaFree(c.d_n);
-    cudaFree(c.d_tile_queue); cudaFree(c.d_block_queue); cudaFree(c.d_tri_queue); cudaFree(c.d_big_queue);
-    cudaFree(c.d_counters); cudaFree(c.d_bigtri);
+    free_scratch_target(c);
+    cudaFree(c.d_e); cudaFree(c.d_n);
+    cudaFree(c.d_tile_queue); cudaFree(c.d_block_queue);
+    cudaFree(c.d_counters);
     cudaFree(c.d_views); cudaFreeHost(c.h_views);
     for(cudaEvent_t e : c.ring_ev) if(e) cudaEventDestroy(e);
-    if(c.graph) cudaGraphExecDestroy(c.graph);
-    cudaFree(c.d_image); cudaFree(c.d_ranges);
     if(c.done) cudaEventDestroy(c.done);
     if(c.stream) cudaStreamDestroy(c.stream);
     c = Scratch{};
@@ -215,9 +237,6 @@ bool alloc_scratch(const Slot& s, Scratch& c, bool own_stream)
     CUDA_TRY(cudaMalloc(&c.d_n, (size_t)s.N * sizeof(float)));
     CUDA_TRY(cudaMalloc(&c.d_tile_queue, (size_t)s.nt * s.nt * sizeof(uint32_t)));
     CUDA_TRY(cudaMalloc(&c.d_block_queue, (size_t)s.nb * s.nb * sizeof(uint32_t)));
-    CUDA_TRY(cudaMalloc(&c.d_tri_queue, (size_t)TRI_CAPACITY * sizeof(uint32_t)));
-    CUDA_TRY(cudaMalloc(&c.d_big_queue, 2 * (size_t)BIG_CAPACITY * sizeof(uint2)));
-    CUDA_TRY(cudaMalloc(&c.d_bigtri, (size_t)BIGTRI_CAPACITY * 6 * sizeof(uint4)));
     CUDA_TRY(cudaMalloc(&c.d_counters, N_COUNTERS * sizeof(uint32_t)));
     CUDA_TRY(cudaMalloc(&c.d_views, HZ_V_COUNT * sizeof(HzView)));
     CUDA_TRY(cudaMallocHost(&c.h_views, (size_t)PARAM_RING * HZ_V_COUNT * sizeof(HzView)));
@@ -237,10 +256,7 @@ bool ensure_lanes(Slot& s, int n)
     while((int)s.lanes.size() < n)
     {
         Scratch c;
-        if(!alloc_scratch(s, c, true) ||
-           cudaMalloc(&c.d_vis, s.target_pixels * sizeof(unsigned long long)) != cudaSuccess ||
-           cudaMalloc(&c.d_image, s.target_pixels * 3) != cudaSuccess ||
-           cudaMalloc(&c.d_ranges, s.target_pixels * sizeof(float)) != cudaSuccess)
+        if(!alloc_scratch(s, c, true) || !alloc_scratch_target(s, c, true))
         {
             MSG("Could not allocate render lane %d", (int)s.lanes.size());
             cudaGetLastError();
@@ -399,11 +415,11 @@ bool enqueue_render(Slot& s, Scratch& sc, const ViewState& vs, int x0, int x1,
     v.vis = sc.d_vis;
     v.stats      = s.collect_stats ? sc.d_counters + STATS_AT : nullptr;
     v.tile_queue = sc.d_tile_queue; v.block_queue = sc.d_block_queue;
-    v.tri_queue = sc.d_tri_queue; v.tri_capacity = TRI_CAPACITY;
-    v.bigtri = sc.d_bigtri; v.bigtri_count = sc.d_counters + 3; v.bigtri_capacity = BIGTRI_CAPACITY;
+    v.tri_queue = sc.d_tri_queue; v.tri_capacity = s.tri_capacity;
+    v.bigtri = sc.d_bigtri; v.bigtri_count = sc.d_counters + 3; v.bigtri_capacity = s.bigtri_capacity;
     v.occl_tile_max_pix = s.occl_tile_max_pix; v.occl_block_max_pix = s.occl_block_max_pix;
     v.small_max_pix = s.small_max_pix;
-    v.big_capacity = BIG_CAPACITY;
+    v.big_capacity = s.big_capacity;
 
     // the eye's tile, and how many rings of tiles around it form the foreground pass
     {
@@ -437,7 +453,7 @@ bool enqueue_render(Slot& s, Scratch& sc, const ViewState& vs, int x0, int x1,
     hv[HZ_V_NEAR].big_queue = sc.d_big_queue;                 hv[HZ_V_NEAR].big_count = sc.d_counters + 0;
     for(int k = HZ_V_FAR; k < HZ_V_COUNT; k++)
     {
-        hv[k].big_queue = sc.d_big_queue + BIG_CAPACITY;      hv[k].big_count = sc.d_counters + 1;
+        hv[k].big_queue = sc.d_big_queue + s.big_capacity;      hv[k].big_count = sc.d_counters + 1;
     }
     {
         int lo = s.near_rings + 1;
@@ -1061,7 +1077,7 @@ bool horizonator_last_render_stats(const horizonator_context_t* ctx, unsigned in
     CUDA_TRY(cudaStreamSynchronize(s->stream));
     unsigned int counters[N_COUNTERS] = {};
     CUDA_TRY(cudaMemcpy(counters, s->main.d_counters, sizeof(counters), cudaMemcpyDeviceToHost));
-    out[0] = counters[0] + counters[1]; out[1] = 2 * BIG_CAPACITY; out[2] = s->launches_last; out[3] = (unsigned)s->device;
+    out[0] = counters[0] + counters[1]; out[1] = 2 * s->big_capacity; out[2] = s->launches_last; out[3] = (unsigned)s->device;
     out[4] = counters[2];
     for(int b = 0; b < MAX_BANDS; b++) out[4] += counters[6 + 3 * b];     // triangle lists of the near pass and the bands
     return true;
