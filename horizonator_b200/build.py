@@ -2,6 +2,7 @@
 
   horizonator_b200/lib/libhorizonator.so   the product: C ABI of include/*.h, CUDA kernels for sm_100a
   horizonator_b200/lib/libsynth.so         synthetic SRTM tile generator (tests/bench input data)
+  horizonator_b200/bin/horizonator-standalone   GL-free command-line renderer (cli/, plain C on the C ABI)
 
 nvcc cross-compiles for sm_100a without a GPU.  -fmad=false: see csrc/hz_math.cuh.
 """
@@ -68,7 +69,22 @@ def build_synth(force=False):
     return out
 
 
+def build_cli(force=False):
+    """cli/horizonator-standalone.c -> horizonator_b200/bin/horizonator-standalone (plain C against the C ABI)."""
+    bindir = os.path.join(HERE, "bin")
+    os.makedirs(bindir, exist_ok=True)
+    out = os.path.join(bindir, "horizonator-standalone")
+    src = os.path.join(ROOT, "cli", "horizonator-standalone.c")
+    lib = os.path.join(LIB, "libhorizonator.so")
+    if force or _newer(out, [src, lib]):
+        subprocess.run(["/usr/bin/gcc" if os.path.exists("/usr/bin/gcc") else "gcc", "-O2", "-std=gnu99", "-Wall",
+                        "-I", os.path.join(ROOT, "include"), src, "-o", out,
+                        "-L", LIB, "-lhorizonator", "-lm", "-Wl,-rpath,$ORIGIN/../lib"], check=True)
+    return out
+
+
 if __name__ == "__main__":
     force = "--force" in sys.argv
     print(build_library(force=force, verbose=True))
     print(build_synth(force=force))
+    print(build_cli(force=force))

@@ -27,6 +27,7 @@ def _native_built():
     hb = load_build_module()
     hb.build_library()
     hb.build_synth()
+    hb.build_cli()
     from oracle import binding
     binding.build(ref=os.path.isdir("/root/reference"))
 
