@@ -206,6 +206,10 @@ bool alloc_target(Slot& s, int W, int H)
     };
     s.target_pixels = px;
     s.tri_capacity = cap((size_t)1 << 22, 2); s.big_capacity = cap((size_t)1 << 20, 8); s.bigtri_capacity = cap((size_t)1 << 16, 16);
+    // tests shrink the queues to exercise the overflow paths
+    if(const char* env = getenv("HORIZONATOR_TRI_CAPACITY"))    s.tri_capacity    = (uint32_t)(atoi(env) > 1 ? atoi(env) : 1);
+    if(const char* env = getenv("HORIZONATOR_BIG_CAPACITY"))    s.big_capacity    = (uint32_t)(atoi(env) > 1 ? atoi(env) : 1);
+    if(const char* env = getenv("HORIZONATOR_BIGTRI_CAPACITY")) s.bigtri_capacity = (uint32_t)(atoi(env) > 1 ? atoi(env) : 1);
     if(!alloc_scratch_target(s, s.main, false)) return false;
     for(Scratch& l : s.lanes) if(!alloc_scratch_target(s, l, true)) return false;
     CUDA_TRY(cudaMalloc(&s.d_image, px * 3));

@@ -334,3 +334,51 @@ def test_reference_python_binding_on_this_library(hz, tiles_c1):
         assert np.array_equal(ia, ib) and np.array_equal(ra, rb)
     assert a.render(0., 90., return_image=False, return_range=False) == ()
     assert a.render(0., 90., return_range=False).shape == (H, W, 3)
+
+
+# ------------------------------------------------------------------------------------------ rarely taken paths
+
+@pytest.mark.parametrize("env", [
+    {"HORIZONATOR_TRI_CAPACITY": "1000"},                                 # triangle list overflows: drawn in the mesh kernel
+    {"HORIZONATOR_BIG_CAPACITY": "50"},                                   # sub-box queue overflows
+    {"HORIZONATOR_BIGTRI_CAPACITY": "7"},                                 # record pool overflows
+    {"HORIZONATOR_BANDS": "4,9,20", "HORIZONATOR_NEAR_RINGS": "0"},       # other band structures
+    {"HORIZONATOR_BANDS": "100000", "HORIZONATOR_NEAR_RINGS": "5", "HORIZONATOR_SMALL_PIX": "1"},
+    {"HORIZONATOR_GRAPHS": "0", "HORIZONATOR_OCCL_TILE_PIX": "0", "HORIZONATOR_OCCL_BLOCK_PIX": "0"},
+], ids=["tri_overflow", "big_overflow", "record_overflow", "bands3", "one_band", "no_graph_no_occlusion"])
+def test_overflow_paths_and_tunables_do_not_change_the_image(hz, tiles_c1, env, monkeypatch):
+    """Queue overflows fall back to a slow in-kernel path, and the band/occlusion tunables only move work around:
+    the image must be the one the default configuration produces, bit for bit."""
+    W, H, R = 1000, 160, 420
+    h0 = hz.horizonator(C1_LAT, C1_LON, W, H, dir_dems=tiles_c1, render_radius_cells=R)
+    want = h0.render(-180.05, 179.95, zfar=100000.)
+    del h0
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    h1 = hz.horizonator(C1_LAT, C1_LON, W, H, dir_dems=tiles_c1, render_radius_cells=R)
+    got = h1.render(-180.05, 179.95, zfar=100000.)
+    assert np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1])
+    views = [(C1_LAT + 0.02 * k, C1_LON - 0.01 * k, -180.05, 179.95) for k in range(3)]
+    h1.set_zextents(100., 100000.)
+    bi, br = h1.render_batch(views)
+    for k, (la, lo, a0, a1) in enumerate(views):
+        for key in env:
+            monkeypatch.delenv(key)
+        hk = hz.horizonator(C1_LAT, C1_LON, W, H, dir_dems=tiles_c1, render_radius_cells=R)
+        wi, wr = hk.render(a0, a1, lat=la, lon=lo, zfar=100000.)
+        for key, v in env.items():
+            monkeypatch.setenv(key, v)
+        assert np.array_equal(bi[k], wi) and np.array_equal(br[k], wr), k
+
+
+def test_batch_with_more_windows_than_table_slots(hz, tiles_c1):
+    """More distinct azimuth spans in one batch than cached per-row tangent tables: the batch falls back to one view
+    at a time and still equals the loop of single renders."""
+    W, H, R = 400, 80, 150
+    h = hz.horizonator(C1_LAT, C1_LON, W, H, dir_dems=tiles_c1, render_radius_cells=R)
+    h.set_zextents(100., 50000.)
+    views = [(C1_LAT, C1_LON, -30.0 - k, 30.0 + 2 * k) for k in range(11)]
+    bi, br = h.render_batch(views)
+    for k, (la, lo, a0, a1) in enumerate(views):
+        wi, wr = h.render(a0, a1, lat=la, lon=lo, zfar=50000.)
+        assert np.array_equal(bi[k], wi) and np.array_equal(br[k], wr), k
