@@ -100,6 +100,7 @@ def _declare(lib):
         "horizonator_last_render_stats": (b, [ctx, P(C.c_uint * 5)]),
         "horizonator_render_counters": (b, [ctx, P(C.c_uint * 16)]),
         "horizonator_horizon_profile_device": (b, [ctx, vp, i, vp, vp, vp]),
+        "horizonator_set_earth_curvature": (b, [ctx, b, f]),
         "horizonator_host_alloc": (vp, [C.c_size_t]),
         "horizonator_host_free": (None, [vp]),
         "horizonator_profile_enable": (b, [ctx, b]),
@@ -128,7 +129,7 @@ EXPORTED_SYMBOLS = (
     "horizonator_download_mosaic", "horizonator_time_mosaic", "horizonator_last_render_stats",
     "horizonator_profile_enable", "horizonator_profile_read",
     "horizonator_host_alloc", "horizonator_host_free",
-    "horizonator_render_counters", "horizonator_horizon_profile_device",
+    "horizonator_render_counters", "horizonator_horizon_profile_device", "horizonator_set_earth_curvature",
 )
 
 if not os.path.exists(LIBRARY_PATH):
@@ -278,6 +279,11 @@ class horizonator:
         if not lib.horizonator_render_wedge_device(C.byref(self._ctx), int(x0), int(x1),
                                                    d_image or None, d_ranges or None, stream or None):
             raise RuntimeError("horizonator_render_wedge_device() failed")
+
+    def set_earth_curvature(self, on=True, refraction=0.13):
+        """Opt-in accuracy mode (off by default; the reference is flat-earth): see horizonator-batch.h."""
+        if not lib.horizonator_set_earth_curvature(C.byref(self._ctx), bool(on), float(refraction)):
+            raise RuntimeError("horizonator_set_earth_curvature() failed")
 
     def pan_zoom(self, az_deg0, az_deg1):
         if not lib.horizonator_pan_zoom(C.byref(self._ctx), az_deg0, az_deg1):

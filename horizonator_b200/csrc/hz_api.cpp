@@ -124,6 +124,7 @@ struct Slot
 
     // optional per-kernel timing: PROF_EVENTS events per recorded render
     bool profiling = false;
+    float curvature = 0.f;           // opt-in (horizonator_set_earth_curvature); 0 = flat earth like the reference
     bool use_graphs = true;
     bool collect_stats = false;      // culling counters (horizonator_render_counters); off: the kernels skip them
     std::vector<cudaEvent_t> prof_events;
@@ -405,6 +406,7 @@ bool enqueue_render(Slot& s, Scratch& sc, const ViewState& vs, int x0, int x1,
     v.viewer_cell_i = vs.viewer_cell_i; v.viewer_cell_j = vs.viewer_cell_j; v.viewer_z = vs.viewer_z;
     v.deg_per_cell = 1.0f / (float)s.cpd;                                // lib:577
     v.cos_viewer_lat = vs.cos_viewer_lat;
+    v.curvature = s.curvature;
 
     // vertex.glsl:139-150, float
     const float az_rad0 = vs.az_deg0 * 0.017453292519943295f;            // radians()
@@ -989,6 +991,19 @@ bool horizonator_render_wedge_device(const horizonator_context_t* ctx, int x0, i
     cudaStream_t st = stream ? (cudaStream_t)stream : s->stream;
     if(!enqueue_render(*s, s->main, s->view, x0, x1, (uint8_t*)d_image, (float*)d_ranges, st)) return false;
     if(stream == nullptr) CUDA_TRY(cudaStreamSynchronize(st));
+    return true;
+}
+
+bool horizonator_set_earth_curvature(const horizonator_context_t* ctx, bool on, float refraction)
+{
+    Slot* s = slot_of(ctx);
+    if(s == nullptr) return false;
+    if(on && !(refraction >= 0.f && refraction < 1.f))
+    {
+        MSG("refraction coefficient %g is not in [0,1)", (double)refraction);
+        return false;
+    }
+    s->curvature = on ? (1.0f - refraction) / (2.0f * 6371000.0f) : 0.0f;
     return true;
 }
 

@@ -65,6 +65,7 @@ struct HzView
     // eye
     float viewer_cell_i, viewer_cell_j, viewer_z;
     float deg_per_cell, cos_viewer_lat;
+    float curvature;             // 0 = the reference's flat earth; else apparent height drops by curvature * distance^2
 
     // azimuth window; scalars the vertex shader derives from az_deg0/az_deg1 (vertex.glsl:139-150),
     // computed once on the host in float exactly as written there

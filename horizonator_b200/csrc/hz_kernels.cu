@@ -208,8 +208,8 @@ struct HzVtx
 // vertex.glsl:132-153 for one vertex at (e, n) metres from the eye with terrain height z
 __device__ __forceinline__ void hz_project(const HzView& P, float e, float n, float z, HzVtx& v)
 {
-    const float h  = z - P.viewer_z;
     const float d2 = e * e + n * n;
+    const float h  = z - P.viewer_z - P.curvature * d2;      // curvature is 0 unless the caller opted in: exactly z - viewer_z
     float az = hz_atan2_az(e, n);
     // unwrap_near_rad(az, az_rad_center), vertex.glsl:34-38; the division by 2*pi is a multiplication by
     // the rounded reciprocal here (the quotient only has to pick the right turn count)
@@ -288,8 +288,8 @@ hz_tri_bounds(const HzView& P, const HzVtx& a, const HzVtx& b, const HzVtx& c, H
 // vertex.glsl:155,159-160 for one vertex: window depth and red channel
 __device__ __forceinline__ void hz_depth_shade(const HzView& P, float e, float n, float z, float& zw, float& r)
 {
-    const float h   = z - P.viewer_z;
     const float d2  = e * e + n * n;
+    const float h   = z - P.viewer_z - P.curvature * d2;
     const float dne = sqrtf(d2);                                             // length(en)
     const float len = sqrtf(d2 + h * h);                                     // length(enh)
     const float zn  = (len - P.znear) / (P.zfar - P.znear) * 2.f - 1.f;
@@ -536,7 +536,9 @@ hz_rect_test(const HzView& P, int c_lo, int c_hi, int r_lo, int r_hi, float zmin
 
     const float e_far = fmaxf(fabsf(e_lo), fabsf(e_hi)), n_far = fmaxf(fabsf(n_lo), fabsf(n_hi));
     const float d2max = e_far * e_far + n_far * n_far;
-    const float hmax = zmax - P.viewer_z, hmin = zmin - P.viewer_z;
+    // (with the opt-in earth curvature every height drops by curvature*d^2: by at least that of the nearest and at
+    // most that of the farthest point)
+    const float hmax = zmax - P.viewer_z - P.curvature * d2min, hmin = zmin - P.viewer_z - P.curvature * d2max;
     const float el_hi = hz_atan_el(hmax, hmax > 0.f ? d2min : d2max);
     const float el_lo = hz_atan_el(hmin, hmin > 0.f ? d2max : d2min);
     const float y_hi = el_hi * P.aspect * P.az_ndc_per_rad * halfH + halfH;

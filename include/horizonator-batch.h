@@ -52,6 +52,14 @@ bool horizonator_render_wedge_device(const horizonator_context_t* ctx,
                                      void* d_image, void* d_ranges,
                                      void* stream);
 
+/* Opt-in accuracy mode; OFF by default, and off in every parity test: the reference renders a flat
+ * tangent plane and says so (vertex.glsl:65-88: "31 m vertical error at 20 km", README.org:158-161).
+ * When on, a point at horizontal distance d appears lower by (1 - refraction) * d^2 / (2 * 6371000 m)
+ * -- the earth's curvature reduced by standard atmospheric refraction (refraction ~ 0.13; 0 = pure
+ * geometry) -- in the elevation angle and in the slant range of every vertex.  Applies to all
+ * later renders of the context. */
+bool horizonator_set_earth_curvature(const horizonator_context_t* ctx, bool on, float refraction);
+
 /* Page-locked host memory for output buffers.  horizonator_render_offscreen() and
  * horizonator_render_batch() accept any host pointer; into memory from this allocator (or any
  * other CUDA-registered host memory) the results arrive by DMA at PCIe speed, into ordinary

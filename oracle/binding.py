@@ -54,6 +54,7 @@ class Oracle:
             L.oracle_get_dem_geometry.argtypes = [vp, C.POINTER(C.c_int * 8)]
             L.oracle_get_viewer.argtypes = [vp, C.POINTER(C.c_float * 4)]
             L.oracle_set_threads.argtypes = [vp, i]
+            L.oracle_set_curvature.argtypes = [vp, f]
             cls._lib = L
         return cls._lib
 
@@ -81,6 +82,10 @@ class Oracle:
         z = C.c_float(-1. if viewer_z is None else viewer_z)
         assert self.lib().oracle_move(self.h, C.byref(z), lat, lon)
         return z.value
+
+    def set_curvature(self, coefficient):
+        """Opt-in extension (not in the reference): height drop = coefficient * distance^2; 0 = off."""
+        self.lib().oracle_set_curvature(self.h, coefficient)
 
     def dem_geometry(self):
         out = (C.c_int * 8)()

@@ -220,6 +220,7 @@ void glDrawElements(GLenum mode, GLsizei count, GLenum type, const void* indices
     u.aspect         = uniform_f("aspect");
     u.znear          = uniform_f("znear");
     u.zfar           = uniform_f("zfar");
+    u.curvature      = 0.0f;     /* the reference has no such uniform */
     u.znear_color    = uniform_f("znear_color");
     u.zfar_color     = uniform_f("zfar_color");
 

@@ -62,7 +62,7 @@ void glp_vertex_stage(const glp_uniforms_t* u, float vi, float vj, float vz, glp
 
     float en_x = (i - u->viewer_cell_i) * u->DEG_PER_CELL * Rearth * pi / 180.f * u->cos_viewer_lat;
     float en_y = (j - u->viewer_cell_j) * u->DEG_PER_CELL * Rearth * pi / 180.f;
-    float enh_z = vz - u->viewer_z;
+    float enh_z = vz - u->viewer_z - u->curvature * (en_x * en_x + en_y * en_y);   /* curvature == 0: the reference */
 
     float distance_ne = sqrtf(en_x * en_x + en_y * en_y);       /* length(en)      :133 */
     float az_rad      = atan2f(en_x, en_y);                     /* atan(en.x,en.y) :134 */

@@ -38,6 +38,9 @@ typedef struct
     float aspect;
     float znear, zfar;
     float znear_color, zfar_color;
+    /* NOT in the reference (its vertex.glsl:65-88 only estimates the error of ignoring it): opt-in earth
+     * curvature + refraction, apparent height drop = curvature * horizontal_distance^2.  0 = the reference. */
+    float curvature;
 } glp_uniforms_t;
 
 /* what the vertex stage hands on: gl_Position.xyz (w is 1) and rgb.r */

@@ -266,3 +266,5 @@ bool oracle_render_offscreen(oracle_context_t* c, char* image, float* ranges)
     }
     return true;
 }
+
+void oracle_set_curvature(oracle_context_t* c, float coefficient) { c->u.curvature = coefficient; }

@@ -46,6 +46,9 @@ int16_t oracle_dem_sample(const oracle_context_t* ctx, int i, int j);
 void oracle_get_dem_geometry(const oracle_context_t* ctx, int out[8]);
 void oracle_get_viewer(const oracle_context_t* ctx, float outf[4]);
 
+/* opt-in extension, not in the reference: apparent height drop = coefficient * distance^2 (0 = off) */
+void oracle_set_curvature(oracle_context_t* ctx, float coefficient);
+
 /* number of OpenMP threads the draw uses (1 = strictly serial). Default 1. */
 void oracle_set_threads(oracle_context_t* ctx, int nthreads);
 

@@ -382,3 +382,38 @@ def test_batch_with_more_windows_than_table_slots(hz, tiles_c1):
     for k, (la, lo, a0, a1) in enumerate(views):
         wi, wr = h.render(a0, a1, lat=la, lon=lo, zfar=50000.)
         assert np.array_equal(bi[k], wi) and np.array_equal(br[k], wr), k
+
+
+# ------------------------------------------------------------------------------------------ opt-in accuracy mode
+
+def test_earth_curvature_is_opt_in_and_matches_the_extended_oracle(hz, tiles_c1):
+    """Off by default (flat earth like the reference).  On: every vertex drops by (1-k) d^2 / (2 R_earth), in the
+    CUDA path and in the oracle's opt-in extension alike; far terrain sinks, near terrain stays."""
+    W, H, R = 1800, 300, 600
+    h = hz.horizonator(C1_LAT, C1_LON, W, H, dir_dems=tiles_c1, render_radius_cells=R)
+    flat_i, flat_r = h.render(-180.05, 179.95, zfar=100000.)
+    h.set_earth_curvature(True, 0.13)
+    img, rng = h.render(-180.05, 179.95, zfar=100000.)
+    o = _oracle(tiles_c1, W, H, R)
+    o.set_curvature(np.float32((1.0 - np.float32(0.13)) / np.float32(2.0 * 6371000.0)))
+    img_o, rng_o = o.render(-180.05, 179.95, zfar=100000.)
+    s = compare_renders(img, rng, img_o, rng_o)
+    print("curved", s)
+    assert s["ok"], s
+    assert not np.array_equal(rng, flat_r)
+    # the skyline of far terrain is lower (larger row index) with curvature, never higher by more than a pixel
+    def skyline(r):
+        hit = r > 0
+        top = np.where(hit.any(axis=0), hit.argmax(axis=0), -1)
+        return top, np.where(top >= 0, r[np.clip(top, 0, H - 1), np.arange(W)], -1.0)
+    t_flat, d_flat = skyline(flat_r)
+    t_curv, _ = skyline(rng)
+    far = (d_flat > 30000.) & (t_curv >= 0)
+    assert far.sum() > 50
+    assert (t_curv[far] >= t_flat[far] - 1).all() and (t_curv[far] > t_flat[far]).mean() > 0.3
+    # and switching it off restores the reference behaviour bit for bit
+    h.set_earth_curvature(False)
+    again_i, again_r = h.render(-180.05, 179.95, zfar=100000.)
+    assert np.array_equal(again_i, flat_i) and np.array_equal(again_r, flat_r)
+    with pytest.raises(RuntimeError):
+        h.set_earth_curvature(True, 1.5)
