@@ -173,6 +173,9 @@ def run_b200(args):
         raise SystemExit("bench.py: no CUDA device; the renderer has no CPU path")
     torch.cuda.set_device(local)
     if world > 1:
+        # stdout carries exactly one JSON line: keep NCCL's version banner (NCCL_DEBUG=VERSION prints it there) out
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     def barrier():
