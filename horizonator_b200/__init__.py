@@ -101,6 +101,11 @@ def _declare(lib):
         "horizonator_render_counters": (b, [ctx, P(C.c_uint * 16)]),
         "horizonator_horizon_profile_device": (b, [ctx, vp, i, vp, vp, vp]),
         "horizonator_set_earth_curvature": (b, [ctx, b, f]),
+        "horizonator_peer_alloc": (b, [ctx, C.c_size_t, P(vp), P(C.c_ubyte * 64)]),
+        "horizonator_peer_open": (b, [ctx, P(C.c_ubyte * 64), P(vp)]),
+        "horizonator_peer_close": (b, [ctx, vp]),
+        "horizonator_peer_free": (b, [ctx, vp]),
+        "horizonator_render_wedge_peers": (b, [ctx, i, i, i, P(vp), P(vp), vp]),
         "horizonator_host_alloc": (vp, [C.c_size_t]),
         "horizonator_host_free": (None, [vp]),
         "horizonator_profile_enable": (b, [ctx, b]),
@@ -130,6 +135,8 @@ EXPORTED_SYMBOLS = (
     "horizonator_profile_enable", "horizonator_profile_read",
     "horizonator_host_alloc", "horizonator_host_free",
     "horizonator_render_counters", "horizonator_horizon_profile_device", "horizonator_set_earth_curvature",
+    "horizonator_peer_alloc", "horizonator_peer_open", "horizonator_peer_close", "horizonator_peer_free",
+    "horizonator_render_wedge_peers",
 )
 
 if not os.path.exists(LIBRARY_PATH):
@@ -284,6 +291,34 @@ class horizonator:
         """Opt-in accuracy mode (off by default; the reference is flat-earth): see horizonator-batch.h."""
         if not lib.horizonator_set_earth_curvature(C.byref(self._ctx), bool(on), float(refraction)):
             raise RuntimeError("horizonator_set_earth_curvature() failed")
+
+    # peer-memory assembly of wedge-sharded panoramas (horizonator-batch.h); used by sharding.PeerPanorama
+    def peer_alloc(self, nbytes):
+        """-> (device address, 64-byte handle) of a buffer other ranks can map."""
+        ptr, handle = C.c_void_p(), (C.c_ubyte * 64)()
+        if not lib.horizonator_peer_alloc(C.byref(self._ctx), nbytes, C.byref(ptr), C.byref(handle)):
+            raise RuntimeError("horizonator_peer_alloc() failed")
+        return ptr.value, bytes(handle)
+
+    def peer_open(self, handle):
+        ptr = C.c_void_p()
+        if not lib.horizonator_peer_open(C.byref(self._ctx), (C.c_ubyte * 64).from_buffer_copy(handle), C.byref(ptr)):
+            raise RuntimeError("horizonator_peer_open() failed")
+        return ptr.value
+
+    def peer_close(self, ptr):
+        lib.horizonator_peer_close(C.byref(self._ctx), ptr)
+
+    def peer_free(self, ptr):
+        lib.horizonator_peer_free(C.byref(self._ctx), ptr)
+
+    def render_wedge_peers(self, x0, x1, d_images, d_ranges, stream=0):
+        """d_images / d_ranges: sequences of device addresses of every rank's full image / range buffer (or None)."""
+        n = len(d_images) if d_images is not None else len(d_ranges)
+        ai = (C.c_void_p * n)(*d_images) if d_images is not None else None
+        ar = (C.c_void_p * n)(*d_ranges) if d_ranges is not None else None
+        if not lib.horizonator_render_wedge_peers(C.byref(self._ctx), int(x0), int(x1), n, ai, ar, stream or None):
+            raise RuntimeError("horizonator_render_wedge_peers() failed")
 
     def pan_zoom(self, az_deg0, az_deg1):
         if not lib.horizonator_pan_zoom(C.byref(self._ctx), az_deg0, az_deg1):

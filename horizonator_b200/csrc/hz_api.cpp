@@ -405,9 +405,28 @@ bool capture_graph(Slot& s, Scratch& sc, const HzView* hv)
 }
 
 // enqueue one render of columns [x0,x1) into d_image / d_ranges (device, either may be null)
-bool enqueue_render(Slot& s, Scratch& sc, const ViewState& vs, int x0, int x1,
-                    uint8_t* d_image, float* d_ranges, cudaStream_t st)
+// where a render's outputs go (see HzView::n_out): one destination shaped like the target, or the full panoramas
+// of several ranks
+struct OutSpec
 {
+    int n = 1;
+    uint8_t* image[HZ_MAX_OUT] = {};
+    float*   ranges[HZ_MAX_OUT] = {};
+    int stride = 0;              // pixels per destination row; 0 = the target's own width (x1-x0)
+    int x_off = 0;               // column of the destination where the target's first column goes
+};
+
+OutSpec single_out(uint8_t* d_image, float* d_ranges)
+{
+    OutSpec o;
+    o.image[0] = d_image; o.ranges[0] = d_ranges;
+    return o;
+}
+
+bool enqueue_render(Slot& s, Scratch& sc, const ViewState& vs, int x0, int x1, const OutSpec& out, cudaStream_t st)
+{
+    uint8_t* const d_image = out.image[0];
+    float* const d_ranges = out.ranges[0];
     HzView v{};
     v.mosaic = s.d_mosaic; v.N = s.N; v.pitch = s.pitch;
     v.e_tab = sc.d_e; v.n_tab = sc.d_n;
@@ -456,7 +475,9 @@ bool enqueue_render(Slot& s, Scratch& sc, const ViewState& vs, int x0, int x1,
     if(d_ranges && !tanel_for(s, vs.az_deg0, vs.az_deg1, st, &d_tanel)) return false;
 
     v.counters = sc.d_counters; v.ncounters = N_COUNTERS;
-    v.tanel = d_tanel; v.out_image = d_image; v.out_ranges = d_ranges;
+    v.tanel = d_tanel;
+    v.n_out = out.n; v.out_stride = out.stride > 0 ? out.stride : x1 - x0; v.out_x0 = out.x_off;
+    for(int d = 0; d < out.n; d++) { v.out_image[d] = out.image[d]; v.out_ranges[d] = out.ranges[d]; }
 
     // ---- the parameter block: variants of v for the near pass, the far queue and each band, into a slot of the
     // pinned ring, then one small copy to the device
@@ -488,7 +509,7 @@ bool enqueue_render(Slot& s, Scratch& sc, const ViewState& vs, int x0, int x1,
 
     // ---- the kernels: a replay of the captured graph where the chain has its standard shape, one by one otherwise
     const bool standard = !s.profiling && s.use_graphs && x0 == 0 && x1 == s.W && (d_image || d_ranges) &&
-                          hz_resolve_is_vectorisable(v);
+                          out.n == 1 && v.out_stride == s.W && out.x_off == 0 && hz_resolve_is_vectorisable(v);
     if(standard && !sc.graph_failed)
     {
         if(sc.graph == nullptr && !capture_graph(s, sc, hv)) sc.graph_failed = true;
@@ -785,7 +806,7 @@ bool horizonator_redraw(const horizonator_context_t* ctx)
     Slot* s = slot_of(ctx);
     if(s == nullptr) return false;
     DeviceGuard g(s->device);
-    if(!enqueue_render(*s, s->main, s->view, 0, s->W, s->d_image, s->d_ranges, s->stream)) return false;
+    if(!enqueue_render(*s, s->main, s->view, 0, s->W, single_out(s->d_image, s->d_ranges), s->stream)) return false;
     CUDA_TRY(cudaStreamSynchronize(s->stream));
     return true;
 }
@@ -802,7 +823,7 @@ bool horizonator_render_offscreen(const horizonator_context_t* ctx, char* image,
     DeviceGuard g(s->device);
     const size_t px = (size_t)s->W * s->H;
     if(!enqueue_render(*s, s->main, s->view, 0, s->W,
-                       image ? s->d_image : nullptr, ranges ? s->d_ranges : nullptr, s->stream)) return false;
+                       single_out(image ? s->d_image : nullptr, ranges ? s->d_ranges : nullptr), s->stream)) return false;
     if(image  && !copy_to_host(image,  s->d_image,  px * 3, s->stream)) return false;
     if(ranges && !copy_to_host(ranges, s->d_ranges, px * sizeof(float), s->stream)) return false;
     CUDA_TRY(cudaStreamSynchronize(s->stream));
@@ -934,7 +955,7 @@ static bool render_batch_common(const horizonator_context_t* ctx, Slot* s, int n
         {
             uint8_t* di = images ? (to_host ? s->d_image  : images + (size_t)k * px * 3) : nullptr;
             float*   dr = ranges ? (to_host ? s->d_ranges : ranges + (size_t)k * px)     : nullptr;
-            if(!enqueue_render(*s, s->main, vs[k], 0, s->W, di, dr, st)) return false;
+            if(!enqueue_render(*s, s->main, vs[k], 0, s->W, single_out(di, dr), st)) return false;
             if(to_host)
             {
                 if(images && !copy_to_host(images + (size_t)k * px * 3, di, px * 3, st)) return false;
@@ -952,7 +973,7 @@ static bool render_batch_common(const horizonator_context_t* ctx, Slot* s, int n
         Scratch& lane = s->lanes[k % n_lanes];
         uint8_t* di = images ? (to_host ? lane.d_image  : images + (size_t)k * px * 3) : nullptr;
         float*   dr = ranges ? (to_host ? lane.d_ranges : ranges + (size_t)k * px)     : nullptr;
-        if(!enqueue_render(*s, lane, vs[k], 0, s->W, di, dr, lane.stream)) return false;
+        if(!enqueue_render(*s, lane, vs[k], 0, s->W, single_out(di, dr), lane.stream)) return false;
         if(to_host)
         {
             if(images && !copy_to_host(images + (size_t)k * px * 3, di, px * 3, lane.stream)) return false;
@@ -1002,7 +1023,93 @@ bool horizonator_render_wedge_device(const horizonator_context_t* ctx, int x0, i
     }
     DeviceGuard g(s->device);
     cudaStream_t st = stream ? (cudaStream_t)stream : s->stream;
-    if(!enqueue_render(*s, s->main, s->view, x0, x1, (uint8_t*)d_image, (float*)d_ranges, st)) return false;
+    if(!enqueue_render(*s, s->main, s->view, x0, x1, single_out((uint8_t*)d_image, (float*)d_ranges), st)) return false;
+    if(stream == nullptr) CUDA_TRY(cudaStreamSynchronize(st));
+    return true;
+}
+
+// ---- wedge-sharded panoramas assembled over NVLink ---------------------------------------------------------
+
+bool horizonator_peer_alloc(const horizonator_context_t* ctx, size_t bytes, void** d_ptr, unsigned char handle[64])
+{
+    Slot* s = slot_of(ctx);
+    if(s == nullptr || d_ptr == nullptr || handle == nullptr || bytes == 0) return false;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    DeviceGuard g(s->device);
+    void* p = nullptr;
+    CUDA_TRY(cudaMalloc(&p, bytes));
+    cudaIpcMemHandle_t h;
+    const cudaError_t e = cudaIpcGetMemHandle(&h, p);
+    if(e != cudaSuccess)
+    {
+        MSG("cudaIpcGetMemHandle failed: %s", cudaGetErrorString(e));
+        cudaFree(p);
+        return false;
+    }
+    memcpy(handle, &h, 64);
+    *d_ptr = p;
+    return true;
+}
+
+bool horizonator_peer_open(const horizonator_context_t* ctx, const unsigned char handle[64], void** d_ptr)
+{
+    Slot* s = slot_of(ctx);
+    if(s == nullptr || d_ptr == nullptr || handle == nullptr) return false;
+    DeviceGuard g(s->device);
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, 64);
+    CUDA_TRY(cudaIpcOpenMemHandle(d_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return true;
+}
+
+bool horizonator_peer_close(const horizonator_context_t* ctx, void* d_ptr)
+{
+    Slot* s = slot_of(ctx);
+    if(s == nullptr || d_ptr == nullptr) return false;
+    DeviceGuard g(s->device);
+    CUDA_TRY(cudaIpcCloseMemHandle(d_ptr));
+    return true;
+}
+
+bool horizonator_peer_free(const horizonator_context_t* ctx, void* d_ptr)
+{
+    Slot* s = slot_of(ctx);
+    if(s == nullptr) return false;
+    DeviceGuard g(s->device);
+    CUDA_TRY(cudaFree(d_ptr));
+    return true;
+}
+
+bool horizonator_render_wedge_peers(const horizonator_context_t* ctx, int x0, int x1, int n_peers,
+                                    void* const* d_images, void* const* d_ranges, void* stream)
+{
+    Slot* s = slot_of(ctx);
+    if(s == nullptr) return false;
+    if(x0 < 0 || x1 > s->W || x0 >= x1)
+    {
+        MSG("wedge columns [%d,%d) are not inside [0,%d)", x0, x1, s->W);
+        return false;
+    }
+    if(n_peers < 1 || n_peers > HZ_MAX_OUT || (d_images == nullptr && d_ranges == nullptr))
+    {
+        MSG("need 1..%d destinations and at least one kind of output", HZ_MAX_OUT);
+        return false;
+    }
+    OutSpec out;
+    out.n = n_peers; out.stride = s->W; out.x_off = x0;
+    for(int d = 0; d < n_peers; d++)
+    {
+        out.image[d]  = d_images ? (uint8_t*)d_images[d] : nullptr;
+        out.ranges[d] = d_ranges ? (float*)d_ranges[d]   : nullptr;
+        if((d_images && out.image[d] == nullptr) || (d_ranges && out.ranges[d] == nullptr))
+        {
+            MSG("destination %d is null", d);
+            return false;
+        }
+    }
+    DeviceGuard g(s->device);
+    cudaStream_t st = stream ? (cudaStream_t)stream : s->stream;
+    if(!enqueue_render(*s, s->main, s->view, x0, x1, out, st)) return false;
     if(stream == nullptr) CUDA_TRY(cudaStreamSynchronize(st));
     return true;
 }

@@ -28,6 +28,7 @@ struct HzTiles
 // ---- culling pyramid over the mosaic (built once at init) -------------------------------------
 // block (bj,bi) = the 4x4 cells whose south-west vertex is (4bj, 4bi): (min,max) height of its 5x5 vertices
 // tile  (tj,ti) = 8x8 blocks = 32x32 cells: (min,max) over its blocks
+constexpr int HZ_MAX_OUT     = 8;   // destinations of one resolve (ranks of a wedge-sharded panorama)
 constexpr int HZ_BLOCK_CELLS = 4;
 constexpr int HZ_TILE_BLOCKS = 8;
 constexpr int HZ_TILE_CELLS  = HZ_BLOCK_CELLS * HZ_TILE_BLOCKS;
@@ -114,8 +115,12 @@ struct HzView
     uint32_t* counters;
     int       ncounters;
     const float* tanel;          // [H] tan(elevation) per GL row, host-computed (lib:1007-1012)
-    uint8_t*  out_image;         // [H][x1-x0][3] B,G,R top row first, or nullptr
-    float*    out_ranges;        // [H][x1-x0] top row first, or nullptr
+    // destinations: normally one, exactly the target ([H][x1-x0], stride x1-x0, offset 0); several (the full
+    // panoramas of all ranks, in peer memory) when a wedge-sharded panorama is assembled by the resolve kernel itself.
+    // Either pointer of a destination may be null; all destinations have the same ones null.
+    int       n_out, out_stride, out_x0;
+    uint8_t*  out_image[HZ_MAX_OUT];    // B,G,R top row first
+    float*    out_ranges[HZ_MAX_OUT];   // top row first
 };
 
 // A render's parameters live in device memory as a small array of HzView variants that differ only in the

@@ -1185,25 +1185,28 @@ __device__ __forceinline__ float hz_range_of_key(unsigned long long key, float t
     return (float)sqrt((double)length_en * (double)length_en + (double)z * (double)z);
 }
 
+// Where k_resolve writes.  Normally one destination that is exactly the target (columns [x0,x1), row stride
+// x1-x0).  For a panorama split by azimuth wedge over several GPUs the destinations are the FULL panoramas of every
+// rank (peer memory, written over NVLink): row stride W, this wedge's columns at offset x0 -- the gather of the
+// shards is fused into the kernel that produces them.
 struct HzResolve
 {
     const unsigned long long* vis;
     int   Wt, H;                 // target width (x1-x0), height
     const float* tanel;          // [H] tan(elevation) per GL row, host-computed (lib:1007-1012)
     float znear, zfar;
-    uint8_t* image;              // [H][Wt][3] B,G,R top row first, or nullptr
-    float*   ranges;             // [H][Wt] top row first, or nullptr
+    int   n_out, out_stride, out_x0;
 };
 
 __device__ __forceinline__ HzResolve hz_resolve_params(const HzView& P)
 {
     HzResolve R;
     R.vis = P.vis; R.Wt = P.x1 - P.x0; R.H = P.H; R.tanel = P.tanel; R.znear = P.znear; R.zfar = P.zfar;
-    R.image = P.out_image; R.ranges = P.out_ranges;
+    R.n_out = P.n_out; R.out_stride = P.out_stride; R.out_x0 = P.out_x0;
     return R;
 }
 
-// 4 pixels per thread: 2x16 B of keys in, 12 B of BGR and 16 B of range out
+// 4 pixels per thread: 2x16 B of keys in, 12 B of BGR and 16 B of range out (per destination)
 __global__ void __launch_bounds__(256)
 k_resolve4(const HzView* __restrict__ V)
 {
@@ -1215,42 +1218,47 @@ k_resolve4(const HzView* __restrict__ V)
     const int y  = (int)(g / groups_per_row);          // GL row (0 = bottom)
     const int x  = (int)(g % groups_per_row) << 2;
     const size_t src = (size_t)y * R.Wt + x;
-    const size_t dst = (size_t)(R.H - 1 - y) * R.Wt + x;   // top row first (lib:949-958, 1026-1038)
+    const size_t dst = (size_t)(R.H - 1 - y) * R.out_stride + R.out_x0 + x;   // top row first (lib:949-958, 1026-1038)
 
     const ulonglong2 k01 = *(const ulonglong2*)(R.vis + src);
     const ulonglong2 k23 = *(const ulonglong2*)(R.vis + src + 2);
     const unsigned long long k[4] = { k01.x, k01.y, k23.x, k23.y };
 
-    if(R.image)
+    // hit: (B,G,R) = (0,0,r8) ; sky: clear colour (0,0,1) read as BGR = (255,0,0)   lib:185, 938-939
+    unsigned char b[12];
+    #pragma unroll
+    for(int p = 0; p < 4; p++)
     {
-        // hit: (B,G,R) = (0,0,r8) ; sky: clear colour (0,0,1) read as BGR = (255,0,0)   lib:185, 938-939
-        unsigned char b[12];
-        #pragma unroll
-        for(int p = 0; p < 4; p++)
-        {
-            const bool hit = (unsigned int)(k[p] >> 40) != HZ_Q_MAX;
-            b[3 * p + 0] = hit ? 0 : 255;
-            b[3 * p + 1] = 0;
-            b[3 * p + 2] = hit ? (unsigned char)(k[p] & 0xFFu) : 0;
-        }
-        uint32_t* o = (uint32_t*)(R.image + dst * 3);      // dst*3 is a multiple of 4 because x and Wt are
-        o[0] = b[0] | (b[1] << 8) | (b[2]  << 16) | ((uint32_t)b[3]  << 24);
-        o[1] = b[4] | (b[5] << 8) | (b[6]  << 16) | ((uint32_t)b[7]  << 24);
-        o[2] = b[8] | (b[9] << 8) | (b[10] << 16) | ((uint32_t)b[11] << 24);
+        const bool hit = (unsigned int)(k[p] >> 40) != HZ_Q_MAX;
+        b[3 * p + 0] = hit ? 0 : 255;
+        b[3 * p + 1] = 0;
+        b[3 * p + 2] = hit ? (unsigned char)(k[p] & 0xFFu) : 0;
     }
-    if(R.ranges)
+    const uint32_t w0 = b[0] | (b[1] << 8) | (b[2]  << 16) | ((uint32_t)b[3]  << 24);
+    const uint32_t w1 = b[4] | (b[5] << 8) | (b[6]  << 16) | ((uint32_t)b[7]  << 24);
+    const uint32_t w2 = b[8] | (b[9] << 8) | (b[10] << 16) | ((uint32_t)b[11] << 24);
+
+    float4 r = make_float4(-1.0f, -1.0f, -1.0f, -1.0f);
+    // most groups of four pixels are sky: skip the FP64 conversion for them altogether
+    if(V->out_ranges[0] != nullptr &&
+       ((unsigned int)(k[0] >> 40) & (unsigned int)(k[1] >> 40) & (unsigned int)(k[2] >> 40) & (unsigned int)(k[3] >> 40)) != HZ_Q_MAX)
     {
-        float4 r = make_float4(-1.0f, -1.0f, -1.0f, -1.0f);
-        // most groups of four pixels are sky: skip the FP64 conversion for them altogether
-        if(((unsigned int)(k[0] >> 40) & (unsigned int)(k[1] >> 40) & (unsigned int)(k[2] >> 40) & (unsigned int)(k[3] >> 40)) != HZ_Q_MAX)
+        const float t = R.tanel[y];
+        r.x = hz_range_of_key(k[0], t, R.znear, R.zfar);
+        r.y = hz_range_of_key(k[1], t, R.znear, R.zfar);
+        r.z = hz_range_of_key(k[2], t, R.znear, R.zfar);
+        r.w = hz_range_of_key(k[3], t, R.znear, R.zfar);
+    }
+    for(int d = 0; d < R.n_out; d++)
+    {
+        uint8_t* image = V->out_image[d];
+        float* ranges = V->out_ranges[d];
+        if(image)
         {
-            const float t = R.tanel[y];
-            r.x = hz_range_of_key(k[0], t, R.znear, R.zfar);
-            r.y = hz_range_of_key(k[1], t, R.znear, R.zfar);
-            r.z = hz_range_of_key(k[2], t, R.znear, R.zfar);
-            r.w = hz_range_of_key(k[3], t, R.znear, R.zfar);
+            uint32_t* o = (uint32_t*)(image + dst * 3);    // dst*3 is a multiple of 4 because x, x0 and the stride are
+            o[0] = w0; o[1] = w1; o[2] = w2;
         }
-        *(float4*)(R.ranges + dst) = r;
+        if(ranges) *(float4*)(ranges + dst) = r;
     }
 }
 
@@ -1264,20 +1272,29 @@ k_resolve1(const HzView* __restrict__ V)
     if(g >= (long long)R.Wt * R.H) return;
     const int y = (int)(g / R.Wt), x = (int)(g % R.Wt);
     const unsigned long long key = R.vis[g];
-    const size_t dst = (size_t)(R.H - 1 - y) * R.Wt + x;
-    if(R.image)
+    const size_t dst = (size_t)(R.H - 1 - y) * R.out_stride + R.out_x0 + x;
+    const bool hit = (unsigned int)(key >> 40) != HZ_Q_MAX;
+    const float range = (V->out_ranges[0] != nullptr) ? hz_range_of_key(key, R.tanel[y], R.znear, R.zfar) : -1.0f;
+    for(int d = 0; d < R.n_out; d++)
     {
-        const bool hit = (unsigned int)(key >> 40) != HZ_Q_MAX;
-        R.image[dst * 3 + 0] = hit ? 0 : 255;
-        R.image[dst * 3 + 1] = 0;
-        R.image[dst * 3 + 2] = hit ? (unsigned char)(key & 0xFFu) : 0;
+        uint8_t* image = V->out_image[d];
+        float* ranges = V->out_ranges[d];
+        if(image)
+        {
+            image[dst * 3 + 0] = hit ? 0 : 255;
+            image[dst * 3 + 1] = 0;
+            image[dst * 3 + 2] = hit ? (unsigned char)(key & 0xFFu) : 0;
+        }
+        if(ranges) ranges[dst] = range;
     }
-    if(R.ranges) R.ranges[dst] = hz_range_of_key(key, R.tanel[y], R.znear, R.zfar);
 }
 
 bool hz_resolve_is_vectorisable(const HzView& v)
 {
-    return ((v.x1 - v.x0) % 4 == 0) && (((uintptr_t)v.out_image & 3) == 0) && (((uintptr_t)v.out_ranges & 15) == 0);
+    if((v.x1 - v.x0) % 4 != 0 || v.out_stride % 4 != 0 || v.out_x0 % 4 != 0) return false;
+    for(int d = 0; d < v.n_out; d++)
+        if(((uintptr_t)v.out_image[d] & 3) != 0 || ((uintptr_t)v.out_ranges[d] & 15) != 0) return false;
+    return true;
 }
 
 cudaError_t hz_launch_resolve(const HzView& v, const HzView* d_v, cudaStream_t stream)

@@ -7,9 +7,10 @@ collective on the data path of a render:
 * viewpoint batch -- every viewpoint is an independent render against the same read-only DEM square, which each
   rank loads for itself.  Viewpoints are block-partitioned; outputs stay sharded on the rank that made them.
   Only reduced products (horizon profiles, a few bytes per image column) are gathered.
-* azimuth wedges  -- one giant panorama: rank g renders columns [edges[g], edges[g+1]) with
-  horizonator_render_wedge_device(), bit-identical to the same columns of an unsharded render, and the slabs
-  are gathered once (all_gather of equal-sized padded slabs + a strided placement).
+* azimuth wedges  -- one giant panorama: rank g renders columns [edges[g], edges[g+1]), bit-identical to the same
+  columns of an unsharded render.  PeerPanorama fuses the exchange into the renderer: each rank's resolve kernel
+  stores its wedge straight into every rank's full panorama over NVLink (peer memory), a barrier is the only
+  collective.  render_wedges() is the plain variant: private slabs + one all_gather + a strided placement.
 
 Everything here except the two render_* drivers is device-agnostic tensor code, so the world_size-2 gloo tests
 exercise exactly what runs over NCCL.
@@ -120,6 +121,76 @@ def render_wedges(h, group=None, return_image=True, return_range=True):
     if return_range:
         out.append(gather_wedges(rng, edges, group))
     return tuple(out)
+
+
+class _DeviceArray:
+    """Minimal __cuda_array_interface__ holder so that torch can view memory the library allocated."""
+
+    def __init__(self, ptr, shape, typestr):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False), "version": 2}
+
+
+class PeerPanorama:
+    """One panorama split by azimuth wedge over the ranks and assembled WITHOUT a gather collective: every rank holds a
+    full-size image and range buffer that its peers have mapped (CUDA IPC over NVLink/NVSwitch), and each rank's resolve
+    kernel stores its wedge straight into all of them (horizonator_render_wedge_peers).  The only collective is the
+    barrier that tells a rank its buffers are complete.
+
+    Build once per context and size (collective: all ranks of `group` must construct it together), render() many
+    times.  render() returns this rank's full (H,W,3) uint8 and (H,W) float32 tensors (views of the peer-mapped
+    buffers: they are overwritten by the next render() of any rank)."""
+
+    def __init__(self, h, group=None):
+        self.h, self.group = h, group
+        self.world, self.rank = _world(group)
+        if self.world > 8:
+            raise ValueError("at most 8 ranks (one NVSwitch domain) are supported")
+        W, H = h.width, h.height
+        self.W, self.H = W, H
+        # column edges on multiples of 4 so that every wedge takes the vectorised resolve path
+        self.edges = [((W * g // self.world) // 4) * 4 for g in range(self.world)] + [W]
+        self.img_ptr, img_handle = h.peer_alloc(W * H * 3)
+        self.rng_ptr, rng_handle = h.peer_alloc(W * H * 4)
+        handles = [None] * self.world
+        if self.world > 1:
+            dist.all_gather_object(handles, (img_handle, rng_handle), group=group)
+        else:
+            handles[0] = (img_handle, rng_handle)
+        self.opened = []
+        self.img_dst, self.rng_dst = [], []
+        for r, (hi, hr) in enumerate(handles):
+            if r == self.rank:
+                self.img_dst.append(self.img_ptr); self.rng_dst.append(self.rng_ptr)
+            else:
+                pi, pr = h.peer_open(hi), h.peer_open(hr)
+                self.opened += [pi, pr]
+                self.img_dst.append(pi); self.rng_dst.append(pr)
+        self.image = torch.as_tensor(_DeviceArray(self.img_ptr, (H, W, 3), "|u1"), device="cuda")
+        self.ranges = torch.as_tensor(_DeviceArray(self.rng_ptr, (H, W), "<f4"), device="cuda")
+
+    def render(self, root=None):
+        """Renders this rank's wedge of h's current view into everybody's buffers (root=None), or only into rank
+        `root`'s (the others' buffers are then left as they were); all ranks call it together."""
+        x0, x1 = self.edges[self.rank], self.edges[self.rank + 1]
+        stream = torch.cuda.current_stream()
+        if self.world > 1:
+            dist.barrier(group=self.group)          # nobody is still reading the previous panorama
+        img_dst = self.img_dst if root is None else [self.img_dst[root]]
+        rng_dst = self.rng_dst if root is None else [self.rng_dst[root]]
+        self.h.render_wedge_peers(x0, x1, img_dst, rng_dst, stream.cuda_stream)
+        if self.world > 1:
+            dist.barrier(group=self.group)          # every wedge has landed everywhere
+        return self.image, self.ranges
+
+    def close(self):
+        for p in self.opened:
+            self.h.peer_close(p)
+        self.opened = []
+        if self.world > 1:
+            dist.barrier(group=self.group)          # peers have unmapped before the owner frees
+        if self.img_ptr:
+            self.h.peer_free(self.img_ptr); self.h.peer_free(self.rng_ptr)
+            self.img_ptr = self.rng_ptr = None
 
 
 def render_batch_sharded(h, views, group=None, gather_profiles=True):

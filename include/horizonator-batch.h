@@ -52,6 +52,27 @@ bool horizonator_render_wedge_device(const horizonator_context_t* ctx,
                                      void* d_image, void* d_ranges,
                                      void* stream);
 
+/* A wedge-sharded panorama assembled by the renderer itself over NVLink: instead of rendering its wedge
+ * into a private slab that a collective then gathers, a rank's final kernel stores the wedge's pixels
+ * straight into the FULL W x H image / range buffers of every rank (peer memory).
+ *   horizonator_peer_alloc()   allocates such a full-size buffer on this context's device and returns a
+ *                              64-byte inter-process handle for it (cudaIpcMemHandle_t)
+ *   horizonator_peer_open()    maps another rank's buffer from its handle (ranks are separate processes;
+ *                              how the handles travel is the caller's business -- the Python driver
+ *                              uses torch.distributed.all_gather_object)
+ *   horizonator_render_wedge_peers()  renders columns [x0,x1) of the context's current view and writes
+ *                              them into column x0.. of each of the n_peers (1..8) destinations;
+ *                              d_images / d_ranges are arrays of n_peers device pointers (either array may
+ *                              be NULL).  The destinations are complete once EVERY rank's call has finished
+ *                              on its stream: synchronise the ranks (a barrier) before reading them.
+ *   horizonator_peer_close() / horizonator_peer_free()  undo open / alloc. */
+bool horizonator_peer_alloc(const horizonator_context_t* ctx, size_t bytes, void** d_ptr, unsigned char handle[64]);
+bool horizonator_peer_open(const horizonator_context_t* ctx, const unsigned char handle[64], void** d_ptr);
+bool horizonator_peer_close(const horizonator_context_t* ctx, void* d_ptr);
+bool horizonator_peer_free(const horizonator_context_t* ctx, void* d_ptr);
+bool horizonator_render_wedge_peers(const horizonator_context_t* ctx, int x0, int x1, int n_peers,
+                                    void* const* d_images, void* const* d_ranges, void* stream);
+
 /* Opt-in accuracy mode; OFF by default, and off in every parity test: the reference renders a flat
  * tangent plane and says so (vertex.glsl:65-88: "31 m vertical error at 20 km", README.org:158-161).
  * When on, a point at horizontal distance d appears lower by (1 - refraction) * d^2 / (2 * 6371000 m)

@@ -36,6 +36,24 @@ def _worker(rank, world, port, tiles, q):
         torch.cuda.synchronize()
         ok = np.array_equal(gi.cpu().numpy(), full_i) and np.array_equal(gr.cpu().numpy(), full_r)
 
+        # the same panorama assembled by the resolve kernels themselves in peer memory (no gather collective)
+        pp = sharding.PeerPanorama(h)
+        for _ in range(2):
+            pi, pr = pp.render()
+            torch.cuda.synchronize()
+            ok = ok and np.array_equal(pi.cpu().numpy(), full_i) and np.array_equal(pr.cpu().numpy(), full_r)
+        # ... and only into rank 0's buffers
+        pp.image.zero_(); pp.ranges.zero_()
+        torch.cuda.synchronize()
+        pi, pr = pp.render(root=0)
+        torch.cuda.synchronize()
+        if rank == 0:
+            ok = ok and np.array_equal(pi.cpu().numpy(), full_i) and np.array_equal(pr.cpu().numpy(), full_r)
+        else:
+            ok = ok and not pi.any().item()
+        dist.barrier()
+        pp.close()
+
         views = [(LAT + 0.01 * k, LON - 0.008 * k, -180.05, 179.95) for k in range(5)]
         img, rng, (lo, hi), prof = sharding.render_batch_sharded(h, views)
         torch.cuda.synchronize()
