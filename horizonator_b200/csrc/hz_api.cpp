@@ -73,6 +73,9 @@ struct Scratch
     HzView* h_views = nullptr;         // pinned [PARAM_RING][HZ_V_COUNT]
     cudaEvent_t ring_ev[PARAM_RING] = {};
     int ring_next = 0;
+    cudaEvent_t  busy = nullptr;       // recorded after the last render that used this set
+    cudaStream_t last_stream = nullptr;
+    bool busy_recorded = false;
     cudaGraphExec_t graph = nullptr;   // the standard chain, captured on first use
     int  graph_launches = 0;
     bool graph_failed = false;
@@ -235,6 +238,7 @@ void free_scratch(Scratch& c)
     cudaFree(c.d_counters);
     cudaFree(c.d_views); cudaFreeHost(c.h_views);
     for(cudaEvent_t e : c.ring_ev) if(e) cudaEventDestroy(e);
+    if(c.busy) cudaEventDestroy(c.busy);
     if(c.done) cudaEventDestroy(c.done);
     if(c.stream) cudaStreamDestroy(c.stream);
     c = Scratch{};
@@ -251,6 +255,7 @@ bool alloc_scratch(const Slot& s, Scratch& c, bool own_stream)
     CUDA_TRY(cudaMalloc(&c.d_views, HZ_V_COUNT * sizeof(HzView)));
     CUDA_TRY(cudaMallocHost(&c.h_views, (size_t)PARAM_RING * HZ_V_COUNT * sizeof(HzView)));
     for(cudaEvent_t& e : c.ring_ev) CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    CUDA_TRY(cudaEventCreateWithFlags(&c.busy, cudaEventDisableTiming));
     if(own_stream)
     {
         CUDA_TRY(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
@@ -404,7 +409,6 @@ bool capture_graph(Slot& s, Scratch& sc, const HzView* hv)
     return true;
 }
 
-// enqueue one render of columns [x0,x1) into d_image / d_ranges (device, either may be null)
 // where a render's outputs go (see HzView::n_out): one destination shaped like the target, or the full panoramas
 // of several ranks
 struct OutSpec
@@ -423,10 +427,13 @@ OutSpec single_out(uint8_t* d_image, float* d_ranges)
     return o;
 }
 
+// enqueue one render of columns [x0,x1) on stream st, using scratch set sc, with outputs to `out` (device memory)
 bool enqueue_render(Slot& s, Scratch& sc, const ViewState& vs, int x0, int x1, const OutSpec& out, cudaStream_t st)
 {
     uint8_t* const d_image = out.image[0];
     float* const d_ranges = out.ranges[0];
+    // a scratch set serves one render at a time: if its previous render went to another stream, wait for that one
+    if(sc.busy_recorded && sc.last_stream != st) CUDA_TRY(cudaStreamWaitEvent(st, sc.busy, 0));
     HzView v{};
     v.mosaic = s.d_mosaic; v.N = s.N; v.pitch = s.pitch;
     v.e_tab = sc.d_e; v.n_tab = sc.d_n;
@@ -516,6 +523,7 @@ bool enqueue_render(Slot& s, Scratch& sc, const ViewState& vs, int x0, int x1, c
         if(sc.graph != nullptr)
         {
             CUDA_TRY(cudaGraphLaunch(sc.graph, st));
+            CUDA_TRY(cudaEventRecord(sc.busy, st)); sc.last_stream = st; sc.busy_recorded = true;
             s.launches_last = sc.graph_launches;
             if(&sc == &s.main) s.have_render = true;
             return true;
@@ -536,6 +544,7 @@ bool enqueue_render(Slot& s, Scratch& sc, const ViewState& vs, int x0, int x1, c
     }
     int launches = 0;
     if(!launch_chain(s, sc, hv, false, d_image || d_ranges, st, ev, &launches)) return false;
+    CUDA_TRY(cudaEventRecord(sc.busy, st)); sc.last_stream = st; sc.busy_recorded = true;
     s.launches_last = launches;
     if(&sc == &s.main) s.have_render = (x0 == 0 && x1 == s.W);
     return true;

@@ -417,3 +417,25 @@ def test_earth_curvature_is_opt_in_and_matches_the_extended_oracle(hz, tiles_c1)
     assert np.array_equal(again_i, flat_i) and np.array_equal(again_r, flat_r)
     with pytest.raises(RuntimeError):
         h.set_earth_curvature(True, 1.5)
+
+
+def test_renders_on_different_streams_do_not_trample_each_other(hz, tiles_c1):
+    """The context's scratch set is shared by the single-view entry points whatever stream they are given: a render
+    queued on one stream right after one on another must wait for it (GPU-side), not corrupt it."""
+    torch = _torch_cuda()
+    W, H, R = 1200, 200, 500
+    h = hz.horizonator(C1_LAT, C1_LON, W, H, dir_dems=tiles_c1, render_radius_cells=R)
+    h.set_zextents(100., 100000.)
+    va = [(C1_LAT, C1_LON, -180.05, 179.95)]
+    vb = [(C1_LAT + 0.05, C1_LON - 0.04, -180.05, 179.95)]
+    want_a = h.render(-180.05, 179.95, lat=va[0][0], lon=va[0][1], zfar=100000.)
+    want_b = h.render(-180.05, 179.95, lat=vb[0][0], lon=vb[0][1], zfar=100000.)
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    ia = torch.empty((H, W, 3), dtype=torch.uint8, device="cuda"); ra = torch.empty((H, W), dtype=torch.float32, device="cuda")
+    ib = torch.empty_like(ia); rb = torch.empty_like(ra)
+    for _ in range(10):
+        h.render_batch_device(va, ia.data_ptr(), ra.data_ptr(), s1.cuda_stream)
+        h.render_batch_device(vb, ib.data_ptr(), rb.data_ptr(), s2.cuda_stream)
+    torch.cuda.synchronize()
+    assert np.array_equal(ia.cpu().numpy(), want_a[0]) and np.array_equal(ra.cpu().numpy(), want_a[1])
+    assert np.array_equal(ib.cpu().numpy(), want_b[0]) and np.array_equal(rb.cpu().numpy(), want_b[1])
