@@ -101,6 +101,7 @@ def _declare(lib):
         "horizonator_render_counters": (b, [ctx, P(C.c_uint * 16)]),
         "horizonator_horizon_profile_device": (b, [ctx, vp, i, vp, vp, vp]),
         "horizonator_set_earth_curvature": (b, [ctx, b, f]),
+        "horizonator_set_seam_wrap": (b, [ctx, b]),
         "horizonator_peer_alloc": (b, [ctx, C.c_size_t, P(vp), P(C.c_ubyte * 64)]),
         "horizonator_peer_open": (b, [ctx, P(C.c_ubyte * 64), P(vp)]),
         "horizonator_peer_close": (b, [ctx, vp]),
@@ -134,7 +135,7 @@ EXPORTED_SYMBOLS = (
     "horizonator_download_mosaic", "horizonator_time_mosaic", "horizonator_last_render_stats",
     "horizonator_profile_enable", "horizonator_profile_read",
     "horizonator_host_alloc", "horizonator_host_free",
-    "horizonator_render_counters", "horizonator_horizon_profile_device", "horizonator_set_earth_curvature",
+    "horizonator_render_counters", "horizonator_horizon_profile_device", "horizonator_set_earth_curvature", "horizonator_set_seam_wrap",
     "horizonator_peer_alloc", "horizonator_peer_open", "horizonator_peer_close", "horizonator_peer_free",
     "horizonator_render_wedge_peers",
 )
@@ -286,6 +287,12 @@ class horizonator:
         if not lib.horizonator_render_wedge_device(C.byref(self._ctx), int(x0), int(x1),
                                                    d_image or None, d_ranges or None, stream or None):
             raise RuntimeError("horizonator_render_wedge_device() failed")
+
+    def set_seam_wrap(self, on=True):
+        """Opt-in (off by default; the reference drops them): draw triangles across the +-180 degree seam at both
+        edges of a full-circle panorama.  See horizonator-batch.h."""
+        if not lib.horizonator_set_seam_wrap(C.byref(self._ctx), bool(on)):
+            raise RuntimeError("horizonator_set_seam_wrap() failed")
 
     def set_earth_curvature(self, on=True, refraction=0.13):
         """Opt-in accuracy mode (off by default; the reference is flat-earth): see horizonator-batch.h."""

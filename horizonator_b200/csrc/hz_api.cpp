@@ -132,6 +132,7 @@ struct Slot
 
     // optional per-kernel timing: PROF_EVENTS events per recorded render
     bool profiling = false;
+    bool  seam_wrap = false;         // opt-in (horizonator_set_seam_wrap); false = seam triangles dropped like the reference
     float curvature = 0.f;           // opt-in (horizonator_set_earth_curvature); 0 = flat earth like the reference
     bool use_graphs = true;
     bool collect_stats = false;      // culling counters (horizonator_render_counters); off: the kernels skip them
@@ -451,6 +452,7 @@ bool enqueue_render(Slot& s, Scratch& sc, const ViewState& vs, int x0, int x1, c
     v.az_center      = (az_rad0 + az_rad1) / 2.f;
     v.az_ndc_per_rad = 2.0f / (az_rad1 - az_rad0);
     v.aspect         = (float)s.W / (float)s.H;                          // lib:658-659
+    v.seam_period    = s.seam_wrap ? v.az_ndc_per_rad * 2.f * PI_F : 0.0f;
 
     v.znear = s.znear; v.zfar = s.zfar; v.znear_color = s.znear_color; v.zfar_color = s.zfar_color;
     v.W = s.W; v.H = s.H; v.x0 = x0; v.x1 = x1;
@@ -1120,6 +1122,14 @@ bool horizonator_render_wedge_peers(const horizonator_context_t* ctx, int x0, in
     cudaStream_t st = stream ? (cudaStream_t)stream : s->stream;
     if(!enqueue_render(*s, s->main, s->view, x0, x1, out, st)) return false;
     if(stream == nullptr) CUDA_TRY(cudaStreamSynchronize(st));
+    return true;
+}
+
+bool horizonator_set_seam_wrap(const horizonator_context_t* ctx, bool on)
+{
+    Slot* s = slot_of(ctx);
+    if(s == nullptr) return false;
+    s->seam_wrap = on;
     return true;
 }
 

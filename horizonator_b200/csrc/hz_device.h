@@ -67,6 +67,8 @@ struct HzView
     float viewer_cell_i, viewer_cell_j, viewer_z;
     float deg_per_cell, cos_viewer_lat;
     float curvature;             // 0 = the reference's flat earth; else apparent height drops by curvature * distance^2
+    float seam_period;           // 0 = the reference (triangles across the window's +-pi seam are dropped); else the
+                                 // period of x_ndc, az_ndc_per_rad * 2 * pi: such triangles are drawn at both edges
 
     // azimuth window; scalars the vertex shader derives from az_deg0/az_deg1 (vertex.glsl:139-150),
     // computed once on the host in float exactly as written there

@@ -251,13 +251,15 @@ struct HzTri
     unsigned int id;
 };
 
-// geometry.glsl:21-27, guard band, back-face cull, bounding box.  False if the triangle produces nothing.
-__device__ __forceinline__ bool
+enum { HZ_SETUP_NOTHING = 0, HZ_SETUP_OK = 1, HZ_SETUP_TOO_WIDE = -1 };
+
+// geometry.glsl:21-27, guard band, back-face cull, bounding box.  HZ_SETUP_OK, or why the triangle produces nothing.
+__device__ __forceinline__ int
 hz_tri_bounds(const HzView& P, const HzVtx& a, const HzVtx& b, const HzVtx& c, HzTri& T)
 {
     const float xmax = fmaxf(fmaxf(a.xn, b.xn), c.xn);
     const float xmin = fminf(fminf(a.xn, b.xn), c.xn);
-    if(xmax - xmin > 0.5f) return false;                                     // geometry.glsl:21-27
+    if(xmax - xmin > 0.5f) return HZ_SETUP_TOO_WIDE;                         // geometry.glsl:21-27
 
     const float halfW = 0.5f * (float)P.W, halfH = 0.5f * (float)P.H;
     T.xw0 = a.xn * halfW + halfW; T.yw0 = a.yn * halfH + halfH;              // viewport transform (F1)
@@ -265,7 +267,7 @@ hz_tri_bounds(const HzView& P, const HzVtx& a, const HzVtx& b, const HzVtx& c, H
     T.xw2 = c.xn * halfW + halfW; T.yw2 = c.yn * halfH + halfH;
     if(!(fabsf(T.xw0) < HZ_GUARD_PX && fabsf(T.yw0) < HZ_GUARD_PX &&
          fabsf(T.xw1) < HZ_GUARD_PX && fabsf(T.yw1) < HZ_GUARD_PX &&
-         fabsf(T.xw2) < HZ_GUARD_PX && fabsf(T.yw2) < HZ_GUARD_PX)) return false;   // F5
+         fabsf(T.xw2) < HZ_GUARD_PX && fabsf(T.yw2) < HZ_GUARD_PX)) return HZ_SETUP_NOTHING;   // F5
 
     T.X0 = hz_snap(T.xw0); T.Y0 = hz_snap(T.yw0);
     T.X1 = hz_snap(T.xw1); T.Y1 = hz_snap(T.yw1);
@@ -273,7 +275,7 @@ hz_tri_bounds(const HzView& P, const HzVtx& a, const HzVtx& b, const HzVtx& c, H
 
     // GL_CULL_FACE, front = counter-clockwise, y up (lib:184; F3)
     const long long area = (long long)(T.X1 - T.X0) * (T.Y2 - T.Y0) - (long long)(T.X2 - T.X0) * (T.Y1 - T.Y0);
-    if(area <= 0) return false;
+    if(area <= 0) return HZ_SETUP_NOTHING;
 
     const int bx0 = min(min(T.X0, T.X1), T.X2), bx1 = max(max(T.X0, T.X1), T.X2);
     const int by0 = min(min(T.Y0, T.Y1), T.Y2), by1 = max(max(T.Y0, T.Y1), T.Y2);
@@ -282,7 +284,7 @@ hz_tri_bounds(const HzView& P, const HzVtx& a, const HzVtx& b, const HzVtx& c, H
     T.px1 = min((bx1 - 128) >> 8, P.x1 - 1);
     T.py0 = max((by0 + 127) >> 8, 0);
     T.py1 = min((by1 - 128) >> 8, P.H - 1);
-    return T.px0 <= T.px1 && T.py0 <= T.py1;
+    return (T.px0 <= T.px1 && T.py0 <= T.py1) ? HZ_SETUP_OK : HZ_SETUP_NOTHING;
 }
 
 // vertex.glsl:155,159-160 for one vertex: window depth and red channel
@@ -322,8 +324,12 @@ hz_tri_planes(const HzView& P, HzTri& T,
     T.zw_hi = zw_max + 4.0f * (zw_max - zw_min);
 }
 
-// complete set-up of triangle `id` from the mosaic; false if it produces nothing
-__device__ __forceinline__ bool hz_tri_setup(const HzView& P, unsigned int id, HzTri& T, bool with_planes)
+// Complete set-up of triangle `id` from the mosaic: HZ_SETUP_OK, or why it produces nothing.
+// copy = 0: the triangle as the reference draws it.  copy = 1, 2: only with the opt-in seam wrap (P.seam_period > 0),
+// for a triangle that straddles the +-pi seam of the window and is therefore "too wide" as it stands: the same
+// triangle with its left-hand vertices moved one period to the right (1), and that moved one period to the left (2)
+// -- its two appearances at the right and left edge of a full-circle panorama.
+__device__ __forceinline__ int hz_tri_setup(const HzView& P, unsigned int id, int copy, HzTri& T)
 {
     int vj[3], vi[3];
     hz_tri_vertices(id, P.N, vj, vi);
@@ -336,17 +342,25 @@ __device__ __forceinline__ bool hz_tri_setup(const HzView& P, unsigned int id, H
         n[k] = __ldg(P.n_tab + vj[k]);
         const float z = (float)__ldg(P.mosaic + (size_t)vj[k] * P.pitch + vi[k]);
         hz_project(P, e[k], n[k], z, v[k]);
+        if(copy >= 1 && v[k].xn < 0.0f) v[k].xn += P.seam_period;
+        if(copy == 2) v[k].xn -= P.seam_period;
     }
-    if(!hz_tri_bounds(P, v[0], v[1], v[2], T)) return false;
+    const int st = hz_tri_bounds(P, v[0], v[1], v[2], T);
+    if(st != HZ_SETUP_OK) return st;
     T.id = id;
-    if(with_planes)
-    {
-        hz_tri_planes(P, T, e[0], n[0], v[0].z, e[1], n[1], v[1].z, e[2], n[2], v[2].z);
-        // every fragment's depth lies in [zw_lo, zw_hi] (F6): entirely in front of the near plane or behind the far
-        // plane means every fragment is clipped (F5).  This removes the giants right under the eye.
-        if(T.zw_hi < 0.0f || T.zw_lo > 1.0f) return false;
-    }
-    return true;
+    hz_tri_planes(P, T, e[0], n[0], v[0].z, e[1], n[1], v[1].z, e[2], n[2], v[2].z);
+    // every fragment's depth lies in [zw_lo, zw_hi] (F6): entirely in front of the near plane or behind the far
+    // plane means every fragment is clipped (F5).  This removes the giants right under the eye.
+    if(T.zw_hi < 0.0f || T.zw_lo > 1.0f) return HZ_SETUP_NOTHING;
+    return HZ_SETUP_OK;
+}
+
+// The copies of a triangle to draw: 0 always; 1 and 2 if 0 came out too wide and the seam wrap is on.  Usage:
+//   for(int copy = 0; copy >= 0; copy = hz_next_copy(P, copy, st)) { st = hz_tri_setup(P, id, copy, T); ... }
+__device__ __forceinline__ int hz_next_copy(const HzView& P, int copy, int status_of_copy)
+{
+    if(copy == 0) return (status_of_copy == HZ_SETUP_TOO_WIDE && P.seam_period > 0.0f) ? 1 : -1;
+    return copy == 1 ? 2 : -1;
 }
 
 // F7: floor(zw * (2^24-1) + 0.5) for 0 <= zw <= 1, exactly as the double-precision expression of the oracle gives it
@@ -591,6 +605,9 @@ hz_tri_alive(const HzView& P, const HzLaneVtx& a, const HzLaneVtx& b, const HzLa
     const int px0 = (bx0 + 127) >> 8, px1 = (bx1 - 128) >> 8;
     const int py0 = (by0 + 127) >> 8, py1 = (by1 - 128) >> 8;
     if(!(px0 <= px1 && py0 <= py1 && px1 >= P.x0 && px0 < P.x1 && py1 >= 0 && py0 < P.H)) return false;
+    // opt-in seam wrap: a triangle about a quarter of the window wide or more may be a seam straddler whose two
+    // copies show at the edges; its facing as it stands says nothing, set-up decides
+    if(P.seam_period > 0.0f && (bx1 - bx0) >= P.W * 64 - 1024) return true;
     const long long area = (long long)(b.X - a.X) * (c.Y - a.Y) - (long long)(c.X - a.X) * (b.Y - a.Y);
     return area > 0;
 }
@@ -621,12 +638,18 @@ __device__ __forceinline__ void hz_draw_box(const HzView& P, const HzTri& T)
 // Never on the normal path: draws one triangle completely, whatever its size, in the calling thread.  Used when a
 // queue is full.  Kept out of line so that its registers (64-bit edge functions) spill here instead of inflating
 // the kernels that merely might call it.
-__device__ __noinline__ void hz_draw_slow(const HzView& P, unsigned int id)
+// only_copy < 0: every copy that applies (see hz_tri_setup); else just that one.
+__device__ __noinline__ void hz_draw_slow(const HzView& P, unsigned int id, int only_copy)
 {
-    HzTri T;
-    if(!hz_tri_setup(P, id, T, true)) return;
-    if(hz_tri_is_small(T)) hz_draw_box<int>(P, T);
-    else                   hz_draw_box<long long>(P, T);
+    int st = HZ_SETUP_NOTHING;
+    for(int copy = max(only_copy, 0); copy >= 0; copy = (only_copy < 0) ? hz_next_copy(P, copy, st) : -1)
+    {
+        HzTri T;
+        st = hz_tri_setup(P, id, copy, T);
+        if(st != HZ_SETUP_OK) continue;
+        if(hz_tri_is_small(T)) hz_draw_box<int>(P, T);
+        else                   hz_draw_box<long long>(P, T);
+    }
 }
 
 // What k_big needs of a set-up triangle, as 6 x 16 bytes in the record pool (set-up is ~500 instructions per
@@ -659,30 +682,37 @@ __device__ __forceinline__ void hz_tri_load(const uint4* rec, HzTri& T)
 // Returns the number of queue entries made.
 __device__ __forceinline__ unsigned int hz_raster_one(const HzView& P, unsigned int id)
 {
-    HzTri T;
-    if(!hz_tri_setup(P, id, T, true)) return 0;
-    const int bw = T.px1 - T.px0 + 1, bh = T.py1 - T.py0 + 1;
-    if(bw * bh <= P.small_max_pix && hz_tri_is_small(T))
+    unsigned int queued = 0;
+    int st = HZ_SETUP_NOTHING;
+    for(int copy = 0; copy >= 0; copy = hz_next_copy(P, copy, st))
     {
-        hz_draw_box<int>(P, T);
-        return 0;
+        HzTri T;
+        st = hz_tri_setup(P, id, copy, T);
+        if(st != HZ_SETUP_OK) continue;
+        const int bw = T.px1 - T.px0 + 1, bh = T.py1 - T.py0 + 1;
+        if(bw * bh <= P.small_max_pix && hz_tri_is_small(T))
+        {
+            hz_draw_box<int>(P, T);
+            continue;
+        }
+        const unsigned int ny = (unsigned int)((bh + HZ_BIG_ROWS - 1) / HZ_BIG_ROWS);
+        const unsigned int nx = (unsigned int)((bw + HZ_BIG_COLS - 1) / HZ_BIG_COLS);
+        const unsigned int rec  = atomicAdd(P.bigtri_count, 1u);
+        const unsigned int slot = atomicAdd(P.big_count, nx * ny);
+        if(rec >= P.bigtri_capacity || slot + nx * ny > P.big_capacity)
+        {
+            // pool or queue full: draw it here, and poison the queue slots it reserved (k_big skips those)
+            for(unsigned int k = slot; k < min(slot + nx * ny, P.big_capacity); k++) P.big_queue[k] = make_uint2(0xFFFFFFFFu, 0u);
+            hz_draw_slow(P, id, copy);
+            continue;
+        }
+        hz_tri_store(P.bigtri + (size_t)rec * HZ_TRI_RECORD_VEC, T);
+        for(unsigned int by = 0; by < ny; by++)
+            for(unsigned int bx = 0; bx < nx; bx++)
+                P.big_queue[slot + by * nx + bx] = make_uint2(rec, by | (bx << 16));
+        queued += nx * ny;
     }
-    const unsigned int ny = (unsigned int)((bh + HZ_BIG_ROWS - 1) / HZ_BIG_ROWS);
-    const unsigned int nx = (unsigned int)((bw + HZ_BIG_COLS - 1) / HZ_BIG_COLS);
-    const unsigned int rec  = atomicAdd(P.bigtri_count, 1u);
-    const unsigned int slot = atomicAdd(P.big_count, nx * ny);
-    if(rec >= P.bigtri_capacity || slot + nx * ny > P.big_capacity)
-    {
-        // pool or queue full: draw it here, and poison the queue slots it reserved (k_big skips those)
-        for(unsigned int k = slot; k < min(slot + nx * ny, P.big_capacity); k++) P.big_queue[k] = make_uint2(0xFFFFFFFFu, 0u);
-        hz_draw_slow(P, id);
-        return 0;
-    }
-    hz_tri_store(P.bigtri + (size_t)rec * HZ_TRI_RECORD_VEC, T);
-    for(unsigned int by = 0; by < ny; by++)
-        for(unsigned int bx = 0; bx < nx; bx++)
-            P.big_queue[slot + by * nx + bx] = make_uint2(rec, by | (bx << 16));
-    return nx * ny;
+    return queued;
 }
 
 __device__ __forceinline__ unsigned int hz_warp_sum(unsigned int v)
@@ -721,7 +751,7 @@ __device__ __forceinline__ void hz_stage_flush(const HzView& P, const unsigned i
     for(int k = lane; k < count; k += 32)
     {
         if(base + k < P.tri_capacity) P.tri_queue[base + k] = stage[k];
-        else                          hz_draw_slow(P, stage[k]);      // list full
+        else                          hz_draw_slow(P, stage[k], -1);  // list full
     }
 }
 
@@ -785,7 +815,7 @@ hz_stage_flush_cta(const HzView& P, const HzMeshWarp& M, int count, unsigned int
     for(int k = lane; k < count; k += 32)
     {
         if(base + k < P.tri_capacity) P.tri_queue[base + k] = M.stage[k];
-        else                          hz_draw_slow(P, M.stage[k]);
+        else                          hz_draw_slow(P, M.stage[k], -1);
     }
 }
 

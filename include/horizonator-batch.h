@@ -81,6 +81,14 @@ bool horizonator_render_wedge_peers(const horizonator_context_t* ctx, int x0, in
  * later renders of the context. */
 bool horizonator_set_earth_curvature(const horizonator_context_t* ctx, bool on, float refraction);
 
+/* Opt-in, OFF by default and in every parity test: the reference DROPS every triangle whose vertices lie
+ * on both sides of the window's +-180-degree seam (geometry.glsl:15-27 discards anything wider than a
+ * quarter of the window), which leaves a gap up to one DEM cell wide at the left and right edge of a
+ * full-circle panorama.  When on, such a triangle is drawn twice instead, once at each edge (its
+ * vertices moved by one period of the azimuth mapping), so a 360-degree panorama closes.  Triangles
+ * that are too wide for another reason stay dropped. */
+bool horizonator_set_seam_wrap(const horizonator_context_t* ctx, bool on);
+
 /* Page-locked host memory for output buffers.  horizonator_render_offscreen() and
  * horizonator_render_batch() accept any host pointer; into memory from this allocator (or any
  * other CUDA-registered host memory) the results arrive by DMA at PCIe speed, into ordinary

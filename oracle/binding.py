@@ -55,6 +55,7 @@ class Oracle:
             L.oracle_get_viewer.argtypes = [vp, C.POINTER(C.c_float * 4)]
             L.oracle_set_threads.argtypes = [vp, i]
             L.oracle_set_curvature.argtypes = [vp, f]
+            L.oracle_set_seam_wrap.argtypes = [vp, b]
             cls._lib = L
         return cls._lib
 
@@ -82,6 +83,10 @@ class Oracle:
         z = C.c_float(-1. if viewer_z is None else viewer_z)
         assert self.lib().oracle_move(self.h, C.byref(z), lat, lon)
         return z.value
+
+    def set_seam_wrap(self, on=True):
+        """Opt-in extension (not in the reference): seam-straddling triangles drawn at both edges."""
+        self.lib().oracle_set_seam_wrap(self.h, on)
 
     def set_curvature(self, coefficient):
         """Opt-in extension (not in the reference): height drop = coefficient * distance^2; 0 = off."""

@@ -221,6 +221,7 @@ void glDrawElements(GLenum mode, GLsizei count, GLenum type, const void* indices
     u.znear          = uniform_f("znear");
     u.zfar           = uniform_f("zfar");
     u.curvature      = 0.0f;     /* the reference has no such uniform */
+    u.seam_wrap      = 0;        /* nor this option */
     u.znear_color    = uniform_f("znear_color");
     u.zfar_color     = uniform_f("zfar_color");
 

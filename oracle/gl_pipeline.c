@@ -153,12 +153,32 @@ static inline int64_t snap(float a)                                          /* 
 
 /* pixel target: (q<<8)|r8 per pixel, so a private buffer is one word per pixel */
 static inline void
-draw_one(uint32_t* zr, int W, int H, const glp_vtx_t* v0, const glp_vtx_t* v1, const glp_vtx_t* v2)
+draw_one(uint32_t* zr, int W, int H, const glp_vtx_t* v0, const glp_vtx_t* v1, const glp_vtx_t* v2, float seam_period)
 {
     /* geometry.glsl:21-27 */
     float xmax = fmaxf(fmaxf(v0->x_ndc, v1->x_ndc), v2->x_ndc);
     float xmin = fminf(fminf(v0->x_ndc, v1->x_ndc), v2->x_ndc);
-    if(xmax - xmin > 0.5f) return;
+    if(xmax - xmin > 0.5f)
+    {
+        /* opt-in extension (seam_period > 0; the reference stops here): the triangle with its left-hand vertices
+         * moved one period of x_ndc to the right, and that moved one period to the left */
+        if(seam_period > 0.0f)
+        {
+            const float halfW = 0.5f * (float)W;
+            for(int copy = 1; copy <= 2; copy++)
+            {
+                glp_vtx_t c[3] = { *v0, *v1, *v2 };
+                for(int k = 0; k < 3; k++)
+                {
+                    if(c[k].x_ndc < 0.0f) c[k].x_ndc += seam_period;
+                    if(copy == 2) c[k].x_ndc -= seam_period;
+                    c[k].xw = c[k].x_ndc * halfW + halfW;
+                }
+                draw_one(zr, W, H, &c[0], &c[1], &c[2], 0.0f);
+            }
+        }
+        return;
+    }
 
     /* F5 guard band; also rejects NaN/Inf */
     if(!(fabsf(v0->xw) < GUARD_PX && fabsf(v0->yw) < GUARD_PX &&
@@ -269,6 +289,15 @@ void glp_draw_triangles(glp_framebuffer_t* fb, const glp_uniforms_t* u,
 
     const float halfW = 0.5f * (float)W, halfH = 0.5f * (float)H;
 
+    /* period of x_ndc for the opt-in seam wrap: az_ndc_per_rad (vertex.glsl:139-150) * 2*pi */
+    float seam_period = 0.0f;
+    if(u->seam_wrap)
+    {
+        float az_rad0 = glsl_radians(u->az_deg0), az_rad1 = glsl_radians(u->az_deg1);
+        az_rad1 = unwrap_near_rad(az_rad1 - az_rad0, pi) + az_rad0;
+        seam_period = 2.0f / (az_rad1 - az_rad0) * 2.f * pi;
+    }
+
     #pragma omp parallel for num_threads(nthreads) schedule(static)
     for(int64_t v = 0; v < nvertices; v++)
     {
@@ -296,7 +325,7 @@ void glp_draw_triangles(glp_framebuffer_t* fb, const glp_uniforms_t* u,
         {
             int64_t i0, i1, i2;
             triangle_indices(indices, t, grid_width, &i0, &i1, &i2);
-            draw_one(target, W, H, &vtx[i0], &vtx[i1], &vtx[i2]);
+            draw_one(target, W, H, &vtx[i0], &vtx[i1], &vtx[i2], seam_period);
         }
     }
     else
@@ -317,7 +346,7 @@ void glp_draw_triangles(glp_framebuffer_t* fb, const glp_uniforms_t* u,
             {
                 int64_t i0, i1, i2;
                 triangle_indices(indices, t, grid_width, &i0, &i1, &i2);
-                draw_one(mine, W, H, &vtx[i0], &vtx[i1], &vtx[i2]);
+                draw_one(mine, W, H, &vtx[i0], &vtx[i1], &vtx[i2], seam_period);
             }
         }
         /* merge in draw order with the same strict LESS */

@@ -41,6 +41,9 @@ typedef struct
     /* NOT in the reference (its vertex.glsl:65-88 only estimates the error of ignoring it): opt-in earth
      * curvature + refraction, apparent height drop = curvature * horizontal_distance^2.  0 = the reference. */
     float curvature;
+    /* NOT in the reference either (geometry.glsl:15-27 drops them): opt-in, nonzero = draw a triangle that
+     * straddles the window's +-pi seam twice, once at each edge of the window. */
+    int   seam_wrap;
 } glp_uniforms_t;
 
 /* what the vertex stage hands on: gl_Position.xyz (w is 1) and rgb.r */

@@ -268,3 +268,4 @@ bool oracle_render_offscreen(oracle_context_t* c, char* image, float* ranges)
 }
 
 void oracle_set_curvature(oracle_context_t* c, float coefficient) { c->u.curvature = coefficient; }
+void oracle_set_seam_wrap(oracle_context_t* c, bool on) { c->u.seam_wrap = on ? 1 : 0; }

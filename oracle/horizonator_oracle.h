@@ -48,6 +48,8 @@ void oracle_get_viewer(const oracle_context_t* ctx, float outf[4]);
 
 /* opt-in extension, not in the reference: apparent height drop = coefficient * distance^2 (0 = off) */
 void oracle_set_curvature(oracle_context_t* ctx, float coefficient);
+/* opt-in extension, not in the reference: draw seam-straddling triangles at both edges instead of dropping them */
+void oracle_set_seam_wrap(oracle_context_t* ctx, bool on);
 
 /* number of OpenMP threads the draw uses (1 = strictly serial). Default 1. */
 void oracle_set_threads(oracle_context_t* ctx, int nthreads);

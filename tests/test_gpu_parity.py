@@ -439,3 +439,35 @@ def test_renders_on_different_streams_do_not_trample_each_other(hz, tiles_c1):
     torch.cuda.synchronize()
     assert np.array_equal(ia.cpu().numpy(), want_a[0]) and np.array_equal(ra.cpu().numpy(), want_a[1])
     assert np.array_equal(ib.cpu().numpy(), want_b[0]) and np.array_equal(rb.cpu().numpy(), want_b[1])
+
+
+def test_seam_wrap_is_opt_in_and_closes_the_full_circle(hz, tiles_c1):
+    """Off by default: triangles across the +-180 degree seam are dropped like the reference does (geometry.glsl:15-27),
+    leaving gaps in the edge columns.  On: they are drawn at both edges, in the CUDA path and in the oracle's opt-in
+    extension alike; everything away from the edges is unchanged."""
+    W, H, R = 1440, 240, 300
+    az0, az1 = -180.0, 179.99                       # seam looking due south; 359.99 degrees wide
+    h = hz.horizonator(C1_LAT, C1_LON, W, H, dir_dems=tiles_c1, render_radius_cells=R)
+    base_i, base_r = h.render(az0, az1, zfar=60000.)
+    h.set_seam_wrap(True)
+    img, rng = h.render(az0, az1, zfar=60000.)
+    o = _oracle(tiles_c1, W, H, R)
+    o.set_seam_wrap(True)
+    img_o, rng_o = o.render(az0, az1, zfar=60000.)
+    s = compare_renders(img, rng, img_o, rng_o)
+    print("wrapped", s)
+    assert s["ok"], s
+    # a seam triangle is at most a quarter of the window wide (wider ones stay dropped), so beyond that distance from
+    # the edges nothing changes; at the edges terrain is gained and none is lost
+    m = W // 4 + 2
+    assert np.array_equal(rng[:, m:-m], base_r[:, m:-m]) and np.array_equal(img[:, m:-m], base_i[:, m:-m])
+    edge = np.r_[0:3, W - 3:W]
+    gained = (rng[:, edge] > 0).sum() - (base_r[:, edge] > 0).sum()
+    assert gained > 0, gained
+    assert ((base_r[:, edge] > 0) <= (rng[:, edge] > 0)).all()
+    # in the wrapped render the first and the last column see (nearly) the same terrain rows: the circle closes
+    top = lambda col: int(np.argmax(rng[:, col] > 0))
+    assert abs(top(0) - top(W - 1)) <= 2
+    h.set_seam_wrap(False)
+    again_i, again_r = h.render(az0, az1, zfar=60000.)
+    assert np.array_equal(again_i, base_i) and np.array_equal(again_r, base_r)
