@@ -471,3 +471,32 @@ def test_seam_wrap_is_opt_in_and_closes_the_full_circle(hz, tiles_c1):
     h.set_seam_wrap(False)
     again_i, again_r = h.render(az0, az1, zfar=60000.)
     assert np.array_equal(again_i, base_i) and np.array_equal(again_r, base_r)
+
+
+@pytest.mark.parametrize("R,W,H", [(1, 64, 32), (2, 90, 45), (3, 128, 48), (17, 200, 60)])
+def test_tiny_meshes(hz, tiles_c1, R, W, H):
+    """Meshes smaller than one culling block / tile, down to the single cell of R=1."""
+    h = hz.horizonator(C1_LAT, C1_LON, W, H, dir_dems=tiles_c1, render_radius_cells=R)
+    img, rng = h.render(-180.05, 179.95, znear=1., zfar=10000.)
+    o = _oracle(tiles_c1, W, H, R)
+    img_o, rng_o = o.render(-180.05, 179.95, znear=1., zfar=10000.)
+    assert np.array_equal(h.mosaic(), o.mosaic())
+    s = compare_renders(img, rng, img_o, rng_o)
+    print("tiny", R, s)
+    assert s["ok"], s
+
+
+def test_eye_outside_the_loaded_square(hz, tiles_c1):
+    """horizonator_move() does not reload DEMs (horizonator.h:120-122): the eye may leave the square, and then sees it
+    from outside (every mesh rectangle in one quadrant, the eye's tile clamped to the edge)."""
+    W, H, R = 600, 120, 200
+    h = hz.horizonator(C1_LAT, C1_LON, W, H, dir_dems=tiles_c1, render_radius_cells=R)
+    o = _oracle(tiles_c1, W, H, R)
+    for dlat, dlon in ((0.3, 0.25), (-0.21, 0.0), (0.0, -0.4)):
+        kw = dict(lat=C1_LAT + dlat, lon=C1_LON + dlon, znear=100., zfar=100000.)
+        img, rng = h.render(-180.05, 179.95, **kw)
+        img_o, rng_o = o.render(-180.05, 179.95, **kw)
+        s = compare_renders(img, rng, img_o, rng_o)
+        print("outside", dlat, dlon, s)
+        assert s["hit_fraction_ref"] > 0.0005
+        assert s["ok"], s
