@@ -112,6 +112,7 @@ struct HzView
 
     float cell_diag2;            // (east cell size)^2 + (north cell size)^2 in metres^2, rounded up
     float inv_zrange;            // 1/(zfar-znear), for the conservative depth bound only
+    float box_margin;            // pixels added around the screen box of a mesh rectangle (hz_rect_test)
 
     // k_prepare zeroes these; k_resolve turns the visibility keys into the outputs
     uint32_t* counters;

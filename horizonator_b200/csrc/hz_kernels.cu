@@ -37,6 +37,18 @@ __device__ __forceinline__ void hz_wait_for_previous_kernel()
     cudaTriggerProgrammaticLaunchCompletion();
 }
 
+// First statements of every render kernel: the CTA copies its parameter block (written by the host->device copy
+// that precedes the whole chain, not by an earlier kernel of it) into shared memory BEFORE it waits for the previous
+// kernel, so that those reads overlap that kernel's tail instead of following it; afterwards every P.field is a
+// shared-memory read.
+#define HZ_KERNEL_PROLOGUE(V, P)                                                                           \
+    __shared__ HzView hz_s_view;                                                                           \
+    for(unsigned int hz_i = threadIdx.x; hz_i < sizeof(HzView) / 4; hz_i += blockDim.x)                    \
+        ((uint32_t*)&hz_s_view)[hz_i] = __ldg((const uint32_t*)(V) + hz_i);                                \
+    __syncthreads();                                                                                       \
+    hz_wait_for_previous_kernel();                                                                         \
+    const HzView& P = hz_s_view
+
 template <typename... KArgs, typename... Args>
 static cudaError_t hz_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, cudaStream_t stream, Args&&... args)
 {
@@ -154,8 +166,7 @@ cudaError_t hz_launch_mosaic(const HzTiles& t, int16_t* mosaic, int N, int pitch
 __global__ void __launch_bounds__(256)
 k_prepare(const HzView* __restrict__ V)
 {
-    hz_wait_for_previous_kernel();
-    const HzView& P = *V;
+    HZ_KERNEL_PROLOGUE(V, P);
     const unsigned int tid = blockIdx.x * blockDim.x + threadIdx.x;
     const unsigned int nth = gridDim.x * blockDim.x;
 
@@ -496,14 +507,13 @@ cudaError_t hz_launch_pyramid(const int16_t* mosaic, int N, int pitch, short2* m
 // Screen box.  Inside one quadrant around the eye the azimuth atan2(e,n) is monotonic in e and in n, so its
 // extremes over the rectangle sit on two known corners; the elevation atan(h/d) is bounded by the extreme heights
 // over the nearest/farthest horizontal distance.  The same device functions as for real vertices are used and
-// HZ_BOX_MARGIN (1/64) pixel is added all around, which covers their few-ulp non-monotonicity (< 1/1000 pixel) and
-// the 1/512 pixel of snapping.
+// P.box_margin (1/64 pixel, plus a few float ulps of the largest window coordinate) is added all around, which
+// covers their few-ulp non-monotonicity and the 1/512 pixel of snapping.
 // Depth.  A vertex depth is a monotonic float function of its slant range >= its horizontal distance >= the
 // rectangle's nearest horizontal distance.  A fragment's depth stays within its triangle's vertex depths widened
 // by 4x their extent (F6), and the slant ranges of one triangle's vertices differ by at most their 3-D distance
 // <= sqrt(cell diagonal^2 + (zmax-zmin)^2).  That gives a lower bound for the depth of every fragment.
 
-#define HZ_BOX_MARGIN 0.015625f
 
 struct HzBox { int px0, px1, py0, py1; unsigned int qmin; };
 enum { HZ_RECT_DEAD_FAR = 0, HZ_RECT_DEAD_WINDOW = 1, HZ_RECT_ALIVE = 2, HZ_RECT_BOXED = 3 };
@@ -559,8 +569,8 @@ hz_rect_test(const HzView& P, int c_lo, int c_hi, int r_lo, int r_hi, float zmin
     const float y_lo = el_lo * P.aspect * P.az_ndc_per_rad * halfH + halfH;
 
     // pixel centres p + 0.5 inside [lo - margin, hi + margin]; the float->int conversions saturate
-    const float fx0 = ceilf(x_lo - 0.5f - HZ_BOX_MARGIN), fx1 = floorf(x_hi - 0.5f + HZ_BOX_MARGIN);
-    const float fy0 = ceilf(y_lo - 0.5f - HZ_BOX_MARGIN), fy1 = floorf(y_hi - 0.5f + HZ_BOX_MARGIN);
+    const float fx0 = ceilf(x_lo - 0.5f - P.box_margin), fx1 = floorf(x_hi - 0.5f + P.box_margin);
+    const float fy0 = ceilf(y_lo - 0.5f - P.box_margin), fy1 = floorf(y_hi - 0.5f + P.box_margin);
     if(!(fx0 <= fx1 && fy0 <= fy1)) return HZ_RECT_DEAD_WINDOW;
     if(fx1 < (float)P.x0 || fx0 > (float)(P.x1 - 1) || fy1 < 0.f || fy0 > (float)(P.H - 1)) return HZ_RECT_DEAD_WINDOW;
     B.px0 = max((int)fx0, P.x0); B.px1 = min((int)fx1, P.x1 - 1);
@@ -832,8 +842,7 @@ __device__ __forceinline__ void hz_near_tiles(const HzView& P, int& ti0, int& ti
 __global__ void __launch_bounds__(HZ_WARPS_PER_CTA * 32, 4)
 k_near(const HzView* __restrict__ V)
 {
-    hz_wait_for_previous_kernel();
-    const HzView& P = *V;
+    HZ_KERNEL_PROLOGUE(V, P);
     __shared__ HzMeshWarp s_warp[HZ_WARPS_PER_CTA];
     __shared__ unsigned int s_total, s_base;
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -975,8 +984,7 @@ __device__ __forceinline__ void hz_cta_stats4(unsigned int* s4, unsigned int* gl
 __global__ void __launch_bounds__(256)
 k_tiles(const HzView* __restrict__ V)
 {
-    hz_wait_for_previous_kernel();
-    const HzView& P = *V;
+    HZ_KERNEL_PROLOGUE(V, P);
     __shared__ HzCtaAppend s_app;
     __shared__ unsigned int s_stats[4];
     const int nt = P.nt, N = P.N;
@@ -1019,8 +1027,7 @@ k_tiles(const HzView* __restrict__ V)
 __global__ void __launch_bounds__(256)
 k_blocks(const HzView* __restrict__ V)
 {
-    hz_wait_for_previous_kernel();
-    const HzView& P = *V;
+    HZ_KERNEL_PROLOGUE(V, P);
     __shared__ HzCtaAppend s_app;
     __shared__ unsigned int s_stats[4];
     const int nt = P.nt, nb = P.nb, N = P.N;
@@ -1059,8 +1066,7 @@ k_blocks(const HzView* __restrict__ V)
 __global__ void __launch_bounds__(HZ_WARPS_PER_CTA * 32, 4)
 k_mesh(const HzView* __restrict__ V)
 {
-    hz_wait_for_previous_kernel();
-    const HzView& P = *V;
+    HZ_KERNEL_PROLOGUE(V, P);
     __shared__ HzMeshWarp s_warp[HZ_WARPS_PER_CTA];
     __shared__ unsigned int s_total, s_base;
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -1106,8 +1112,7 @@ k_mesh(const HzView* __restrict__ V)
 __global__ void __launch_bounds__(256, 3)
 k_raster(const HzView* __restrict__ V)
 {
-    hz_wait_for_previous_kernel();
-    const HzView& P = *V;
+    HZ_KERNEL_PROLOGUE(V, P);
     const unsigned int n = min(*P.tri_count, P.tri_capacity);
     const unsigned int nth = gridDim.x * blockDim.x;
     unsigned int n_big = 0;
@@ -1170,8 +1175,7 @@ __device__ __forceinline__ void hz_draw_subbox(const HzView& P, const HzTri& T, 
 __global__ void __launch_bounds__(256)
 k_big(const HzView* __restrict__ V)
 {
-    hz_wait_for_previous_kernel();
-    const HzView& P = *V;
+    HZ_KERNEL_PROLOGUE(V, P);
     // every slot below min(count, capacity) was written: with a record index, or poisoned by a triangle that found
     // the record pool or the queue exhausted and drew itself (hz_raster_one)
     unsigned int count = *P.big_count;
@@ -1240,8 +1244,8 @@ __device__ __forceinline__ HzResolve hz_resolve_params(const HzView& P)
 __global__ void __launch_bounds__(256)
 k_resolve4(const HzView* __restrict__ V)
 {
-    hz_wait_for_previous_kernel();
-    const HzResolve R = hz_resolve_params(*V);
+    HZ_KERNEL_PROLOGUE(V, P);
+    const HzResolve R = hz_resolve_params(P);
     const int groups_per_row = R.Wt >> 2;
     const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if(g >= (long long)groups_per_row * R.H) return;
@@ -1270,7 +1274,7 @@ k_resolve4(const HzView* __restrict__ V)
 
     float4 r = make_float4(-1.0f, -1.0f, -1.0f, -1.0f);
     // most groups of four pixels are sky: skip the FP64 conversion for them altogether
-    if(V->out_ranges[0] != nullptr &&
+    if(P.out_ranges[0] != nullptr &&
        ((unsigned int)(k[0] >> 40) & (unsigned int)(k[1] >> 40) & (unsigned int)(k[2] >> 40) & (unsigned int)(k[3] >> 40)) != HZ_Q_MAX)
     {
         const float t = R.tanel[y];
@@ -1281,8 +1285,8 @@ k_resolve4(const HzView* __restrict__ V)
     }
     for(int d = 0; d < R.n_out; d++)
     {
-        uint8_t* image = V->out_image[d];
-        float* ranges = V->out_ranges[d];
+        uint8_t* image = P.out_image[d];
+        float* ranges = P.out_ranges[d];
         if(image)
         {
             uint32_t* o = (uint32_t*)(image + dst * 3);    // dst*3 is a multiple of 4 because x, x0 and the stride are
@@ -1296,19 +1300,19 @@ k_resolve4(const HzView* __restrict__ V)
 __global__ void __launch_bounds__(256)
 k_resolve1(const HzView* __restrict__ V)
 {
-    hz_wait_for_previous_kernel();
-    const HzResolve R = hz_resolve_params(*V);
+    HZ_KERNEL_PROLOGUE(V, P);
+    const HzResolve R = hz_resolve_params(P);
     const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if(g >= (long long)R.Wt * R.H) return;
     const int y = (int)(g / R.Wt), x = (int)(g % R.Wt);
     const unsigned long long key = R.vis[g];
     const size_t dst = (size_t)(R.H - 1 - y) * R.out_stride + R.out_x0 + x;
     const bool hit = (unsigned int)(key >> 40) != HZ_Q_MAX;
-    const float range = (V->out_ranges[0] != nullptr) ? hz_range_of_key(key, R.tanel[y], R.znear, R.zfar) : -1.0f;
+    const float range = (P.out_ranges[0] != nullptr) ? hz_range_of_key(key, R.tanel[y], R.znear, R.zfar) : -1.0f;
     for(int d = 0; d < R.n_out; d++)
     {
-        uint8_t* image = V->out_image[d];
-        float* ranges = V->out_ranges[d];
+        uint8_t* image = P.out_image[d];
+        float* ranges = P.out_ranges[d];
         if(image)
         {
             image[dst * 3 + 0] = hit ? 0 : 255;
