@@ -111,3 +111,19 @@ def test_horizon_profile_kernel_matches_reference_implementation(pair_c2):
     want_rows, want_top = sharding.horizon_profile(d_rng)
     assert torch.equal(rows, want_rows) and torch.equal(top, want_top)
     assert (rows >= 0).float().mean() > 0.9        # nearly every column sees terrain somewhere
+
+
+def test_very_wide_panorama_matches_oracle(tiles_c2):
+    """36000 columns (0.01 degrees per pixel, BASELINE config 4's width): window coordinates reach 36000, where a float
+    ulp is 1/256 pixel -- the margins of the conservative culling boxes have to allow for that."""
+    import horizonator_b200 as hz
+    from oracle.binding import Oracle
+    W, H, R = 36000, 400, 500
+    h = hz.horizonator(C2_LAT, C2_LON, W, H, SRTM1=True, dir_dems=tiles_c2, render_radius_cells=R)
+    img, rng = h.render(-180.005, 179.995, znear=50., zfar=30000.)
+    o = Oracle(C2_LAT, C2_LON, W, H, SRTM1=True, dir_dems=tiles_c2, render_radius_cells=R, threads=8)
+    img_o, rng_o = o.render(-180.005, 179.995, znear=50., zfar=30000.)
+    s = compare_renders(img, rng, img_o, rng_o)
+    print("very wide", s)
+    assert s["hit_fraction_ref"] > 0.01
+    assert s["ok"], s
