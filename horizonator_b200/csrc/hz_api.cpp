@@ -35,8 +35,8 @@ constexpr float PI_F            = 3.14159265358979f;       // vertex.glsl:31
 // Queue capacities grow with the image (set in alloc_target); whatever does not fit is drawn by a slow in-kernel
 // path, so these only have to be generous, not safe.
 //   triangles of one stage awaiting set-up:                    max(2^22, pixels/2)
-//   (record, sub-box) pairs for the large-triangle kernel:     max(2^20, pixels/8) per pass
-//   set-up records of those triangles:                         max(2^16, pixels/16)
+//   (record, sub-box) pairs for the large-triangle kernel:     max(2^21, pixels) per pass
+//   set-up records of those triangles:                         max(2^17, pixels/8); beyond that k_big repeats the set-up
 constexpr int   PROF_EVENTS     = 7;            // 6 stages per render
 constexpr int   MAX_BANDS       = HZ_MAX_BANDS;
 // [0] big_count near, [1] big_count bands, [2] tri_count near, [3] big-triangle records, [4+3b] tile_count,
@@ -215,7 +215,7 @@ bool alloc_target(Slot& s, int W, int H)
         return (uint32_t)(c > 0x7FFFFFFFu ? 0x7FFFFFFFu : c);
     };
     s.target_pixels = px;
-    s.tri_capacity = cap((size_t)1 << 22, 2); s.big_capacity = cap((size_t)1 << 20, 8); s.bigtri_capacity = cap((size_t)1 << 16, 16);
+    s.tri_capacity = cap((size_t)1 << 22, 2); s.big_capacity = cap((size_t)1 << 21, 1); s.bigtri_capacity = cap((size_t)1 << 17, 8);
     // tests shrink the queues to exercise the overflow paths
     if(const char* env = getenv("HORIZONATOR_TRI_CAPACITY"))    s.tri_capacity    = (uint32_t)(atoi(env) > 1 ? atoi(env) : 1);
     if(const char* env = getenv("HORIZONATOR_BIG_CAPACITY"))    s.big_capacity    = (uint32_t)(atoi(env) > 1 ? atoi(env) : 1);

@@ -591,7 +591,9 @@ __device__ __forceinline__ unsigned int hz_vis_depth(const HzView& P, int px, in
 
 #define HZ_WARPS_PER_CTA 8
 #define HZ_BIG_ROWS      4         /* large bounding boxes are cut into sub-boxes of this size for k_big: */
-#define HZ_BIG_COLS      32        /* lane = column, a few rows each */
+#define HZ_BIG_COLS      32        /* lane = column, a few rows each (more for very large triangles) */
+#define HZ_BIG_MAX_ENTRIES 64u
+#define HZ_BIG_RECOMPUTE   0x80000000u   /* queue entry: .x is a triangle number (set up again), not a record */
 
 struct HzLaneVtx { int X, Y; };
 
@@ -705,21 +707,27 @@ __device__ __forceinline__ unsigned int hz_raster_one(const HzView& P, unsigned 
             hz_draw_box<int>(P, T);
             continue;
         }
-        const unsigned int ny = (unsigned int)((bh + HZ_BIG_ROWS - 1) / HZ_BIG_ROWS);
+        // sub-boxes: HZ_BIG_COLS columns wide and HZ_BIG_ROWS << k rows tall, k the smallest that keeps the number of
+        // queue entries of this triangle (written by this one thread) at or below HZ_BIG_MAX_ENTRIES where possible
         const unsigned int nx = (unsigned int)((bw + HZ_BIG_COLS - 1) / HZ_BIG_COLS);
-        const unsigned int rec  = atomicAdd(P.bigtri_count, 1u);
+        unsigned int k = 0, ny = (unsigned int)((bh + HZ_BIG_ROWS - 1) / HZ_BIG_ROWS);
+        while(nx * ny > HZ_BIG_MAX_ENTRIES && ny > 1) { k++; ny = (unsigned int)((bh + (HZ_BIG_ROWS << k) - 1) / (HZ_BIG_ROWS << k)); }
         const unsigned int slot = atomicAdd(P.big_count, nx * ny);
-        if(rec >= P.bigtri_capacity || slot + nx * ny > P.big_capacity)
+        if(slot + nx * ny > P.big_capacity)
         {
-            // pool or queue full: draw it here, and poison the queue slots it reserved (k_big skips those)
-            for(unsigned int k = slot; k < min(slot + nx * ny, P.big_capacity); k++) P.big_queue[k] = make_uint2(0xFFFFFFFFu, 0u);
+            // queue full: draw it here, and poison the queue slots it reserved (k_big skips those)
+            for(unsigned int q = slot; q < min(slot + nx * ny, P.big_capacity); q++) P.big_queue[q] = make_uint2(0xFFFFFFFFu, 0u);
             hz_draw_slow(P, id, copy);
             continue;
         }
-        hz_tri_store(P.bigtri + (size_t)rec * HZ_TRI_RECORD_VEC, T);
+        // the set-up triangle goes to the record pool; if that is full the entries carry the triangle's number
+        // instead and k_big repeats the set-up (slower, still one warp per sub-box)
+        unsigned int first = atomicAdd(P.bigtri_count, 1u), tag = k << 24;
+        if(first < P.bigtri_capacity) hz_tri_store(P.bigtri + (size_t)first * HZ_TRI_RECORD_VEC, T);
+        else { first = id; tag |= HZ_BIG_RECOMPUTE | ((unsigned int)copy << 28); }
         for(unsigned int by = 0; by < ny; by++)
             for(unsigned int bx = 0; bx < nx; bx++)
-                P.big_queue[slot + by * nx + bx] = make_uint2(rec, by | (bx << 16));
+                P.big_queue[slot + by * nx + bx] = make_uint2(first, by | (bx << 12) | tag);
         queued += nx * ny;
     }
     return queued;
@@ -1176,8 +1184,8 @@ __global__ void __launch_bounds__(256)
 k_big(const HzView* __restrict__ V)
 {
     HZ_KERNEL_PROLOGUE(V, P);
-    // every slot below min(count, capacity) was written: with a record index, or poisoned by a triangle that found
-    // the record pool or the queue exhausted and drew itself (hz_raster_one)
+    // every slot below min(count, capacity) was written: with a record index or a triangle number, or poisoned by a
+    // triangle that found the queue exhausted and drew itself (hz_raster_one)
     unsigned int count = *P.big_count;
     if(count > P.big_capacity) count = P.big_capacity;
     const int lane = threadIdx.x & 31;
@@ -1185,11 +1193,16 @@ k_big(const HzView* __restrict__ V)
     for(unsigned int t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); t < count; t += nwarps)
     {
         const uint2 entry = __ldcg(P.big_queue + t);
-        if(entry.x >= P.bigtri_capacity) continue;
+        if(entry.x == 0xFFFFFFFFu) continue;                                   // poisoned slot
         HzTri T;
-        hz_tri_load(P.bigtri + (size_t)entry.x * HZ_TRI_RECORD_VEC, T);
-        const int y0 = T.py0 + (int)(entry.y & 0xFFFFu) * HZ_BIG_ROWS, y1 = min(y0 + HZ_BIG_ROWS - 1, T.py1);
-        const int x0 = T.px0 + (int)(entry.y >> 16) * HZ_BIG_COLS,     x1 = min(x0 + HZ_BIG_COLS - 1, T.px1);
+        if(entry.y & HZ_BIG_RECOMPUTE)
+        {
+            if(hz_tri_setup(P, entry.x, (int)((entry.y >> 28) & 3u), T) != HZ_SETUP_OK) continue;   // cannot happen
+        }
+        else hz_tri_load(P.bigtri + (size_t)entry.x * HZ_TRI_RECORD_VEC, T);
+        const int rows = HZ_BIG_ROWS << ((entry.y >> 24) & 15u);
+        const int y0 = T.py0 + (int)(entry.y & 0xFFFu) * rows,                y1 = min(y0 + rows - 1, T.py1);
+        const int x0 = T.px0 + (int)((entry.y >> 12) & 0xFFFu) * HZ_BIG_COLS, x1 = min(x0 + HZ_BIG_COLS - 1, T.px1);
         if(hz_tri_is_small(T)) hz_draw_subbox<int>(P, T, x0, x1, y0, y1, lane);
         else                   hz_draw_subbox<long long>(P, T, x0, x1, y0, y1, lane);
     }
