@@ -39,9 +39,9 @@ constexpr float PI_F            = 3.14159265358979f;       // vertex.glsl:31
 //   set-up records of those triangles:                         max(2^17, pixels/8); beyond that k_big repeats the set-up
 constexpr int   PROF_EVENTS     = 7;            // 6 stages per render
 constexpr int   MAX_BANDS       = HZ_MAX_BANDS;
-// [0] big_count near, [1] big_count bands, [2] tri_count near, [3] big-triangle records, [4+3b] tile_count,
-// [5+3b] block_count, [6+3b] tri_count of band b, then the stats
-constexpr int   STATS_AT        = 4 + 3 * MAX_BANDS;
+// [0] big_count near, [1] spare, [2] tri_count near, [3] big-triangle records, [4+4b] tile_count,
+// [5+4b] block_count, [6+4b] tri_count, [7+4b] big_count of band b, then the stats
+constexpr int   STATS_AT        = 4 + 4 * MAX_BANDS;
 constexpr int   N_COUNTERS      = STATS_AT + HZ_STAT_COUNT;
 
 // what the reference keeps in GL uniforms
@@ -367,14 +367,16 @@ bool launch_chain(Slot& s, Scratch& sc, const HzView* hv, bool worst_case, bool 
     if(ev) CUDA_TRY(cudaEventRecord(ev[2], st));
     CUDA_TRY(hz_launch_big(dv + HZ_V_NEAR, st)); n++;
     if(ev) CUDA_TRY(cudaEventRecord(ev[3], st));
+    // every band draws its own large triangles before the next band is tested against the visibility buffer (they
+    // are most of what a zoomed-in view shows)
     for(int b = 0; b < bands_of(s, sc).n; b++)
     {
         int k = 0;
         CUDA_TRY(hz_launch_band(hv[HZ_V_BAND0 + b], dv + HZ_V_BAND0 + b, worst_case, st, &k));
         n += k;
+        if(b + 1 == bands_of(s, sc).n && ev) CUDA_TRY(cudaEventRecord(ev[4], st));
+        if(k > 0 || b + 1 == bands_of(s, sc).n) { CUDA_TRY(hz_launch_big(dv + HZ_V_BAND0 + b, st)); n++; }
     }
-    if(ev) CUDA_TRY(cudaEventRecord(ev[4], st));
-    CUDA_TRY(hz_launch_big(dv + HZ_V_FAR, st)); n++;
     if(ev) CUDA_TRY(cudaEventRecord(ev[5], st));
     if(resolve) { CUDA_TRY(hz_launch_resolve(hv[HZ_V_NEAR], dv + HZ_V_NEAR, st)); n++; }
     if(ev) CUDA_TRY(cudaEventRecord(ev[6], st));
@@ -511,8 +513,8 @@ bool enqueue_render(Slot& s, Scratch& sc, const ViewState& vs, int x0, int x1, c
         {
             HzView& vb = hv[HZ_V_BAND0 + b];
             vb.ring_lo = lo; vb.ring_hi = bands.end[b] > lo ? bands.end[b] : lo;
-            vb.tile_count = sc.d_counters + 4 + 3 * b; vb.block_count = sc.d_counters + 5 + 3 * b;
-            vb.tri_count  = sc.d_counters + 6 + 3 * b;
+            vb.tile_count = sc.d_counters + 4 + 4 * b; vb.block_count = sc.d_counters + 5 + 4 * b;
+            vb.tri_count  = sc.d_counters + 6 + 4 * b; vb.big_count   = sc.d_counters + 7 + 4 * b;
             lo = vb.ring_hi;
         }
     }
@@ -1238,9 +1240,11 @@ bool horizonator_last_render_stats(const horizonator_context_t* ctx, unsigned in
     CUDA_TRY(cudaStreamSynchronize(s->stream));
     unsigned int counters[N_COUNTERS] = {};
     CUDA_TRY(cudaMemcpy(counters, s->main.d_counters, sizeof(counters), cudaMemcpyDeviceToHost));
-    out[0] = counters[0] + counters[1]; out[1] = 2 * s->big_capacity; out[2] = s->launches_last; out[3] = (unsigned)s->device;
+    out[0] = counters[0];
+    for(int b = 0; b < MAX_BANDS; b++) out[0] += counters[7 + 4 * b];
+    out[1] = 2 * s->big_capacity; out[2] = s->launches_last; out[3] = (unsigned)s->device;
     out[4] = counters[2];
-    for(int b = 0; b < MAX_BANDS; b++) out[4] += counters[6 + 3 * b];     // triangle lists of the near pass and the bands
+    for(int b = 0; b < MAX_BANDS; b++) out[4] += counters[6 + 4 * b];     // triangle lists of the near pass and the bands
     return true;
 }
 
