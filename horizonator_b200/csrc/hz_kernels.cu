@@ -688,47 +688,59 @@ __device__ __forceinline__ void hz_tri_load(const uint4* rec, HzTri& T)
     T.id = f.x;
 }
 
-// set-up + rasterisation of one triangle by one thread (GL primitive assembly .. depth test).  Bounding boxes above
-// P.small_max_pix pixels, and triangles too large for 32-bit edge functions, go to k_big instead: the set-up
-// triangle into the record pool and one queue entry per HZ_BIG_ROWS x HZ_BIG_COLS sub-box of its bounding box.
-// Returns the number of queue entries made.
-__device__ __forceinline__ unsigned int hz_raster_one(const HzView& P, unsigned int id)
+// How a set-up triangle is drawn: by the thread that set it up if its bounding box has at most P.small_max_pix pixels
+// and 32-bit edge functions do, otherwise by k_big, one warp per sub-box of HZ_BIG_COLS columns x (HZ_BIG_ROWS << k)
+// rows -- k the smallest that keeps the number of queue entries of the triangle (written by one thread) at or below
+// HZ_BIG_MAX_ENTRIES where possible.  Returns the number of sub-boxes, 0 = draw it yourself.
+__device__ __forceinline__ unsigned int hz_big_layout(const HzView& P, const HzTri& T, unsigned int& nx, unsigned int& k)
+{
+    const int bw = T.px1 - T.px0 + 1, bh = T.py1 - T.py0 + 1;
+    if(bw * bh <= P.small_max_pix && hz_tri_is_small(T)) return 0;
+    nx = (unsigned int)((bw + HZ_BIG_COLS - 1) / HZ_BIG_COLS);
+    k = 0;
+    unsigned int ny = (unsigned int)((bh + HZ_BIG_ROWS - 1) / HZ_BIG_ROWS);
+    while(nx * ny > HZ_BIG_MAX_ENTRIES && ny > 1) { k++; ny = (unsigned int)((bh + (HZ_BIG_ROWS << k) - 1) / (HZ_BIG_ROWS << k)); }
+    return nx * ny;
+}
+
+// Queues a large triangle: `slot` = first of its n = nx*ny reserved queue slots, `rec` = its reserved record.
+__device__ __forceinline__ void
+hz_big_enqueue(const HzView& P, const HzTri& T, unsigned int id, int copy, unsigned int nx, unsigned int k, unsigned int n,
+               unsigned int slot, unsigned int rec)
+{
+    if(slot + n > P.big_capacity)
+    {
+        // queue full: draw it here, and poison the queue slots it reserved (k_big skips those)
+        for(unsigned int q = slot; q < min(slot + n, P.big_capacity); q++) P.big_queue[q] = make_uint2(0xFFFFFFFFu, 0u);
+        hz_draw_slow(P, id, copy);
+        return;
+    }
+    // the set-up triangle goes to the record pool; if that is full the entries carry the triangle's number instead and
+    // k_big repeats the set-up (slower, still one warp per sub-box)
+    unsigned int first = rec, tag = k << 24;
+    if(rec < P.bigtri_capacity) hz_tri_store(P.bigtri + (size_t)rec * HZ_TRI_RECORD_VEC, T);
+    else { first = id; tag |= HZ_BIG_RECOMPUTE | ((unsigned int)copy << 28); }
+    const unsigned int ny = n / nx;
+    for(unsigned int by = 0; by < ny; by++)
+        for(unsigned int bx = 0; bx < nx; bx++)
+            P.big_queue[slot + by * nx + bx] = make_uint2(first, by | (bx << 12) | tag);
+}
+
+// The two seam copies of a triangle that came out too wide (opt-in seam wrap; rare): one thread does it all, with
+// its own reservations.  Returns the number of queue entries made.
+__device__ __noinline__ unsigned int hz_raster_seam_copies(const HzView& P, unsigned int id)
 {
     unsigned int queued = 0;
-    int st = HZ_SETUP_NOTHING;
-    for(int copy = 0; copy >= 0; copy = hz_next_copy(P, copy, st))
+    for(int copy = 1; copy <= 2; copy++)
     {
         HzTri T;
-        st = hz_tri_setup(P, id, copy, T);
-        if(st != HZ_SETUP_OK) continue;
-        const int bw = T.px1 - T.px0 + 1, bh = T.py1 - T.py0 + 1;
-        if(bw * bh <= P.small_max_pix && hz_tri_is_small(T))
-        {
-            hz_draw_box<int>(P, T);
-            continue;
-        }
-        // sub-boxes: HZ_BIG_COLS columns wide and HZ_BIG_ROWS << k rows tall, k the smallest that keeps the number of
-        // queue entries of this triangle (written by this one thread) at or below HZ_BIG_MAX_ENTRIES where possible
-        const unsigned int nx = (unsigned int)((bw + HZ_BIG_COLS - 1) / HZ_BIG_COLS);
-        unsigned int k = 0, ny = (unsigned int)((bh + HZ_BIG_ROWS - 1) / HZ_BIG_ROWS);
-        while(nx * ny > HZ_BIG_MAX_ENTRIES && ny > 1) { k++; ny = (unsigned int)((bh + (HZ_BIG_ROWS << k) - 1) / (HZ_BIG_ROWS << k)); }
-        const unsigned int slot = atomicAdd(P.big_count, nx * ny);
-        if(slot + nx * ny > P.big_capacity)
-        {
-            // queue full: draw it here, and poison the queue slots it reserved (k_big skips those)
-            for(unsigned int q = slot; q < min(slot + nx * ny, P.big_capacity); q++) P.big_queue[q] = make_uint2(0xFFFFFFFFu, 0u);
-            hz_draw_slow(P, id, copy);
-            continue;
-        }
-        // the set-up triangle goes to the record pool; if that is full the entries carry the triangle's number
-        // instead and k_big repeats the set-up (slower, still one warp per sub-box)
-        unsigned int first = atomicAdd(P.bigtri_count, 1u), tag = k << 24;
-        if(first < P.bigtri_capacity) hz_tri_store(P.bigtri + (size_t)first * HZ_TRI_RECORD_VEC, T);
-        else { first = id; tag |= HZ_BIG_RECOMPUTE | ((unsigned int)copy << 28); }
-        for(unsigned int by = 0; by < ny; by++)
-            for(unsigned int bx = 0; bx < nx; bx++)
-                P.big_queue[slot + by * nx + bx] = make_uint2(first, by | (bx << 12) | tag);
-        queued += nx * ny;
+        if(hz_tri_setup(P, id, copy, T) != HZ_SETUP_OK) continue;
+        unsigned int nx = 0, k = 0;
+        const unsigned int n = hz_big_layout(P, T, nx, k);
+        if(n == 0) { hz_draw_box<int>(P, T); continue; }
+        const unsigned int slot = atomicAdd(P.big_count, n), rec = atomicAdd(P.bigtri_count, 1u);
+        hz_big_enqueue(P, T, id, copy, nx, k, n, slot, rec);
+        queued += n;
     }
     return queued;
 }
@@ -1123,11 +1135,50 @@ k_raster(const HzView* __restrict__ V)
     HZ_KERNEL_PROLOGUE(V, P);
     const unsigned int n = min(*P.tri_count, P.tri_capacity);
     const unsigned int nth = gridDim.x * blockDim.x;
+    const unsigned int lane = threadIdx.x & 31u;
     unsigned int n_big = 0;
-    for(unsigned int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += nth)
-        n_big += hz_raster_one(P, P.tri_queue[t]);
+    for(unsigned int t0 = blockIdx.x * blockDim.x + threadIdx.x - lane; t0 < n; t0 += nth)    // warp-uniform trips
+    {
+        const unsigned int t = t0 + lane;
+        HzTri T;
+        unsigned int id = 0, nx = 0, k = 0, nsub = 0;
+        int st = HZ_SETUP_NOTHING;
+        if(t < n)
+        {
+            id = P.tri_queue[t];
+            st = hz_tri_setup(P, id, 0, T);
+            if(st == HZ_SETUP_OK)
+            {
+                nsub = hz_big_layout(P, T, nx, k);
+                if(nsub == 0) hz_draw_box<int>(P, T);
+            }
+        }
+        // the large ones of the warp reserve their queue slots and records with ONE atomic each: in a zoomed-in view
+        // nearly every triangle is large, and a million same-address atomics would be the whole kernel
+        const unsigned int ballot = __ballot_sync(0xffffffffu, nsub != 0);
+        if(ballot)
+        {
+            unsigned int incl = nsub;
+            #pragma unroll
+            for(int d = 1; d < 32; d <<= 1)
+            {
+                const unsigned int up = __shfl_up_sync(0xffffffffu, incl, d);
+                if((int)lane >= d) incl += up;
+            }
+            const unsigned int total = __shfl_sync(0xffffffffu, incl, 31);
+            unsigned int slot0 = 0, rec0 = 0;
+            if(lane == 0) { slot0 = atomicAdd(P.big_count, total); rec0 = atomicAdd(P.bigtri_count, (unsigned int)__popc(ballot)); }
+            slot0 = __shfl_sync(0xffffffffu, slot0, 0); rec0 = __shfl_sync(0xffffffffu, rec0, 0);
+            if(nsub != 0)
+            {
+                hz_big_enqueue(P, T, id, 0, nx, k, nsub, slot0 + incl - nsub, rec0 + __popc(ballot & ((1u << lane) - 1u)));
+                n_big += nsub;
+            }
+        }
+        if(st == HZ_SETUP_TOO_WIDE && P.seam_period > 0.0f) n_big += hz_raster_seam_copies(P, id);
+    }
     n_big = hz_warp_sum(n_big);
-    if(P.stats && (threadIdx.x & 31) == 0 && n_big) atomicAdd(P.stats + HZ_STAT_BIG_ENTRIES, n_big);
+    if(P.stats && lane == 0 && n_big) atomicAdd(P.stats + HZ_STAT_BIG_ENTRIES, n_big);
 }
 
 cudaError_t hz_launch_raster(const HzView* d_v, cudaStream_t stream)
