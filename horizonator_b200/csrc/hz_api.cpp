@@ -78,6 +78,7 @@ struct Scratch
     bool busy_recorded = false;
     cudaGraphExec_t graph = nullptr;   // the standard chain, captured on first use
     int  graph_launches = 0;
+    bool graph_big_per_band = false;   // the shape the captured chain has (see big_after_every_band)
     bool graph_failed = false;
 };
 
@@ -354,7 +355,15 @@ const Slot::Bands& bands_of(const Slot& s, const Scratch& sc)
     return (&sc == &s.main) ? s.bands_single : s.bands_batch;
 }
 
-bool launch_chain(Slot& s, Scratch& sc, const HzView* hv, bool worst_case, bool resolve, cudaStream_t st,
+// Zoomed-in views (small angle per pixel) show triangles many pixels large even far from the eye: each band then draws
+// its large triangles before the next band is tested against the visibility buffer.  In wide views the far bands have
+// hardly any, and one k_big after the last band saves a launch per band.
+bool big_after_every_band(const Slot& s, const ViewState& vs)
+{
+    return fabsf(vs.az_deg1 - vs.az_deg0) < 0.05f * (float)s.W;
+}
+
+bool launch_chain(Slot& s, Scratch& sc, const HzView* hv, bool big_per_band, bool worst_case, bool resolve, cudaStream_t st,
                   cudaEvent_t* ev, int* launches)
 {
     const HzView* dv = sc.d_views;
@@ -367,15 +376,15 @@ bool launch_chain(Slot& s, Scratch& sc, const HzView* hv, bool worst_case, bool 
     if(ev) CUDA_TRY(cudaEventRecord(ev[2], st));
     CUDA_TRY(hz_launch_big(dv + HZ_V_NEAR, st)); n++;
     if(ev) CUDA_TRY(cudaEventRecord(ev[3], st));
-    // every band draws its own large triangles before the next band is tested against the visibility buffer (they
-    // are most of what a zoomed-in view shows)
     for(int b = 0; b < bands_of(s, sc).n; b++)
     {
+        const bool last = (b + 1 == bands_of(s, sc).n);
         int k = 0;
         CUDA_TRY(hz_launch_band(hv[HZ_V_BAND0 + b], dv + HZ_V_BAND0 + b, worst_case, st, &k));
         n += k;
-        if(b + 1 == bands_of(s, sc).n && ev) CUDA_TRY(cudaEventRecord(ev[4], st));
-        if(k > 0 || b + 1 == bands_of(s, sc).n) { CUDA_TRY(hz_launch_big(dv + HZ_V_BAND0 + b, st)); n++; }
+        if(last && ev) CUDA_TRY(cudaEventRecord(ev[4], st));
+        // all bands share one queue and counter unless every band has its own k_big (see enqueue_render)
+        if(last || (big_per_band && k > 0)) { CUDA_TRY(hz_launch_big(dv + HZ_V_BAND0 + b, st)); n++; }
     }
     if(ev) CUDA_TRY(cudaEventRecord(ev[5], st));
     if(resolve) { CUDA_TRY(hz_launch_resolve(hv[HZ_V_NEAR], dv + HZ_V_NEAR, st)); n++; }
@@ -387,7 +396,7 @@ bool launch_chain(Slot& s, Scratch& sc, const HzView* hv, bool worst_case, bool 
 // Captures the standard chain (full width, vectorised resolve, grids sized for any eye position) once per scratch
 // set; every later standard render is one cudaGraphLaunch after the parameter copy.  A dozen separate launches cost
 // more host time than the GPU needs for the render.
-bool capture_graph(Slot& s, Scratch& sc, const HzView* hv)
+bool capture_graph(Slot& s, Scratch& sc, const HzView* hv, bool big_per_band)
 {
     cudaStream_t cs = nullptr;
     if(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); return false; }
@@ -396,7 +405,7 @@ bool capture_graph(Slot& s, Scratch& sc, const HzView* hv)
     int launches = 0;
     if(ok)
     {
-        ok = launch_chain(s, sc, hv, true, true, cs, nullptr, &launches);
+        ok = launch_chain(s, sc, hv, big_per_band, true, true, cs, nullptr, &launches);
         if(cudaStreamEndCapture(cs, &g) != cudaSuccess) ok = false;
     }
     if(ok && cudaGraphInstantiate(&sc.graph, g, 0) != cudaSuccess) { ok = false; sc.graph = nullptr; }
@@ -409,6 +418,7 @@ bool capture_graph(Slot& s, Scratch& sc, const HzView* hv)
         return false;
     }
     sc.graph_launches = launches;
+    sc.graph_big_per_band = big_per_band;
     return true;
 }
 
@@ -506,6 +516,7 @@ bool enqueue_render(Slot& s, Scratch& sc, const ViewState& vs, int x0, int x1, c
     {
         hv[k].big_queue = sc.d_big_queue + s.big_capacity;      hv[k].big_count = sc.d_counters + 1;
     }
+    const bool big_per_band = big_after_every_band(s, vs);
     {
         int lo = s.near_rings + 1;
         const Slot::Bands& bands = bands_of(s, sc);
@@ -514,7 +525,10 @@ bool enqueue_render(Slot& s, Scratch& sc, const ViewState& vs, int x0, int x1, c
             HzView& vb = hv[HZ_V_BAND0 + b];
             vb.ring_lo = lo; vb.ring_hi = bands.end[b] > lo ? bands.end[b] : lo;
             vb.tile_count = sc.d_counters + 4 + 4 * b; vb.block_count = sc.d_counters + 5 + 4 * b;
-            vb.tri_count  = sc.d_counters + 6 + 4 * b; vb.big_count   = sc.d_counters + 7 + 4 * b;
+            vb.tri_count  = sc.d_counters + 6 + 4 * b;
+            // one k_big per band: each band counts its own entries from 0 (the queue memory is reused, the bands run
+            // one after the other); one k_big at the end: all bands append to the same count
+            vb.big_count  = sc.d_counters + 7 + (big_per_band ? 4 * b : 0);
             lo = vb.ring_hi;
         }
     }
@@ -526,7 +540,14 @@ bool enqueue_render(Slot& s, Scratch& sc, const ViewState& vs, int x0, int x1, c
                           out.n == 1 && v.out_stride == s.W && out.x_off == 0 && hz_resolve_is_vectorisable(v);
     if(standard && !sc.graph_failed)
     {
-        if(sc.graph == nullptr && !capture_graph(s, sc, hv)) sc.graph_failed = true;
+        if(sc.graph != nullptr && sc.graph_big_per_band != big_per_band)
+        {
+            // the chain changes shape (rare: the caller went from a wide to a zoomed-in window or back): let the old
+            // graph's last launch finish before it is destroyed
+            if(sc.busy_recorded) CUDA_TRY(cudaEventSynchronize(sc.busy));
+            drop_graph(sc);
+        }
+        if(sc.graph == nullptr && !capture_graph(s, sc, hv, big_per_band)) sc.graph_failed = true;
         if(sc.graph != nullptr)
         {
             CUDA_TRY(cudaGraphLaunch(sc.graph, st));
@@ -550,7 +571,7 @@ bool enqueue_render(Slot& s, Scratch& sc, const ViewState& vs, int x0, int x1, c
         s.prof_used += PROF_EVENTS;
     }
     int launches = 0;
-    if(!launch_chain(s, sc, hv, false, d_image || d_ranges, st, ev, &launches)) return false;
+    if(!launch_chain(s, sc, hv, big_per_band, false, d_image || d_ranges, st, ev, &launches)) return false;
     CUDA_TRY(cudaEventRecord(sc.busy, st)); sc.last_stream = st; sc.busy_recorded = true;
     s.launches_last = launches;
     if(&sc == &s.main) s.have_render = (x0 == 0 && x1 == s.W);
