@@ -72,6 +72,21 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     peer_ms = float(t.item())
     peer_same = bool(torch.equal(pimg, img)) and bool(torch.equal(prng, rng))
+    # ... and with rank 0 as the only destination
+    for _ in range(2):
+        pp.render(root=0)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(n):
+        pp.render(root=0)
+    e1.record()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1) / n], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    peer_root_ms = float(t.item())
+    if rank == 0:
+        peer_same = peer_same and bool(torch.equal(pp.image, img)) and bool(torch.equal(pp.ranges, rng))
     # render-only part (no gather) of this rank's wedge
     edges = sharding.wedge_edges(W, world)
     x0, x1 = edges[rank], edges[rank + 1]
@@ -99,7 +114,8 @@ def main():
         same = bool(torch.equal(fi, img)) and bool(torch.equal(fr, rng))
         print(json.dumps({"config": "BASELINE configs[3]: %dx%d full circle, C2 DEM (R=5858), azimuth wedges" % (W, H),
                           "n_gpus": world, "sharded_ms_per_panorama_incl_gather": sharded_ms, "wedge_render_ms_max_over_ranks": wedge_ms,
-                          "peer_store_ms_per_panorama": peer_ms, "peer_store_equals_gathered": peer_same,
+                          "peer_store_ms_per_panorama": peer_ms, "peer_store_to_rank0_only_ms": peer_root_ms,
+                          "peer_store_equals_gathered": peer_same,
                           "unsharded_ms_one_gpu": whole_ms, "speedup_allgather": whole_ms / sharded_ms,
                           "speedup_peer_store": whole_ms / peer_ms, "gathered_equals_unsharded": same,
                           "gather_bytes_total": 7 * W * H, "checksum": ck}), flush=True)
