@@ -107,6 +107,7 @@ def _declare(lib):
         "horizonator_peer_close": (b, [ctx, vp]),
         "horizonator_peer_free": (b, [ctx, vp]),
         "horizonator_render_wedge_peers": (b, [ctx, i, i, i, P(vp), P(vp), vp]),
+        "horizonator_peer_barrier": (b, [ctx, i, i, P(vp), C.c_uint, vp]),
         "horizonator_host_alloc": (vp, [C.c_size_t]),
         "horizonator_host_free": (None, [vp]),
         "horizonator_profile_enable": (b, [ctx, b]),
@@ -137,7 +138,7 @@ EXPORTED_SYMBOLS = (
     "horizonator_host_alloc", "horizonator_host_free",
     "horizonator_render_counters", "horizonator_horizon_profile_device", "horizonator_set_earth_curvature", "horizonator_set_seam_wrap",
     "horizonator_peer_alloc", "horizonator_peer_open", "horizonator_peer_close", "horizonator_peer_free",
-    "horizonator_render_wedge_peers",
+    "horizonator_render_wedge_peers", "horizonator_peer_barrier",
 )
 
 if not os.path.exists(LIBRARY_PATH):
@@ -318,6 +319,12 @@ class horizonator:
 
     def peer_free(self, ptr):
         lib.horizonator_peer_free(C.byref(self._ctx), ptr)
+
+    def peer_barrier(self, rank, d_flags, epoch, stream=0):
+        """GPU-side barrier between ranks (horizonator_peer_barrier); d_flags: every rank's flag block address."""
+        arr = (C.c_void_p * len(d_flags))(*d_flags)
+        if not lib.horizonator_peer_barrier(C.byref(self._ctx), len(d_flags), int(rank), arr, int(epoch), stream or None):
+            raise RuntimeError("horizonator_peer_barrier() failed")
 
     def render_wedge_peers(self, x0, x1, d_images, d_ranges, stream=0):
         """d_images / d_ranges: sequences of device addresses of every rank's full image / range buffer (or None)."""

@@ -1151,6 +1151,25 @@ bool horizonator_render_wedge_peers(const horizonator_context_t* ctx, int x0, in
     return true;
 }
 
+bool horizonator_peer_barrier(const horizonator_context_t* ctx, int n_ranks, int rank, void* const* d_flags,
+                              unsigned int epoch, void* stream)
+{
+    Slot* s = slot_of(ctx);
+    if(s == nullptr || d_flags == nullptr || n_ranks < 1 || n_ranks > HZ_MAX_OUT || rank < 0 || rank >= n_ranks) return false;
+    HzPeerFlags f{};
+    f.n = n_ranks; f.rank = rank;
+    for(int r = 0; r < n_ranks; r++)
+    {
+        if(d_flags[r] == nullptr) return false;
+        f.arrive[r] = (uint32_t*)d_flags[r];
+    }
+    DeviceGuard g(s->device);
+    cudaStream_t st = stream ? (cudaStream_t)stream : s->stream;
+    CUDA_TRY(hz_launch_peer_barrier(f, epoch, st));
+    if(stream == nullptr) CUDA_TRY(cudaStreamSynchronize(st));
+    return true;
+}
+
 bool horizonator_set_seam_wrap(const horizonator_context_t* ctx, bool on)
 {
     Slot* s = slot_of(ctx);

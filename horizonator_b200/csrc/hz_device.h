@@ -133,6 +133,14 @@ enum { HZ_V_NEAR = 0, HZ_V_FAR = 1, HZ_V_BAND0 = 2 };
 constexpr int HZ_MAX_BANDS = 6;
 constexpr int HZ_V_COUNT   = HZ_V_BAND0 + HZ_MAX_BANDS;
 
+// flags of the GPU-side barrier between the ranks of a wedge-sharded panorama (k_peer_barrier)
+struct HzPeerFlags
+{
+    uint32_t* arrive[HZ_MAX_OUT];    // arrive[r] = rank r's array of HZ_MAX_OUT + 1 words, mapped here
+    int n, rank;
+};
+cudaError_t hz_launch_peer_barrier(const HzPeerFlags& f, unsigned int epoch, cudaStream_t stream);
+
 // All launches are asynchronous on `stream`.  `v` is the host copy of the variant (for grid sizing), `d_v` the device
 // copy the kernel reads.
 cudaError_t hz_launch_mosaic (const HzTiles& t, int16_t* mosaic, int N, int pitch, cudaStream_t stream);

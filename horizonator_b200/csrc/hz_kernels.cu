@@ -1411,6 +1411,38 @@ cudaError_t hz_launch_resolve(const HzView& v, const HzView* d_v, cudaStream_t s
 }
 
 // ================================================================================================
+// k_peer_barrier: barrier between the ranks of a wedge-sharded panorama, on the GPUs, through peer memory
+// ================================================================================================
+//
+// Every rank owns an array arrive[HZ_MAX_OUT] (+ one error word) that its peers have mapped.  Rank i announces epoch e
+// by storing e into arrive[i] of every rank (release, system scope: everything this stream did before, e.g. the
+// resolve kernel's peer stores, is visible first), then waits until all entries of its own array have reached e.
+// The wait is bounded: a rank that never arrives must not hang the others' GPUs; a timeout is recorded in the
+// error word (the caller checks it) and the kernel returns.
+__global__ void __launch_bounds__(32)
+k_peer_barrier(HzPeerFlags F, unsigned int epoch)
+{
+    const unsigned int r = threadIdx.x;
+    if(r >= (unsigned int)F.n) return;
+    __threadfence_system();
+    asm volatile("st.release.sys.global.u32 [%0], %1;" :: "l"(F.arrive[r] + F.rank), "r"(epoch) : "memory");
+    unsigned int seen = 0;
+    for(unsigned int spin = 0; spin < (1u << 20); spin++)
+    {
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(F.arrive[F.rank] + r) : "memory");
+        if((int)(seen - epoch) >= 0) return;
+        __nanosleep(64);
+    }
+    atomicAdd(F.arrive[F.rank] + HZ_MAX_OUT, 1u);            // timed out
+}
+
+cudaError_t hz_launch_peer_barrier(const HzPeerFlags& f, unsigned int epoch, cudaStream_t stream)
+{
+    k_peer_barrier<<<1, 32, 0, stream>>>(f, epoch);
+    return cudaGetLastError();
+}
+
+// ================================================================================================
 // k_horizon: per image column, the topmost terrain pixel (row, range); -1 / -1.0f if the column is all sky
 // ================================================================================================
 

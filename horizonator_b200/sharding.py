@@ -133,8 +133,9 @@ class _DeviceArray:
 class PeerPanorama:
     """One panorama split by azimuth wedge over the ranks and assembled WITHOUT a gather collective: every rank holds a
     full-size image and range buffer that its peers have mapped (CUDA IPC over NVLink/NVSwitch), and each rank's resolve
-    kernel stores its wedge straight into all of them (horizonator_render_wedge_peers).  The only collective is the
-    barrier that tells a rank its buffers are complete.
+    kernel stores its wedge straight into all of them (horizonator_render_wedge_peers).  No collective library is
+    involved in a render: the barriers that tell a rank its buffers are complete run on the GPUs through flags in peer
+    memory (horizonator_peer_barrier), in stream order.
 
     Build once per context and size (collective: all ranks of `group` must construct it together), render() many
     times.  render() returns this rank's full (H,W,3) uint8 and (H,W) float32 tensors (views of the peer-mapped
@@ -151,46 +152,64 @@ class PeerPanorama:
         self.edges = [((W * g // self.world) // 4) * 4 for g in range(self.world)] + [W]
         self.img_ptr, img_handle = h.peer_alloc(W * H * 3)
         self.rng_ptr, rng_handle = h.peer_alloc(W * H * 4)
+        self.flag_ptr, flag_handle = h.peer_alloc(64)        # HORIZONATOR_PEER_FLAG_BYTES
+        self.flags = torch.as_tensor(_DeviceArray(self.flag_ptr, (16,), "<u4"), device="cuda")
+        self.flags.zero_()
+        torch.cuda.synchronize()
         handles = [None] * self.world
         if self.world > 1:
-            dist.all_gather_object(handles, (img_handle, rng_handle), group=group)
+            dist.all_gather_object(handles, (img_handle, rng_handle, flag_handle), group=group)   # also: flags are zeroed
         else:
-            handles[0] = (img_handle, rng_handle)
+            handles[0] = (img_handle, rng_handle, flag_handle)
         self.opened = []
-        self.img_dst, self.rng_dst = [], []
-        for r, (hi, hr) in enumerate(handles):
+        self.img_dst, self.rng_dst, self.flag_dst = [], [], []
+        for r, (hi, hr, hf) in enumerate(handles):
             if r == self.rank:
-                self.img_dst.append(self.img_ptr); self.rng_dst.append(self.rng_ptr)
+                self.img_dst.append(self.img_ptr); self.rng_dst.append(self.rng_ptr); self.flag_dst.append(self.flag_ptr)
             else:
-                pi, pr = h.peer_open(hi), h.peer_open(hr)
-                self.opened += [pi, pr]
-                self.img_dst.append(pi); self.rng_dst.append(pr)
+                pi, pr, pf = h.peer_open(hi), h.peer_open(hr), h.peer_open(hf)
+                self.opened += [pi, pr, pf]
+                self.img_dst.append(pi); self.rng_dst.append(pr); self.flag_dst.append(pf)
+        self.epoch = 0
         self.image = torch.as_tensor(_DeviceArray(self.img_ptr, (H, W, 3), "|u1"), device="cuda")
         self.ranges = torch.as_tensor(_DeviceArray(self.rng_ptr, (H, W), "<f4"), device="cuda")
+        if self.world > 1:
+            dist.barrier(group=group)                        # everybody has mapped everything
 
     def render(self, root=None):
         """Renders this rank's wedge of h's current view into everybody's buffers (root=None), or only into rank
         `root`'s (the others' buffers are then left as they were); all ranks call it together."""
         x0, x1 = self.edges[self.rank], self.edges[self.rank + 1]
-        stream = torch.cuda.current_stream()
-        if self.world > 1:
-            dist.barrier(group=self.group)          # nobody is still reading the previous panorama
+        stream = torch.cuda.current_stream().cuda_stream
         img_dst = self.img_dst if root is None else [self.img_dst[root]]
         rng_dst = self.rng_dst if root is None else [self.rng_dst[root]]
-        self.h.render_wedge_peers(x0, x1, img_dst, rng_dst, stream.cuda_stream)
-        if self.world > 1:
-            dist.barrier(group=self.group)          # every wedge has landed everywhere
+        # both barriers run on the GPUs, in stream order: nothing here waits on the host
+        self._barrier(stream)                       # nobody's stream is still reading the previous panorama
+        self.h.render_wedge_peers(x0, x1, img_dst, rng_dst, stream)
+        self._barrier(stream)                       # every wedge has landed everywhere
         return self.image, self.ranges
 
+    def _barrier(self, stream):
+        if self.world > 1:
+            self.epoch += 1
+            self.h.peer_barrier(self.rank, self.flag_dst, self.epoch, stream)
+
+    def timeouts(self):
+        """Number of GPU-side barriers of this rank that gave up waiting (0 unless a rank died or lagged badly)."""
+        torch.cuda.synchronize()
+        return int(self.flags[8].item())
+
     def close(self):
+        torch.cuda.synchronize()
         for p in self.opened:
             self.h.peer_close(p)
         self.opened = []
         if self.world > 1:
             dist.barrier(group=self.group)          # peers have unmapped before the owner frees
         if self.img_ptr:
-            self.h.peer_free(self.img_ptr); self.h.peer_free(self.rng_ptr)
-            self.img_ptr = self.rng_ptr = None
+            self.image = self.ranges = self.flags = None
+            self.h.peer_free(self.img_ptr); self.h.peer_free(self.rng_ptr); self.h.peer_free(self.flag_ptr)
+            self.img_ptr = self.rng_ptr = self.flag_ptr = None
 
 
 def render_batch_sharded(h, views, group=None, gather_profiles=True):

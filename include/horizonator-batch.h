@@ -73,6 +73,17 @@ bool horizonator_peer_free(const horizonator_context_t* ctx, void* d_ptr);
 bool horizonator_render_wedge_peers(const horizonator_context_t* ctx, int x0, int x1, int n_peers,
                                     void* const* d_images, void* const* d_ranges, void* stream);
 
+/* Barrier between the ranks of such a panorama ON THE GPUS (no host synchronisation, no collective
+ * library): d_flags[r] is rank r's flag block -- HORIZONATOR_PEER_FLAG_BYTES bytes from
+ * horizonator_peer_alloc(), zeroed once, mapped by every rank -- and `epoch` a number that every rank
+ * increases by one per barrier.  Enqueued on `stream`: work queued after it starts once every rank's
+ * stream has reached its own barrier of the same epoch, and sees everything those streams wrote before.
+ * A rank that does not arrive within a few tenths of a second is given up on: the barrier returns and the
+ * word at index 8 of the caller's own flag block counts the time-outs. */
+#define HORIZONATOR_PEER_FLAG_BYTES 64
+bool horizonator_peer_barrier(const horizonator_context_t* ctx, int n_ranks, int rank, void* const* d_flags,
+                              unsigned int epoch, void* stream);
+
 /* Opt-in accuracy mode; OFF by default, and off in every parity test: the reference renders a flat
  * tangent plane and says so (vertex.glsl:65-88: "31 m vertical error at 20 km", README.org:158-161).
  * When on, a point at horizontal distance d appears lower by (1 - refraction) * d^2 / (2 * 6371000 m)

@@ -51,6 +51,7 @@ def _worker(rank, world, port, tiles, q):
             ok = ok and np.array_equal(pi.cpu().numpy(), full_i) and np.array_equal(pr.cpu().numpy(), full_r)
         else:
             ok = ok and not pi.any().item()
+        ok = ok and pp.timeouts() == 0
         dist.barrier()
         pp.close()
 

@@ -119,6 +119,7 @@ def main():
                           "unsharded_ms_one_gpu": whole_ms, "speedup_allgather": whole_ms / sharded_ms,
                           "speedup_peer_store": whole_ms / peer_ms, "gathered_equals_unsharded": same,
                           "gather_bytes_total": 7 * W * H, "checksum": ck}), flush=True)
+    assert pp.timeouts() == 0
     pp.close()
     if world > 1:
         dist.barrier()
