@@ -13,7 +13,8 @@
 //                        through the same exact stages as in k_near -> list of triangles
 //   k_raster   (render)  set-up, rasterisation and depth test of a list,          vertex.glsl, geometry.glsl, GL raster,
 //                        one thread per triangle                                  depth test, fragment.glsl
-//   k_big      (render)  the few triangles with large bounding boxes, one warp per 8x64-pixel sub-box
+//   k_big      (render)  the triangles with large bounding boxes, one warp per 32-column sub-box (lane = column)
+//   k_peer_barrier (multi-GPU)  barrier between the ranks of a wedge-sharded panorama through peer memory
 //   k_resolve  (render)  keys -> BGR8 image + float range image, top row first lib:936-1048
 //   k_horizon  (extra)   range image -> per-column topmost terrain row and its range
 //
@@ -29,8 +30,8 @@
 // ---- launches ----------------------------------------------------------------------------------
 // A render is a chain of a dozen short kernels on one stream.  Each is launched with programmatic stream
 // serialisation (PDL): its CTAs may be placed on the SMs while the previous kernel is still draining, and wait at
-// hz_wait_for_previous_kernel() -- the first statement of every render kernel -- until that kernel has completed and
-// its writes are visible.  That hides most of the launch latency between the kernels; the ordering is unchanged.
+// hz_wait_for_previous_kernel() -- part of the prologue of every render kernel -- until that kernel has completed
+// and its writes are visible.  That hides most of the launch latency between the kernels; the ordering is unchanged.
 __device__ __forceinline__ void hz_wait_for_previous_kernel()
 {
     cudaGridDependencySynchronize();
@@ -204,7 +205,7 @@ cudaError_t hz_launch_prepare(const HzView& v, const HzView* d_v, cudaStream_t s
 }
 
 // ================================================================================================
-// projection and triangle set-up shared by k_march, k_raster and k_big
+// projection and triangle set-up shared by the mesh kernels, k_raster and k_big
 // ================================================================================================
 
 #define HZ_GUARD_PX   2097152.0f      /* 2^21: triangles reaching beyond are dropped (oracle rule F5) */

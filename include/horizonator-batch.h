@@ -127,10 +127,11 @@ bool horizonator_horizon_profile_device(const horizonator_context_t* ctx,
 /* Per-kernel device times.  While enabled, every render records CUDA events around each of
  * its kernels on the stream it runs on.  horizonator_profile_read() waits for them and reports
  * the MEAN duration in milliseconds per render of: out_ms[0] k_prepare (clear + axis tables),
- * [1] k_near (foreground tiles: mesh, projection, cull, rasterise), [2] k_big of the
- * foreground, [3] k_march (the rest of the mesh, hierarchically culled), [4] k_big of the
- * rest, [5] k_resolve (keys -> image + ranges), over the *renders recorded since the last
- * read. */
+ * [1] the foreground tiles (k_near: mesh, projection, exact cull; k_raster), [2] k_big of the
+ * foreground, [3] the bands of the rest of the mesh (k_tiles, k_blocks, k_mesh, k_raster each, and
+ * k_big between bands for zoomed-in views), [4] the last k_big, [5] k_resolve (keys -> image +
+ * ranges), over the *renders recorded since the last read.  Profiled renders launch their kernels
+ * one by one instead of replaying the captured CUDA graph. */
 bool horizonator_profile_enable(const horizonator_context_t* ctx, bool on);
 bool horizonator_profile_read(const horizonator_context_t* ctx, float out_ms[6], int* renders);
 
