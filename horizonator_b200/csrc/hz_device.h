@@ -89,9 +89,9 @@ struct HzView
     // it is tested against it.
     int eye_ti, eye_tj, near_rings;
     int ring_lo, ring_hi;        // the band this launch works on
-    uint32_t* tile_queue;        // live tiles of the band (tj*nt+ti)
+    uint32_t* tile_queue;        // live tiles of the band (tj << 16 | ti)
     uint32_t* tile_count;
-    uint32_t* block_queue;       // live blocks of the band (bj*nb+bi)
+    uint32_t* block_queue;       // live blocks of the band (bj << 16 | bi)
     uint32_t* block_count;
     uint32_t* tri_queue;         // triangles of the stage that passed the exact integer tests
     uint32_t* tri_count;

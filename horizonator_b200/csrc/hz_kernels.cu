@@ -1037,7 +1037,7 @@ k_tiles(const HzView* __restrict__ V)
                 if(r == HZ_RECT_DEAD_FAR)         n_far++;
                 else if(r == HZ_RECT_DEAD_WINDOW) n_window++;
                 else if(r == HZ_RECT_BOXED && hz_box_occluded_thread(P, B, P.occl_tile_max_pix)) n_occl++;
-                else { on = true; id = (unsigned int)(tj * nt + ti); }
+                else { on = true; id = ((unsigned int)tj << 16) | (unsigned int)ti; }
             }
         }
         hz_cta_append(s_app, on, id, P.tile_queue, P.tile_count);
@@ -1051,7 +1051,7 @@ k_blocks(const HzView* __restrict__ V)
     HZ_KERNEL_PROLOGUE(V, P);
     __shared__ HzCtaAppend s_app;
     __shared__ unsigned int s_stats[4];
-    const int nt = P.nt, nb = P.nb, N = P.N;
+    const int nb = P.nb, N = P.N;
     const unsigned int total = *P.tile_count * (unsigned int)(HZ_TILE_BLOCKS * HZ_TILE_BLOCKS);
     const unsigned int nth = gridDim.x * blockDim.x;
     unsigned int n_all = 0, n_far = 0, n_window = 0, n_occl = 0;
@@ -1063,7 +1063,7 @@ k_blocks(const HzView* __restrict__ V)
         if(t < total)
         {
             const unsigned int tile = P.tile_queue[t >> 6];
-            const int tj = (int)(tile / (unsigned int)nt), ti = (int)(tile % (unsigned int)nt);
+            const int tj = (int)(tile >> 16), ti = (int)(tile & 0xFFFFu);
             const int bj = tj * HZ_TILE_BLOCKS + (int)((t >> 3) & 7u), bi = ti * HZ_TILE_BLOCKS + (int)(t & 7u);
             if(bj < nb && bi < nb)
             {
@@ -1076,7 +1076,7 @@ k_blocks(const HzView* __restrict__ V)
                 if(r == HZ_RECT_DEAD_FAR)         n_far++;
                 else if(r == HZ_RECT_DEAD_WINDOW) n_window++;
                 else if(r == HZ_RECT_BOXED && hz_box_occluded_thread(P, B, P.occl_block_max_pix)) n_occl++;
-                else { on = true; id = (unsigned int)(bj * nb + bi); }
+                else { on = true; id = ((unsigned int)bj << 16) | (unsigned int)bi; }
             }
         }
         hz_cta_append(s_app, on, id, P.block_queue, P.block_count);
@@ -1099,7 +1099,7 @@ k_mesh(const HzView* __restrict__ V)
     if(b < n)
     {
         const unsigned int id = P.block_queue[b];
-        bj = (int)(id / (unsigned int)P.nb); bi = (int)(id % (unsigned int)P.nb);
+        bj = (int)(id >> 16); bi = (int)(id & 0xFFFFu);
         z = hz_block_vertex_z(P, bj, bi, lane);
     }
     unsigned int n_meshed = 0, n_tris = 0;
@@ -1113,7 +1113,7 @@ k_mesh(const HzView* __restrict__ V)
         if(b_next < n)
         {
             const unsigned int id = P.block_queue[b_next];
-            bj_next = (int)(id / (unsigned int)P.nb); bi_next = (int)(id % (unsigned int)P.nb);
+            bj_next = (int)(id >> 16); bi_next = (int)(id & 0xFFFFu);
             z_next = hz_block_vertex_z(P, bj_next, bi_next, lane);
         }
         n_tris += hz_mesh_block(P, bj, bi, lane, z, s_warp[wib], count);
