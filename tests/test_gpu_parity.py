@@ -529,3 +529,23 @@ def test_random_views_match_oracle(hz, tiles_c1):
         worst = min(worst, s["agreement"])
         assert s["ok"], (case, R, W, H, lat, lon, az0, span, znear, zfar, s)
     print("random views: worst agreement", worst)
+
+
+def _golden_scenes():
+    g = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    return sorted(f[len("render_"):-len(".npz")] for f in os.listdir(g) if f.startswith("render_"))
+
+
+@pytest.mark.parametrize("name", _golden_scenes())
+def test_render_matches_committed_golden_vectors(hz, tiles_c1, name):
+    """The CUDA path against the fixtures of tests/golden/ directly: renders recorded from the reference's own
+    horizonator-lib.c + dem.c (compiled unmodified; tests/golden/make_golden.py) -- no oracle library involved."""
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "render_%s.npz" % name))
+    W, H, R, az0, az1, zn, zf, znc, zfc, lat, lon = g["params"]
+    h = hz.horizonator(C1_LAT, C1_LON, int(W), int(H), dir_dems=tiles_c1, render_radius_cells=int(R))
+    kw = {} if lat <= -1000. else dict(lat=float(lat), lon=float(lon))
+    img, rng = h.render(float(az0), float(az1), znear=float(zn), zfar=float(zf), znear_color=float(znc),
+                        zfar_color=float(zfc), **kw)
+    s = compare_renders(img, rng, g["image"], g["ranges"])
+    print("golden", name, s)
+    assert s["ok"], s
