@@ -35,8 +35,8 @@ constexpr float PI_F            = 3.14159265358979f;       // vertex.glsl:31
 // Queue capacities grow with the image (set in alloc_target); whatever does not fit is drawn by a slow in-kernel
 // path, so these only have to be generous, not safe.
 //   triangles of one stage awaiting set-up:                    max(2^22, pixels/2)
-//   (record, sub-box) pairs for the large-triangle kernel:     max(2^21, pixels) per pass
-//   set-up records of those triangles:                         max(2^17, pixels/8); beyond that k_big repeats the set-up
+//   (record, sub-box) pairs for the large-triangle kernel:     max(2^21, pixels/4) per pass
+//   set-up records of those triangles:                         max(2^18, pixels/16); beyond that k_big repeats the set-up
 constexpr int   PROF_EVENTS     = 7;            // 6 stages per render
 constexpr int   MAX_BANDS       = HZ_MAX_BANDS;
 // [0] big_count near, [1] spare, [2] tri_count near, [3] big-triangle records, [4+4b] tile_count,
@@ -216,7 +216,7 @@ bool alloc_target(Slot& s, int W, int H)
         return (uint32_t)(c > 0x7FFFFFFFu ? 0x7FFFFFFFu : c);
     };
     s.target_pixels = px;
-    s.tri_capacity = cap((size_t)1 << 22, 2); s.big_capacity = cap((size_t)1 << 21, 1); s.bigtri_capacity = cap((size_t)1 << 17, 8);
+    s.tri_capacity = cap((size_t)1 << 22, 2); s.big_capacity = cap((size_t)1 << 21, 4); s.bigtri_capacity = cap((size_t)1 << 18, 16);
     // tests shrink the queues to exercise the overflow paths
     if(const char* env = getenv("HORIZONATOR_TRI_CAPACITY"))    s.tri_capacity    = (uint32_t)(atoi(env) > 1 ? atoi(env) : 1);
     if(const char* env = getenv("HORIZONATOR_BIG_CAPACITY"))    s.big_capacity    = (uint32_t)(atoi(env) > 1 ? atoi(env) : 1);
@@ -266,23 +266,35 @@ bool alloc_scratch(const Slot& s, Scratch& c, bool own_stream)
     return true;
 }
 
-// makes sure n lanes exist (n <= n_lanes_max)
-bool ensure_lanes(Slot& s, int n)
+// bytes of device memory one scratch set takes (what ensure_lanes() budgets with)
+size_t scratch_bytes(const Slot& s)
 {
-    if(s.fork_ev == nullptr) CUDA_TRY(cudaEventCreateWithFlags(&s.fork_ev, cudaEventDisableTiming));
+    const size_t px = s.target_pixels;
+    return px * (sizeof(unsigned long long) + 3 + sizeof(float)) +
+           ((size_t)s.tri_capacity + (size_t)s.nt * s.nt + (size_t)s.nb * s.nb + 2 * (size_t)s.N) * sizeof(uint32_t) +
+           2 * (size_t)s.big_capacity * sizeof(uint2) + (size_t)s.bigtri_capacity * 6 * sizeof(uint4);
+}
+
+// Makes sure up to n lanes exist (n <= n_lanes_max) and returns how many there are to use: lanes are only added
+// while they fit into half of the device memory that is free right now (a 36000 x 4000 panorama needs ~3 GB per lane).
+int ensure_lanes(Slot& s, int n)
+{
+    if(s.fork_ev == nullptr && cudaEventCreateWithFlags(&s.fork_ev, cudaEventDisableTiming) != cudaSuccess) return 0;
     while((int)s.lanes.size() < n)
     {
+        size_t free_b = 0, total_b = 0;
+        if(cudaMemGetInfo(&free_b, &total_b) != cudaSuccess || scratch_bytes(s) > free_b / 2) break;
         Scratch c;
         if(!alloc_scratch(s, c, true) || !alloc_scratch_target(s, c, true))
         {
             MSG("Could not allocate render lane %d", (int)s.lanes.size());
             cudaGetLastError();
             free_scratch(c);
-            return false;
+            break;
         }
         s.lanes.push_back(c);
     }
-    return true;
+    return (int)s.lanes.size() < n ? (int)s.lanes.size() : n;
 }
 
 void destroy_slot(Slot* s)
@@ -984,7 +996,7 @@ static bool render_batch_common(const horizonator_context_t* ctx, Slot* s, int n
         for(int k = 0; k < n; k++) if(!tanel_for(*s, vs[k].az_deg0, vs[k].az_deg1, st, &dummy)) return false;
         if(s->tanel_next != before) n_lanes = 1;      // more distinct windows than table slots: one at a time
     }
-    if(n_lanes > 1 && !ensure_lanes(*s, n_lanes)) n_lanes = 1;
+    if(n_lanes > 1) n_lanes = ensure_lanes(*s, n_lanes);      // as many as fit; fewer than 2: one view at a time
 
     if(n_lanes <= 1)
     {
