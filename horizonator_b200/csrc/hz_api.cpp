@@ -95,6 +95,7 @@ struct Slot
     int nb = 0, nt = 0;
     int near_rings = 2;
     int occl_tile_max_pix = 64, occl_block_max_pix = 32, small_max_pix = 16;
+    int grid_percent_single = 150, grid_percent_batch = 35;   // see hz_grid() in hz_kernels.cu
     // Rings (in tiles around the eye's tile) at which the bands end; the last band runs to the edge of the mesh.
     // More bands = more of the mesh culled by what nearer bands drew, but four more kernels each.  A lone view is
     // latency-bound and gets two bands; the views of a batch overlap each other's latencies and get three (measured
@@ -384,9 +385,9 @@ bool launch_chain(Slot& s, Scratch& sc, const HzView* hv, bool big_per_band, boo
     CUDA_TRY(hz_launch_prepare(hv[HZ_V_NEAR], dv + HZ_V_NEAR, st)); n++;
     if(ev) CUDA_TRY(cudaEventRecord(ev[1], st));
     CUDA_TRY(hz_launch_near(hv[HZ_V_NEAR], dv + HZ_V_NEAR, st)); n++;
-    CUDA_TRY(hz_launch_raster(dv + HZ_V_NEAR, st)); n++;
+    CUDA_TRY(hz_launch_raster(hv[HZ_V_NEAR], dv + HZ_V_NEAR, st)); n++;
     if(ev) CUDA_TRY(cudaEventRecord(ev[2], st));
-    CUDA_TRY(hz_launch_big(dv + HZ_V_NEAR, st)); n++;
+    CUDA_TRY(hz_launch_big(hv[HZ_V_NEAR], dv + HZ_V_NEAR, st)); n++;
     if(ev) CUDA_TRY(cudaEventRecord(ev[3], st));
     for(int b = 0; b < bands_of(s, sc).n; b++)
     {
@@ -396,7 +397,7 @@ bool launch_chain(Slot& s, Scratch& sc, const HzView* hv, bool big_per_band, boo
         n += k;
         if(last && ev) CUDA_TRY(cudaEventRecord(ev[4], st));
         // all bands share one queue and counter unless every band has its own k_big (see enqueue_render)
-        if(last || (big_per_band && k > 0)) { CUDA_TRY(hz_launch_big(dv + HZ_V_BAND0 + b, st)); n++; }
+        if(last || (big_per_band && k > 0)) { CUDA_TRY(hz_launch_big(hv[HZ_V_BAND0 + b], dv + HZ_V_BAND0 + b, st)); n++; }
     }
     if(ev) CUDA_TRY(cudaEventRecord(ev[5], st));
     if(resolve) { CUDA_TRY(hz_launch_resolve(hv[HZ_V_NEAR], dv + HZ_V_NEAR, st)); n++; }
@@ -487,6 +488,7 @@ bool enqueue_render(Slot& s, Scratch& sc, const ViewState& vs, int x0, int x1, c
     v.bigtri = sc.d_bigtri; v.bigtri_count = sc.d_counters + 3; v.bigtri_capacity = s.bigtri_capacity;
     v.occl_tile_max_pix = s.occl_tile_max_pix; v.occl_block_max_pix = s.occl_block_max_pix;
     v.small_max_pix = s.small_max_pix;
+    v.grid_percent = (&sc == &s.main) ? s.grid_percent_single : s.grid_percent_batch;
     v.big_capacity = s.big_capacity;
 
     // the eye's tile, and how many rings of tiles around it form the foreground pass
@@ -712,6 +714,8 @@ bool horizonator_init(horizonator_context_t* ctx,
         if(const char* env = getenv("HORIZONATOR_OCCL_TILE_PIX"))  s->occl_tile_max_pix  = atoi(env);
         if(const char* env = getenv("HORIZONATOR_OCCL_BLOCK_PIX")) s->occl_block_max_pix = atoi(env);
         if(const char* env = getenv("HORIZONATOR_SMALL_PIX"))      s->small_max_pix = atoi(env);
+        if(const char* env = getenv("HORIZONATOR_GRID_SCALE"))       s->grid_percent_single = atoi(env);
+        if(const char* env = getenv("HORIZONATOR_GRID_SCALE_BATCH")) s->grid_percent_batch  = atoi(env);
         // HORIZONATOR_BANDS / HORIZONATOR_BANDS_BATCH: comma-separated rings at which the bands end (lone views / views
         // of a batch; the first also sets the second unless that is given); the last band always runs to the edge
         auto parse_bands = [](const char* env, Slot::Bands& out) {

@@ -97,6 +97,7 @@ struct HzView
     uint32_t* tri_count;
     uint32_t  tri_capacity;
     int occl_tile_max_pix, occl_block_max_pix;   // largest screen box one thread checks against the visibility buffer
+    int grid_percent;            // host only: scale of the device-counted kernels' grids (hz_grid)
     int small_max_pix;           // a lane rasterises bounding boxes up to this many pixels itself; larger ones go to k_big
 
     // triangles too big for one thread: the set-up triangle goes to the record pool (6 x 16 bytes each), and one
@@ -148,9 +149,9 @@ cudaError_t hz_launch_pyramid(const int16_t* mosaic, int N, int pitch, short2* m
                               short2* mm_tile, int nt, cudaStream_t stream);
 cudaError_t hz_launch_prepare(const HzView& v, const HzView* d_v, cudaStream_t stream);  // clear keys, axis tables, counters
 cudaError_t hz_launch_near   (const HzView& v, const HzView* d_v, cudaStream_t stream);  // foreground tiles -> triangle list
-cudaError_t hz_launch_raster (const HzView* d_v, cudaStream_t stream);                   // set-up + rasterise a triangle list
+cudaError_t hz_launch_raster (const HzView& v, const HzView* d_v, cudaStream_t stream);  // set-up + rasterise a triangle list
 cudaError_t hz_launch_band   (const HzView& v, const HzView* d_v, bool worst_case, cudaStream_t stream, int* launches);
-cudaError_t hz_launch_big    (const HzView* d_v, cudaStream_t stream);                   // queued large triangles of one pass
+cudaError_t hz_launch_big    (const HzView& v, const HzView* d_v, cudaStream_t stream);  // queued large triangles of one pass
 cudaError_t hz_launch_resolve(const HzView& v, const HzView* d_v, cudaStream_t stream);
 bool        hz_resolve_is_vectorisable(const HzView& v);
 cudaError_t hz_launch_horizon(const float* ranges, int n, int W, int H, int* rows, float* range, cudaStream_t stream);

@@ -26,6 +26,7 @@
 #include "hz_math.cuh"
 
 #include <cstdint>
+#include <cstdlib>
 
 // ---- launches ----------------------------------------------------------------------------------
 // A render is a chain of a dozen short kernels on one stream.  Each is launched with programmatic stream
@@ -49,6 +50,16 @@ __device__ __forceinline__ void hz_wait_for_previous_kernel()
     __syncthreads();                                                                                       \
     hz_wait_for_previous_kernel();                                                                         \
     const HzView& P = hz_s_view
+
+// The kernels whose amount of work is only known on the device (queue lengths) are launched with a multiple of the SM
+// count and loop: ctas_per_sm as tuned for a lone view, times v.grid_percent/100.  Views that render concurrently
+// (the lanes of a batch) do better with smaller grids -- most CTAs of a worst-case grid find nothing to do, and
+// their launch and prologue compete with the other views' real work -- a lone view with larger ones.
+static unsigned int hz_grid(const HzView& v, unsigned int ctas_per_sm)
+{
+    const unsigned int g = 148u * ctas_per_sm * (unsigned int)(v.grid_percent > 0 ? v.grid_percent : 100) / 100u;
+    return g < 148u ? 148u : g;
+}
 
 template <typename... KArgs, typename... Args>
 static cudaError_t hz_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, cudaStream_t stream, Args&&... args)
@@ -1182,9 +1193,9 @@ k_raster(const HzView* __restrict__ V)
     if(P.stats && lane == 0 && n_big) atomicAdd(P.stats + HZ_STAT_BIG_ENTRIES, n_big);
 }
 
-cudaError_t hz_launch_raster(const HzView* d_v, cudaStream_t stream)
+cudaError_t hz_launch_raster(const HzView& v, const HzView* d_v, cudaStream_t stream)
 {
-    return hz_launch(k_raster, dim3(148 * 6), dim3(256), stream, d_v);
+    return hz_launch(k_raster, dim3(hz_grid(v, 6)), dim3(256), stream, d_v);
 }
 
 // `worst_case`: size the tile kernel for any eye position (a CUDA graph is captured once per context and replayed
@@ -1201,9 +1212,9 @@ cudaError_t hz_launch_band(const HzView& v, const HzView* d_v, bool worst_case, 
     if(ctas > 148 * 8) ctas = 148 * 8;
     cudaError_t e;
     if((e = hz_launch(k_tiles,  dim3((unsigned)ctas), dim3(256), stream, d_v)) != cudaSuccess) return e;
-    if((e = hz_launch(k_blocks, dim3(148 * 8), dim3(256), stream, d_v)) != cudaSuccess) return e;
-    if((e = hz_launch(k_mesh,   dim3(148 * 4), dim3(HZ_WARPS_PER_CTA * 32), stream, d_v)) != cudaSuccess) return e;
-    if((e = hz_launch(k_raster, dim3(148 * 6), dim3(256), stream, d_v)) != cudaSuccess) return e;
+    if((e = hz_launch(k_blocks, dim3(hz_grid(v, 8)), dim3(256), stream, d_v)) != cudaSuccess) return e;
+    if((e = hz_launch(k_mesh,   dim3(hz_grid(v, 4)), dim3(HZ_WARPS_PER_CTA * 32), stream, d_v)) != cudaSuccess) return e;
+    if((e = hz_launch(k_raster, dim3(hz_grid(v, 6)), dim3(256), stream, d_v)) != cudaSuccess) return e;
     *launches = 4;
     return cudaSuccess;
 }
@@ -1260,9 +1271,9 @@ k_big(const HzView* __restrict__ V)
     }
 }
 
-cudaError_t hz_launch_big(const HzView* d_v, cudaStream_t stream)
+cudaError_t hz_launch_big(const HzView& v, const HzView* d_v, cudaStream_t stream)
 {
-    return hz_launch(k_big, dim3(148 * 8), dim3(256), stream, d_v);
+    return hz_launch(k_big, dim3(hz_grid(v, 8)), dim3(256), stream, d_v);
 }
 
 // ================================================================================================
