@@ -1209,7 +1209,7 @@ cudaError_t hz_launch_band(const HzView& v, const HzView* d_v, bool worst_case, 
     if(v.ring_lo >= ring_hi) return cudaSuccess;
     const long long ntiles = (long long)(2 * ring_hi - 1) * (2 * ring_hi - 1) - (long long)(2 * v.ring_lo - 1) * (2 * v.ring_lo - 1);
     long long ctas = (ntiles + 255) / 256;
-    if(ctas > 148 * 8) ctas = 148 * 8;
+    if(ctas > (long long)hz_grid(v, 8)) ctas = hz_grid(v, 8);
     cudaError_t e;
     if((e = hz_launch(k_tiles,  dim3((unsigned)ctas), dim3(256), stream, d_v)) != cudaSuccess) return e;
     if((e = hz_launch(k_blocks, dim3(hz_grid(v, 8)), dim3(256), stream, d_v)) != cudaSuccess) return e;
