@@ -366,7 +366,7 @@ def run_b200(args):
                      "latency_ms_single_panorama": latency_ms,
                      "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum summed over the 14 kernels of one "
                                      "panorama (one CUDA-graph launch), from the ncu capture summarised in "
-                                     "profiles/r01z_kernels_per_panorama.txt",
+                                     "profiles/r01A_kernels_per_panorama.txt",
                      "note": "achieved = algorithmic bytes per panorama (one read of the int16 DEM square + one write of "
                              "image and range, SURVEY 8d) x measured panoramas/s over the whole timed region.  Hierarchical culling makes the kernels read far less DRAM than the "
                              "algorithmic figure (see traffic) and leaves them latency-bound, which is why several "
