@@ -162,7 +162,26 @@ def viewpoints(n_ranks, rank, steps):
 
 # ------------------------------------------------------------------------------------------------ our arm
 
+class StdoutToStderr:
+    """stdout carries exactly one JSON line.  Libraries print there too (NCCL writes its version banner to file
+    descriptor 1 when NCCL_DEBUG=VERSION): while this is active, descriptor 1 points at stderr; restore() puts it
+    back right before the line is printed."""
+
+    def __init__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+
+    def restore(self):
+        if self.saved is not None:
+            sys.stdout.flush()
+            os.dup2(self.saved, 1)
+            os.close(self.saved)
+            self.saved = None
+
+
 def run_b200(args):
+    quiet = StdoutToStderr()
     import torch
     import torch.distributed as dist
 
@@ -173,9 +192,6 @@ def run_b200(args):
         raise SystemExit("bench.py: no CUDA device; the renderer has no CPU path")
     torch.cuda.set_device(local)
     if world > 1:
-        # stdout carries exactly one JSON line: keep NCCL's version banner (NCCL_DEBUG=VERSION prints it there) out
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     def barrier():
@@ -380,6 +396,7 @@ def run_b200(args):
     }
     if world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline(tiles, use_ref=False, steps=3)
+    quiet.restore()
     print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -19,8 +19,8 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0")); local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     os.environ["HORIZONATOR_DEVICE"] = str(local)
-    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-        os.environ["NCCL_DEBUG"] = "WARN"
+    from bench import StdoutToStderr
+    quiet = StdoutToStderr()     # NCCL prints its version banner on descriptor 1
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     import horizonator_b200 as hz
@@ -112,6 +112,7 @@ def main():
         e1.record(); torch.cuda.synchronize()
         whole_ms = e0.elapsed_time(e1) / 3
         same = bool(torch.equal(fi, img)) and bool(torch.equal(fr, rng))
+        quiet.restore()
         print(json.dumps({"config": "BASELINE configs[3]: %dx%d full circle, C2 DEM (R=5858), azimuth wedges" % (W, H),
                           "n_gpus": world, "sharded_ms_per_panorama_incl_gather": sharded_ms, "wedge_render_ms_max_over_ranks": wedge_ms,
                           "peer_store_ms_per_panorama": peer_ms, "peer_store_to_rank0_only_ms": peer_root_ms,
