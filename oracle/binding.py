@@ -5,6 +5,8 @@ Only tests/, __graft_entry__.smoke() and bench.py's CPU-baseline legs may import
   Oracle      liboracle.so: the CPU restatement (horizonator_oracle.c + gl_pipeline.c)
   Reference   _ref/libhorizonator_ref.so: the reference's own horizonator-lib.c + dem.c, compiled
               unmodified from /root/reference on the fake GL of oracle/fakegl (prebuilt .so travels)
+  MesaReference  _ref/libhorizonator_mesa.so: the same two files, unmodified, on a REAL OpenGL driver -- the
+              Mesa llvmpipe libGL inside the image (oracle/mesa/): what pins the GL rules of gl_pipeline.c
 """
 import ctypes as C
 import os
@@ -15,16 +17,32 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 ORACLE_SO = os.path.join(HERE, "liboracle.so")
 REF_SO = os.path.join(HERE, "_ref", "libhorizonator_ref.so")
+MESA_SO = os.path.join(HERE, "_ref", "libhorizonator_mesa.so")
 
 
 def build(ref=True):
-    """make liboracle.so (+ _ref when /root/reference is present)."""
-    targets = ["liboracle.so"] + (["ref"] if ref else [])
+    """make liboracle.so (+ _ref, on the fake GL and on Mesa, when /root/reference is present)."""
+    targets = ["liboracle.so"] + (["ref", "mesa"] if ref else [])
     subprocess.run(["make", "-s", "-C", HERE] + targets, check=True)
 
 
 def have_ref():
     return os.path.exists(REF_SO)
+
+
+def mesa_libgl():
+    """Path of the Mesa libGL the llvmpipe build links to (inside Nsight Compute), or None."""
+    import glob
+    hits = sorted(glob.glob("/opt/nvidia/nsight-compute/*/host/linux-desktop-glibc_2_11_3-x64/Mesa/libGL.so.1"))
+    return hits[0] if hits else None
+
+
+def have_mesa():
+    """True where the reference-on-llvmpipe build exists AND the libGL it was linked to is in the image."""
+    if not os.path.exists(MESA_SO):
+        return False
+    out = subprocess.run(["ldd", MESA_SO], capture_output=True, text=True).stdout
+    return "not found" not in out and "libGL.so.1" in out
 
 
 class Oracle:
@@ -133,11 +151,13 @@ class Reference:
     """The reference's horizonator-lib.c + dem.c (unmodified) on the fake GL.  One live instance at a time:
     the fake GL, like the code it serves, keeps one current program/framebuffer."""
     _lib = None
+    SO = REF_SO
+    FAKE_GL = True
 
     @classmethod
     def lib(cls):
-        if cls._lib is None:
-            L = C.CDLL(REF_SO)
+        if cls.__dict__.get("_lib") is None:
+            L = C.CDLL(cls.SO)
             f, d, i, b, vp, cp = C.c_float, C.c_double, C.c_int, C.c_bool, C.c_void_p, C.c_char_p
             L.horizonator_init.restype = b
             L.horizonator_init.argtypes = [vp, f, f, C.POINTER(f), i, i, i, f, b, b, b, cp, cp, cp, cp, b]
@@ -162,7 +182,13 @@ class Reference:
             L.horizonator_project.argtypes = [C.POINTER(d)] * 3 + [d] * 9 + [i, i]
             L.horizonator_unproject.restype = b
             L.horizonator_unproject.argtypes = [C.POINTER(f), C.POINTER(f), i, i] + [d] * 7 + [i, i]
-            L.fakegl_set_threads.argtypes = [i]
+            L.horizonator_deinit.restype = None
+            L.horizonator_deinit.argtypes = [vp]
+            if cls.FAKE_GL:
+                L.fakegl_set_threads.argtypes = [i]
+            else:
+                L.glut_glx_renderer.restype = cp
+                L.glut_glx_version.restype = cp
             cls._lib = L
         return cls._lib
 
@@ -170,15 +196,27 @@ class Reference:
                  render_radius_cells=-1, render_radius_m=-1., viewer_z=None, threads=1):
         from horizonator_b200 import context_t   # layout only; no product code runs
         L = self.lib()
-        L.fakegl_set_threads(threads)
-        self.ctx = context_t()
+        self._set_threads(threads)
+        self.ctx = None
+        ctx = context_t()
         z = C.c_float(-1. if viewer_z is None else viewer_z)
-        if not L.horizonator_init(C.byref(self.ctx), lat, lon, C.byref(z), width, height,
+        if not L.horizonator_init(C.byref(ctx), lat, lon, C.byref(z), width, height,
                                   render_radius_cells, render_radius_m, True, False, SRTM1,
                                   os.fsencode(dir_dems), None, None, None, False):
             raise RuntimeError("reference horizonator_init() failed")
+        self.ctx = ctx
         self.viewer_z = z.value
         self.W, self.H = width, height
+
+    def _set_threads(self, threads):
+        self.lib().fakegl_set_threads(threads)
+
+    def close(self):
+        """horizonator_deinit() (horizonator-lib.c:682-689): gives the GL context back."""
+        if self.ctx is not None:
+            self.lib().horizonator_deinit(C.byref(self.ctx))
+            self.lib().horizonator_dem_deinit(C.byref(self.ctx.dems))
+            self.ctx = None
 
     def move(self, lat, lon, viewer_z=None):
         z = C.c_float(-1. if viewer_z is None else viewer_z)
@@ -204,3 +242,22 @@ class Reference:
         ranges = np.empty((self.H, self.W), np.float32)
         assert L.horizonator_render_offscreen(C.byref(self.ctx), image.ctypes.data, ranges.ctypes.data)
         return image, ranges
+
+
+class MesaReference(Reference):
+    """The reference's horizonator-lib.c + dem.c (unmodified) on Mesa's llvmpipe: a real OpenGL implementation
+    (shader compiler, clipper, rasteriser, depth buffer, read-back), not a restatement.  One live instance per
+    process at a time (one GLX context); close() before making the next.  llvmpipe sizes its rasteriser thread
+    pool when the first context is created (LP_NUM_THREADS, default: all cores, at most 16); its vertex and
+    geometry stages run on the calling thread."""
+    _lib = None
+    SO = MESA_SO
+    FAKE_GL = False
+
+    def _set_threads(self, threads):
+        if threads and threads > 0:
+            os.environ.setdefault("LP_NUM_THREADS", str(min(int(threads), 16)))
+
+    def gl_strings(self):
+        L = self.lib()
+        return L.glut_glx_version().decode(), L.glut_glx_renderer().decode()

@@ -549,3 +549,42 @@ def test_render_matches_committed_golden_vectors(hz, tiles_c1, name):
     s = compare_renders(img, rng, g["image"], g["ranges"])
     print("golden", name, s)
     assert s["ok"], s
+
+
+# ------------------------------------------------------------------------------------------ a real GL driver
+
+def _llvmpipe_scenes():
+    g = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    return sorted(f[len("llvmpipe_"):-len(".npz")] for f in os.listdir(g) if f.startswith("llvmpipe_") and f.endswith(".npz"))
+
+
+def _render_c_api(hb, tiles, W, H, R, az0, az1, zn, zf, znc, zfc, lat, lon, vz):
+    """One render through the C ABI with an explicit eye height (the Python API has none, like the reference's)."""
+    ctx = hb.context_t()
+    z = C.c_float(vz)
+    assert hb.lib.horizonator_init(C.byref(ctx), C1_LAT, C1_LON, C.byref(z), W, H, R, -1.0, True, False, False,
+                                   os.fsencode(tiles), None, None, None, False)
+    try:
+        assert hb.lib.horizonator_pan_zoom(C.byref(ctx), az0, az1)
+        if lat > -1000.:
+            assert hb.lib.horizonator_move(C.byref(ctx), None, lat, lon)
+        assert hb.lib.horizonator_set_zextents(C.byref(ctx), zn, zf, znc, zfc)
+        img = np.empty((H, W, 3), np.uint8)
+        rng = np.empty((H, W), np.float32)
+        assert hb.lib.horizonator_render_offscreen(C.byref(ctx), img.ctypes.data, rng.ctypes.data)
+    finally:
+        hb.lib.horizonator_deinit(C.byref(ctx))
+    return img, rng
+
+
+@pytest.mark.parametrize("name", _llvmpipe_scenes())
+def test_render_matches_reference_on_llvmpipe(hz, tiles_c1, name):
+    """The CUDA path against renders of the UNMODIFIED reference on a real OpenGL implementation (Mesa llvmpipe;
+    tests/golden/make_golden_llvmpipe.py) -- neither the oracle nor its GL restatement is involved."""
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "llvmpipe_%s.npz" % name))
+    W, H, R, az0, az1, zn, zf, znc, zfc, lat, lon, vz = (float(x) for x in g["params"])
+    img, rng = _render_c_api(hz, tiles_c1, int(W), int(H), int(R), az0, az1, zn, zf, znc, zfc, lat, lon, vz)
+    s = compare_renders(img, rng, g["image"], g["ranges"])
+    print("llvmpipe", name, s)
+    assert s["ok"], s
+    assert s["coverage_agreement"] >= 0.9995, s
