@@ -433,47 +433,108 @@ def cpu_baseline(tiles, use_ref, steps=1, warmup=0, budget_s=25.0):
             "ms_per_render": mean * 1e3}
 
 
+def _timed_renders(o, steps, warmup, budget_s):
+    """warm-up renders (at most a quarter of the budget), then up to `steps` timed ones until the budget is spent"""
+    t_begin = time.perf_counter()
+    done_w = 0
+    for _ in range(warmup):
+        o.render(C2["az0"], C2["az1"], znear=C2["znear"], zfar=C2["zfar"])
+        done_w += 1
+        if time.perf_counter() - t_begin > budget_s / 4:
+            break
+    times = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        o.render(C2["az0"], C2["az1"], znear=C2["znear"], zfar=C2["zfar"])
+        times.append(time.perf_counter() - t0)
+        if time.perf_counter() - t_begin > budget_s:
+            break
+    return times, done_w
+
+
+def llvmpipe_child(args):
+    """Child process of the reference arm: the reference's horizonator-lib.c + dem.c, unmodified, on Mesa llvmpipe
+    (oracle/_ref/libhorizonator_mesa.so).  Own process because a GL driver owns process-wide state (JIT, thread pool)
+    and because the parent must survive whatever the driver does.  Prints one JSON line."""
+    from oracle import binding
+    cores = os.cpu_count() or 1
+    t0 = time.perf_counter()
+    o = binding.MesaReference(C2["lat"], C2["lon"], C2["W"], C2["H"], SRTM1=True, dir_dems=TILES_DIR,
+                              render_radius_m=C2["radius_m"], threads=cores)
+    init_s = time.perf_counter() - t0
+    version, renderer = o.gl_strings()
+    times, done_w = _timed_renders(o, args.steps, args.warmup, float(os.environ.get("HZ_REF_BUDGET_S", "120")))
+    print("LLVMPIPE " + json.dumps({"times": times, "warmup": done_w, "gl_version": version, "gl_renderer": renderer,
+                                    "init_s": init_s, "lp_threads": min(cores, 16)}), flush=True)
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if rank != 0:
         return
+    import subprocess
     from tools import synth
     from oracle import binding
     synth.config2_tiles(TILES_DIR)
-    use_ref = binding.have_ref()
     if not os.path.exists(binding.ORACLE_SO):
         binding.build(ref=False)
-    # bounded: every step is one full C2 panorama; the run stops early once ~4 minutes are spent
     cores = os.cpu_count() or 1
+    budget = float(os.environ.get("HZ_REF_BUDGET_S", "120"))
+
+    # (1) the real thing (north_star: "the reference llvmpipe render timed on the box's host cores"): the unmodified
+    #     reference on Mesa llvmpipe, in a child process
+    llvmpipe = None
+    if binding.have_mesa() and os.environ.get("HZ_REF_GL", "llvmpipe") == "llvmpipe":
+        try:
+            p = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--llvmpipe-child",
+                                "--steps", str(args.steps), "--warmup", str(args.warmup)],
+                               capture_output=True, text=True, timeout=2.5 * budget + 300)
+            lines = [l for l in p.stdout.splitlines() if l.startswith("LLVMPIPE ")]
+            if p.returncode == 0 and lines:
+                llvmpipe = json.loads(lines[-1][len("LLVMPIPE "):])
+            else:
+                sys.stderr.write("bench: llvmpipe child failed (rc %d): %s\n" % (p.returncode, p.stderr[-1000:]))
+        except Exception as e:      # timeout, missing interpreter, ...
+            sys.stderr.write("bench: llvmpipe child failed: %r\n" % (e,))
+
+    # (2) the same reference sources on the software-GL restatement (oracle/_ref), or the oracle port where the
+    #     reference was never compiled: the whole arm when (1) is unavailable, a short second opinion when it is not
+    use_ref = binding.have_ref()
     cls = binding.Reference if use_ref else binding.Oracle
     o = cls(C2["lat"], C2["lon"], C2["W"], C2["H"], SRTM1=True, dir_dems=TILES_DIR,
             render_radius_m=C2["radius_m"], threads=cores)
-    budget = float(os.environ.get("HZ_REF_BUDGET_S", "200"))
-    t_begin = time.perf_counter()
-    done_w = 0
-    for _ in range(args.warmup):
-        o.render(C2["az0"], C2["az1"], znear=C2["znear"], zfar=C2["zfar"])
-        done_w += 1
-        if time.perf_counter() - t_begin > budget / 4:
-            break
-    times = []
-    for _ in range(args.steps):
-        t0 = time.perf_counter()
-        o.render(C2["az0"], C2["az1"], znear=C2["znear"], zfar=C2["zfar"])
-        times.append(time.perf_counter() - t0)
-        if time.perf_counter() - t_begin > budget:
-            break
-    mean = sum(times) / len(times)
+    if llvmpipe is None:
+        times_r, done_w_r = _timed_renders(o, args.steps, args.warmup, budget)
+    else:
+        times_r, done_w_r = _timed_renders(o, min(args.steps, 3), 1, 20.0)
+    mean_r = sum(times_r) / len(times_r)
+    what_r = ("the reference's horizonator-lib.c + dem.c compiled unmodified (oracle/_ref) on a software-GL "
+              "restatement of the driver (oracle/gl_pipeline.c)" if use_ref
+              else "CPU restatement of the reference GL path (oracle/)")
+    restated = {"value": 1.0 / mean_r, "unit": "panoramas/s", "cores": cores, "kind": "reference" if use_ref else "port",
+                "sample": "%d full C2 panorama(s), %.2f s each; %s; OpenMP over %d host threads" %
+                          (len(times_r), mean_r, what_r, cores)}
+
+    if llvmpipe is not None:
+        times, done_w = llvmpipe["times"], llvmpipe["warmup"]
+        mean = sum(times) / len(times)
+        kind = "reference"
+        sample = ("%d of the requested %d steps timed (budget %.0f s), each one full C2 panorama (3600x600, R=5858, "
+                  "274 M triangles) through horizonator_render_offscreen() into host buffers, %.1f s each; the "
+                  "reference's horizonator-lib.c + dem.c compiled UNMODIFIED, running its own GLSL shaders on a real "
+                  "OpenGL driver: %s, %s (oracle/_ref/libhorizonator_mesa.so; context on GLX pbuffers, no X server); "
+                  "llvmpipe rasterises on %d threads, its vertex and geometry stages run on one; %d host cores; "
+                  "1 process regardless of --gpus" %
+                  (len(times), args.steps, budget, mean, llvmpipe["gl_renderer"], llvmpipe["gl_version"],
+                   llvmpipe["lp_threads"], cores))
+    else:
+        times, done_w, mean, kind = times_r, done_w_r, mean_r, restated["kind"]
+        sample = ("%d of the requested %d steps timed (budget %.0f s), each one full C2 panorama (3600x600, R=5858, "
+                  "274 M triangles) into host buffers, %.2f s each; %s (Mesa llvmpipe build not available here); "
+                  "OpenMP over %d host threads; 1 process regardless of --gpus" %
+                  (len(times), args.steps, budget, mean, what_r, cores))
     value = 1.0 / mean
-    kind = "reference" if use_ref else "port"
-    sample = ("%d of the requested %d steps timed (budget %.0f s), each one full C2 panorama (3600x600, R=5858, "
-              "274 M triangles) into host buffers, %.2f s each; %s; OpenMP over %d host threads; "
-              "1 process regardless of --gpus" %
-              (len(times), args.steps, budget, mean,
-               "the reference's horizonator-lib.c + dem.c compiled unmodified (oracle/_ref) on a software-GL "
-               "restatement of the driver (no GL driver exists in this image; real llvmpipe not measurable)"
-               if use_ref else "CPU restatement of the reference GL path (oracle/)", cores))
     out = {
         "impl": "reference",
         "metric": "panoramas/sec (SRTM1, 3600x600 px)",
@@ -489,6 +550,9 @@ def run_reference(args):
         "e2e": {"value": value, "unit": "panoramas/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
+    if llvmpipe is not None:
+        out["gl"] = {"version": llvmpipe["gl_version"], "renderer": llvmpipe["gl_renderer"], "init_s": llvmpipe["init_s"]}
+        out["restated_gl"] = restated     # the same sources on the oracle's GL restatement: a much faster CPU rasteriser
     print(json.dumps(out), flush=True)
 
 
@@ -500,7 +564,10 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--batch", type=int, default=16, help="panoramas per step (rendered concurrently)")
+    ap.add_argument("--llvmpipe-child", action="store_true", help=argparse.SUPPRESS)
     args = ap.parse_args()
+    if args.llvmpipe_child:
+        return llvmpipe_child(args)
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3
     if args.impl == "reference":

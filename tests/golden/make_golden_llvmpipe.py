@@ -13,7 +13,10 @@ oracle/gl_pipeline.c is involved.  These files are what pins the oracle's GL rul
 and, on the GPU, the CUDA path itself (tests/test_gpu_parity.py).
 
 The scenes of make_golden.py are repeated here on llvmpipe, plus larger ones that cover what small scenes cannot:
-zoomed-in windows (triangles of hundreds of pixels), an eye high above the terrain, a wide full circle.
+zoomed-in windows (triangles of hundreds of pixels), an eye high above the terrain, a wide full circle -- and the
+two BASELINE workloads at FULL size (fullsize_c1_llvmpipe.npz: configs[0], 3600x300 over 2x2 SRTM3 tiles, 11.5 M
+triangles, ~2 s on llvmpipe; fullsize_c2_llvmpipe.npz: configs[1], the benchmark panorama, 3600x600 over 150 km of
+SRTM1, 274 M triangles, ~40 s on llvmpipe; ~0.6 MB each because most of a panorama is sky).
 """
 import json
 import os
@@ -73,6 +76,19 @@ def main():
     for m in moves[1:]:
         assert float(r.move(m["lat"], m["lon"])) == m["viewer_z"], m
     r.close()
+
+    # the two BASELINE workloads at full size
+    C2_LAT, C2_LON = 34.0 + 1.0 / 7200.0, -117.0 + 1.0 / 7200.0
+    tiles2 = synth.config2_tiles(os.environ.get("HZ_BENCH_TILES", "/tmp/hz_tiles_c2"))
+    for name, lat0, lon0, W, H, kw_init, zf, t in (
+            ("c1", C1_LAT, C1_LON, 3600, 300, dict(dir_dems=tiles, render_radius_cells=1200), 100000., tiles),
+            ("c2", C2_LAT, C2_LON, 3600, 600, dict(dir_dems=tiles2, render_radius_m=150000., SRTM1=True), 150000., tiles2)):
+        r = binding.MesaReference(lat0, lon0, W, H, threads=os.cpu_count() or 1, **kw_init)
+        img, rng = r.render(-180.05, 179.95, znear=100., zfar=zf)
+        np.savez_compressed(os.path.join(HERE, "fullsize_%s_llvmpipe.npz" % name), image=img, ranges=rng,
+                            viewer_z=np.float32(r.viewer_z))
+        summary["fullsize_" + name] = dict(viewer_z_at_init=float(r.viewer_z), hit_fraction=float((rng > 0).mean()))
+        r.close()
 
     with open(os.path.join(HERE, "llvmpipe.json"), "w") as f:
         json.dump(dict(gl_version=version, gl_renderer=renderer, move_json_reproduced=len(moves), scenes=summary),

@@ -33,7 +33,8 @@ def _load(name):
 def test_fixture_set():
     meta = json.load(open(os.path.join(GOLDEN, "llvmpipe.json")))
     assert "llvmpipe" in meta["gl_renderer"] and "Mesa" in meta["gl_version"]
-    assert sorted(meta["scenes"]) == SCENES and len(SCENES) >= 7
+    assert sorted(k for k in meta["scenes"] if not k.startswith("fullsize_")) == SCENES and len(SCENES) >= 7
+    assert {"fullsize_c1", "fullsize_c2"} <= set(meta["scenes"])
     # horizonator_move()'s automatic eye heights (a render + read-back each) came out the same on llvmpipe as on the
     # fake GL: the generator asserts it vector by vector and records how many it checked
     assert meta["move_json_reproduced"] == len(json.load(open(os.path.join(GOLDEN, "move.json"))))
@@ -66,6 +67,32 @@ def test_fake_gl_fixtures_agree_with_llvmpipe(name):
     assert list(f["params"]) == p[:11] and f["viewer_z"] == g["viewer_z"]
     s = compare_renders(f["image"], f["ranges"], g["image"], g["ranges"])
     assert s["ok"] and s["coverage_agreement"] == 1.0 and s["off_silhouette"] == 0, s
+
+
+C2_LAT, C2_LON = 34.0 + 1.0 / 7200.0, -117.0 + 1.0 / 7200.0
+
+
+@pytest.mark.parametrize("which", ["c1", "c2"])
+def test_oracle_agrees_with_llvmpipe_at_full_size(tiles_c1, which):
+    """BASELINE configs[0] (3600x300, 2x2 SRTM3 tiles, 11.5 M triangles) and configs[1] (the benchmark panorama:
+    3600x600, 150 km of SRTM1, 274 M triangles): the oracle against the reference's render on llvmpipe."""
+    from oracle.binding import Oracle
+    from tools import synth
+    g = np.load(os.path.join(GOLDEN, "fullsize_%s_llvmpipe.npz" % which))
+    threads = os.cpu_count() or 1
+    if which == "c1":
+        o = Oracle(C1_LAT, C1_LON, 3600, 300, dir_dems=tiles_c1, render_radius_cells=1200, threads=threads)
+        zfar = 100000.
+    else:
+        tiles = synth.config2_tiles(os.environ.get("HZ_BENCH_TILES", "/tmp/hz_tiles_c2"))
+        o = Oracle(C2_LAT, C2_LON, 3600, 600, SRTM1=True, dir_dems=tiles, render_radius_m=150000., threads=threads)
+        zfar = 150000.
+    assert np.float32(o.viewer_z) == g["viewer_z"]
+    img, rng = o.render(-180.05, 179.95, znear=100., zfar=zfar)
+    s = compare_renders(img, rng, g["image"], g["ranges"])
+    print("oracle vs llvmpipe, full size", which, s)
+    assert s["ok"], s
+    assert s["coverage_agreement"] >= 0.99999 and s["agreement"] >= 0.9995 and s["off_silhouette"] == 0, s
 
 
 WORKER = r"""
