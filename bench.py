@@ -395,7 +395,11 @@ def run_b200(args):
                 "host_enqueue_us_per_panorama": host_enqueue_s / (K * B) * 1e6},
     }
     if world == 1 and not args.no_cpu_baseline:
-        out["cpu_baseline"] = cpu_baseline(tiles, use_ref=False, steps=3)
+        port = cpu_baseline(tiles, use_ref=False, steps=3)
+        real = llvmpipe_baseline()
+        out["cpu_baseline"] = real or port
+        if real:
+            out["cpu_baseline_port"] = port
     quiet.restore()
     print(json.dumps(out), flush=True)
     if world > 1:
@@ -468,12 +472,47 @@ def llvmpipe_child(args):
                                     "init_s": init_s, "lp_threads": min(cores, 16)}), flush=True)
 
 
+def _llvmpipe_run(steps, warmup, budget_s):
+    """The llvmpipe child process; returns its report or None (stderr says why)."""
+    import subprocess
+    from oracle import binding
+    if not binding.have_mesa() or os.environ.get("HZ_REF_GL", "llvmpipe") != "llvmpipe":
+        return None
+    try:
+        p = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--llvmpipe-child",
+                            "--steps", str(steps), "--warmup", str(warmup)],
+                           env=dict(os.environ, HZ_REF_BUDGET_S=str(budget_s)),
+                           capture_output=True, text=True, timeout=2.5 * budget_s + 300)
+        lines = [l for l in p.stdout.splitlines() if l.startswith("LLVMPIPE ")]
+        if p.returncode == 0 and lines:
+            return json.loads(lines[-1][len("LLVMPIPE "):])
+        sys.stderr.write("bench: llvmpipe child failed (rc %d): %s\n" % (p.returncode, p.stderr[-1000:]))
+    except Exception as e:      # timeout, missing interpreter, ...
+        sys.stderr.write("bench: llvmpipe child failed: %r\n" % (e,))
+    return None
+
+
+def llvmpipe_baseline():
+    """cpu_baseline of the B200 arm: ONE full benchmark panorama by the unmodified reference on Mesa llvmpipe on this
+    box's host cores (~30 s of CPU work), or None where that build is absent."""
+    r = _llvmpipe_run(steps=1, warmup=0, budget_s=1.0)
+    if r is None:
+        return None
+    cores = os.cpu_count() or 1
+    t = r["times"][0]
+    return {"value": 1.0 / t, "unit": "panoramas/s", "cores": cores, "kind": "reference",
+            "sample": "1 full C2 panorama (3600x600, 274 M triangles), first frame after init, %.1f s; the reference's "
+                      "horizonator-lib.c + dem.c + GLSL shaders compiled UNMODIFIED on a real OpenGL driver: %s, %s "
+                      "(oracle/_ref/libhorizonator_mesa.so); llvmpipe rasterises on %d threads, its vertex and geometry "
+                      "stages run on one" % (t, r["gl_renderer"], r["gl_version"], r["lp_threads"]),
+            "ms_per_render": t * 1e3}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if rank != 0:
         return
-    import subprocess
     from tools import synth
     from oracle import binding
     synth.config2_tiles(TILES_DIR)
@@ -484,19 +523,7 @@ def run_reference(args):
 
     # (1) the real thing (north_star: "the reference llvmpipe render timed on the box's host cores"): the unmodified
     #     reference on Mesa llvmpipe, in a child process
-    llvmpipe = None
-    if binding.have_mesa() and os.environ.get("HZ_REF_GL", "llvmpipe") == "llvmpipe":
-        try:
-            p = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--llvmpipe-child",
-                                "--steps", str(args.steps), "--warmup", str(args.warmup)],
-                               capture_output=True, text=True, timeout=2.5 * budget + 300)
-            lines = [l for l in p.stdout.splitlines() if l.startswith("LLVMPIPE ")]
-            if p.returncode == 0 and lines:
-                llvmpipe = json.loads(lines[-1][len("LLVMPIPE "):])
-            else:
-                sys.stderr.write("bench: llvmpipe child failed (rc %d): %s\n" % (p.returncode, p.stderr[-1000:]))
-        except Exception as e:      # timeout, missing interpreter, ...
-            sys.stderr.write("bench: llvmpipe child failed: %r\n" % (e,))
+    llvmpipe = _llvmpipe_run(args.steps, args.warmup, budget)
 
     # (2) the same reference sources on the software-GL restatement (oracle/_ref), or the oracle port where the
     #     reference was never compiled: the whole arm when (1) is unavailable, a short second opinion when it is not

@@ -12,13 +12,16 @@
  *                    viewport :657, clear+draw :896-897; everything else GL defaults.
  *
  * The GL driver itself (Mesa; no version is pinned by the reference, see rpmpackage.spec)
- * is a third-party dependency that is absent from /root/reference and cannot run in this
- * image, so the fixed-function rules below restate the OpenGL 4.2 core specification
- * (sections 2.14 "coordinate transformations", 3.6.1 "basic polygon rasterization",
- * 4.1.5 "depth buffer test") with the implementation-defined choices written down in
- * gl_pipeline.c.  PARITY OF THE RASTERISATION RULES IS THEREFORE UNPINNED against a real
- * driver; the host-side logic around them is pinned against the reference's own code
- * (oracle/_ref, built by oracle/Makefile).
+ * is a third-party dependency that is absent from /root/reference.  The fixed-function
+ * rules below restate the OpenGL 4.2 core specification (sections 2.14 "coordinate
+ * transformations", 3.6.1 "basic polygon rasterization", 4.1.5 "depth buffer test") with
+ * the implementation-defined choices written down in gl_pipeline.c.  PINNING: they are
+ * checked against a real driver -- the unmodified reference running on Mesa 18.1.9
+ * llvmpipe (oracle/mesa/, oracle/_ref/libhorizonator_mesa.so; renders recorded in
+ * tests/golden/llvmpipe_*.npz and fullsize_c{1,2}_llvmpipe.npz, compared by
+ * tests/test_llvmpipe.py at the north_star tolerances: coverage differs on a handful of
+ * pixels per million, range disagreements only on silhouettes).  The host-side logic
+ * around them is pinned bit for bit against the reference's own code (oracle/_ref).
  */
 #pragma once
 #include <stdint.h>

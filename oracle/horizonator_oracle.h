@@ -6,13 +6,14 @@
  * the depth->range readback), on top of the GL-pipeline restatement in gl_pipeline.c.
  * Each function cites the reference lines it follows.
  *
- * Pinning: tests/test_oracle_vs_ref.py checks this restatement bit-for-bit against the
+ * Pinning: tests/test_oracle.py checks this restatement bit-for-bit against the
  * reference's own dem.c and horizonator-lib.c compiled from /root/reference (oracle/_ref,
  * where horizonator-lib.c runs unmodified on a fake GL whose draw call is gl_pipeline.c),
  * and against the golden vectors in tests/golden/ that were generated from that build.
- * The reference ships no tests or golden vectors of its own, and no real GL driver can run
- * in this image, so the rasterisation rules themselves (gl_pipeline.c, F1-F9) are a
- * restatement of the OpenGL specification: "parity unpinned" for that stage.
+ * The reference ships no tests or golden vectors of its own.  The rasterisation rules
+ * (gl_pipeline.c, F1-F9) restate the OpenGL specification and are pinned against a real GL
+ * driver: the unmodified reference on Mesa llvmpipe (oracle/mesa/; tests/test_llvmpipe.py
+ * compares this oracle with its recorded and live renders at the north_star tolerances).
  */
 #pragma once
 #include <stdbool.h>

@@ -16,9 +16,10 @@ therefore pinned by the reference's own arithmetic:
   move.json           horizonator_move(): automatic viewer height (via the read-back of a flat render)
   geometry.json       horizonator_x_from_az / _project / _unproject
   render_*.npz        horizonator_render_offscreen(): BGR image + range image of small scenes.  The GL
-                      driver below the reference is the software restatement oracle/gl_pipeline.c (no GL
-                      driver can run in this image): the host logic, read-back, flips and the depth->range
-                      conversion are the reference's, the rasterisation rules are the restatement's.
+                      driver below the reference is the software restatement oracle/gl_pipeline.c: the host
+                      logic, read-back, flips and the depth->range conversion are the reference's, the
+                      rasterisation rules are the restatement's.  (The same scenes rendered by the reference
+                      on a REAL driver, Mesa llvmpipe, are made by make_golden_llvmpipe.py.)
 
 The synthetic tiles come from tools/synth_hgt.c (integer hash noise, seeded); tiles_sha256.json records
 what the generator produced here, and the tests check that first.

@@ -6,9 +6,10 @@ judged against) before anything trusts it:
   * where oracle/_ref is present on this machine, against that build directly, on more scenes;
   * against analytic properties that need no reference at all (flat world, conventions, thread invariance).
 
-What stays unpinned: the rasterisation rules of the GL driver (gl_pipeline.c F1-F9).  No GL driver can run in this
-image, and the reference build renders through the same restated rules, so those rules are checked here only
-for self-consistency and against the GL specification's invariants (watertight shared edges, top row first...).
+The rasterisation rules of the GL driver (gl_pipeline.c F1-F9) are not pinned HERE -- the fake-GL reference build
+renders through the same restated rules, so this file checks them only for self-consistency and against the GL
+specification's invariants (watertight shared edges, top row first...).  They are pinned in tests/test_llvmpipe.py,
+against the reference running on a real OpenGL driver (Mesa llvmpipe).
 """
 import json
 import os
