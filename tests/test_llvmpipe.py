@@ -139,3 +139,20 @@ def test_reference_runs_live_on_llvmpipe(tiles_c1):
         # leaves the odd far-plane pixel black with depth 1.0 ("what llvmpipe does differently")
         assert s["coverage_agreement"] >= 0.9999 and s["agreement"] >= 0.999 and s["off_silhouette"] == 0, (name, s)
         assert s["red_max_diff_where_agree"] <= 1, (name, s)
+
+
+def test_random_scenes_oracle_vs_live_llvmpipe():
+    """tools/llvmpipe_sweep.py on a fresh seed: random windows (full circles, zooms, windows across the +-180 seam),
+    sizes, radii, eye positions and heights, depth ranges, tiles with holes -- the oracle against the reference running
+    live on llvmpipe.  (60 scenes of seed 1 are recorded in profiles/r01C_oracle_vs_llvmpipe_sweep.json.)"""
+    from oracle import binding
+    if not binding.have_mesa():
+        pytest.skip("oracle/_ref/libhorizonator_mesa.so or the image's Mesa libGL is absent")
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "llvmpipe_sweep.py"), "--scenes", "10", "--seed", "5"],
+                       capture_output=True, text=True, timeout=900)
+    assert p.returncode == 0, p.stderr[-2000:]
+    tot = json.loads(p.stdout.strip().splitlines()[-1])
+    print(tot)
+    assert tot["not_ok"] == 0 and tot["off_silhouette"] == 0 and tot["eye_height_differs"] == 0, tot
+    assert tot["coverage_agreement_overall"] >= 0.9999 and tot["worst_agreement"] >= 0.995, tot
+    assert tot["terrain_pixels"] > 10000
