@@ -77,6 +77,21 @@ def main():
         assert float(r.move(m["lat"], m["lon"])) == m["viewer_z"], m
     r.close()
 
+    # horizonator_pick() (horizonator-lib.c:1216-1296: a one-pixel depth read-back + unproject) on the wide circle
+    import ctypes as C
+    PW, PH, PR = 900, 150, 400
+    r = binding.MesaReference(C1_LAT, C1_LON, PW, PH, dir_dems=tiles, render_radius_cells=PR, threads=4)
+    img, rng = r.render(-180.05, 179.95, znear=100., zfar=100000.)
+    ys, xs = np.where(rng > 0)
+    idx = np.random.default_rng(11).choice(len(ys), 60, replace=False)
+    picks = []
+    for x, y in [(int(xs[k]), int(ys[k])) for k in idx] + [(10, 5), (450, 0), (899, 149), (0, 149)]:
+        la, lo = C.c_float(), C.c_float()
+        ok = bool(r.lib().horizonator_pick(C.byref(r.ctx), C.byref(la), C.byref(lo), x, y))
+        picks.append(dict(x=x, y=y, ok=ok, lat=float(la.value) if ok else None, lon=float(lo.value) if ok else None))
+    r.close()
+    assert sum(p["ok"] for p in picks) >= 60 and not all(p["ok"] for p in picks)
+
     # the two BASELINE workloads at full size
     C2_LAT, C2_LON = 34.0 + 1.0 / 7200.0, -117.0 + 1.0 / 7200.0
     tiles2 = synth.config2_tiles(os.environ.get("HZ_BENCH_TILES", "/tmp/hz_tiles_c2"))
@@ -91,7 +106,8 @@ def main():
         r.close()
 
     with open(os.path.join(HERE, "llvmpipe.json"), "w") as f:
-        json.dump(dict(gl_version=version, gl_renderer=renderer, move_json_reproduced=len(moves), scenes=summary),
+        json.dump(dict(gl_version=version, gl_renderer=renderer, move_json_reproduced=len(moves), scenes=summary,
+                       pick=dict(scene=[PW, PH, PR, -180.05, 179.95, 100., 100000.], points=picks)),
                   f, indent=0, separators=(",", ":"))
         f.write("\n")
     print("llvmpipe golden renders written to", HERE, "--", version, "/", renderer)

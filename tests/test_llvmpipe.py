@@ -156,3 +156,25 @@ def test_random_scenes_oracle_vs_live_llvmpipe():
     assert tot["not_ok"] == 0 and tot["off_silhouette"] == 0 and tot["eye_height_differs"] == 0, tot
     assert tot["coverage_agreement_overall"] >= 0.9999 and tot["worst_agreement"] >= 0.995, tot
     assert tot["terrain_pixels"] > 10000
+
+
+def test_pick_on_fake_gl_equals_pick_on_llvmpipe(tiles_c1):
+    """horizonator_pick() (a one-pixel depth read-back + unproject, horizonator-lib.c:1216-1296) of the reference on
+    the oracle's GL restatement against the same calls recorded from the reference on llvmpipe."""
+    import ctypes as C
+    from oracle import binding
+    if not binding.have_ref():
+        pytest.skip("oracle/_ref not built")
+    pick = json.load(open(os.path.join(GOLDEN, "llvmpipe.json")))["pick"]
+    W, H, R, az0, az1, zn, zf = pick["scene"]
+    r = binding.Reference(C1_LAT, C1_LON, int(W), int(H), dir_dems=tiles_c1, render_radius_cells=int(R), threads=2)
+    try:
+        r.render(az0, az1, znear=zn, zfar=zf)
+        for p in pick["points"]:
+            la, lo = C.c_float(), C.c_float()
+            ok = bool(r.lib().horizonator_pick(C.byref(r.ctx), C.byref(la), C.byref(lo), p["x"], p["y"]))
+            assert ok == p["ok"], p
+            if ok:
+                assert la.value == np.float32(p["lat"]) and lo.value == np.float32(p["lon"]), (p, la.value, lo.value)
+    finally:
+        r.close()

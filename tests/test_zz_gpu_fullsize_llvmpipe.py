@@ -39,3 +39,25 @@ def test_config2_full_size_matches_llvmpipe():
     print("CUDA vs llvmpipe, config 2 full size", s)
     assert s["ok"], s
     assert s["coverage_agreement"] >= 0.9995, s
+
+
+def test_pick_matches_llvmpipe(tiles_c1):
+    """horizonator_pick() of the product against the picks recorded from the reference on llvmpipe (the reference on
+    the oracle's GL restatement reproduces them bit for bit, tests/test_llvmpipe.py)."""
+    import ctypes as C
+    import json
+    import horizonator_b200 as hz
+    pick = json.load(open(os.path.join(GOLDEN, "llvmpipe.json")))["pick"]
+    W, H, R, az0, az1, zn, zf = pick["scene"]
+    h = hz.horizonator(C1_LAT, C1_LON, int(W), int(H), dir_dems=tiles_c1, render_radius_cells=int(R))
+    h.render(az0, az1, znear=zn, zfar=zf)
+    close = flags_differ = 0
+    for p in pick["points"]:
+        la, lo = C.c_float(), C.c_float()
+        ok = bool(hz.lib.horizonator_pick(C.byref(h.context), C.byref(la), C.byref(lo), p["x"], p["y"]))
+        flags_differ += ok != p["ok"]
+        if ok and p["ok"] and abs(la.value - p["lat"]) <= 2e-5 and abs(lo.value - p["lon"]) <= 2e-5:
+            close += 1
+    n_ok = sum(1 for p in pick["points"] if p["ok"])
+    print("picks within 2e-5 degrees of llvmpipe's:", close, "of", n_ok, "; hit/miss differs on", flags_differ)
+    assert flags_differ <= 1 and close >= n_ok - 3      # a silhouette pixel may see the neighbouring surface
