@@ -153,8 +153,10 @@ static Screen  g_screen;
 static Display g_display;
 static int     g_open = 0;
 
-#define MAX_DRAWABLES 64
-static struct { XID id; unsigned w, h, depth; } g_drawables[MAX_DRAWABLES];
+/* pixmaps behind pbuffers; Mesa does not give them all back, so the table grows */
+typedef struct { XID id; unsigned w, h, depth; } drawable_t;
+static drawable_t* g_drawables = NULL;
+static int g_ndrawables = 0;
 static XID g_next_id = 0x400001;
 
 /* Xlib's locking hooks (data symbols libGL imports); NULL = single-threaded Xlib */
@@ -238,25 +240,29 @@ int XPutImage(Display* dpy, XID d, void* gc, XImage* img, int sx, int sy, int dx
 XID XCreatePixmap(Display* dpy, XID d, unsigned w, unsigned h, unsigned depth)
 {
     (void)dpy; (void)d;
-    for(int k = 0; k < MAX_DRAWABLES; k++)
-        if(!g_drawables[k].id) {
-            g_drawables[k].id = g_next_id++; g_drawables[k].w = w; g_drawables[k].h = h; g_drawables[k].depth = depth;
-            return g_drawables[k].id;
-        }
-    fprintf(stderr, "fakex11: out of drawables\n");
-    return 0;
+    int k = 0;
+    while(k < g_ndrawables && g_drawables[k].id) k++;
+    if(k == g_ndrawables) {
+        int n = g_ndrawables ? 2 * g_ndrawables : 64;
+        drawable_t* grown = realloc(g_drawables, (size_t)n * sizeof(*grown));
+        if(!grown) { fprintf(stderr, "fakex11: out of memory\n"); return 0; }
+        memset(grown + g_ndrawables, 0, (size_t)(n - g_ndrawables) * sizeof(*grown));
+        g_drawables = grown; g_ndrawables = n;
+    }
+    g_drawables[k].id = g_next_id++; g_drawables[k].w = w; g_drawables[k].h = h; g_drawables[k].depth = depth;
+    return g_drawables[k].id;
 }
 int XFreePixmap(Display* dpy, XID p)
 {
     (void)dpy;
-    for(int k = 0; k < MAX_DRAWABLES; k++) if(g_drawables[k].id == p) g_drawables[k].id = 0;
+    for(int k = 0; k < g_ndrawables; k++) if(g_drawables[k].id == p) g_drawables[k].id = 0;
     return 1;
 }
 int XGetGeometry(Display* dpy, XID d, XID* root, int* x, int* y, unsigned* w, unsigned* h, unsigned* bw, unsigned* depth)
 {
     (void)dpy;
     *root = g_screen.root; *x = *y = 0; *bw = 0;
-    for(int k = 0; k < MAX_DRAWABLES; k++)
+    for(int k = 0; k < g_ndrawables; k++)
         if(g_drawables[k].id == d) { *w = g_drawables[k].w; *h = g_drawables[k].h; *depth = g_drawables[k].depth; return 1; }
     *w = (unsigned)g_screen.width; *h = (unsigned)g_screen.height; *depth = 24;
     return d == g_screen.root;

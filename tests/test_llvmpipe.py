@@ -142,9 +142,9 @@ def test_reference_runs_live_on_llvmpipe(tiles_c1):
 
 
 def test_random_scenes_oracle_vs_live_llvmpipe():
-    """tools/llvmpipe_sweep.py on a fresh seed: random windows (full circles, zooms, windows across the +-180 seam),
+    """tools/llvmpipe_sweep.py: its 15 fixed edge cases, then a fresh seed of random windows (full circles, zooms, windows across the +-180 seam),
     sizes, radii, eye positions and heights, depth ranges, tiles with holes -- the oracle against the reference running
-    live on llvmpipe.  (60 scenes of seed 1 are recorded in profiles/r01C_oracle_vs_llvmpipe_sweep.json.)"""
+    live on llvmpipe.  (The edge cases + 60 scenes of seed 1 are recorded in profiles/r01C_oracle_vs_llvmpipe_sweep.json.)"""
     from oracle import binding
     if not binding.have_mesa():
         pytest.skip("oracle/_ref/libhorizonator_mesa.so or the image's Mesa libGL is absent")

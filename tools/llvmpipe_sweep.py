@@ -6,6 +6,8 @@ OpenGL driver, over many more views than the committed fixtures hold.
 
     python tools/llvmpipe_sweep.py [--scenes 60] [--seed 1] [--out profiles/r01C_oracle_vs_llvmpipe_sweep.json]
 
+The 15 fixed EDGE_CASES run first, then --scenes random ones.
+
 Prints one JSON document: per scene the parameters and the comparison, then the totals.
 """
 import argparse
@@ -50,6 +52,30 @@ def random_scene(rs):
                 znear=znear, zfar=zfar, znear_color=znc, zfar_color=zfc, holes=holes)
 
 
+_BASE = dict(W=400, H=120, R=200, kind="edge", az0=-180.05, az1=179.95, lat=None, lon=None, viewer_z=None,
+             znear=100., zfar=100000., znear_color=100., zfar_color=100000., holes=False)
+# fixed scenes at the corners of the parameter space: windows wider than a circle (span 720: nothing is drawn, by
+# either), near-plane clipping through the terrain, a far plane short of it, an eye outside the loaded square, extreme
+# aspect ratios, one-pixel images, a two-cell mesh
+EDGE_CASES = [dict(_BASE, kind=name, **upd) for name, upd in [
+    ("span400", dict(az0=-200., az1=200.)),
+    ("span720", dict(az0=-360., az1=360.)),
+    ("znear2km", dict(znear=2000., znear_color=2000.)),
+    ("znear5km", dict(znear=5000., znear_color=5000., az0=20., az1=50.)),
+    ("zfar3km", dict(zfar=3000., zfar_color=3000.)),
+    ("tall", dict(W=90, H=400, az0=10., az1=40.)),
+    ("outside", dict(lat=C1_LAT + 0.25, lon=C1_LON + 0.2)),
+    ("far_out", dict(lat=C1_LAT + 0.6, lon=C1_LON - 0.5, az0=180., az1=270.)),
+    ("low_eye", dict(viewer_z=5.0)),
+    ("W1", dict(W=1, H=50, az0=44., az1=46.)),
+    ("H1", dict(W=300, H=1)),
+    ("az<-360", dict(az0=-400., az1=-300.)),
+    ("az>700", dict(az0=700., az1=800.)),
+    ("R2", dict(R=2)),
+    ("zoom1", dict(az0=100., az1=101., W=300, H=200)),
+]]
+
+
 def render_pair(scene, tiles, tiles_holes, threads):
     from oracle import binding
     d = tiles_holes if scene["holes"] else tiles
@@ -75,6 +101,7 @@ def main():
     ap.add_argument("--scenes", type=int, default=60)
     ap.add_argument("--seed", type=int, default=1)
     ap.add_argument("--out", default=None)
+    ap.add_argument("--no-edge-cases", action="store_true", help="random scenes only")
     args = ap.parse_args()
     from oracle import binding
     from tools import synth
@@ -92,8 +119,8 @@ def main():
     scenes, tot = [], dict(pixels=0, terrain_pixels=0, coverage_mismatch=0, range_mismatch=0, off_silhouette=0,
                            range_bit_identical=0, both_hit=0, not_ok=0, eye_height_differs=0)
     worst = 1.0
-    for k in range(args.scenes):
-        sc = random_scene(rs)
+    todo = ([] if args.no_edge_cases else list(EDGE_CASES)) + [random_scene(rs) for _ in range(args.scenes)]
+    for k, sc in enumerate(todo):
         (img_m, rng_m), (img_o, rng_o), vz_m, vz_o = render_pair(sc, tiles, holes, threads)
         s = compare_renders(img_o, rng_o, img_m, rng_m)          # llvmpipe is the reference side
         both = (rng_m > 0) & (rng_o > 0)
@@ -113,7 +140,8 @@ def main():
     tot["worst_agreement"] = worst
     tot["coverage_agreement_overall"] = 1.0 - tot["coverage_mismatch"] / tot["pixels"]
     doc = dict(what="oracle (oracle/liboracle.so) vs the unmodified reference on Mesa llvmpipe, random scenes on the "
-                    "synthetic SRTM3 tiles (seed %d); tolerances of tests/compare.py" % args.seed,
+                    "synthetic SRTM3 tiles: %d fixed edge cases + %d random (seed %d); tolerances of tests/compare.py"
+                    % (0 if args.no_edge_cases else len(EDGE_CASES), args.scenes, args.seed),
                totals=tot, scenes=scenes)
     text = json.dumps(doc, indent=1)
     if args.out:
