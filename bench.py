@@ -36,6 +36,7 @@ sys.path.insert(0, ROOT)
 C2 = dict(lat=34.0 + 1.0 / 7200.0, lon=-117.0 + 1.0 / 7200.0, W=3600, H=600, radius_m=150000.0,
           az0=-180.05, az1=179.95, znear=100.0, zfar=150000.0, R=5858)
 TILES_DIR = os.environ.get("HZ_BENCH_TILES", "/tmp/hz_tiles_c2")
+WARP_INST_PER_PANORAMA = 42.29e6    # ncu smsp__inst_executed.sum, all kernels of one C2 panorama (profiles/r01A_*)
 
 
 def algorithmic_bytes(R, W, H):
@@ -380,6 +381,13 @@ def run_b200(args):
                      "algorithmic_bytes_per_launch": alg,
                      "stage_ms_single_panorama": {"%s [%s]" % (k, stages[k]): prof[k] for k in stages},
                      "latency_ms_single_panorama": latency_ms,
+                     # the resource that actually binds in batch mode: instruction issue.  Instructions per panorama
+                     # from the same ncu launch list as `traffic`; peak = SMs x 4 schedulers x SM clock
+                     "issue": {"warp_instructions_per_panorama": WARP_INST_PER_PANORAMA,
+                               "peak_warp_instructions_per_s": 148 * 4 * (clocks.get("sm_mhz") or 1965.0) * 1e6,
+                               "frac": value / world * WARP_INST_PER_PANORAMA
+                                       / (148 * 4 * (clocks.get("sm_mhz") or 1965.0) * 1e6),
+                               "source": "smsp__inst_executed.sum over the 14 kernels, profiles/r01A_kernels_per_panorama.txt"},
                      "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum summed over the 14 kernels of one "
                                      "panorama (one CUDA-graph launch), from the ncu capture summarised in "
                                      "profiles/r01A_kernels_per_panorama.txt",
