@@ -221,3 +221,57 @@ def test_pinned_pool_recycles_blocks_with_array_lifetime(hz, monkeypatch):
     del b, c
     gc.collect()
     assert pool.kept == 60 and FakeBlock.made == 2
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libhorizonator_ref.so")),
+                    reason="oracle/_ref not built on this machine")
+def test_projection_helpers_against_reference_build_directly(hz):
+    """Differential run of horizonator_x_from_az / _project / _unproject against the reference's own compiled code
+    (oracle/_ref) on a few thousand random inputs, windows across the +-180 seam and wider than a circle included:
+    same return flag and bit-identical outputs."""
+    from oracle import binding
+    L = binding.Reference.lib()
+    d = C.c_double
+    rs = np.random.default_rng(42)
+    n_true = n_false = 0
+    for _ in range(3000):
+        az0 = float(rs.uniform(-4 * np.pi, 4 * np.pi))
+        az1 = az0 + float(rs.choice([rs.uniform(0.01, 2 * np.pi), 2 * np.pi, rs.uniform(2 * np.pi, 4 * np.pi), -rs.uniform(0.01, 3.)]))
+        az = float(rs.uniform(-4 * np.pi, 4 * np.pi))
+        W = int(rs.integers(1, 40000))
+        xa, pa, xb, pb = d(), d(), d(), d()
+        oka = bool(hz.lib.horizonator_x_from_az(C.byref(xa), C.byref(pa), az, az0, az1, W))
+        okb = bool(L.horizonator_x_from_az(C.byref(xb), C.byref(pb), az, az0, az1, W))
+        assert oka == okb, (az, az0, az1, W)
+        if oka:
+            assert xa.value == xb.value and pa.value == pb.value, (az, az0, az1, W)
+        n_true += oka; n_false += not oka
+    assert n_true > 500 and n_false > 50
+
+    n_true = n_false = 0
+    for _ in range(3000):
+        latv, lonv = float(rs.uniform(-60., 60.)), float(rs.uniform(-179., 179.))
+        coslat = float(np.cos(np.radians(latv)))
+        lat, lon = latv + float(rs.uniform(-.8, .8)), lonv + float(rs.uniform(-.8, .8))
+        az0 = float(rs.uniform(-2 * np.pi, 2 * np.pi)); az1 = az0 + float(rs.uniform(0.02, 2 * np.pi - 1e-3))
+        W, H = int(rs.integers(16, 40000)), int(rs.integers(8, 5000))
+        args = (latv, coslat, lonv, float(rs.uniform(0., 4000.)), lat, lon, float(rs.uniform(-100., 5000.)), az0, az1, W, H)
+        a, b = [d(), d(), d()], [d(), d(), d()]
+        oka = bool(hz.lib.horizonator_project(*[C.byref(v) for v in a], *args))
+        okb = bool(L.horizonator_project(*[C.byref(v) for v in b], *args))
+        assert oka == okb, args
+        if oka:
+            assert [v.value for v in a] == [v.value for v in b], args
+        n_true += oka; n_false += not oka
+
+        px, py = int(rs.integers(0, W)), int(rs.integers(0, H))
+        which = int(rs.integers(0, 3)); r = float(rs.uniform(10., 150000.))
+        r_enh, r_en = (r, -1.) if which == 0 else ((-1., r) if which == 1 else (r, r))
+        uargs = (px, py, r_enh, r_en, latv, coslat, lonv, float(np.degrees(az0)), float(np.degrees(az1)), W, H)
+        la, lo, lb, lob = C.c_float(), C.c_float(), C.c_float(), C.c_float()
+        oka = bool(hz.lib.horizonator_unproject(C.byref(la), C.byref(lo), *uargs))
+        okb = bool(L.horizonator_unproject(C.byref(lb), C.byref(lob), *uargs))
+        assert oka == okb, uargs
+        if oka:
+            assert la.value == lb.value and lo.value == lob.value, uargs
+    assert n_true > 300 and n_false > 300
