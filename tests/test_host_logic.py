@@ -275,3 +275,43 @@ def test_projection_helpers_against_reference_build_directly(hz):
         if oka:
             assert la.value == lb.value and lo.value == lob.value, uargs
     assert n_true > 300 and n_false > 300
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libhorizonator_ref.so")),
+                    reason="oracle/_ref not built on this machine")
+def test_dem_init_geometry_against_reference_build_on_random_viewpoints(hz, tmp_path):
+    """Tile selection is float/int arithmetic that must come out the same as dem.c:78-243 everywhere on the globe:
+    random viewpoints (both hemispheres, near the date line, near tile edges), radii in cells or metres, SRTM3 and
+    SRTM1, against the reference's compiled dem.c.  The tile directory is empty (all tiles read as sea level), so
+    only the geometry is compared: success flag and every integer field of the context."""
+    from oracle import binding
+    L = binding.Reference.lib()
+    empty = os.fsencode(str(tmp_path))
+    rs = np.random.default_rng(9)
+    n_ok = n_fail = 0
+    devnull = os.open(os.devnull, os.O_WRONLY)
+    saved = os.dup(2)
+    os.dup2(devnull, 2)                      # both libraries warn about every missing tile
+    try:
+        for k in range(400):
+            lat = float(rs.uniform(-59., 59.)); lon = float(rs.uniform(-179.5, 179.5))
+            if k % 5 == 0:                   # on or next to a tile corner
+                lat = float(np.round(lat)) + float(rs.choice([0., 1e-4, -1e-4, 1. / 2400.]))
+                lon = float(np.round(lon)) + float(rs.choice([0., 1e-4, -1e-4, 1. / 2400.]))
+            srtm1 = bool(rs.random() < 0.4)
+            if rs.random() < 0.5:
+                rc, rm = int(rs.integers(1, 7300 if srtm1 else 2500)), -1.0
+            else:
+                rc, rm = -1, float(rs.uniform(500., 260000.))
+            a, b = hz.dem_context_t(), hz.dem_context_t()
+            oka = bool(hz.lib.horizonator_dem_init(C.byref(a), lat, lon, rc, rm, empty, srtm1))
+            okb = bool(L.horizonator_dem_init(C.byref(b), lat, lon, rc, rm, empty, srtm1))
+            assert oka == okb, (lat, lon, rc, rm, srtm1)
+            if oka:
+                assert bytes(a)[320:] == bytes(b)[320:], (lat, lon, rc, rm, srtm1)
+                hz.lib.horizonator_dem_deinit(C.byref(a))
+                L.horizonator_dem_deinit(C.byref(b))
+            n_ok += oka; n_fail += not oka
+    finally:
+        os.dup2(saved, 2); os.close(saved); os.close(devnull)
+    assert n_ok > 100 and n_fail > 5, (n_ok, n_fail)
