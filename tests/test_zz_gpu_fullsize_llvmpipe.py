@@ -61,3 +61,49 @@ def test_pick_matches_llvmpipe(tiles_c1):
     n_ok = sum(1 for p in pick["points"] if p["ok"])
     print("picks within 2e-5 degrees of llvmpipe's:", close, "of", n_ok, "; hit/miss differs on", flags_differ)
     assert flags_differ <= 1 and close >= n_ok - 3      # a silhouette pixel may see the neighbouring surface
+
+
+def test_random_scenes_match_live_llvmpipe(tiles_c1, tiles_holes, tmp_path):
+    """Random views (tools/llvmpipe_sweep.py, seed 3: full circles, zooms, windows across the seam, eye heights, depth
+    ranges, tiles with holes) rendered by the reference on llvmpipe in a child process, right here on the box's host
+    cores, and by the CUDA path; compared at the north_star tolerances.  No oracle result is used."""
+    import ctypes as C
+    import json
+    import subprocess
+    import sys
+    import horizonator_b200 as hz
+    from oracle import binding                      # only to ask whether the llvmpipe build exists
+    if not binding.have_mesa():
+        pytest.skip("oracle/_ref/libhorizonator_mesa.so or the image's Mesa libGL is absent")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    dump = str(tmp_path / "llvmpipe")
+    p = subprocess.run([sys.executable, os.path.join(root, "tools", "llvmpipe_sweep.py"), "--scenes", "12", "--seed", "3",
+                        "--no-edge-cases", "--dump", dump], capture_output=True, text=True, timeout=900)
+    assert p.returncode == 0, p.stderr[-2000:]
+    scenes = json.load(open(os.path.join(dump, "scenes.json")))["scenes"]
+    assert len(scenes) == 12
+    worst, terrain = 1.0, 0
+    for k, sc in enumerate(scenes):
+        g = np.load(os.path.join(dump, "scene_%03d.npz" % k))
+        ctx = hz.context_t()
+        z = C.c_float(-1. if sc["viewer_z"] is None else sc["viewer_z"])
+        tiles = tiles_holes if sc["holes"] else tiles_c1
+        assert hz.lib.horizonator_init(C.byref(ctx), C1_LAT, C1_LON, C.byref(z), sc["W"], sc["H"], sc["R"], -1.0, True, False,
+                                       False, os.fsencode(tiles), None, None, None, False)
+        try:
+            assert np.float32(z.value) == g["viewer_z"], sc
+            assert hz.lib.horizonator_pan_zoom(C.byref(ctx), sc["az0"], sc["az1"])
+            if sc["lat"] is not None:
+                assert hz.lib.horizonator_move(C.byref(ctx), None, sc["lat"], sc["lon"])
+            assert hz.lib.horizonator_set_zextents(C.byref(ctx), sc["znear"], sc["zfar"], sc["znear_color"], sc["zfar_color"])
+            img = np.empty((sc["H"], sc["W"], 3), np.uint8)
+            rng = np.empty((sc["H"], sc["W"]), np.float32)
+            assert hz.lib.horizonator_render_offscreen(C.byref(ctx), img.ctypes.data, rng.ctypes.data)
+        finally:
+            hz.lib.horizonator_deinit(C.byref(ctx))
+        s = compare_renders(img, rng, g["image"], g["ranges"])
+        print("CUDA vs live llvmpipe", k, sc["kind"], "%dx%d" % (sc["W"], sc["H"]), s)
+        assert s["ok"], (sc, s)
+        worst = min(worst, s["agreement"]); terrain += int((g["ranges"] > 0).sum())
+    assert terrain > 10000
+    print("worst agreement over the random scenes:", worst)

@@ -102,6 +102,9 @@ def main():
     ap.add_argument("--seed", type=int, default=1)
     ap.add_argument("--out", default=None)
     ap.add_argument("--no-edge-cases", action="store_true", help="random scenes only")
+    ap.add_argument("--dump", default=None, metavar="DIR",
+                    help="also save scenes.json and the llvmpipe renders (scene_%%03d.npz) there, for a third renderer "
+                         "to be compared with (tests/test_zz_gpu_fullsize_llvmpipe.py does that with the CUDA path)")
     args = ap.parse_args()
     from oracle import binding
     from tools import synth
@@ -114,6 +117,8 @@ def main():
     synth.write_tiles(holes, (34, 35), (-118, -117), seed=7, skip=((35, -118), (34, -117)))
     open(os.path.join(holes, synth.tile_name(34, -117)), "wb").close()
 
+    if args.dump:
+        os.makedirs(args.dump, exist_ok=True)
     rs = np.random.default_rng(args.seed)
     threads = min(8, os.cpu_count() or 1)
     scenes, tot = [], dict(pixels=0, terrain_pixels=0, coverage_mismatch=0, range_mismatch=0, off_silhouette=0,
@@ -122,6 +127,9 @@ def main():
     todo = ([] if args.no_edge_cases else list(EDGE_CASES)) + [random_scene(rs) for _ in range(args.scenes)]
     for k, sc in enumerate(todo):
         (img_m, rng_m), (img_o, rng_o), vz_m, vz_o = render_pair(sc, tiles, holes, threads)
+        if args.dump:
+            np.savez_compressed(os.path.join(args.dump, "scene_%03d.npz" % k), image=img_m, ranges=rng_m,
+                                viewer_z=np.float32(vz_m))
         s = compare_renders(img_o, rng_o, img_m, rng_m)          # llvmpipe is the reference side
         both = (rng_m > 0) & (rng_o > 0)
         cov = int(((rng_m > 0) != (rng_o > 0)).sum())
@@ -143,6 +151,9 @@ def main():
                     "synthetic SRTM3 tiles: %d fixed edge cases + %d random (seed %d); tolerances of tests/compare.py"
                     % (0 if args.no_edge_cases else len(EDGE_CASES), args.scenes, args.seed),
                totals=tot, scenes=scenes)
+    if args.dump:
+        with open(os.path.join(args.dump, "scenes.json"), "w") as f:
+            json.dump(dict(holes_skip=[[35, -118], [34, -117]], scenes=todo), f)
     text = json.dumps(doc, indent=1)
     if args.out:
         with open(args.out, "w") as f:
