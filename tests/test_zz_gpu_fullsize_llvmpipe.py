@@ -107,3 +107,26 @@ def test_random_scenes_match_live_llvmpipe(tiles_c1, tiles_holes, tmp_path):
         worst = min(worst, s["agreement"]); terrain += int((g["ranges"] > 0).sum())
     assert terrain > 10000
     print("worst agreement over the random scenes:", worst)
+
+
+def test_config2_batch_of_16_equals_single_renders():
+    """The configuration bench.py times -- 16 benchmark-size panoramas per call on the render lanes, with the smaller
+    grids views of a batch get -- gives, view by view, exactly what single renders give."""
+    import horizonator_b200 as hz
+    from tools import synth
+    tiles = synth.config2_tiles(os.environ.get("HZ_BENCH_TILES", "/tmp/hz_tiles_c2"))
+    W, H = 3600, 600
+    h = hz.horizonator(C2_LAT, C2_LON, W, H, SRTM1=True, dir_dems=tiles, render_radius_m=150000.)
+    h.set_zextents(100., 150000.)
+    views = [(C2_LAT, C2_LON, -180.05, 179.95)] * 13 + [(C2_LAT + 0.05 * k, C2_LON - 0.04 * k, -180.05, 179.95) for k in (1, 2, 3)]
+    bi, br = h.render_batch(views)
+    singles = {}
+    for k, v in enumerate(views):
+        if v not in singles:
+            singles[v] = h.render(v[2], v[3], lat=v[0], lon=v[1], znear=100., zfar=150000.)
+        i1, r1 = singles[v]
+        assert np.array_equal(i1, bi[k]) and np.array_equal(r1, br[k]), k
+    g = np.load(os.path.join(GOLDEN, "fullsize_c2_llvmpipe.npz"))
+    s = compare_renders(bi[0], br[0], g["image"], g["ranges"])
+    print("batch view 0 vs llvmpipe, config 2 full size", s)
+    assert s["ok"], s
