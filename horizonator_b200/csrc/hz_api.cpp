@@ -30,7 +30,6 @@ namespace {
         }                                                                           \
     } while(0)
 
-constexpr int   TANEL_SLOTS     = 8;
 constexpr float PI_F            = 3.14159265358979f;       // vertex.glsl:31
 // Queue capacities grow with the image (set in alloc_target); whatever does not fit is drawn by a slow in-kernel
 // path, so these only have to be generous, not safe.
@@ -53,32 +52,56 @@ struct ViewState
 
 constexpr int PARAM_RING = 16;
 
-// everything one render writes besides its outputs
+// which per-row tan(elevation) table a buffer holds (fill_tanel(): a function of the window's width in degrees and of
+// the image size only)
+struct TanelKey
+{
+    bool valid = false; float daz = 0; int W = 0, H = 0;
+    bool is(float daz_, int W_, int H_) const { return valid && W == W_ && H == H_ && memcmp(&daz, &daz_, sizeof(float)) == 0; }
+};
+
+// everything one view in flight writes besides its outputs
 struct Scratch
 {
-    cudaStream_t stream = nullptr;     // lanes only
-    cudaEvent_t  done = nullptr;       // lanes only
     unsigned long long* d_vis = nullptr;
     float *d_e = nullptr, *d_n = nullptr;
     uint32_t *d_tile_queue = nullptr, *d_block_queue = nullptr, *d_tri_queue = nullptr;
     uint2*    d_big_queue = nullptr;   // [2][BIG_CAPACITY]: near pass, bands
     uint4*    d_bigtri = nullptr;      // [BIGTRI_CAPACITY][6]
     uint32_t* d_counters  = nullptr;   // [N_COUNTERS]
-    uint8_t*  d_image  = nullptr;      // lanes only: staging of one view's outputs for the host-pointer batch call
+    uint8_t*  d_image  = nullptr;      // batch sets only: staging of one view's outputs for the host-pointer batch call
     float*    d_ranges = nullptr;
+    // tan(elevation) per row of the window this scratch last rendered (lib:1007-1012; computed on the host like the
+    // reference's read-back does, uploaded on the stream of the render that needs it -- so nothing else can be
+    // reading the row when it is replaced)
+    float*    d_tanel = nullptr;       // [H]
+    TanelKey  tanel_key;
+};
 
-    // parameters of the render in flight: the kernels read d_views; the host fills a slot of the pinned ring and
+// Up to `cap` views that are rendered TOGETHER: one chain of kernel launches whose grids have a view dimension
+// (gridDim.y), each view with its own scratch.  The context's own view is a set of one; the batch calls use sets of
+// up to Slot::views_per_set, each with its own stream, so that the tail of one set's kernels overlaps another's.
+struct ViewSet
+{
+    int  cap = 0;
+    bool batch = false;                // band structure and grid scale of batched views
+    cudaStream_t stream = nullptr;     // batch sets only
+    cudaEvent_t  done = nullptr;       // batch sets only
+    std::vector<Scratch> sc;           // grows on demand up to cap (ensure_views)
+
+    // parameters of the renders in flight: the kernels read d_views; the host fills a slot of the pinned ring and
     // copies it over (the ring lets several renders be queued without waiting)
-    HzView* d_views = nullptr;         // [HZ_V_COUNT]
-    HzView* h_views = nullptr;         // pinned [PARAM_RING][HZ_V_COUNT]
+    HzView* d_views = nullptr;         // [cap][HZ_V_COUNT]
+    HzView* h_views = nullptr;         // pinned [PARAM_RING][cap][HZ_V_COUNT]
+    float*  h_tanel = nullptr;         // pinned [PARAM_RING][cap][H] (alloc_target)
     cudaEvent_t ring_ev[PARAM_RING] = {};
     int ring_next = 0;
     cudaEvent_t  busy = nullptr;       // recorded after the last render that used this set
     cudaStream_t last_stream = nullptr;
     bool busy_recorded = false;
-    cudaGraphExec_t graph = nullptr;   // the standard chain, captured on first use
-    int  graph_launches = 0;
-    bool graph_big_per_band = false;   // the shape the captured chain has (see big_after_every_band)
+    // the standard chain, captured on first use per (number of views, shape)
+    struct Graph { int m; bool big_per_band; cudaGraphExec_t exec; int launches; };
+    std::vector<Graph> graphs;
     bool graph_failed = false;
 };
 
@@ -95,7 +118,7 @@ struct Slot
     int nb = 0, nt = 0;
     int near_rings = 2;
     int occl_tile_max_pix = 64, occl_block_max_pix = 32, small_max_pix = 16;
-    int grid_percent_single = 150, grid_percent_batch = 35;   // see hz_grid() in hz_kernels.cu
+    int grid_percent_single = 150, grid_percent_batch = 200;   // see hz_grid() in hz_kernels.cu
     // Rings (in tiles around the eye's tile) at which the bands end; the last band runs to the edge of the mesh.
     // More bands = more of the mesh culled by what nearer bands drew, but four more kernels each.  A lone view is
     // latency-bound and gets two bands; the views of a batch overlap each other's latencies and get three (measured
@@ -103,7 +126,7 @@ struct Slot
     struct Bands { int n; int end[MAX_BANDS]; };
     Bands bands_single = { 2, { 48, 1 << 20, 0, 0, 0, 0 } };
     Bands bands_batch  = { 3, { 24, 72, 1 << 20, 0, 0, 0 } };
-    int n_lanes_max = 16;
+    int views_per_set = 16, n_sets_max = 2;
 
     // target
     int W = 0, H = 0;
@@ -112,24 +135,22 @@ struct Slot
     size_t   target_pixels = 0;      // capacity of the buffers above
     uint32_t tri_capacity = 0, big_capacity = 0, bigtri_capacity = 0;
 
-    // tan(elevation) per row, computed on the host like the reference's read-back does
-    float*   d_tanel = nullptr;      // [TANEL_SLOTS][H]
-    float*   h_tanel = nullptr;      // pinned, same shape
-    struct { bool valid; float daz; int W, H; } tanel_key[TANEL_SLOTS] = {};
-    int      tanel_next = 0;
+    // host-side cache of tan(elevation) row tables (tanf() per row is not free; callers re-render the same few windows)
+    struct TanelRow { TanelKey key; std::vector<float> row; };
+    std::vector<TanelRow> tanel_cache;
+    size_t tanel_cache_next = 0;
 
-    // Scratch of one render in flight.  `main` serves the single-view entry points (and keeps the last
-    // visibility buffer for horizonator_pick); `lanes` are made on demand by the batch entry points so that
-    // several views of one batch render concurrently, each on its own stream.
-    Scratch main;
-    std::vector<Scratch> lanes;
+    // `main` serves the single-view entry points (and keeps the last visibility buffer for horizonator_pick);
+    // `sets` are made on demand by the batch entry points.
+    ViewSet main;
+    std::vector<ViewSet*> sets;
     cudaEvent_t fork_ev = nullptr;
 
     ViewState view;
     float znear = HORIZONATOR_ZNEAR_DEFAULT, zfar = HORIZONATOR_ZFAR_DEFAULT;
     float znear_color = HORIZONATOR_ZNEAR_DEFAULT, zfar_color = HORIZONATOR_ZFAR_DEFAULT;
 
-    bool have_render = false;        // d_vis holds a complete full-width render (for pick)
+    bool have_render = false;        // main's d_vis holds a complete full-width render (for pick)
     unsigned launches_last = 0;
 
     // optional per-kernel timing: PROF_EVENTS events per recorded render
@@ -165,20 +186,21 @@ struct DeviceGuard
     ~DeviceGuard() { if(prev >= 0) cudaSetDevice(prev); }
 };
 
-void drop_graph(Scratch& c)
+void drop_graphs(ViewSet& vs)
 {
-    if(c.graph) cudaGraphExecDestroy(c.graph);
-    c.graph = nullptr; c.graph_failed = false;
+    for(ViewSet::Graph& g : vs.graphs) if(g.exec) cudaGraphExecDestroy(g.exec);
+    vs.graphs.clear();
+    vs.graph_failed = false;
 }
 
-// the part of a scratch set whose size depends on the image
+// the part of a scratch whose size depends on the image
 void free_scratch_target(Scratch& c)
 {
-    drop_graph(c);
     cudaFree(c.d_vis); cudaFree(c.d_image); cudaFree(c.d_ranges);
-    cudaFree(c.d_tri_queue); cudaFree(c.d_big_queue); cudaFree(c.d_bigtri);
+    cudaFree(c.d_tri_queue); cudaFree(c.d_big_queue); cudaFree(c.d_bigtri); cudaFree(c.d_tanel);
     c.d_vis = nullptr; c.d_image = nullptr; c.d_ranges = nullptr;
-    c.d_tri_queue = nullptr; c.d_big_queue = nullptr; c.d_bigtri = nullptr;
+    c.d_tri_queue = nullptr; c.d_big_queue = nullptr; c.d_bigtri = nullptr; c.d_tanel = nullptr;
+    c.tanel_key = TanelKey{};
 }
 
 bool alloc_scratch_target(const Slot& s, Scratch& c, bool staging)
@@ -188,6 +210,7 @@ bool alloc_scratch_target(const Slot& s, Scratch& c, bool staging)
     CUDA_TRY(cudaMalloc(&c.d_tri_queue, (size_t)s.tri_capacity * sizeof(uint32_t)));
     CUDA_TRY(cudaMalloc(&c.d_big_queue, 2 * (size_t)s.big_capacity * sizeof(uint2)));
     CUDA_TRY(cudaMalloc(&c.d_bigtri, (size_t)s.bigtri_capacity * 6 * sizeof(uint4)));
+    CUDA_TRY(cudaMalloc(&c.d_tanel, (size_t)s.H * sizeof(float)));
     if(staging)
     {
         CUDA_TRY(cudaMalloc(&c.d_image, px * 3));
@@ -196,40 +219,58 @@ bool alloc_scratch_target(const Slot& s, Scratch& c, bool staging)
     return true;
 }
 
-void free_target(Slot& s)
+void free_set_target(ViewSet& vs)
 {
-    free_scratch_target(s.main);
-    for(Scratch& l : s.lanes) free_scratch_target(l);
-    cudaFree(s.d_image);  s.d_image = nullptr;
-    cudaFree(s.d_ranges); s.d_ranges = nullptr;
-    cudaFree(s.d_tanel);  s.d_tanel = nullptr;
-    cudaFreeHost(s.h_tanel);  s.h_tanel = nullptr;
-    s.target_pixels = 0;
-    for(auto& k : s.tanel_key) k.valid = false;
+    drop_graphs(vs);
+    for(Scratch& c : vs.sc) free_scratch_target(c);
+    cudaFreeHost(vs.h_tanel); vs.h_tanel = nullptr;
 }
 
+bool alloc_set_target(const Slot& s, ViewSet& vs)
+{
+    CUDA_TRY(cudaMallocHost(&vs.h_tanel, (size_t)PARAM_RING * vs.cap * s.H * sizeof(float)));
+    for(Scratch& c : vs.sc) if(!alloc_scratch_target(s, c, vs.batch)) return false;
+    return true;
+}
+
+void free_target(Slot& s)
+{
+    free_set_target(s.main);
+    for(ViewSet* g : s.sets) free_set_target(*g);
+    cudaFree(s.d_image);  s.d_image = nullptr;
+    cudaFree(s.d_ranges); s.d_ranges = nullptr;
+    s.target_pixels = 0;
+    s.tanel_cache.clear();
+}
+
+// A failure part way leaves the context without a target (W = H = 0): later renders return false instead of
+// running kernels on buffers that are not there.
 bool alloc_target(Slot& s, int W, int H)
 {
     free_target(s);
+    s.W = 0; s.H = 0; s.have_render = false;
     const size_t px = (size_t)W * (size_t)H;
     auto cap = [px](size_t floor_, size_t div) {
         const size_t c = px / div > floor_ ? px / div : floor_;
         return (uint32_t)(c > 0x7FFFFFFFu ? 0x7FFFFFFFu : c);
     };
-    s.target_pixels = px;
     s.tri_capacity = cap((size_t)1 << 22, 2); s.big_capacity = cap((size_t)1 << 21, 4); s.bigtri_capacity = cap((size_t)1 << 18, 16);
     // tests shrink the queues to exercise the overflow paths
     if(const char* env = getenv("HORIZONATOR_TRI_CAPACITY"))    s.tri_capacity    = (uint32_t)(atoi(env) > 1 ? atoi(env) : 1);
     if(const char* env = getenv("HORIZONATOR_BIG_CAPACITY"))    s.big_capacity    = (uint32_t)(atoi(env) > 1 ? atoi(env) : 1);
     if(const char* env = getenv("HORIZONATOR_BIGTRI_CAPACITY")) s.bigtri_capacity = (uint32_t)(atoi(env) > 1 ? atoi(env) : 1);
-    if(!alloc_scratch_target(s, s.main, false)) return false;
-    for(Scratch& l : s.lanes) if(!alloc_scratch_target(s, l, true)) return false;
-    CUDA_TRY(cudaMalloc(&s.d_image, px * 3));
-    CUDA_TRY(cudaMalloc(&s.d_ranges, px * sizeof(float)));
-    CUDA_TRY(cudaMalloc(&s.d_tanel, (size_t)TANEL_SLOTS * H * sizeof(float)));
-    CUDA_TRY(cudaMallocHost(&s.h_tanel, (size_t)TANEL_SLOTS * H * sizeof(float)));
-    s.W = W; s.H = H; s.target_pixels = px;
-    s.have_render = false;
+    s.target_pixels = px; s.W = W; s.H = H;       // alloc_*_target() size their buffers from these
+    bool ok = alloc_set_target(s, s.main);
+    for(ViewSet* g : s.sets) ok = ok && alloc_set_target(s, *g);
+    ok = ok && cudaMalloc(&s.d_image, px * 3) == cudaSuccess && cudaMalloc(&s.d_ranges, px * sizeof(float)) == cudaSuccess;
+    if(!ok)
+    {
+        MSG("Could not allocate the %d x %d render target", W, H);
+        cudaGetLastError();
+        free_target(s);
+        s.W = 0; s.H = 0;
+        return false;
+    }
     return true;
 }
 
@@ -239,35 +280,50 @@ void free_scratch(Scratch& c)
     cudaFree(c.d_e); cudaFree(c.d_n);
     cudaFree(c.d_tile_queue); cudaFree(c.d_block_queue);
     cudaFree(c.d_counters);
-    cudaFree(c.d_views); cudaFreeHost(c.h_views);
-    for(cudaEvent_t e : c.ring_ev) if(e) cudaEventDestroy(e);
-    if(c.busy) cudaEventDestroy(c.busy);
-    if(c.done) cudaEventDestroy(c.done);
-    if(c.stream) cudaStreamDestroy(c.stream);
     c = Scratch{};
 }
 
-// everything but the visibility buffer (alloc_target owns that: it depends on the image size)
-bool alloc_scratch(const Slot& s, Scratch& c, bool own_stream)
+// everything but the image-sized part (alloc_scratch_target)
+bool alloc_scratch(const Slot& s, Scratch& c)
 {
     CUDA_TRY(cudaMalloc(&c.d_e, (size_t)s.N * sizeof(float)));
     CUDA_TRY(cudaMalloc(&c.d_n, (size_t)s.N * sizeof(float)));
     CUDA_TRY(cudaMalloc(&c.d_tile_queue, (size_t)s.nt * s.nt * sizeof(uint32_t)));
     CUDA_TRY(cudaMalloc(&c.d_block_queue, (size_t)s.nb * s.nb * sizeof(uint32_t)));
     CUDA_TRY(cudaMalloc(&c.d_counters, N_COUNTERS * sizeof(uint32_t)));
-    CUDA_TRY(cudaMalloc(&c.d_views, HZ_V_COUNT * sizeof(HzView)));
-    CUDA_TRY(cudaMallocHost(&c.h_views, (size_t)PARAM_RING * HZ_V_COUNT * sizeof(HzView)));
-    for(cudaEvent_t& e : c.ring_ev) CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-    CUDA_TRY(cudaEventCreateWithFlags(&c.busy, cudaEventDisableTiming));
-    if(own_stream)
+    return true;
+}
+
+void free_set(ViewSet& vs)
+{
+    free_set_target(vs);
+    for(Scratch& c : vs.sc) free_scratch(c);
+    vs.sc.clear();
+    cudaFree(vs.d_views); cudaFreeHost(vs.h_views);
+    for(cudaEvent_t e : vs.ring_ev) if(e) cudaEventDestroy(e);
+    if(vs.busy) cudaEventDestroy(vs.busy);
+    if(vs.done) cudaEventDestroy(vs.done);
+    if(vs.stream) cudaStreamDestroy(vs.stream);
+    vs = ViewSet{};
+}
+
+// the set's own resources; its scratches come with ensure_views()
+bool alloc_set(ViewSet& vs, int cap, bool batch)
+{
+    vs.cap = cap; vs.batch = batch;
+    CUDA_TRY(cudaMalloc(&vs.d_views, (size_t)cap * HZ_V_COUNT * sizeof(HzView)));
+    CUDA_TRY(cudaMallocHost(&vs.h_views, (size_t)PARAM_RING * cap * HZ_V_COUNT * sizeof(HzView)));
+    for(cudaEvent_t& e : vs.ring_ev) CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    CUDA_TRY(cudaEventCreateWithFlags(&vs.busy, cudaEventDisableTiming));
+    if(batch)
     {
-        CUDA_TRY(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
-        CUDA_TRY(cudaEventCreateWithFlags(&c.done, cudaEventDisableTiming));
+        CUDA_TRY(cudaStreamCreateWithFlags(&vs.stream, cudaStreamNonBlocking));
+        CUDA_TRY(cudaEventCreateWithFlags(&vs.done, cudaEventDisableTiming));
     }
     return true;
 }
 
-// bytes of device memory one scratch set takes (what ensure_lanes() budgets with)
+// bytes of device memory one scratch takes (what ensure_views() budgets with)
 size_t scratch_bytes(const Slot& s)
 {
     const size_t px = s.target_pixels;
@@ -276,26 +332,53 @@ size_t scratch_bytes(const Slot& s)
            2 * (size_t)s.big_capacity * sizeof(uint2) + (size_t)s.bigtri_capacity * 6 * sizeof(uint4);
 }
 
-// Makes sure up to n lanes exist (n <= n_lanes_max) and returns how many there are to use: lanes are only added
-// while they fit into half of the device memory that is free right now (a 36000 x 4000 panorama needs ~3 GB per lane).
-int ensure_lanes(Slot& s, int n)
+// Makes sure the set has scratch for up to n views (n <= cap) and returns how many it has to use.  Batch sets only
+// grow while the new scratch fits into half of the device memory that is free right now (a 36000 x 4000 panorama
+// needs ~3 GB per view in flight).
+int ensure_views(Slot& s, ViewSet& vs, int n)
 {
-    if(s.fork_ev == nullptr && cudaEventCreateWithFlags(&s.fork_ev, cudaEventDisableTiming) != cudaSuccess) return 0;
-    while((int)s.lanes.size() < n)
+    if(n > vs.cap) n = vs.cap;
+    while((int)vs.sc.size() < n)
     {
-        size_t free_b = 0, total_b = 0;
-        if(cudaMemGetInfo(&free_b, &total_b) != cudaSuccess || scratch_bytes(s) > free_b / 2) break;
-        Scratch c;
-        if(!alloc_scratch(s, c, true) || !alloc_scratch_target(s, c, true))
+        if(vs.batch)
         {
-            MSG("Could not allocate render lane %d", (int)s.lanes.size());
+            size_t free_b = 0, total_b = 0;
+            if(cudaMemGetInfo(&free_b, &total_b) != cudaSuccess || scratch_bytes(s) > free_b / 2) break;
+        }
+        Scratch c;
+        if(!alloc_scratch(s, c) || (s.target_pixels > 0 && !alloc_scratch_target(s, c, vs.batch)))
+        {
+            MSG("Could not allocate the scratch of view %d of a set", (int)vs.sc.size());
             cudaGetLastError();
             free_scratch(c);
             break;
         }
-        s.lanes.push_back(c);
+        vs.sc.push_back(c);
     }
-    return (int)s.lanes.size() < n ? (int)s.lanes.size() : n;
+    return (int)vs.sc.size() < n ? (int)vs.sc.size() : n;
+}
+
+// the batch sets: up to n_sets_max, created on demand
+ViewSet* batch_set(Slot& s, int k)
+{
+    if(s.fork_ev == nullptr && cudaEventCreateWithFlags(&s.fork_ev, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    while((int)s.sets.size() <= k)
+    {
+        ViewSet* g = new ViewSet;
+        bool ok = alloc_set(*g, s.views_per_set, true);
+        if(ok && s.target_pixels > 0)
+            ok = cudaMallocHost(&g->h_tanel, (size_t)PARAM_RING * g->cap * s.H * sizeof(float)) == cudaSuccess;
+        if(!ok)
+        {
+            MSG("Could not allocate view set %d", (int)s.sets.size());
+            cudaGetLastError();
+            free_set(*g);
+            delete g;
+            return nullptr;
+        }
+        s.sets.push_back(g);
+    }
+    return s.sets[k];
 }
 
 void destroy_slot(Slot* s)
@@ -303,10 +386,10 @@ void destroy_slot(Slot* s)
     if(s == nullptr) return;
     DeviceGuard g(s->device);
     if(s->stream) cudaStreamSynchronize(s->stream);
-    for(Scratch& l : s->lanes) if(l.stream) cudaStreamSynchronize(l.stream);
+    for(ViewSet* v : s->sets) if(v->stream) cudaStreamSynchronize(v->stream);
     free_target(*s);
-    free_scratch(s->main);
-    for(Scratch& l : s->lanes) free_scratch(l);
+    free_set(s->main);
+    for(ViewSet* v : s->sets) { free_set(*v); delete v; }
     if(s->fork_ev) cudaEventDestroy(s->fork_ev);
     cudaFree(s->d_mosaic);
     for(int i = 0; i < 4; i++) for(int j = 0; j < 4; j++) cudaFree((void*)s->tiles.tile[i][j]);
@@ -338,34 +421,24 @@ void fill_tanel(float* out, int W, int H, float az_deg0, float az_deg1)
     }
 }
 
-// returns the device pointer of the row table for this window, uploading it if it is not cached
-bool tanel_for(Slot& s, float az_deg0, float az_deg1, cudaStream_t st, const float** d_out)
+// the row table of a window from the host cache, computing it if it is not there
+const float* tanel_row(Slot& s, float az_deg0, float az_deg1)
 {
     const float daz = az_deg1 - az_deg0;
-    for(int k = 0; k < TANEL_SLOTS; k++)
-        if(s.tanel_key[k].valid && s.tanel_key[k].W == s.W && s.tanel_key[k].H == s.H &&
-           memcmp(&s.tanel_key[k].daz, &daz, sizeof(float)) == 0)
-        {
-            *d_out = s.d_tanel + (size_t)k * s.H;
-            return true;
-        }
-    const int k = s.tanel_next;
-    s.tanel_next = (s.tanel_next + 1) % TANEL_SLOTS;
-    // the pinned row may still be in flight from an earlier upload, the device row may still be in use
-    CUDA_TRY(cudaStreamSynchronize(st));
-    if(st != s.stream) CUDA_TRY(cudaStreamSynchronize(s.stream));
-    fill_tanel(s.h_tanel + (size_t)k * s.H, s.W, s.H, az_deg0, az_deg1);
-    CUDA_TRY(cudaMemcpyAsync(s.d_tanel + (size_t)k * s.H, s.h_tanel + (size_t)k * s.H,
-                             (size_t)s.H * sizeof(float), cudaMemcpyHostToDevice, st));
-    s.tanel_key[k] = { true, daz, s.W, s.H };
-    *d_out = s.d_tanel + (size_t)k * s.H;
-    return true;
+    for(const Slot::TanelRow& r : s.tanel_cache) if(r.key.is(daz, s.W, s.H)) return r.row.data();
+    constexpr size_t CACHE = 64;
+    if(s.tanel_cache.size() < CACHE) { s.tanel_cache.emplace_back(); s.tanel_cache_next = s.tanel_cache.size() - 1; }
+    else s.tanel_cache_next = (s.tanel_cache_next + 1) % CACHE;
+    Slot::TanelRow& r = s.tanel_cache[s.tanel_cache_next];
+    r.row.resize((size_t)s.H);
+    fill_tanel(r.row.data(), s.W, s.H, az_deg0, az_deg1);
+    r.key.valid = true; r.key.daz = daz; r.key.W = s.W; r.key.H = s.H;
+    return r.row.data();
 }
 
-// the kernels of one render, in order, reading their parameters from sc.d_views; hv = the host copy of those
-const Slot::Bands& bands_of(const Slot& s, const Scratch& sc)
+const Slot::Bands& bands_of(const Slot& s, const ViewSet& set)
 {
-    return (&sc == &s.main) ? s.bands_single : s.bands_batch;
+    return set.batch ? s.bands_batch : s.bands_single;
 }
 
 // Zoomed-in views (small angle per pixel) show triangles many pixels large even far from the eye: each band then draws
@@ -376,63 +449,65 @@ bool big_after_every_band(const Slot& s, const ViewState& vs)
     return fabsf(vs.az_deg1 - vs.az_deg0) < 0.05f * (float)s.W;
 }
 
-bool launch_chain(Slot& s, Scratch& sc, const HzView* hv, bool big_per_band, bool worst_case, bool resolve, cudaStream_t st,
-                  cudaEvent_t* ev, int* launches)
+// the kernels of one render of m views, in order, reading their parameters from set.d_views; hv = the host copy of those
+bool launch_chain(Slot& s, ViewSet& set, const HzView* hv, int m, bool big_per_band, bool worst_case, bool resolve,
+                  cudaStream_t st, cudaEvent_t* ev, int* launches)
 {
-    const HzView* dv = sc.d_views;
+    const HzView* dv = set.d_views;
     int n = 0;
     if(ev) CUDA_TRY(cudaEventRecord(ev[0], st));
-    CUDA_TRY(hz_launch_prepare(hv[HZ_V_NEAR], dv + HZ_V_NEAR, st)); n++;
+    CUDA_TRY(hz_launch_prepare(hv[HZ_V_NEAR], dv + HZ_V_NEAR, m, st)); n++;
     if(ev) CUDA_TRY(cudaEventRecord(ev[1], st));
-    CUDA_TRY(hz_launch_near(hv[HZ_V_NEAR], dv + HZ_V_NEAR, st)); n++;
-    CUDA_TRY(hz_launch_raster(hv[HZ_V_NEAR], dv + HZ_V_NEAR, st)); n++;
+    CUDA_TRY(hz_launch_near(hv[HZ_V_NEAR], dv + HZ_V_NEAR, m, st)); n++;
+    CUDA_TRY(hz_launch_raster(hv[HZ_V_NEAR], dv + HZ_V_NEAR, m, st)); n++;
     if(ev) CUDA_TRY(cudaEventRecord(ev[2], st));
-    CUDA_TRY(hz_launch_big(hv[HZ_V_NEAR], dv + HZ_V_NEAR, st)); n++;
+    CUDA_TRY(hz_launch_big(hv[HZ_V_NEAR], dv + HZ_V_NEAR, m, st)); n++;
     if(ev) CUDA_TRY(cudaEventRecord(ev[3], st));
-    for(int b = 0; b < bands_of(s, sc).n; b++)
+    const Slot::Bands& bands = bands_of(s, set);
+    for(int b = 0; b < bands.n; b++)
     {
-        const bool last = (b + 1 == bands_of(s, sc).n);
+        const bool last = (b + 1 == bands.n);
         int k = 0;
-        CUDA_TRY(hz_launch_band(hv[HZ_V_BAND0 + b], dv + HZ_V_BAND0 + b, worst_case, st, &k));
+        CUDA_TRY(hz_launch_band(hv[HZ_V_BAND0 + b], dv + HZ_V_BAND0 + b, m, worst_case, st, &k));
         n += k;
         if(last && ev) CUDA_TRY(cudaEventRecord(ev[4], st));
-        // all bands share one queue and counter unless every band has its own k_big (see enqueue_render)
-        if(last || (big_per_band && k > 0)) { CUDA_TRY(hz_launch_big(hv[HZ_V_BAND0 + b], dv + HZ_V_BAND0 + b, st)); n++; }
+        // all bands share one queue and counter unless every band has its own k_big (see fill_views)
+        if(last || (big_per_band && k > 0)) { CUDA_TRY(hz_launch_big(hv[HZ_V_BAND0 + b], dv + HZ_V_BAND0 + b, m, st)); n++; }
     }
     if(ev) CUDA_TRY(cudaEventRecord(ev[5], st));
-    if(resolve) { CUDA_TRY(hz_launch_resolve(hv[HZ_V_NEAR], dv + HZ_V_NEAR, st)); n++; }
+    if(resolve) { CUDA_TRY(hz_launch_resolve(hv[HZ_V_NEAR], dv + HZ_V_NEAR, m, st)); n++; }
     if(ev) CUDA_TRY(cudaEventRecord(ev[6], st));
     *launches = n;
     return true;
 }
 
-// Captures the standard chain (full width, vectorised resolve, grids sized for any eye position) once per scratch
-// set; every later standard render is one cudaGraphLaunch after the parameter copy.  A dozen separate launches cost
-// more host time than the GPU needs for the render.
-bool capture_graph(Slot& s, Scratch& sc, const HzView* hv, bool big_per_band)
+// Captures the standard chain (full width, vectorised resolve, grids sized for any eye position) for m views of the
+// set; every later standard render of m views is one cudaGraphLaunch after the parameter copy.  A dozen separate
+// launches cost more host time than the GPU needs for the render.
+const ViewSet::Graph* capture_graph(Slot& s, ViewSet& set, const HzView* hv, int m, bool big_per_band)
 {
     cudaStream_t cs = nullptr;
-    if(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); return false; }
+    if(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); return nullptr; }
     cudaGraph_t g = nullptr;
+    cudaGraphExec_t exec = nullptr;
     bool ok = cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
     int launches = 0;
     if(ok)
     {
-        ok = launch_chain(s, sc, hv, big_per_band, true, true, cs, nullptr, &launches);
+        ok = launch_chain(s, set, hv, m, big_per_band, true, true, cs, nullptr, &launches);
         if(cudaStreamEndCapture(cs, &g) != cudaSuccess) ok = false;
     }
-    if(ok && cudaGraphInstantiate(&sc.graph, g, 0) != cudaSuccess) { ok = false; sc.graph = nullptr; }
+    if(ok && cudaGraphInstantiate(&exec, g, 0) != cudaSuccess) { ok = false; exec = nullptr; }
     if(g) cudaGraphDestroy(g);
     cudaStreamDestroy(cs);
     if(!ok)
     {
         cudaGetLastError();
         MSG("CUDA graph capture of the render chain failed; launching the kernels one by one instead");
-        return false;
+        return nullptr;
     }
-    sc.graph_launches = launches;
-    sc.graph_big_per_band = big_per_band;
-    return true;
+    set.graphs.push_back(ViewSet::Graph{ m, big_per_band, exec, launches });
+    return &set.graphs.back();
 }
 
 // where a render's outputs go (see HzView::n_out): one destination shaped like the target, or the full panoramas
@@ -453,14 +528,11 @@ OutSpec single_out(uint8_t* d_image, float* d_ranges)
     return o;
 }
 
-// enqueue one render of columns [x0,x1) on stream st, using scratch set sc, with outputs to `out` (device memory)
-bool enqueue_render(Slot& s, Scratch& sc, const ViewState& vs, int x0, int x1, const OutSpec& out, cudaStream_t st)
+// the parameters of one view: everything but the queue/counter/band fields that differ between the variants
+void fill_view(const Slot& s, const ViewSet& set, const Scratch& sc, const ViewState& vs, int x0, int x1, const OutSpec& out,
+               HzView& v)
 {
-    uint8_t* const d_image = out.image[0];
-    float* const d_ranges = out.ranges[0];
-    // a scratch set serves one render at a time: if its previous render went to another stream, wait for that one
-    if(sc.busy_recorded && sc.last_stream != st) CUDA_TRY(cudaStreamWaitEvent(st, sc.busy, 0));
-    HzView v{};
+    v = HzView{};
     v.mosaic = s.d_mosaic; v.N = s.N; v.pitch = s.pitch;
     v.e_tab = sc.d_e; v.n_tab = sc.d_n;
     v.mm_block = s.d_mm_block; v.nb = s.nb;
@@ -488,7 +560,7 @@ bool enqueue_render(Slot& s, Scratch& sc, const ViewState& vs, int x0, int x1, c
     v.bigtri = sc.d_bigtri; v.bigtri_count = sc.d_counters + 3; v.bigtri_capacity = s.bigtri_capacity;
     v.occl_tile_max_pix = s.occl_tile_max_pix; v.occl_block_max_pix = s.occl_block_max_pix;
     v.small_max_pix = s.small_max_pix;
-    v.grid_percent = (&sc == &s.main) ? s.grid_percent_single : s.grid_percent_batch;
+    v.grid_percent = set.batch ? s.grid_percent_batch : s.grid_percent_single;
     v.big_capacity = s.big_capacity;
 
     // the eye's tile, and how many rings of tiles around it form the foreground pass
@@ -509,34 +581,47 @@ bool enqueue_render(Slot& s, Scratch& sc, const ViewState& vs, int x0, int x1, c
         v.inv_zrange = (s.zfar > s.znear) ? 1.0f / (s.zfar - s.znear) : 0.0f;   // 0: no far/occlusion culling
     }
 
-    const float* d_tanel = nullptr;
-    if(d_ranges && !tanel_for(s, vs.az_deg0, vs.az_deg1, st, &d_tanel)) return false;
-
     v.counters = sc.d_counters; v.ncounters = N_COUNTERS;
-    v.tanel = d_tanel;
+    v.tanel = sc.d_tanel;
     v.n_out = out.n; v.out_stride = out.stride > 0 ? out.stride : x1 - x0; v.out_x0 = out.x_off;
     for(int d = 0; d < out.n; d++) { v.out_image[d] = out.image[d]; v.out_ranges[d] = out.ranges[d]; }
+}
 
-    // ---- the parameter block: variants of v for the near pass, the far queue and each band, into a slot of the
+// Enqueues one render of columns [x0,x1) of m views (m <= what ensure_views() gave) on stream st: view k uses scratch
+// set.sc[k] and writes to outs[k] (device memory).  All views of one call must have the same kinds of output.
+bool enqueue_views(Slot& s, ViewSet& set, int m, const ViewState* vs, int x0, int x1, const OutSpec* outs, cudaStream_t st)
+{
+    if(s.W <= 0 || s.H <= 0 || m < 1 || m > (int)set.sc.size()) return false;
+    const bool want_image = outs[0].image[0] != nullptr, want_ranges = outs[0].ranges[0] != nullptr;
+    // a set serves one render at a time: if its previous render went to another stream, wait for that one
+    if(set.busy_recorded && set.last_stream != st) CUDA_TRY(cudaStreamWaitEvent(st, set.busy, 0));
+
+    // ---- the parameter block: per view, variants for the near pass, the far queue and each band, into a slot of the
     // pinned ring, then one small copy to the device
-    const int slot = sc.ring_next;
-    sc.ring_next = (sc.ring_next + 1) % PARAM_RING;
-    CUDA_TRY(cudaEventSynchronize(sc.ring_ev[slot]));             // the copy that last used this slot is done
-    HzView* hv = sc.h_views + (size_t)slot * HZ_V_COUNT;
-    for(int k = 0; k < HZ_V_COUNT; k++) hv[k] = v;
-    hv[HZ_V_NEAR].tri_count = sc.d_counters + 2;
-    hv[HZ_V_NEAR].big_queue = sc.d_big_queue;                 hv[HZ_V_NEAR].big_count = sc.d_counters + 0;
-    for(int k = HZ_V_FAR; k < HZ_V_COUNT; k++)
+    const int slot = set.ring_next;
+    set.ring_next = (set.ring_next + 1) % PARAM_RING;
+    CUDA_TRY(cudaEventSynchronize(set.ring_ev[slot]));            // the copies that last used this slot are done
+    HzView* hv = set.h_views + (size_t)slot * set.cap * HZ_V_COUNT;
+    const Slot::Bands& bands = bands_of(s, set);
+    bool big_per_band = false, vectorisable = true;
+    for(int k = 0; k < m; k++) big_per_band = big_per_band || big_after_every_band(s, vs[k]);
+    for(int k = 0; k < m; k++)
     {
-        hv[k].big_queue = sc.d_big_queue + s.big_capacity;      hv[k].big_count = sc.d_counters + 1;
-    }
-    const bool big_per_band = big_after_every_band(s, vs);
-    {
+        Scratch& sc = set.sc[k];
+        HzView* hk = hv + (size_t)k * HZ_V_COUNT;
+        fill_view(s, set, sc, vs[k], x0, x1, outs[k], hk[0]);
+        vectorisable = vectorisable && hz_resolve_is_vectorisable(hk[0]);
+        for(int j = 1; j < HZ_V_COUNT; j++) hk[j] = hk[0];
+        hk[HZ_V_NEAR].tri_count = sc.d_counters + 2;
+        hk[HZ_V_NEAR].big_queue = sc.d_big_queue;                 hk[HZ_V_NEAR].big_count = sc.d_counters + 0;
+        for(int j = HZ_V_FAR; j < HZ_V_COUNT; j++)
+        {
+            hk[j].big_queue = sc.d_big_queue + s.big_capacity;      hk[j].big_count = sc.d_counters + 1;
+        }
         int lo = s.near_rings + 1;
-        const Slot::Bands& bands = bands_of(s, sc);
         for(int b = 0; b < bands.n; b++)
         {
-            HzView& vb = hv[HZ_V_BAND0 + b];
+            HzView& vb = hk[HZ_V_BAND0 + b];
             vb.ring_lo = lo; vb.ring_hi = bands.end[b] > lo ? bands.end[b] : lo;
             vb.tile_count = sc.d_counters + 4 + 4 * b; vb.block_count = sc.d_counters + 5 + 4 * b;
             vb.tri_count  = sc.d_counters + 6 + 4 * b;
@@ -545,29 +630,33 @@ bool enqueue_render(Slot& s, Scratch& sc, const ViewState& vs, int x0, int x1, c
             vb.big_count  = sc.d_counters + 7 + (big_per_band ? 4 * b : 0);
             lo = vb.ring_hi;
         }
+        // the row table of this view's window, unless the scratch still holds it from its previous render
+        if(want_ranges && !sc.tanel_key.is(vs[k].az_deg1 - vs[k].az_deg0, s.W, s.H))
+        {
+            float* h_row = set.h_tanel + ((size_t)slot * set.cap + k) * s.H;
+            memcpy(h_row, tanel_row(s, vs[k].az_deg0, vs[k].az_deg1), (size_t)s.H * sizeof(float));
+            CUDA_TRY(cudaMemcpyAsync(sc.d_tanel, h_row, (size_t)s.H * sizeof(float), cudaMemcpyHostToDevice, st));
+            sc.tanel_key.valid = true; sc.tanel_key.daz = vs[k].az_deg1 - vs[k].az_deg0; sc.tanel_key.W = s.W; sc.tanel_key.H = s.H;
+        }
     }
-    CUDA_TRY(cudaMemcpyAsync(sc.d_views, hv, HZ_V_COUNT * sizeof(HzView), cudaMemcpyHostToDevice, st));
-    CUDA_TRY(cudaEventRecord(sc.ring_ev[slot], st));
+    CUDA_TRY(cudaMemcpyAsync(set.d_views, hv, (size_t)m * HZ_V_COUNT * sizeof(HzView), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaEventRecord(set.ring_ev[slot], st));
 
     // ---- the kernels: a replay of the captured graph where the chain has its standard shape, one by one otherwise
-    const bool standard = !s.profiling && s.use_graphs && x0 == 0 && x1 == s.W && (d_image || d_ranges) &&
-                          out.n == 1 && v.out_stride == s.W && out.x_off == 0 && hz_resolve_is_vectorisable(v);
-    if(standard && !sc.graph_failed)
+    const bool is_main = (&set == &s.main);
+    const bool standard = !s.profiling && s.use_graphs && x0 == 0 && x1 == s.W && (want_image || want_ranges) &&
+                          outs[0].n == 1 && hv[0].out_stride == s.W && outs[0].x_off == 0 && vectorisable;
+    if(standard && !set.graph_failed)
     {
-        if(sc.graph != nullptr && sc.graph_big_per_band != big_per_band)
+        const ViewSet::Graph* g = nullptr;
+        for(const ViewSet::Graph& c : set.graphs) if(c.m == m && c.big_per_band == big_per_band) g = &c;
+        if(g == nullptr && (g = capture_graph(s, set, hv, m, big_per_band)) == nullptr) set.graph_failed = true;
+        if(g != nullptr)
         {
-            // the chain changes shape (rare: the caller went from a wide to a zoomed-in window or back): let the old
-            // graph's last launch finish before it is destroyed
-            if(sc.busy_recorded) CUDA_TRY(cudaEventSynchronize(sc.busy));
-            drop_graph(sc);
-        }
-        if(sc.graph == nullptr && !capture_graph(s, sc, hv, big_per_band)) sc.graph_failed = true;
-        if(sc.graph != nullptr)
-        {
-            CUDA_TRY(cudaGraphLaunch(sc.graph, st));
-            CUDA_TRY(cudaEventRecord(sc.busy, st)); sc.last_stream = st; sc.busy_recorded = true;
-            s.launches_last = sc.graph_launches;
-            if(&sc == &s.main) s.have_render = true;
+            CUDA_TRY(cudaGraphLaunch(g->exec, st));
+            CUDA_TRY(cudaEventRecord(set.busy, st)); set.last_stream = st; set.busy_recorded = true;
+            s.launches_last = g->launches;
+            if(is_main) s.have_render = true;
             return true;
         }
     }
@@ -585,11 +674,51 @@ bool enqueue_render(Slot& s, Scratch& sc, const ViewState& vs, int x0, int x1, c
         s.prof_used += PROF_EVENTS;
     }
     int launches = 0;
-    if(!launch_chain(s, sc, hv, big_per_band, false, d_image || d_ranges, st, ev, &launches)) return false;
-    CUDA_TRY(cudaEventRecord(sc.busy, st)); sc.last_stream = st; sc.busy_recorded = true;
+    // grids sized for this view's eye tile only when there is just one view
+    if(!launch_chain(s, set, hv, m, big_per_band, m > 1, want_image || want_ranges, st, ev, &launches)) return false;
+    CUDA_TRY(cudaEventRecord(set.busy, st)); set.last_stream = st; set.busy_recorded = true;
     s.launches_last = launches;
-    if(&sc == &s.main) s.have_render = (x0 == 0 && x1 == s.W);
+    if(is_main) s.have_render = (x0 == 0 && x1 == s.W);
     return true;
+}
+
+// one view on the context's own scratch
+bool enqueue_render(Slot& s, const ViewState& vs, int x0, int x1, const OutSpec& out, cudaStream_t st)
+{
+    return enqueue_views(s, s.main, 1, &vs, x0, x1, &out, st);
+}
+
+// The tunables of the render chain, from the environment (defaults in Slot).  Read at init; horizonator_reload_tunables()
+// reads them again.
+void read_tunables(Slot& s)
+{
+    if(const char* env = getenv("HORIZONATOR_NEAR_RINGS")) s.near_rings = atoi(env) < 0 ? 0 : atoi(env);
+    if(const char* env = getenv("HORIZONATOR_OCCL_TILE_PIX"))  s.occl_tile_max_pix  = atoi(env);
+    if(const char* env = getenv("HORIZONATOR_OCCL_BLOCK_PIX")) s.occl_block_max_pix = atoi(env);
+    if(const char* env = getenv("HORIZONATOR_SMALL_PIX"))      s.small_max_pix = atoi(env);
+    if(const char* env = getenv("HORIZONATOR_GRID_SCALE"))       s.grid_percent_single = atoi(env);
+    if(const char* env = getenv("HORIZONATOR_GRID_SCALE_BATCH")) s.grid_percent_batch  = atoi(env);
+    // HORIZONATOR_BANDS / HORIZONATOR_BANDS_BATCH: comma-separated rings at which the bands end (lone views / views
+    // of a batch; the first also sets the second unless that is given); the last band always runs to the edge
+    auto parse_bands = [](const char* env, Slot::Bands& out) {
+        int n = 0;
+        for(const char* p = env; *p && n < MAX_BANDS - 1; )
+        {
+            const int r = atoi(p);
+            if(r > 0) out.end[n++] = r;
+            while(*p && *p != ',') p++;
+            if(*p == ',') p++;
+        }
+        out.end[n++] = 1 << 20;
+        out.n = n;
+    };
+    if(const char* env = getenv("HORIZONATOR_BANDS")) { parse_bands(env, s.bands_single); s.bands_batch = s.bands_single; }
+    if(const char* env = getenv("HORIZONATOR_BANDS_BATCH")) parse_bands(env, s.bands_batch);
+    if(const char* env = getenv("HORIZONATOR_GRAPHS")) s.use_graphs = atoi(env) != 0;
+    // HORIZONATOR_LANES: most views of a batch rendered by one chain of launches; HORIZONATOR_SETS: how many such
+    // sets may be in flight (each on its own stream)
+    if(const char* env = getenv("HORIZONATOR_LANES")) s.views_per_set = atoi(env) < 1 ? 1 : (atoi(env) > 64 ? 64 : atoi(env));
+    if(const char* env = getenv("HORIZONATOR_SETS"))  s.n_sets_max = atoi(env) < 1 ? 1 : (atoi(env) > 8 ? 8 : atoi(env));
 }
 
 // lib:765-789, float as written there.  The four samples come from the host mmaps (dem.h).
@@ -710,33 +839,10 @@ bool horizonator_init(horizonator_context_t* ctx,
         if(fail(cudaMalloc(&s->d_mosaic, (size_t)s->N * s->pitch * sizeof(int16_t)), "cudaMalloc(mosaic)")) break;
         s->nb = (s->N - 1 + HZ_BLOCK_CELLS - 1) / HZ_BLOCK_CELLS;
         s->nt = (s->N - 1 + HZ_TILE_CELLS - 1) / HZ_TILE_CELLS;
-        if(const char* env = getenv("HORIZONATOR_NEAR_RINGS")) s->near_rings = atoi(env) < 0 ? 0 : atoi(env);
-        if(const char* env = getenv("HORIZONATOR_OCCL_TILE_PIX"))  s->occl_tile_max_pix  = atoi(env);
-        if(const char* env = getenv("HORIZONATOR_OCCL_BLOCK_PIX")) s->occl_block_max_pix = atoi(env);
-        if(const char* env = getenv("HORIZONATOR_SMALL_PIX"))      s->small_max_pix = atoi(env);
-        if(const char* env = getenv("HORIZONATOR_GRID_SCALE"))       s->grid_percent_single = atoi(env);
-        if(const char* env = getenv("HORIZONATOR_GRID_SCALE_BATCH")) s->grid_percent_batch  = atoi(env);
-        // HORIZONATOR_BANDS / HORIZONATOR_BANDS_BATCH: comma-separated rings at which the bands end (lone views / views
-        // of a batch; the first also sets the second unless that is given); the last band always runs to the edge
-        auto parse_bands = [](const char* env, Slot::Bands& out) {
-            int n = 0;
-            for(const char* p = env; *p && n < MAX_BANDS - 1; )
-            {
-                const int r = atoi(p);
-                if(r > 0) out.end[n++] = r;
-                while(*p && *p != ',') p++;
-                if(*p == ',') p++;
-            }
-            out.end[n++] = 1 << 20;
-            out.n = n;
-        };
-        if(const char* env = getenv("HORIZONATOR_BANDS")) { parse_bands(env, s->bands_single); s->bands_batch = s->bands_single; }
-        if(const char* env = getenv("HORIZONATOR_BANDS_BATCH")) parse_bands(env, s->bands_batch);
-        if(const char* env = getenv("HORIZONATOR_GRAPHS")) s->use_graphs = atoi(env) != 0;
-        if(const char* env = getenv("HORIZONATOR_LANES")) s->n_lanes_max = atoi(env) < 1 ? 1 : (atoi(env) > 32 ? 32 : atoi(env));
+        read_tunables(*s);
         if(fail(cudaMalloc(&s->d_mm_block, (size_t)s->nb * s->nb * sizeof(short2)), "cudaMalloc(pyramid)")) break;
         if(fail(cudaMalloc(&s->d_mm_tile, (size_t)s->nt * s->nt * sizeof(short2)), "cudaMalloc(pyramid)")) break;
-        if(!alloc_scratch(*s, s->main, false)) break;
+        if(!alloc_set(s->main, 1, false) || ensure_views(*s, s->main, 1) != 1) break;
         if(fail(hz_launch_mosaic(s->tiles, s->d_mosaic, s->N, s->pitch, s->stream), "k_mosaic")) break;
         if(fail(hz_launch_pyramid(s->d_mosaic, s->N, s->pitch, s->d_mm_block, s->nb, s->d_mm_tile, s->nt, s->stream),
                 "k_minmax")) break;
@@ -859,7 +965,7 @@ bool horizonator_redraw(const horizonator_context_t* ctx)
     Slot* s = slot_of(ctx);
     if(s == nullptr) return false;
     DeviceGuard g(s->device);
-    if(!enqueue_render(*s, s->main, s->view, 0, s->W, single_out(s->d_image, s->d_ranges), s->stream)) return false;
+    if(!enqueue_render(*s, s->view, 0, s->W, single_out(s->d_image, s->d_ranges), s->stream)) return false;
     CUDA_TRY(cudaStreamSynchronize(s->stream));
     return true;
 }
@@ -875,7 +981,7 @@ bool horizonator_render_offscreen(const horizonator_context_t* ctx, char* image,
     }
     DeviceGuard g(s->device);
     const size_t px = (size_t)s->W * s->H;
-    if(!enqueue_render(*s, s->main, s->view, 0, s->W,
+    if(!enqueue_render(*s, s->view, 0, s->W,
                        single_out(image ? s->d_image : nullptr, ranges ? s->d_ranges : nullptr), s->stream)) return false;
     if(image  && !copy_to_host(image,  s->d_image,  px * 3, s->stream)) return false;
     if(ranges && !copy_to_host(ranges, s->d_ranges, px * sizeof(float), s->stream)) return false;
@@ -891,7 +997,7 @@ bool horizonator_pick(const horizonator_context_t* ctx, float* lat, float* lon, 
     DeviceGuard g(s->device);
     unsigned long long key = 0;
     CUDA_TRY(cudaStreamSynchronize(s->stream));
-    CUDA_TRY(cudaMemcpy(&key, s->main.d_vis + (size_t)(s->H - 1 - y) * s->W + x, sizeof(key), cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(&key, s->main.sc[0].d_vis + (size_t)(s->H - 1 - y) * s->W + x, sizeof(key), cudaMemcpyDeviceToHost));
     const float depth = (float)((double)(unsigned)(key >> 40) * (1.0 / 16777215.0));
     if(depth >= 1.0f) return false;                                     // lib:1272
     // lib:1282-1295: the depth is treated as horizontal distance
@@ -973,10 +1079,12 @@ bool horizonator_unproject(float* lat, float* lon, int x, int y,
 
 // ---- additive API (include/horizonator-batch.h) -----------------------------------------------------------
 
-// Common part of the two batch calls.  The views are dealt round-robin to render lanes, each with its own stream
-// and scratch, so that the (latency-bound) kernel chains of different views overlap; the lanes start after
-// everything already queued on `st` and `st` continues after all of them.  to_host: outputs go through the lane's
-// device staging buffers and a device->host copy on the lane's stream, which overlaps the next views' kernels.
+// Common part of the two batch calls.  The views are cut into chunks of up to views_per_set; a chunk is rendered by
+// ONE chain of kernel launches whose grids have a view dimension (one parameter copy and one CUDA-graph launch per
+// chunk, whatever its size), on the stream of one of up to n_sets_max view sets, so that the tails of one chunk's
+// kernels overlap another chunk's.  The sets start after everything already queued on `st`, and `st` continues after
+// all of them.  to_host: outputs go through the views' device staging buffers and device->host copies on the set's
+// stream, which overlap the other sets' kernels.
 static bool render_batch_common(const horizonator_context_t* ctx, Slot* s, int n, const horizonator_view_t* views,
                                 uint8_t* images, float* ranges, bool to_host, cudaStream_t st)
 {
@@ -988,27 +1096,37 @@ static bool render_batch_common(const horizonator_context_t* ctx, Slot* s, int n
         if(!compute_move(ctx, &z, views[k].lat, views[k].lon, vs[k])) return false;
         vs[k].az_deg0 = views[k].az_deg0; vs[k].az_deg1 = views[k].az_deg1;
     }
+    if(n == 0) return true;
 
-    // Lanes need every per-window row table of the batch resident before they start (tanel_for() synchronises
-    // when it has to upload one): resolve them all on `st`, then check that none evicted another.
-    int n_lanes = n < s->n_lanes_max ? n : s->n_lanes_max;
-    if(n_lanes > 1 && ranges != nullptr)
+    // chunk size: the views spread evenly over the sets, at most views_per_set each, at most what fits in memory
+    int n_sets = 0, chunk = 0;
+    if(n > 1)
     {
-        const float* dummy;
-        for(int k = 0; k < n; k++) if(!tanel_for(*s, vs[k].az_deg0, vs[k].az_deg1, st, &dummy)) return false;
-        const int before = s->tanel_next;
-        for(int k = 0; k < n; k++) if(!tanel_for(*s, vs[k].az_deg0, vs[k].az_deg1, st, &dummy)) return false;
-        if(s->tanel_next != before) n_lanes = 1;      // more distinct windows than table slots: one at a time
+        n_sets = s->n_sets_max;
+        chunk = (n + n_sets - 1) / n_sets;
+        if(chunk > s->views_per_set) chunk = s->views_per_set;
+        n_sets = (n + chunk - 1) / chunk < n_sets ? (n + chunk - 1) / chunk : n_sets;
+        for(int g = 0; g < n_sets; g++)
+        {
+            ViewSet* set = batch_set(*s, g);
+            const int have = set ? ensure_views(*s, *set, chunk) : 0;
+            if(have < chunk)
+            {
+                if(g == 0) chunk = have;              // every set gets what the first one could have
+                else       n_sets = g;                // later sets: do without them
+                if(chunk < 1) { n_sets = 0; break; }
+            }
+        }
     }
-    if(n_lanes > 1) n_lanes = ensure_lanes(*s, n_lanes);      // as many as fit; fewer than 2: one view at a time
 
-    if(n_lanes <= 1)
+    if(n_sets == 0)
     {
+        // one view, or no memory for a set: one at a time on the context's own scratch
         for(int k = 0; k < n; k++)
         {
             uint8_t* di = images ? (to_host ? s->d_image  : images + (size_t)k * px * 3) : nullptr;
             float*   dr = ranges ? (to_host ? s->d_ranges : ranges + (size_t)k * px)     : nullptr;
-            if(!enqueue_render(*s, s->main, vs[k], 0, s->W, single_out(di, dr), st)) return false;
+            if(!enqueue_render(*s, vs[k], 0, s->W, single_out(di, dr), st)) return false;
             if(to_host)
             {
                 if(images && !copy_to_host(images + (size_t)k * px * 3, di, px * 3, st)) return false;
@@ -1020,23 +1138,34 @@ static bool render_batch_common(const horizonator_context_t* ctx, Slot* s, int n
     }
 
     CUDA_TRY(cudaEventRecord(s->fork_ev, st));
-    for(int l = 0; l < n_lanes; l++) CUDA_TRY(cudaStreamWaitEvent(s->lanes[l].stream, s->fork_ev, 0));
-    for(int k = 0; k < n; k++)
+    for(int g = 0; g < n_sets; g++) CUDA_TRY(cudaStreamWaitEvent(s->sets[g]->stream, s->fork_ev, 0));
+    bool ok = true;
+    std::vector<OutSpec> outs((size_t)chunk);
+    for(int k0 = 0, c = 0; k0 < n && ok; k0 += chunk, c++)
     {
-        Scratch& lane = s->lanes[k % n_lanes];
-        uint8_t* di = images ? (to_host ? lane.d_image  : images + (size_t)k * px * 3) : nullptr;
-        float*   dr = ranges ? (to_host ? lane.d_ranges : ranges + (size_t)k * px)     : nullptr;
-        if(!enqueue_render(*s, lane, vs[k], 0, s->W, single_out(di, dr), lane.stream)) return false;
-        if(to_host)
+        ViewSet& set = *s->sets[c % n_sets];
+        const int m = n - k0 < chunk ? n - k0 : chunk;
+        for(int k = 0; k < m; k++)
+            outs[k] = single_out(images ? (to_host ? set.sc[k].d_image  : images + (size_t)(k0 + k) * px * 3) : nullptr,
+                                 ranges ? (to_host ? set.sc[k].d_ranges : ranges + (size_t)(k0 + k) * px)     : nullptr);
+        ok = enqueue_views(*s, set, m, &vs[k0], 0, s->W, outs.data(), set.stream);
+        for(int k = 0; k < m && ok && to_host; k++)
         {
-            if(images && !copy_to_host(images + (size_t)k * px * 3, di, px * 3, lane.stream)) return false;
-            if(ranges && !copy_to_host(ranges + (size_t)k * px, dr, px * sizeof(float), lane.stream)) return false;
+            if(images) ok = ok && copy_to_host(images + (size_t)(k0 + k) * px * 3, set.sc[k].d_image, px * 3, set.stream);
+            if(ranges) ok = ok && copy_to_host(ranges + (size_t)(k0 + k) * px, set.sc[k].d_ranges, px * sizeof(float), set.stream);
         }
     }
-    for(int l = 0; l < n_lanes; l++)
+    if(!ok)
     {
-        CUDA_TRY(cudaEventRecord(s->lanes[l].done, s->lanes[l].stream));
-        CUDA_TRY(cudaStreamWaitEvent(st, s->lanes[l].done, 0));
+        // whatever was queued may still be writing into the caller's buffers: let it finish before reporting failure
+        for(int g = 0; g < n_sets; g++) cudaStreamSynchronize(s->sets[g]->stream);
+        cudaGetLastError();
+        return false;
+    }
+    for(int g = 0; g < n_sets; g++)
+    {
+        CUDA_TRY(cudaEventRecord(s->sets[g]->done, s->sets[g]->stream));
+        CUDA_TRY(cudaStreamWaitEvent(st, s->sets[g]->done, 0));
     }
     return true;
 }
@@ -1076,7 +1205,7 @@ bool horizonator_render_wedge_device(const horizonator_context_t* ctx, int x0, i
     }
     DeviceGuard g(s->device);
     cudaStream_t st = stream ? (cudaStream_t)stream : s->stream;
-    if(!enqueue_render(*s, s->main, s->view, x0, x1, single_out((uint8_t*)d_image, (float*)d_ranges), st)) return false;
+    if(!enqueue_render(*s, s->view, x0, x1, single_out((uint8_t*)d_image, (float*)d_ranges), st)) return false;
     if(stream == nullptr) CUDA_TRY(cudaStreamSynchronize(st));
     return true;
 }
@@ -1162,7 +1291,7 @@ bool horizonator_render_wedge_peers(const horizonator_context_t* ctx, int x0, in
     }
     DeviceGuard g(s->device);
     cudaStream_t st = stream ? (cudaStream_t)stream : s->stream;
-    if(!enqueue_render(*s, s->main, s->view, x0, x1, out, st)) return false;
+    if(!enqueue_render(*s, s->view, x0, x1, out, st)) return false;
     if(stream == nullptr) CUDA_TRY(cudaStreamSynchronize(st));
     return true;
 }
@@ -1204,6 +1333,30 @@ bool horizonator_set_earth_curvature(const horizonator_context_t* ctx, bool on, 
         return false;
     }
     s->curvature = on ? (1.0f - refraction) / (2.0f * 6371000.0f) : 0.0f;
+    return true;
+}
+
+bool horizonator_reload_tunables(const horizonator_context_t* ctx)
+{
+    Slot* s = slot_of(ctx);
+    if(s == nullptr) return false;
+    DeviceGuard g(s->device);
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    for(ViewSet* v : s->sets) CUDA_TRY(cudaStreamSynchronize(v->stream));
+    if(s->main.busy_recorded) CUDA_TRY(cudaEventSynchronize(s->main.busy));
+    for(ViewSet* v : s->sets) if(v->busy_recorded) CUDA_TRY(cudaEventSynchronize(v->busy));
+    // the captured chains and the batch sets embody the old values
+    drop_graphs(s->main);
+    for(ViewSet* v : s->sets) { free_set(*v); delete v; }
+    s->sets.clear();
+    {
+        const Slot d;       // the defaults
+        s->near_rings = d.near_rings; s->occl_tile_max_pix = d.occl_tile_max_pix; s->occl_block_max_pix = d.occl_block_max_pix;
+        s->small_max_pix = d.small_max_pix; s->grid_percent_single = d.grid_percent_single;
+        s->grid_percent_batch = d.grid_percent_batch; s->bands_single = d.bands_single; s->bands_batch = d.bands_batch;
+        s->use_graphs = d.use_graphs; s->views_per_set = d.views_per_set; s->n_sets_max = d.n_sets_max;
+    }
+    read_tunables(*s);
     return true;
 }
 
@@ -1295,7 +1448,7 @@ bool horizonator_last_render_stats(const horizonator_context_t* ctx, unsigned in
     DeviceGuard g(s->device);
     CUDA_TRY(cudaStreamSynchronize(s->stream));
     unsigned int counters[N_COUNTERS] = {};
-    CUDA_TRY(cudaMemcpy(counters, s->main.d_counters, sizeof(counters), cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(counters, s->main.sc[0].d_counters, sizeof(counters), cudaMemcpyDeviceToHost));
     out[0] = counters[0];
     for(int b = 0; b < MAX_BANDS; b++) out[0] += counters[7 + 4 * b];
     out[1] = 2 * s->big_capacity; out[2] = s->launches_last; out[3] = (unsigned)s->device;
@@ -1310,7 +1463,7 @@ bool horizonator_render_counters(const horizonator_context_t* ctx, unsigned int 
     if(s == nullptr || out == nullptr) return false;
     DeviceGuard g(s->device);
     CUDA_TRY(cudaStreamSynchronize(s->stream));
-    CUDA_TRY(cudaMemcpy(out, s->main.d_counters + STATS_AT, HZ_STAT_COUNT * sizeof(unsigned int), cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(out, s->main.sc[0].d_counters + STATS_AT, HZ_STAT_COUNT * sizeof(unsigned int), cudaMemcpyDeviceToHost));
     return true;
 }
 

@@ -142,16 +142,18 @@ struct HzPeerFlags
 };
 cudaError_t hz_launch_peer_barrier(const HzPeerFlags& f, unsigned int epoch, cudaStream_t stream);
 
-// All launches are asynchronous on `stream`.  `v` is the host copy of the variant (for grid sizing), `d_v` the device
-// copy the kernel reads.
+// All launches are asynchronous on `stream`.  One launch serves `nviews` views at once (gridDim.y = view): `v` is the
+// host copy of the variant of view 0 (for grid sizing; every view of a launch has the same image size and band
+// structure), `d_v` the device copy of that variant.  View y's copy of the same variant sits HZ_V_COUNT elements
+// further per view: d_v + y * HZ_V_COUNT.
 cudaError_t hz_launch_mosaic (const HzTiles& t, int16_t* mosaic, int N, int pitch, cudaStream_t stream);
 cudaError_t hz_launch_pyramid(const int16_t* mosaic, int N, int pitch, short2* mm_block, int nb,
                               short2* mm_tile, int nt, cudaStream_t stream);
-cudaError_t hz_launch_prepare(const HzView& v, const HzView* d_v, cudaStream_t stream);  // clear keys, axis tables, counters
-cudaError_t hz_launch_near   (const HzView& v, const HzView* d_v, cudaStream_t stream);  // foreground tiles -> triangle list
-cudaError_t hz_launch_raster (const HzView& v, const HzView* d_v, cudaStream_t stream);  // set-up + rasterise a triangle list
-cudaError_t hz_launch_band   (const HzView& v, const HzView* d_v, bool worst_case, cudaStream_t stream, int* launches);
-cudaError_t hz_launch_big    (const HzView& v, const HzView* d_v, cudaStream_t stream);  // queued large triangles of one pass
-cudaError_t hz_launch_resolve(const HzView& v, const HzView* d_v, cudaStream_t stream);
+cudaError_t hz_launch_prepare(const HzView& v, const HzView* d_v, int nviews, cudaStream_t stream);  // clear keys, axis tables, counters
+cudaError_t hz_launch_near   (const HzView& v, const HzView* d_v, int nviews, cudaStream_t stream);  // foreground tiles -> triangle list
+cudaError_t hz_launch_raster (const HzView& v, const HzView* d_v, int nviews, cudaStream_t stream);  // set-up + rasterise a triangle list
+cudaError_t hz_launch_band   (const HzView& v, const HzView* d_v, int nviews, bool worst_case, cudaStream_t stream, int* launches);
+cudaError_t hz_launch_big    (const HzView& v, const HzView* d_v, int nviews, cudaStream_t stream);  // queued large triangles of one pass
+cudaError_t hz_launch_resolve(const HzView& v, const HzView* d_v, int nviews, cudaStream_t stream);
 bool        hz_resolve_is_vectorisable(const HzView& v);
 cudaError_t hz_launch_horizon(const float* ranges, int n, int W, int H, int* rows, float* range, cudaStream_t stream);

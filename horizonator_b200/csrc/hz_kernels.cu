@@ -43,10 +43,11 @@ __device__ __forceinline__ void hz_wait_for_previous_kernel()
 // that precedes the whole chain, not by an earlier kernel of it) into shared memory BEFORE it waits for the previous
 // kernel, so that those reads overlap that kernel's tail instead of following it; afterwards every P.field is a
 // shared-memory read.
+// One launch serves gridDim.y views: view y reads its copy of the launch's variant, HZ_V_COUNT elements per view on.
 #define HZ_KERNEL_PROLOGUE(V, P)                                                                           \
     __shared__ HzView hz_s_view;                                                                           \
     for(unsigned int hz_i = threadIdx.x; hz_i < sizeof(HzView) / 4; hz_i += blockDim.x)                    \
-        ((uint32_t*)&hz_s_view)[hz_i] = __ldg((const uint32_t*)(V) + hz_i);                                \
+        ((uint32_t*)&hz_s_view)[hz_i] = __ldg((const uint32_t*)((V) + blockIdx.y * HZ_V_COUNT) + hz_i);    \
     __syncthreads();                                                                                       \
     hz_wait_for_previous_kernel();                                                                         \
     const HzView& P = hz_s_view
@@ -55,10 +56,13 @@ __device__ __forceinline__ void hz_wait_for_previous_kernel()
 // count and loop: ctas_per_sm as tuned for a lone view, times v.grid_percent/100.  Views that render concurrently
 // (the lanes of a batch) do better with smaller grids -- most CTAs of a worst-case grid find nothing to do, and
 // their launch and prologue compete with the other views' real work -- a lone view with larger ones.
-static unsigned int hz_grid(const HzView& v, unsigned int ctas_per_sm)
+// With several views per launch (gridDim.y) that total is divided among them.
+static unsigned int hz_grid(const HzView& v, unsigned int ctas_per_sm, int nviews)
 {
-    const unsigned int g = 148u * ctas_per_sm * (unsigned int)(v.grid_percent > 0 ? v.grid_percent : 100) / 100u;
-    return g < 148u ? 148u : g;
+    const unsigned int nv = (unsigned int)(nviews > 0 ? nviews : 1);
+    const unsigned int total = 148u * ctas_per_sm * (unsigned int)(v.grid_percent > 0 ? v.grid_percent : 100) / 100u;
+    const unsigned int g = (total + nv - 1u) / nv, floor_ = 148u / nv > 8u ? 148u / nv : 8u;
+    return g < floor_ ? floor_ : g;
 }
 
 template <typename... KArgs, typename... Args>
@@ -207,12 +211,14 @@ k_prepare(const HzView* __restrict__ V)
     if(tid < (unsigned int)P.ncounters) P.counters[tid] = 0;
 }
 
-cudaError_t hz_launch_prepare(const HzView& v, const HzView* d_v, cudaStream_t stream)
+cudaError_t hz_launch_prepare(const HzView& v, const HzView* d_v, int nviews, cudaStream_t stream)
 {
-    // enough threads to cover the axis tables in one trip and to keep the stores of the clear flowing
-    unsigned int blocks = (unsigned int)((v.N + 255) / 256);
-    if(blocks < 148 * 2) blocks = 148 * 2;
-    return hz_launch(k_prepare, dim3(blocks), dim3(256), stream, d_v);
+    // enough threads to keep the stores of the clear flowing; the axis tables take a few trips
+    unsigned int blocks = 148u * 2u;
+    if(nviews > 1) blocks = 148u * 8u / (unsigned int)nviews;
+    if(blocks < 16u) blocks = 16u;
+    (void)v;
+    return hz_launch(k_prepare, dim3(blocks, (unsigned)nviews), dim3(256), stream, d_v);
 }
 
 // ================================================================================================
@@ -399,6 +405,15 @@ __device__ __forceinline__ unsigned int hz_quantise24(float zw)
     return (unsigned int)((mant * 16777215ull + (1ull << (shift - 1u))) >> shift);
 }
 
+// The depth test: min() into the pixel's key.  P.vis comes out of the shared-memory copy of the parameters, so the
+// compiler only knows it as a generic pointer and atomicMin() would become a run-time dispatch on the address space
+// with a compare-and-swap loop for the shared-memory case; nothing needs the old value either.  Said explicitly:
+// a reduction on a global address (RED.E.MIN.64).
+__device__ __forceinline__ void hz_red_min(unsigned long long* p, unsigned long long key)
+{
+    asm volatile("red.relaxed.gpu.global.min.u64 [%0], %1;" :: "l"(__cvta_generic_to_global(p)), "l"(key) : "memory");
+}
+
 // depth test + colour write for one covered pixel centre
 __device__ __forceinline__ void hz_fragment(const HzView& P, const HzTri& T, int px, int py)
 {
@@ -413,7 +428,7 @@ __device__ __forceinline__ void hz_fragment(const HzView& P, const HzTri& T, int
     r = fmaxf(fminf(r, 1.0f), 0.0f);
     const unsigned int r8 = (unsigned int)(r * 255.0f + 0.5f);              // F8
     const unsigned long long key = ((unsigned long long)q << 40) | ((unsigned long long)T.id << 8) | r8;
-    atomicMin(&P.vis[(size_t)py * (size_t)(P.x1 - P.x0) + (size_t)(px - P.x0)], key);
+    hz_red_min(&P.vis[(size_t)py * (size_t)(P.x1 - P.x0) + (size_t)(px - P.x0)], key);
 }
 
 // Edge functions E_k(P) = dx_k*(Py - Y_k) - dy_k*(Px - X_k) on the snapped positions (F3); an edge owns its
@@ -904,14 +919,15 @@ k_near(const HzView* __restrict__ V)
     }
 }
 
-cudaError_t hz_launch_near(const HzView& v, const HzView* d_v, cudaStream_t stream)
+cudaError_t hz_launch_near(const HzView& v, const HzView* d_v, int nviews, cudaStream_t stream)
 {
     const int side = min(2 * v.near_rings + 1, v.nt) * HZ_TILE_BLOCKS;
     const int nblocks = side * side;
     int ctas = (nblocks + HZ_WARPS_PER_CTA - 1) / HZ_WARPS_PER_CTA;
-    if(ctas > 148 * 8) ctas = 148 * 8;
+    const int cap = max(148 * 8 / max(nviews, 1), 37);
+    if(ctas > cap) ctas = cap;
     if(ctas < 1) ctas = 1;
-    return hz_launch(k_near, dim3(ctas), dim3(HZ_WARPS_PER_CTA * 32), stream, d_v);
+    return hz_launch(k_near, dim3(ctas, (unsigned)nviews), dim3(HZ_WARPS_PER_CTA * 32), stream, d_v);
 }
 
 // ================================================================================================
@@ -1193,14 +1209,14 @@ k_raster(const HzView* __restrict__ V)
     if(P.stats && lane == 0 && n_big) atomicAdd(P.stats + HZ_STAT_BIG_ENTRIES, n_big);
 }
 
-cudaError_t hz_launch_raster(const HzView& v, const HzView* d_v, cudaStream_t stream)
+cudaError_t hz_launch_raster(const HzView& v, const HzView* d_v, int nviews, cudaStream_t stream)
 {
-    return hz_launch(k_raster, dim3(hz_grid(v, 6)), dim3(256), stream, d_v);
+    return hz_launch(k_raster, dim3(hz_grid(v, 6, nviews), (unsigned)nviews), dim3(256), stream, d_v);
 }
 
 // `worst_case`: size the tile kernel for any eye position (a CUDA graph is captured once per context and replayed
 // for every view); otherwise for this view's eye tile, and nothing is launched if the band is empty.
-cudaError_t hz_launch_band(const HzView& v, const HzView* d_v, bool worst_case, cudaStream_t stream, int* launches)
+cudaError_t hz_launch_band(const HzView& v, const HzView* d_v, int nviews, bool worst_case, cudaStream_t stream, int* launches)
 {
     *launches = 0;
     const int rmax = worst_case ? v.nt - 1
@@ -1209,12 +1225,13 @@ cudaError_t hz_launch_band(const HzView& v, const HzView* d_v, bool worst_case, 
     if(v.ring_lo >= ring_hi) return cudaSuccess;
     const long long ntiles = (long long)(2 * ring_hi - 1) * (2 * ring_hi - 1) - (long long)(2 * v.ring_lo - 1) * (2 * v.ring_lo - 1);
     long long ctas = (ntiles + 255) / 256;
-    if(ctas > (long long)hz_grid(v, 8)) ctas = hz_grid(v, 8);
+    if(ctas > (long long)hz_grid(v, 8, nviews)) ctas = hz_grid(v, 8, nviews);
+    const unsigned int ny = (unsigned int)nviews;
     cudaError_t e;
-    if((e = hz_launch(k_tiles,  dim3((unsigned)ctas), dim3(256), stream, d_v)) != cudaSuccess) return e;
-    if((e = hz_launch(k_blocks, dim3(hz_grid(v, 8)), dim3(256), stream, d_v)) != cudaSuccess) return e;
-    if((e = hz_launch(k_mesh,   dim3(hz_grid(v, 4)), dim3(HZ_WARPS_PER_CTA * 32), stream, d_v)) != cudaSuccess) return e;
-    if((e = hz_launch(k_raster, dim3(hz_grid(v, 6)), dim3(256), stream, d_v)) != cudaSuccess) return e;
+    if((e = hz_launch(k_tiles,  dim3((unsigned)ctas, ny), dim3(256), stream, d_v)) != cudaSuccess) return e;
+    if((e = hz_launch(k_blocks, dim3(hz_grid(v, 8, nviews), ny), dim3(256), stream, d_v)) != cudaSuccess) return e;
+    if((e = hz_launch(k_mesh,   dim3(hz_grid(v, 4, nviews), ny), dim3(HZ_WARPS_PER_CTA * 32), stream, d_v)) != cudaSuccess) return e;
+    if((e = hz_launch(k_raster, dim3(hz_grid(v, 6, nviews), ny), dim3(256), stream, d_v)) != cudaSuccess) return e;
     *launches = 4;
     return cudaSuccess;
 }
@@ -1271,9 +1288,9 @@ k_big(const HzView* __restrict__ V)
     }
 }
 
-cudaError_t hz_launch_big(const HzView& v, const HzView* d_v, cudaStream_t stream)
+cudaError_t hz_launch_big(const HzView& v, const HzView* d_v, int nviews, cudaStream_t stream)
 {
-    return hz_launch(k_big, dim3(hz_grid(v, 8)), dim3(256), stream, d_v);
+    return hz_launch(k_big, dim3(hz_grid(v, 8, nviews), (unsigned)nviews), dim3(256), stream, d_v);
 }
 
 // ================================================================================================
@@ -1407,18 +1424,19 @@ bool hz_resolve_is_vectorisable(const HzView& v)
     return true;
 }
 
-cudaError_t hz_launch_resolve(const HzView& v, const HzView* d_v, cudaStream_t stream)
+// every view of one launch must pass the same hz_resolve_is_vectorisable() (the caller checks)
+cudaError_t hz_launch_resolve(const HzView& v, const HzView* d_v, int nviews, cudaStream_t stream)
 {
     const int Wt = v.x1 - v.x0;
     if(hz_resolve_is_vectorisable(v))
     {
         const long long n = (long long)(Wt / 4) * v.H;
-        return hz_launch(k_resolve4, dim3((unsigned)((n + 255) / 256)), dim3(256), stream, d_v);
+        return hz_launch(k_resolve4, dim3((unsigned)((n + 255) / 256), (unsigned)nviews), dim3(256), stream, d_v);
     }
     else
     {
         const long long n = (long long)Wt * v.H;
-        return hz_launch(k_resolve1, dim3((unsigned)((n + 255) / 256)), dim3(256), stream, d_v);
+        return hz_launch(k_resolve1, dim3((unsigned)((n + 255) / 256), (unsigned)nviews), dim3(256), stream, d_v);
     }
 }
 

@@ -100,6 +100,11 @@ bool horizonator_set_earth_curvature(const horizonator_context_t* ctx, bool on, 
  * that are too wide for another reason stay dropped. */
 bool horizonator_set_seam_wrap(const horizonator_context_t* ctx, bool on);
 
+/* Reads the HORIZONATOR_* tuning variables again -- they are otherwise read once, by
+ * horizonator_init() -- after waiting for everything the context has in flight.  Variables that are not set
+ * go back to their defaults.  For parameter sweeps inside one process; the images do not depend on them. */
+bool horizonator_reload_tunables(const horizonator_context_t* ctx);
+
 /* Page-locked host memory for output buffers.  horizonator_render_offscreen() and
  * horizonator_render_batch() accept any host pointer; into memory from this allocator (or any
  * other CUDA-registered host memory) the results arrive by DMA at PCIe speed, into ordinary

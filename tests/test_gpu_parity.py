@@ -372,16 +372,60 @@ def test_overflow_paths_and_tunables_do_not_change_the_image(hz, tiles_c1, env, 
 
 
 def test_batch_with_more_windows_than_table_slots(hz, tiles_c1):
-    """More distinct azimuth spans in one batch than cached per-row tangent tables: the batch falls back to one view
-    at a time and still equals the loop of single renders."""
+    """Many distinct azimuth spans in one batch (each needs its own per-row tangent table; round 1 kept 8 in a shared
+    cache that a batch could overrun): the batch still equals the loop of single renders."""
     W, H, R = 400, 80, 150
     h = hz.horizonator(C1_LAT, C1_LON, W, H, dir_dems=tiles_c1, render_radius_cells=R)
     h.set_zextents(100., 50000.)
-    views = [(C1_LAT, C1_LON, -30.0 - k, 30.0 + 2 * k) for k in range(11)]
+    views = [(C1_LAT, C1_LON, -30.0 - k, 30.0 + 2 * k) for k in range(35)]
     bi, br = h.render_batch(views)
     for k, (la, lo, a0, a1) in enumerate(views):
         wi, wr = h.render(a0, a1, lat=la, lon=lo, zfar=50000.)
         assert np.array_equal(bi[k], wi) and np.array_equal(br[k], wr), k
+
+
+@pytest.mark.parametrize("lanes,sets", [(16, 2), (5, 3), (64, 1), (1, 1)])
+def test_ragged_mixed_batch_equals_single_renders(hz, tiles_c1, lanes, sets):
+    """A batch is rendered in chunks by launches with a view dimension: more views than one chunk holds, a ragged last
+    chunk, wide and zoomed-in windows (different chain shapes) and explicit eye heights in one call -- every view must
+    equal its single render bit for bit, whatever the chunking."""
+    torch = _torch_cuda()
+    W, H, R = 480, 96, 180
+    h = hz.horizonator(C1_LAT, C1_LON, W, H, dir_dems=tiles_c1, render_radius_cells=R)
+    h.set_zextents(100., 60000.)
+    h.reload_tunables(HORIZONATOR_LANES=lanes, HORIZONATOR_SETS=sets)
+    rs = np.random.RandomState(5)
+    views = []
+    for k in range(37):
+        la, lo = C1_LAT + rs.uniform(-0.05, 0.05), C1_LON + rs.uniform(-0.05, 0.05)
+        c = rs.uniform(-180, 180)
+        half = (180.0, 45.0, 6.0)[k % 3]
+        z = -1.0 if k % 4 else float(rs.uniform(800, 3000))
+        views.append((la, lo, c - half, c + half - (0.1 if half == 180.0 else 0.0), z))
+    di = torch.empty((len(views), H, W, 3), dtype=torch.uint8, device="cuda")
+    dr = torch.empty((len(views), H, W), dtype=torch.float32, device="cuda")
+    for rep in range(2):        # the second pass replays the captured graphs
+        di.zero_(); dr.zero_()
+        h.render_batch_device(views, di.data_ptr(), dr.data_ptr(), torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        bi, br = di.cpu().numpy(), dr.cpu().numpy()
+        hi, hr = h.render_batch(views)
+        assert np.array_equal(hi, bi) and np.array_equal(hr, br)
+        for k, (la, lo, a0, a1, z) in enumerate(views):
+            h.move(la, lo, viewer_z=None if z < 0 else z)
+            h.pan_zoom(a0, a1)
+            wi = hz.pinned_array((H, W, 3), np.uint8); wr = hz.pinned_array((H, W), np.float32)
+            h.render_into(wi, wr)
+            assert np.array_equal(bi[k], wi) and np.array_equal(br[k], wr), (rep, k)
+    h.reload_tunables(HORIZONATOR_LANES=None, HORIZONATOR_SETS=None)
+    # image only / ranges only
+    h.render_batch_device(views[:7], di.data_ptr(), 0, torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    assert np.array_equal(di[:7].cpu().numpy(), bi[:7])
+    dr.zero_()
+    h.render_batch_device(views[:7], 0, dr.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    assert np.array_equal(dr[:7].cpu().numpy(), br[:7])
 
 
 # ------------------------------------------------------------------------------------------ opt-in accuracy mode
