@@ -779,78 +779,143 @@ __device__ __forceinline__ unsigned int hz_warp_sum(unsigned int v)
     return v;
 }
 
-// height of the vertex lane `lane` (< 25) projects for block (bj,bi): fetched apart from the meshing so that the
-// caller can have the next block's DRAM reads in flight while it works on the current one
-__device__ __forceinline__ float hz_block_vertex_z(const HzView& P, int bj, int bi, int lane)
-{
-    if(lane >= 25) return 0.f;
-    const int r = lane / 5, c = lane - 5 * r;
-    const int vj = min(bj * HZ_BLOCK_CELLS + r, P.N - 1), vi = min(bi * HZ_BLOCK_CELLS + c, P.N - 1);
-    return (float)__ldg(P.mosaic + (size_t)vj * P.pitch + vi);
-}
-
-// What a warp carries while it meshes blocks: 25 snapped vertices of the current block and the numbers of the
-// triangles that passed the exact tests but have not been written to the stage's triangle list yet.
+// A warp meshes HZ_MESH_GROUP blocks per trip: their 5x5 vertices are projected as ONE list of up to 125, in 4 rounds
+// of 32 lanes (a block at a time would leave 7 of 32 lanes idle while its 25 vertices are projected, and pay the
+// loop's fixed cost five times), then each block's 32 triangles are tested with lane = triangle.
+#define HZ_MESH_GROUP  5
+#define HZ_MESH_ROUNDS 4           /* ceil(5 * 25 / 32) */
 #define HZ_STAGE_SLOTS 64          /* < 32 pending + at most 32 new per block */
 struct HzMeshWarp
 {
-    HzLaneVtx    verts[25];
-    unsigned int stage[HZ_STAGE_SLOTS];
+    HzLaneVtx    verts[HZ_MESH_GROUP * 25];
+    unsigned int stage[HZ_STAGE_SLOTS];       // triangles that passed the exact tests, not yet in the stage's list
 };
 
-// writes stage[0..count) to the triangle list with one atomic; all lanes call
-__device__ __forceinline__ void hz_stage_flush(const HzView& P, const unsigned int* stage, int count, int lane)
+// Which vertex lane `lane` handles in round `round` of a group: block k of the group (blocks are bj << 16 | bi,
+// lane k of `ids` holds block k), mesh row vj, mesh column vi.  False beyond the group's last vertex.  All lanes call.
+__device__ __forceinline__ bool
+hz_group_vertex(const HzView& P, unsigned int ids, int nblk, int lane, int round, int& v, int& vj, int& vi)
 {
-    if(count == 0) return;
+    v = round * 32 + lane;
+    const int k = min(v / 25, HZ_MESH_GROUP - 1), idx = v - 25 * k;
+    const unsigned int id = __shfl_sync(0xffffffffu, ids, k);
+    const int r = idx / 5, c = idx - 5 * r;
+    vj = min((int)(id >> 16) * HZ_BLOCK_CELLS + r, P.N - 1);
+    vi = min((int)(id & 0xFFFFu) * HZ_BLOCK_CELLS + c, P.N - 1);
+    return v < nblk * 25;
+}
+
+// heights of the vertices this lane projects for a group: fetched apart from the meshing so that the caller can have
+// the next group's DRAM reads in flight while it works on the current one
+struct HzGroupZ { float z[HZ_MESH_ROUNDS]; };
+
+__device__ __forceinline__ HzGroupZ hz_group_heights(const HzView& P, unsigned int ids, int nblk, int lane)
+{
+    HzGroupZ g;
+    #pragma unroll
+    for(int round = 0; round < HZ_MESH_ROUNDS; round++)
+    {
+        int v, vj, vi;
+        g.z[round] = hz_group_vertex(P, ids, nblk, lane, round, v, vj, vi)
+                         ? (float)__ldg(P.mosaic + (unsigned int)vj * (unsigned int)P.pitch + (unsigned int)vi) : 0.f;
+    }
+    return g;
+}
+
+// Writes stage[0..count) to the triangle list with one atomic; all lanes call.  Returns how many did NOT fit (list
+// full): those are moved to the front of the stage, and the caller stops staging and draws them itself (hz_mesh_slow).
+// No call to the slow path from here: a call inside the meshing loop makes ptxas keep that loop's registers in local
+// memory around it.
+__device__ __forceinline__ int hz_stage_flush(const HzView& P, unsigned int* stage, int count, int lane)
+{
+    if(count == 0) return 0;
     unsigned int base = 0;
     if(lane == 0) base = atomicAdd(P.tri_count, (unsigned int)count);
     base = __shfl_sync(0xffffffffu, base, 0);
-    for(int k = lane; k < count; k += 32)
-    {
-        if(base + k < P.tri_capacity) P.tri_queue[base + k] = stage[k];
-        else                          hz_draw_slow(P, stage[k], -1);  // list full
-    }
+    const int fits = (int)min((unsigned int)count, P.tri_capacity - min(base, P.tri_capacity));
+    for(int k = lane; k < fits; k += 32) P.tri_queue[base + k] = stage[k];
+    if(fits == count) return 0;
+    __syncwarp();
+    // (count <= 64: two strided passes move the rest down without overlap problems, reads before writes)
+    const unsigned int m0 = (fits + lane < count) ? stage[fits + lane] : 0u, m1 = (fits + 32 + lane < count) ? stage[fits + 32 + lane] : 0u;
+    __syncwarp();
+    if(fits + lane < count) stage[lane] = m0;
+    if(fits + 32 + lane < count) stage[32 + lane] = m1;
+    __syncwarp();
+    return count - fits;
 }
 
-// The 32 triangles of block (bj,bi): lanes 0..24 project one vertex each (height z), then lane = triangle; the
-// numbers of the triangles that pass the exact integer tests go to the warp's stage, which is written out whenever
-// it holds 32 or more.  `count` is the stage's fill (the same in all lanes).  Returns how many passed.
-__device__ __forceinline__ unsigned int
-hz_mesh_block(const HzView& P, int bj, int bi, int lane, float z, HzMeshWarp& M, int& count)
+// Projects the vertices of the group's nblk blocks (ids / Z as above) into M.verts.  All lanes call.
+__device__ __forceinline__ void
+hz_group_project(const HzView& P, unsigned int ids, int nblk, int lane, const HzGroupZ& Z, HzMeshWarp& M)
+{
+    const float halfW = 0.5f * (float)P.W, halfH = 0.5f * (float)P.H;
+    #pragma unroll 1            // one projection's registers at a time (unrolled, ptxas interleaves the four and spills)
+    for(int round = 0; round < HZ_MESH_ROUNDS; round++)
+    {
+        int v, vj, vi;
+        const float z = round == 0 ? Z.z[0] : round == 1 ? Z.z[1] : round == 2 ? Z.z[2] : Z.z[3];
+        if(hz_group_vertex(P, ids, nblk, lane, round, v, vj, vi))
+            M.verts[v] = hz_lane_vertex(P, __ldg(P.e_tab + vi), __ldg(P.n_tab + vj), z, halfW, halfH);
+    }
+    __syncwarp();
+}
+
+// The triangles of blocks k0 .. nblk-1 of a projected group, lane = triangle: the numbers of those that pass the exact
+// integer tests go to the warp's stage, which is written to the stage's triangle list whenever it holds 32 or more
+// (`count` = the stage's fill, the same in all lanes; `passed` counts them).  Returns -1 -- or, if the list turned
+// out to be full, the block to resume at (<= nblk): the stage then holds `count` (< 64) triangles that the caller must
+// draw itself, and it goes on with SLOW = true, where every triangle that passes is drawn on the spot (hz_draw_slow).  That
+// call is kept out of the fast variant: a call inside the meshing loop makes ptxas keep the loop's registers in local
+// memory around it.
+template <bool SLOW>
+__device__ __forceinline__ int
+hz_group_triangles(const HzView& P, unsigned int ids, int k0, int nblk, int lane, HzMeshWarp& M, int& count, unsigned int& passed)
 {
     const int N = P.N;
-    const float halfW = 0.5f * (float)P.W, halfH = 0.5f * (float)P.H;
-    if(lane < 25)
-    {
-        const int r = lane / 5, c = lane - 5 * r;
-        const int vj = min(bj * HZ_BLOCK_CELLS + r, N - 1), vi = min(bi * HZ_BLOCK_CELLS + c, N - 1);
-        M.verts[lane] = hz_lane_vertex(P, __ldg(P.e_tab + vi), __ldg(P.n_tab + vj), z, halfW, halfH);
-    }
-    __syncwarp();
+    // cell (cr, cc) of the block, its lower-left vertex a, upper-right vertex d, and the third one
+    // lib:496-508: even triangle (j,i),(j+1,i+1),(j+1,i) ; odd triangle (j,i),(j,i+1),(j+1,i+1)
     const int cell = lane >> 1, cr = cell >> 2, cc = cell & 3;
-    const int j = bj * HZ_BLOCK_CELLS + cr, i = bi * HZ_BLOCK_CELLS + cc;
-    bool on = false;
-    if(j < N - 1 && i < N - 1)
+    const bool odd = (lane & 1) != 0;
+    const int ia = cr * 5 + cc, id_ = ia + 6, io = odd ? ia + 1 : ia + 5;
+    for(int k = k0; k < nblk; k++)
     {
-        // lib:496-508: even triangle (j,i),(j+1,i+1),(j+1,i) ; odd triangle (j,i),(j,i+1),(j+1,i+1)
-        const HzLaneVtx a = M.verts[cr * 5 + cc];
-        const HzLaneVtx d = M.verts[(cr + 1) * 5 + cc + 1];
-        if((lane & 1) == 0) on = hz_tri_alive(P, a, d, M.verts[(cr + 1) * 5 + cc]);
-        else                on = hz_tri_alive(P, a, M.verts[cr * 5 + cc + 1], d);
-    }
-    const unsigned int ballot = __ballot_sync(0xffffffffu, on);     // also orders the reads of verts before the next block
-    if(ballot == 0) return 0;
-    if(on) M.stage[count + __popc(ballot & ((1u << lane) - 1u))] =
-               2u * ((unsigned int)j * (unsigned int)(N - 1) + (unsigned int)i) + (unsigned int)(lane & 1);
-    count += __popc(ballot);
-    __syncwarp();
-    if(count >= 32)
-    {
-        hz_stage_flush(P, M.stage, count, lane);
-        count = 0;
+        const unsigned int id = __shfl_sync(0xffffffffu, ids, k);
+        const int j = (int)(id >> 16) * HZ_BLOCK_CELLS + cr, i = (int)(id & 0xFFFFu) * HZ_BLOCK_CELLS + cc;
+        bool on = false;
+        if(j < N - 1 && i < N - 1)
+        {
+            // (one call with selected operands: two calls under the odd/even branch would run with half the lanes each)
+            const HzLaneVtx* vb = M.verts + 25 * k;
+            const HzLaneVtx a = vb[ia], d = vb[id_], o = vb[io];
+            on = hz_tri_alive(P, a, odd ? o : d, odd ? d : o);
+        }
+        const unsigned int ballot = __ballot_sync(0xffffffffu, on);
+        if(ballot == 0) continue;
+        const unsigned int tri = 2u * ((unsigned int)j * (unsigned int)(N - 1) + (unsigned int)i) + (unsigned int)(lane & 1);
+        passed += (unsigned int)__popc(ballot);
+        if(SLOW)
+        {
+            if(on) hz_draw_slow(P, tri, -1);
+            continue;
+        }
+        if(on) M.stage[count + __popc(ballot & ((1u << lane) - 1u))] = tri;
+        count += __popc(ballot);
         __syncwarp();
+        if(count >= 32)
+        {
+            count = hz_stage_flush(P, M.stage, count, lane);
+            __syncwarp();
+            if(count > 0) return k + 1;         // list full
+        }
     }
-    return (unsigned int)__popc(ballot);
+    return -1;
+}
+
+// What a meshing warp does once the stage's list is full (never on the normal path): draws what is staged.
+__device__ __noinline__ void hz_stage_draw_slow(const HzView& P, const unsigned int* stage, int count)
+{
+    for(int q = (int)(threadIdx.x & 31u); q < count; q += 32) hz_draw_slow(P, stage[q], -1);
 }
 
 // end of a meshing kernel: the leftovers of all warps of the CTA go out with one atomic.  Every thread calls.
@@ -872,7 +937,7 @@ hz_stage_flush_cta(const HzView& P, const HzMeshWarp& M, int count, unsigned int
     for(int k = lane; k < count; k += 32)
     {
         if(base + k < P.tri_capacity) P.tri_queue[base + k] = M.stage[k];
-        else                          hz_draw_slow(P, M.stage[k], -1);
+        else                          hz_draw_slow(P, M.stage[k], -1);     // list full; after the meshing loop, so harmless
     }
 }
 
@@ -901,14 +966,37 @@ k_near(const HzView* __restrict__ V)
     const int nbi = bi1 - bi0, nblocks = nbi * (bj1 - bj0);
     const int nwarps = gridDim.x * HZ_WARPS_PER_CTA;
     // no conservative tests here: next to the eye nearly every block shows, and what does not falls to the exact
-    // integer tests of hz_mesh_block anyway
+    // integer tests of hz_mesh_group anyway
     unsigned int n_blocks = 0, n_tris = 0;
-    int count = 0;
-    for(int b = blockIdx.x * HZ_WARPS_PER_CTA + wib; b < nblocks; b += nwarps)
+    int count = 0, b = (blockIdx.x * HZ_WARPS_PER_CTA + wib) * HZ_MESH_GROUP, k_resume = -1;
+    HzMeshWarp& M = s_warp[wib];
+    for(; b < nblocks && k_resume < 0; b += nwarps * HZ_MESH_GROUP)
     {
-        n_blocks++;
-        const int bj = bj0 + b / nbi, bi = bi0 + b % nbi;
-        n_tris += hz_mesh_block(P, bj, bi, lane, hz_block_vertex_z(P, bj, bi, lane), s_warp[wib], count);
+        const int nblk = min(HZ_MESH_GROUP, nblocks - b), bk = min(b + lane, nblocks - 1);
+        const unsigned int ids = ((unsigned int)(bj0 + bk / nbi) << 16) | (unsigned int)(bi0 + bk % nbi);
+        n_blocks += (unsigned int)nblk;
+        hz_group_project(P, ids, nblk, lane, hz_group_heights(P, ids, nblk, lane), M);
+        k_resume = hz_group_triangles<false>(P, ids, 0, nblk, lane, M, count, n_tris);
+        __syncwarp();
+    }
+    if(k_resume >= 0)
+    {
+        // the triangle list is full: this warp draws everything else it finds itself (b already points at the next group)
+        hz_stage_draw_slow(P, M.stage, count);
+        count = 0;
+        b -= nwarps * HZ_MESH_GROUP;
+        for(bool first = true; b < nblocks; b += nwarps * HZ_MESH_GROUP, first = false)
+        {
+            const int nblk = min(HZ_MESH_GROUP, nblocks - b), bk = min(b + lane, nblocks - 1);
+            const unsigned int ids = ((unsigned int)(bj0 + bk / nbi) << 16) | (unsigned int)(bi0 + bk % nbi);
+            if(!first)
+            {
+                n_blocks += (unsigned int)nblk;
+                hz_group_project(P, ids, nblk, lane, hz_group_heights(P, ids, nblk, lane), M);
+            }
+            hz_group_triangles<true>(P, ids, first ? k_resume : 0, nblk, lane, M, count, n_tris);
+            __syncwarp();
+        }
     }
     hz_stage_flush_cta(P, s_warp[wib], count, &s_total, &s_base);
     if(P.stats && lane == 0 && n_blocks)
@@ -923,7 +1011,7 @@ cudaError_t hz_launch_near(const HzView& v, const HzView* d_v, int nviews, cudaS
 {
     const int side = min(2 * v.near_rings + 1, v.nt) * HZ_TILE_BLOCKS;
     const int nblocks = side * side;
-    int ctas = (nblocks + HZ_WARPS_PER_CTA - 1) / HZ_WARPS_PER_CTA;
+    int ctas = (nblocks + HZ_WARPS_PER_CTA * HZ_MESH_GROUP - 1) / (HZ_WARPS_PER_CTA * HZ_MESH_GROUP);
     const int cap = max(148 * 8 / max(nviews, 1), 37);
     if(ctas > cap) ctas = cap;
     if(ctas < 1) ctas = 1;
@@ -1120,32 +1208,46 @@ k_mesh(const HzView* __restrict__ V)
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const unsigned int n = *P.block_count;
     const unsigned int nwarps = gridDim.x * HZ_WARPS_PER_CTA;
-    unsigned int b = blockIdx.x * HZ_WARPS_PER_CTA + wib;
-    int bj = 0, bi = 0;
-    float z = 0.f;
-    if(b < n)
-    {
-        const unsigned int id = P.block_queue[b];
-        bj = (int)(id >> 16); bi = (int)(id & 0xFFFFu);
-        z = hz_block_vertex_z(P, bj, bi, lane);
-    }
+    unsigned int b = (blockIdx.x * HZ_WARPS_PER_CTA + wib) * HZ_MESH_GROUP;
+    // lane k holds the k-th block of the group
+    unsigned int ids = (b + lane < n && lane < HZ_MESH_GROUP) ? P.block_queue[b + lane] : 0u;
+    HzGroupZ Z = {};
+    if(b < n) Z = hz_group_heights(P, ids, (int)min((unsigned int)HZ_MESH_GROUP, n - b), lane);
     unsigned int n_meshed = 0, n_tris = 0;
-    int count = 0;
-    while(b < n)
+    int count = 0, k_resume = -1;
+    HzMeshWarp& M = s_warp[wib];
+    while(b < n && k_resume < 0)
     {
-        // next block's queue entry and heights first: their latency hides behind this block's arithmetic
-        const unsigned int b_next = b + nwarps;
-        int bj_next = 0, bi_next = 0;
-        float z_next = 0.f;
-        if(b_next < n)
+        // next group's queue entries and heights first: their latency hides behind this group's arithmetic
+        const unsigned int b_next = b + nwarps * HZ_MESH_GROUP;
+        const unsigned int ids_next = (b_next + lane < n && lane < HZ_MESH_GROUP) ? P.block_queue[b_next + lane] : 0u;
+        HzGroupZ Z_next = {};
+        if(b_next < n) Z_next = hz_group_heights(P, ids_next, (int)min((unsigned int)HZ_MESH_GROUP, n - b_next), lane);
+        const int nblk = (int)min((unsigned int)HZ_MESH_GROUP, n - b);
+        hz_group_project(P, ids, nblk, lane, Z, M);
+        k_resume = hz_group_triangles<false>(P, ids, 0, nblk, lane, M, count, n_tris);
+        __syncwarp();
+        n_meshed += (unsigned int)nblk;
+        if(k_resume < 0) { b = b_next; ids = ids_next; Z = Z_next; }
+    }
+    if(k_resume >= 0)
+    {
+        // the triangle list is full: this warp draws everything else it finds itself (b, ids: the group it stopped in,
+        // already projected)
+        hz_stage_draw_slow(P, M.stage, count);
+        count = 0;
+        for(bool first = true; b < n; b += nwarps * HZ_MESH_GROUP, first = false)
         {
-            const unsigned int id = P.block_queue[b_next];
-            bj_next = (int)(id >> 16); bi_next = (int)(id & 0xFFFFu);
-            z_next = hz_block_vertex_z(P, bj_next, bi_next, lane);
+            const int nblk = (int)min((unsigned int)HZ_MESH_GROUP, n - b);
+            if(!first)
+            {
+                ids = (b + lane < n && lane < HZ_MESH_GROUP) ? P.block_queue[b + lane] : 0u;
+                hz_group_project(P, ids, nblk, lane, hz_group_heights(P, ids, nblk, lane), M);
+                n_meshed += (unsigned int)nblk;
+            }
+            hz_group_triangles<true>(P, ids, first ? k_resume : 0, nblk, lane, M, count, n_tris);
+            __syncwarp();
         }
-        n_tris += hz_mesh_block(P, bj, bi, lane, z, s_warp[wib], count);
-        n_meshed++;
-        b = b_next; bj = bj_next; bi = bi_next; z = z_next;
     }
     hz_stage_flush_cta(P, s_warp[wib], count, &s_total, &s_base);
     if(P.stats && lane == 0 && n_meshed)

@@ -53,6 +53,8 @@ def main():
     ap.add_argument("--out", default=None)
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--batches", default="16,64")
+    ap.add_argument("--once", type=int, default=0, help="for ncu: after two warm-up calls, ONE call of this many "
+                    "panoramas of the benchmark viewpoint, nothing else")
     ap.add_argument("configs", nargs="*", default=[""])
     a = ap.parse_args()
     tiles = synth.config2_tiles(os.environ.get("HZ_BENCH_TILES", "/tmp/hz_tiles_c2"))
@@ -61,6 +63,12 @@ def main():
     Bmax = max(int(b) for b in a.batches.split(","))
     d_img = torch.empty((Bmax, 600, 3600, 3), dtype=torch.uint8, device="cuda")
     d_rng = torch.empty((Bmax, 600, 3600), dtype=torch.float32, device="cuda")
+    if a.once:
+        v = [(C2_LAT, C2_LON, -180.05, 179.95)] * a.once
+        for _ in range(3):
+            h.render_batch_device(v, d_img.data_ptr(), d_rng.data_ptr(), torch.cuda.current_stream().cuda_stream)
+            torch.cuda.synchronize()
+        return
     grid = grid_views()
     out = open(a.out, "a") if a.out else None
     for cfg in a.configs:
