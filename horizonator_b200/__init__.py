@@ -15,7 +15,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIBRARY_PATH = os.path.join(_HERE, "lib", "libhorizonator.so")
+# HORIZONATOR_LIBRARY: another build of the same library (A/B comparisons of compile-time variants); still in-tree
+LIBRARY_PATH = os.environ.get("HORIZONATOR_LIBRARY") or os.path.join(_HERE, "lib", "libhorizonator.so")
 
 HORIZONATOR_ZNEAR_DEFAULT = 100.0   # include/horizonator.h
 HORIZONATOR_ZFAR_DEFAULT = 40000.0

@@ -40,9 +40,10 @@ def find_nvcc():
     raise RuntimeError("nvcc not found: the CUDA renderer cannot be built (there is no CPU fallback)")
 
 
-def build_library(force=False, extra_flags=(), verbose=False):
+def build_library(force=False, extra_flags=(), verbose=False, name="libhorizonator.so"):
+    """name: another file name for a compile-time variant (extra_flags), loaded with HORIZONATOR_LIBRARY=<path>."""
     os.makedirs(LIB, exist_ok=True)
-    out = os.path.join(LIB, "libhorizonator.so")
+    out = os.path.join(LIB, name)
     srcs = [os.path.join(CSRC, f) for f in ("hz_kernels.cu", "hz_api.cpp", "hz_dem.cpp")]
     deps = srcs + [os.path.join(CSRC, f) for f in ("hz_device.h", "hz_math.cuh")] + \
         [os.path.join(ROOT, "include", f) for f in ("horizonator.h", "horizonator-batch.h", "dem.h", "util.h")] + \
@@ -52,6 +53,8 @@ def build_library(force=False, extra_flags=(), verbose=False):
         if verbose:
             print(" ".join(cmd))
         subprocess.run(cmd, check=True)
+    if name != "libhorizonator.so":
+        return out
     # the SONAME is libhorizonator.so.0: give the dynamic loader that name too
     link = out + ".0"
     if not os.path.islink(link) and not os.path.exists(link):

@@ -117,7 +117,7 @@ struct Slot
     short2 *d_mm_block = nullptr, *d_mm_tile = nullptr;   // culling pyramid
     int nb = 0, nt = 0;
     int near_rings = 2;
-    int occl_tile_max_pix = 64, occl_block_max_pix = 32, small_max_pix = 16;
+    int occl_tile_max_pix = 64, occl_block_max_pix = 32, small_max_pix = 16, mid_max_pix = 64;
     int grid_percent_single = 150, grid_percent_batch = 200;   // see hz_grid() in hz_kernels.cu
     // Rings (in tiles around the eye's tile) at which the bands end; the last band runs to the edge of the mesh.
     // More bands = more of the mesh culled by what nearer bands drew, but four more kernels each.  A lone view is
@@ -286,8 +286,8 @@ void free_scratch(Scratch& c)
 // everything but the image-sized part (alloc_scratch_target)
 bool alloc_scratch(const Slot& s, Scratch& c)
 {
-    CUDA_TRY(cudaMalloc(&c.d_e, (size_t)s.N * sizeof(float)));
-    CUDA_TRY(cudaMalloc(&c.d_n, (size_t)s.N * sizeof(float)));
+    CUDA_TRY(cudaMalloc(&c.d_e, (size_t)(s.N + HZ_MESH_PAD) * sizeof(float)));
+    CUDA_TRY(cudaMalloc(&c.d_n, (size_t)(s.N + HZ_MESH_PAD) * sizeof(float)));
     CUDA_TRY(cudaMalloc(&c.d_tile_queue, (size_t)s.nt * s.nt * sizeof(uint32_t)));
     CUDA_TRY(cudaMalloc(&c.d_block_queue, (size_t)s.nb * s.nb * sizeof(uint32_t)));
     CUDA_TRY(cudaMalloc(&c.d_counters, N_COUNTERS * sizeof(uint32_t)));
@@ -559,7 +559,7 @@ void fill_view(const Slot& s, const ViewSet& set, const Scratch& sc, const ViewS
     v.tri_queue = sc.d_tri_queue; v.tri_capacity = s.tri_capacity;
     v.bigtri = sc.d_bigtri; v.bigtri_count = sc.d_counters + 3; v.bigtri_capacity = s.bigtri_capacity;
     v.occl_tile_max_pix = s.occl_tile_max_pix; v.occl_block_max_pix = s.occl_block_max_pix;
-    v.small_max_pix = s.small_max_pix;
+    v.small_max_pix = s.small_max_pix; v.mid_max_pix = s.mid_max_pix;
     v.grid_percent = set.batch ? s.grid_percent_batch : s.grid_percent_single;
     v.big_capacity = s.big_capacity;
 
@@ -696,6 +696,7 @@ void read_tunables(Slot& s)
     if(const char* env = getenv("HORIZONATOR_OCCL_TILE_PIX"))  s.occl_tile_max_pix  = atoi(env);
     if(const char* env = getenv("HORIZONATOR_OCCL_BLOCK_PIX")) s.occl_block_max_pix = atoi(env);
     if(const char* env = getenv("HORIZONATOR_SMALL_PIX"))      s.small_max_pix = atoi(env);
+    if(const char* env = getenv("HORIZONATOR_MID_PIX"))        s.mid_max_pix = atoi(env);
     if(const char* env = getenv("HORIZONATOR_GRID_SCALE"))       s.grid_percent_single = atoi(env);
     if(const char* env = getenv("HORIZONATOR_GRID_SCALE_BATCH")) s.grid_percent_batch  = atoi(env);
     // HORIZONATOR_BANDS / HORIZONATOR_BANDS_BATCH: comma-separated rings at which the bands end (lone views / views
@@ -817,7 +818,7 @@ bool horizonator_init(horizonator_context_t* ctx,
         const horizonator_dem_context_t* d = &ctx->dems;
         s->cpd = d->cells_per_deg;
         s->N   = 2 * d->radius_cells;
-        s->pitch = ((s->N + 2) + 63) / 64 * 64;
+        s->pitch = ((s->N + HZ_MESH_PAD) + 63) / 64 * 64;
 
         // raw tiles to the device (16 spare bytes: k_mosaic's aligned 32-bit loads may touch them)
         s->tiles.cpd = s->cpd;
@@ -836,7 +837,10 @@ bool horizonator_init(horizonator_context_t* ctx,
             }
         if(bad) break;
 
-        if(fail(cudaMalloc(&s->d_mosaic, (size_t)s->N * s->pitch * sizeof(int16_t)), "cudaMalloc(mosaic)")) break;
+        // (HZ_MESH_PAD zero rows after the last: see hz_device.h)
+        if(fail(cudaMalloc(&s->d_mosaic, (size_t)(s->N + HZ_MESH_PAD) * s->pitch * sizeof(int16_t)), "cudaMalloc(mosaic)")) break;
+        if(fail(cudaMemsetAsync(s->d_mosaic + (size_t)s->N * s->pitch, 0, (size_t)HZ_MESH_PAD * s->pitch * sizeof(int16_t), s->stream),
+                "cudaMemset(mosaic)")) break;
         s->nb = (s->N - 1 + HZ_BLOCK_CELLS - 1) / HZ_BLOCK_CELLS;
         s->nt = (s->N - 1 + HZ_TILE_CELLS - 1) / HZ_TILE_CELLS;
         read_tunables(*s);
@@ -1352,7 +1356,7 @@ bool horizonator_reload_tunables(const horizonator_context_t* ctx)
     {
         const Slot d;       // the defaults
         s->near_rings = d.near_rings; s->occl_tile_max_pix = d.occl_tile_max_pix; s->occl_block_max_pix = d.occl_block_max_pix;
-        s->small_max_pix = d.small_max_pix; s->grid_percent_single = d.grid_percent_single;
+        s->small_max_pix = d.small_max_pix; s->mid_max_pix = d.mid_max_pix; s->grid_percent_single = d.grid_percent_single;
         s->grid_percent_batch = d.grid_percent_batch; s->bands_single = d.bands_single; s->bands_batch = d.bands_batch;
         s->use_graphs = d.use_graphs; s->views_per_set = d.views_per_set; s->n_sets_max = d.n_sets_max;
     }

@@ -32,6 +32,10 @@ constexpr int HZ_MAX_OUT     = 8;   // destinations of one resolve (ranks of a w
 constexpr int HZ_BLOCK_CELLS = 4;
 constexpr int HZ_TILE_BLOCKS = 8;
 constexpr int HZ_TILE_CELLS  = HZ_BLOCK_CELLS * HZ_TILE_BLOCKS;
+// The blocks along the far edges of the mesh may reach up to 3 vertices beyond its last row/column: the mosaic has this
+// many extra (zero) rows, its pitch covers as many extra columns, and the axis tables as many extra entries, so that the
+// meshing kernels read those vertices without clamping (their triangles are left out).
+constexpr int HZ_MESH_PAD    = 4;
 
 // ---- counters a render leaves behind (diagnostics; bench.py and the tests read them) -----------
 enum HzStat
@@ -54,11 +58,11 @@ enum HzStat
 struct HzView
 {
     // terrain (resident in HBM): N x N int16, row j = north index, column i = east index
-    const int16_t* mosaic;
+    const int16_t* mosaic;       // [N + HZ_MESH_PAD][pitch]
     int   N;                     // 2R
-    int   pitch;                 // elements per row (multiple of 64)
-    float* e_tab;                // [N] metres east of the eye for column i   (vertex.glsl:128-130)
-    float* n_tab;                // [N] metres north of the eye for row j
+    int   pitch;                 // elements per row (multiple of 64, >= N + HZ_MESH_PAD)
+    float* e_tab;                // [N + HZ_MESH_PAD] metres east of the eye for column i   (vertex.glsl:128-130)
+    float* n_tab;                // [N + HZ_MESH_PAD] metres north of the eye for row j
     const short2* mm_block;      // [nb][nb] (min,max) per block
     const short2* mm_tile;       // [nt][nt] (min,max) per tile
     int   nb, nt;
@@ -99,6 +103,7 @@ struct HzView
     int occl_tile_max_pix, occl_block_max_pix;   // largest screen box one thread checks against the visibility buffer
     int grid_percent;            // host only: scale of the device-counted kernels' grids (hz_grid)
     int small_max_pix;           // a lane rasterises bounding boxes up to this many pixels itself; larger ones go to k_big
+    int mid_max_pix;             // ... and up to this many where enough lanes of its warp have one (k_raster)
 
     // triangles too big for one thread: the set-up triangle goes to the record pool (6 x 16 bytes each), and one
     // (record, sub-box) entry per sub-box of its bounding box to a queue -- one queue for the near pass, one for all

@@ -202,7 +202,8 @@ k_prepare(const HzView* __restrict__ V)
     // vertex.glsl:128-130, operator by operator:
     //   e = (i - viewer_cell_i) * DEG_PER_CELL * Rearth * pi/180. * cos_viewer_lat
     //   n = (j - viewer_cell_j) * DEG_PER_CELL * Rearth * pi/180.
-    for(unsigned int c = tid; c < (unsigned int)P.N; c += nth)
+    // (HZ_MESH_PAD more than the mesh has: the last blocks may hang over its edge, see hz_group_vertex)
+    for(unsigned int c = tid; c < (unsigned int)(P.N + HZ_MESH_PAD); c += nth)
     {
         const float f = (float)(int)c;
         P.e_tab[c] = (f - P.viewer_cell_i) * P.deg_per_cell * HZ_REARTH_F * HZ_PI_F / 180.f * P.cos_viewer_lat;
@@ -617,9 +618,13 @@ __device__ __forceinline__ unsigned int hz_vis_depth(const HzView& P, int px, in
 // ================================================================================================
 
 #define HZ_WARPS_PER_CTA 8
+#ifndef HZ_MESH_CTAS
+#define HZ_MESH_CTAS 4             /* resident CTAs per SM the meshing kernels are compiled for (register budget) */
+#endif
 #define HZ_BIG_ROWS      4         /* large bounding boxes are cut into sub-boxes of this size for k_big: */
 #define HZ_BIG_COLS      32        /* lane = column, a few rows each (more for very large triangles) */
 #define HZ_BIG_MAX_ENTRIES 64u
+#define HZ_MID_LANES     16        /* lanes of a warp with a middle-sized triangle from which on they draw them themselves */
 #define HZ_BIG_RECOMPUTE   0x80000000u   /* queue entry: .x is a triangle number (set up again), not a record */
 
 struct HzLaneVtx { int X, Y; };
@@ -635,18 +640,20 @@ __device__ __forceinline__ HzLaneVtx hz_lane_vertex(const HzView& P, float e, fl
 }
 
 // the rasteriser's integer tests for one triangle (hz_tri_bounds without the float-only seam/guard tests,
-// which set-up applies; a triangle that fails here cannot produce a fragment there)
+// which set-up applies; a triangle that fails here cannot produce a fragment there).  [x0, x1) x [0, H) = the target;
+// wide: see below.
 __device__ __forceinline__ bool
-hz_tri_alive(const HzView& P, const HzLaneVtx& a, const HzLaneVtx& b, const HzLaneVtx& c)
+hz_tri_alive(int x0, int x1, int H, int wide, const HzLaneVtx& a, const HzLaneVtx& b, const HzLaneVtx& c)
 {
     const int bx0 = min(min(a.X, b.X), c.X), bx1 = max(max(a.X, b.X), c.X);
     const int by0 = min(min(a.Y, b.Y), c.Y), by1 = max(max(a.Y, b.Y), c.Y);
-    const int px0 = (bx0 + 127) >> 8, px1 = (bx1 - 128) >> 8;
-    const int py0 = (by0 + 127) >> 8, py1 = (by1 - 128) >> 8;
-    if(!(px0 <= px1 && py0 <= py1 && px1 >= P.x0 && px0 < P.x1 && py1 >= 0 && py0 < P.H)) return false;
-    // opt-in seam wrap: a triangle about a quarter of the window wide or more may be a seam straddler whose two
-    // copies show at the edges; its facing as it stands says nothing, set-up decides
-    if(P.seam_period > 0.0f && (bx1 - bx0) >= P.W * 64 - 1024) return true;
+    const int px0 = max((bx0 + 127) >> 8, x0), px1 = min((bx1 - 128) >> 8, x1 - 1);
+    const int py0 = max((by0 + 127) >> 8, 0),  py1 = min((by1 - 128) >> 8, H - 1);
+    if(px0 > px1 || py0 > py1) return false;            // no pixel centre of the target inside the bounding box
+    // opt-in seam wrap (wide = W * 64 - 1024 in 1/256 pixel, else never): a triangle about a quarter of the window
+    // wide or more may be a seam straddler whose two copies show at the edges; its facing as it stands says nothing,
+    // set-up decides
+    if(bx1 - bx0 >= wide) return true;
     const long long area = (long long)(b.X - a.X) * (c.Y - a.Y) - (long long)(c.X - a.X) * (b.Y - a.Y);
     return area > 0;
 }
@@ -791,33 +798,50 @@ struct HzMeshWarp
     unsigned int stage[HZ_STAGE_SLOTS];       // triangles that passed the exact tests, not yet in the stage's list
 };
 
-// Which vertex lane `lane` handles in round `round` of a group: block k of the group (blocks are bj << 16 | bi,
-// lane k of `ids` holds block k), mesh row vj, mesh column vi.  False beyond the group's last vertex.  All lanes call.
-__device__ __forceinline__ bool
-hz_group_vertex(const HzView& P, unsigned int ids, int nblk, int lane, int round, int& v, int& vj, int& vi)
+// Which vertex a lane handles in each round of a group, worked out once per kernel: vertex v = 32 * round + lane is
+// vertex (r, c) of the 5x5 of block k = v / 25 of the group, packed as k | r << 8 | c << 16 (k = 7: none).
+struct HzLaneMap { unsigned int code[HZ_MESH_ROUNDS]; };
+
+__device__ __forceinline__ HzLaneMap hz_lane_map(int lane)
 {
-    v = round * 32 + lane;
-    const int k = min(v / 25, HZ_MESH_GROUP - 1), idx = v - 25 * k;
+    HzLaneMap m;
+    #pragma unroll
+    for(int round = 0; round < HZ_MESH_ROUNDS; round++)
+    {
+        const int v = round * 32 + lane, k = v / 25, idx = v - 25 * k, r = idx / 5, c = idx - 5 * r;
+        m.code[round] = k < HZ_MESH_GROUP ? (unsigned int)(k | (r << 8) | (c << 16)) : 7u;
+    }
+    return m;
+}
+
+// Mesh row vj and column vi of the vertex `code` stands for (blocks are bj << 16 | bi; lane k of `ids` holds block k
+// of the group); false beyond the group's last vertex.  All lanes call.  The mosaic and the axis tables are padded
+// (HZ_MESH_PAD), so the vertices of blocks that hang over the mesh's last row/column need no clamping: their triangles
+// are left out later.
+__device__ __forceinline__ bool hz_group_vertex(unsigned int ids, int nblk, unsigned int code, int& vj, int& vi)
+{
+    const int k = (int)(code & 7u);
     const unsigned int id = __shfl_sync(0xffffffffu, ids, k);
-    const int r = idx / 5, c = idx - 5 * r;
-    vj = min((int)(id >> 16) * HZ_BLOCK_CELLS + r, P.N - 1);
-    vi = min((int)(id & 0xFFFFu) * HZ_BLOCK_CELLS + c, P.N - 1);
-    return v < nblk * 25;
+    vj = (int)(id >> 16) * HZ_BLOCK_CELLS + (int)((code >> 8) & 7u);
+    vi = (int)(id & 0xFFFFu) * HZ_BLOCK_CELLS + (int)(code >> 16);
+    return k < nblk;
 }
 
 // heights of the vertices this lane projects for a group: fetched apart from the meshing so that the caller can have
 // the next group's DRAM reads in flight while it works on the current one
 struct HzGroupZ { float z[HZ_MESH_ROUNDS]; };
 
-__device__ __forceinline__ HzGroupZ hz_group_heights(const HzView& P, unsigned int ids, int nblk, int lane)
+__device__ __forceinline__ HzGroupZ hz_group_heights(const HzView& P, unsigned int ids, int nblk, const HzLaneMap& map)
 {
     HzGroupZ g;
+    const int16_t* mosaic = P.mosaic;
+    const unsigned int pitch = (unsigned int)P.pitch;
     #pragma unroll
     for(int round = 0; round < HZ_MESH_ROUNDS; round++)
     {
-        int v, vj, vi;
-        g.z[round] = hz_group_vertex(P, ids, nblk, lane, round, v, vj, vi)
-                         ? (float)__ldg(P.mosaic + (unsigned int)vj * (unsigned int)P.pitch + (unsigned int)vi) : 0.f;
+        int vj, vi;
+        g.z[round] = hz_group_vertex(ids, nblk, map.code[round], vj, vi)
+                         ? (float)__ldg(mosaic + (unsigned int)vj * pitch + (unsigned int)vi) : 0.f;
     }
     return g;
 }
@@ -847,16 +871,19 @@ __device__ __forceinline__ int hz_stage_flush(const HzView& P, unsigned int* sta
 
 // Projects the vertices of the group's nblk blocks (ids / Z as above) into M.verts.  All lanes call.
 __device__ __forceinline__ void
-hz_group_project(const HzView& P, unsigned int ids, int nblk, int lane, const HzGroupZ& Z, HzMeshWarp& M)
+hz_group_project(const HzView& P, unsigned int ids, int nblk, int lane, const HzLaneMap& map, const HzGroupZ& Z, HzMeshWarp& M)
 {
     const float halfW = 0.5f * (float)P.W, halfH = 0.5f * (float)P.H;
+    const float* e_tab = P.e_tab;
+    const float* n_tab = P.n_tab;
     #pragma unroll 1            // one projection's registers at a time (unrolled, ptxas interleaves the four and spills)
     for(int round = 0; round < HZ_MESH_ROUNDS; round++)
     {
-        int v, vj, vi;
+        int vj, vi;
         const float z = round == 0 ? Z.z[0] : round == 1 ? Z.z[1] : round == 2 ? Z.z[2] : Z.z[3];
-        if(hz_group_vertex(P, ids, nblk, lane, round, v, vj, vi))
-            M.verts[v] = hz_lane_vertex(P, __ldg(P.e_tab + vi), __ldg(P.n_tab + vj), z, halfW, halfH);
+        const unsigned int code = round == 0 ? map.code[0] : round == 1 ? map.code[1] : round == 2 ? map.code[2] : map.code[3];
+        if(hz_group_vertex(ids, nblk, code, vj, vi))
+            M.verts[round * 32 + lane] = hz_lane_vertex(P, __ldg(e_tab + vi), __ldg(n_tab + vj), z, halfW, halfH);
     }
     __syncwarp();
 }
@@ -872,7 +899,9 @@ template <bool SLOW>
 __device__ __forceinline__ int
 hz_group_triangles(const HzView& P, unsigned int ids, int k0, int nblk, int lane, HzMeshWarp& M, int& count, unsigned int& passed)
 {
-    const int N = P.N;
+    // (copies: P lives in shared memory like M, and every store to M would make the compiler read these again)
+    const int N1 = P.N - 1, x0 = P.x0, x1 = P.x1, H = P.H;
+    const int wide = P.seam_period > 0.0f ? P.W * 64 - 1024 : 0x7FFFFFFF;      // see hz_tri_alive
     // cell (cr, cc) of the block, its lower-left vertex a, upper-right vertex d, and the third one
     // lib:496-508: even triangle (j,i),(j+1,i+1),(j+1,i) ; odd triangle (j,i),(j,i+1),(j+1,i+1)
     const int cell = lane >> 1, cr = cell >> 2, cc = cell & 3;
@@ -882,17 +911,13 @@ hz_group_triangles(const HzView& P, unsigned int ids, int k0, int nblk, int lane
     {
         const unsigned int id = __shfl_sync(0xffffffffu, ids, k);
         const int j = (int)(id >> 16) * HZ_BLOCK_CELLS + cr, i = (int)(id & 0xFFFFu) * HZ_BLOCK_CELLS + cc;
-        bool on = false;
-        if(j < N - 1 && i < N - 1)
-        {
-            // (one call with selected operands: two calls under the odd/even branch would run with half the lanes each)
-            const HzLaneVtx* vb = M.verts + 25 * k;
-            const HzLaneVtx a = vb[ia], d = vb[id_], o = vb[io];
-            on = hz_tri_alive(P, a, odd ? o : d, odd ? d : o);
-        }
+        // (one evaluation with selected operands: under an odd/even branch each half would run with half the lanes)
+        const HzLaneVtx* vb = M.verts + 25 * k;
+        const HzLaneVtx a = vb[ia], d = vb[id_], o = vb[io];
+        const bool on = j < N1 && i < N1 && hz_tri_alive(x0, x1, H, wide, a, odd ? o : d, odd ? d : o);
         const unsigned int ballot = __ballot_sync(0xffffffffu, on);
         if(ballot == 0) continue;
-        const unsigned int tri = 2u * ((unsigned int)j * (unsigned int)(N - 1) + (unsigned int)i) + (unsigned int)(lane & 1);
+        const unsigned int tri = 2u * ((unsigned int)j * (unsigned int)N1 + (unsigned int)i) + (unsigned int)(lane & 1);
         passed += (unsigned int)__popc(ballot);
         if(SLOW)
         {
@@ -951,13 +976,14 @@ __device__ __forceinline__ void hz_near_tiles(const HzView& P, int& ti0, int& ti
     tj0 = max(P.eye_tj - P.near_rings, 0); tj1 = min(P.eye_tj + P.near_rings, P.nt - 1);
 }
 
-__global__ void __launch_bounds__(HZ_WARPS_PER_CTA * 32, 4)
+__global__ void __launch_bounds__(HZ_WARPS_PER_CTA * 32, HZ_MESH_CTAS)
 k_near(const HzView* __restrict__ V)
 {
     HZ_KERNEL_PROLOGUE(V, P);
     __shared__ HzMeshWarp s_warp[HZ_WARPS_PER_CTA];
     __shared__ unsigned int s_total, s_base;
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const HzLaneMap map = hz_lane_map(lane);
 
     int ti0, ti1, tj0, tj1;
     hz_near_tiles(P, ti0, ti1, tj0, tj1);
@@ -967,15 +993,18 @@ k_near(const HzView* __restrict__ V)
     const int nwarps = gridDim.x * HZ_WARPS_PER_CTA;
     // no conservative tests here: next to the eye nearly every block shows, and what does not falls to the exact
     // integer tests of hz_mesh_group anyway
+    // blocks per warp and trip: as many as a group holds when there is enough work for that, fewer when the warps would
+    // otherwise go idle (a lone view: the pass is latency-bound)
+    const int per = min(HZ_MESH_GROUP, max(1, (nblocks + nwarps - 1) / nwarps));
     unsigned int n_blocks = 0, n_tris = 0;
-    int count = 0, b = (blockIdx.x * HZ_WARPS_PER_CTA + wib) * HZ_MESH_GROUP, k_resume = -1;
+    int count = 0, b = (blockIdx.x * HZ_WARPS_PER_CTA + wib) * per, k_resume = -1;
     HzMeshWarp& M = s_warp[wib];
-    for(; b < nblocks && k_resume < 0; b += nwarps * HZ_MESH_GROUP)
+    for(; b < nblocks && k_resume < 0; b += nwarps * per)
     {
-        const int nblk = min(HZ_MESH_GROUP, nblocks - b), bk = min(b + lane, nblocks - 1);
+        const int nblk = min(per, nblocks - b), bk = min(b + lane, nblocks - 1);
         const unsigned int ids = ((unsigned int)(bj0 + bk / nbi) << 16) | (unsigned int)(bi0 + bk % nbi);
         n_blocks += (unsigned int)nblk;
-        hz_group_project(P, ids, nblk, lane, hz_group_heights(P, ids, nblk, lane), M);
+        hz_group_project(P, ids, nblk, lane, map, hz_group_heights(P, ids, nblk, map), M);
         k_resume = hz_group_triangles<false>(P, ids, 0, nblk, lane, M, count, n_tris);
         __syncwarp();
     }
@@ -984,15 +1013,15 @@ k_near(const HzView* __restrict__ V)
         // the triangle list is full: this warp draws everything else it finds itself (b already points at the next group)
         hz_stage_draw_slow(P, M.stage, count);
         count = 0;
-        b -= nwarps * HZ_MESH_GROUP;
-        for(bool first = true; b < nblocks; b += nwarps * HZ_MESH_GROUP, first = false)
+        b -= nwarps * per;
+        for(bool first = true; b < nblocks; b += nwarps * per, first = false)
         {
-            const int nblk = min(HZ_MESH_GROUP, nblocks - b), bk = min(b + lane, nblocks - 1);
+            const int nblk = min(per, nblocks - b), bk = min(b + lane, nblocks - 1);
             const unsigned int ids = ((unsigned int)(bj0 + bk / nbi) << 16) | (unsigned int)(bi0 + bk % nbi);
             if(!first)
             {
                 n_blocks += (unsigned int)nblk;
-                hz_group_project(P, ids, nblk, lane, hz_group_heights(P, ids, nblk, lane), M);
+                hz_group_project(P, ids, nblk, lane, map, hz_group_heights(P, ids, nblk, map), M);
             }
             hz_group_triangles<true>(P, ids, first ? k_resume : 0, nblk, lane, M, count, n_tris);
             __syncwarp();
@@ -1011,7 +1040,7 @@ cudaError_t hz_launch_near(const HzView& v, const HzView* d_v, int nviews, cudaS
 {
     const int side = min(2 * v.near_rings + 1, v.nt) * HZ_TILE_BLOCKS;
     const int nblocks = side * side;
-    int ctas = (nblocks + HZ_WARPS_PER_CTA * HZ_MESH_GROUP - 1) / (HZ_WARPS_PER_CTA * HZ_MESH_GROUP);
+    int ctas = (nblocks + HZ_WARPS_PER_CTA - 1) / HZ_WARPS_PER_CTA;      // (k_near fits its group size to the grid)
     const int cap = max(148 * 8 / max(nviews, 1), 37);
     if(ctas > cap) ctas = cap;
     if(ctas < 1) ctas = 1;
@@ -1199,32 +1228,35 @@ k_blocks(const HzView* __restrict__ V)
     if(P.stats) hz_cta_stats4(s_stats, P.stats + HZ_STAT_BLOCKS, n_all, n_far, n_window, n_occl);
 }
 
-__global__ void __launch_bounds__(HZ_WARPS_PER_CTA * 32, 4)
+__global__ void __launch_bounds__(HZ_WARPS_PER_CTA * 32, HZ_MESH_CTAS)
 k_mesh(const HzView* __restrict__ V)
 {
     HZ_KERNEL_PROLOGUE(V, P);
     __shared__ HzMeshWarp s_warp[HZ_WARPS_PER_CTA];
     __shared__ unsigned int s_total, s_base;
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const HzLaneMap map = hz_lane_map(lane);
     const unsigned int n = *P.block_count;
     const unsigned int nwarps = gridDim.x * HZ_WARPS_PER_CTA;
-    unsigned int b = (blockIdx.x * HZ_WARPS_PER_CTA + wib) * HZ_MESH_GROUP;
+    // blocks per warp and trip: a full group when there is enough work for that, fewer when warps would otherwise go idle
+    const unsigned int per = min((unsigned int)HZ_MESH_GROUP, max(1u, (n + nwarps - 1u) / nwarps));
+    unsigned int b = (blockIdx.x * HZ_WARPS_PER_CTA + wib) * per;
     // lane k holds the k-th block of the group
-    unsigned int ids = (b + lane < n && lane < HZ_MESH_GROUP) ? P.block_queue[b + lane] : 0u;
+    unsigned int ids = (b + lane < n && lane < per) ? P.block_queue[b + lane] : 0u;
     HzGroupZ Z = {};
-    if(b < n) Z = hz_group_heights(P, ids, (int)min((unsigned int)HZ_MESH_GROUP, n - b), lane);
+    if(b < n) Z = hz_group_heights(P, ids, (int)min(per, n - b), map);
     unsigned int n_meshed = 0, n_tris = 0;
     int count = 0, k_resume = -1;
     HzMeshWarp& M = s_warp[wib];
     while(b < n && k_resume < 0)
     {
         // next group's queue entries and heights first: their latency hides behind this group's arithmetic
-        const unsigned int b_next = b + nwarps * HZ_MESH_GROUP;
-        const unsigned int ids_next = (b_next + lane < n && lane < HZ_MESH_GROUP) ? P.block_queue[b_next + lane] : 0u;
+        const unsigned int b_next = b + nwarps * per;
+        const unsigned int ids_next = (b_next + lane < n && lane < per) ? P.block_queue[b_next + lane] : 0u;
         HzGroupZ Z_next = {};
-        if(b_next < n) Z_next = hz_group_heights(P, ids_next, (int)min((unsigned int)HZ_MESH_GROUP, n - b_next), lane);
-        const int nblk = (int)min((unsigned int)HZ_MESH_GROUP, n - b);
-        hz_group_project(P, ids, nblk, lane, Z, M);
+        if(b_next < n) Z_next = hz_group_heights(P, ids_next, (int)min(per, n - b_next), map);
+        const int nblk = (int)min(per, n - b);
+        hz_group_project(P, ids, nblk, lane, map, Z, M);
         k_resume = hz_group_triangles<false>(P, ids, 0, nblk, lane, M, count, n_tris);
         __syncwarp();
         n_meshed += (unsigned int)nblk;
@@ -1236,13 +1268,13 @@ k_mesh(const HzView* __restrict__ V)
         // already projected)
         hz_stage_draw_slow(P, M.stage, count);
         count = 0;
-        for(bool first = true; b < n; b += nwarps * HZ_MESH_GROUP, first = false)
+        for(bool first = true; b < n; b += nwarps * per, first = false)
         {
-            const int nblk = (int)min((unsigned int)HZ_MESH_GROUP, n - b);
+            const int nblk = (int)min(per, n - b);
             if(!first)
             {
-                ids = (b + lane < n && lane < HZ_MESH_GROUP) ? P.block_queue[b + lane] : 0u;
-                hz_group_project(P, ids, nblk, lane, hz_group_heights(P, ids, nblk, lane), M);
+                ids = (b + lane < n && lane < per) ? P.block_queue[b + lane] : 0u;
+                hz_group_project(P, ids, nblk, lane, map, hz_group_heights(P, ids, nblk, map), M);
                 n_meshed += (unsigned int)nblk;
             }
             hz_group_triangles<true>(P, ids, first ? k_resume : 0, nblk, lane, M, count, n_tris);
@@ -1281,6 +1313,17 @@ k_raster(const HzView* __restrict__ V)
             {
                 nsub = hz_big_layout(P, T, nx, k);
                 if(nsub == 0) hz_draw_box<int>(P, T);
+            }
+        }
+        // Middle-sized bounding boxes (up to P.mid_max_pix pixels): a warp of its own in k_big is a lot for a few dozen
+        // pixels, and a lone lane walking them here holds up its 31 neighbours.  But where many lanes of the warp have
+        // one -- zoomed-in views, where neighbouring triangles are all that size -- they walk them side by side.
+        {
+            const bool mid = nsub != 0 && (T.px1 - T.px0 + 1) * (T.py1 - T.py0 + 1) <= P.mid_max_pix && hz_tri_is_small(T);
+            if(__popc(__ballot_sync(0xffffffffu, mid)) >= HZ_MID_LANES && mid)
+            {
+                hz_draw_box<int>(P, T);
+                nsub = 0;
             }
         }
         // the large ones of the warp reserve their queue slots and records with ONE atomic each: in a zoomed-in view
@@ -1342,23 +1385,45 @@ cudaError_t hz_launch_band(const HzView& v, const HzView* d_v, int nviews, bool 
 // k_big: one warp per (triangle, sub-box), lanes spread over the sub-box's pixels
 // ================================================================================================
 
-// lane = column of the sub-box; each lane steps its edge functions down the rows
+// Coverage and shading are separated: lane = column of the sub-box steps its edge functions down the rows, four rows
+// at a time, and the covered pixel centres of those four rows are compacted through shared memory (`slots`, 128 bytes
+// per warp); then the lanes shade them densely, 32 at a time.  (Shading where the coverage test ran would leave most
+// lanes idle through the ~45 instructions of a fragment: a triangle covers a few pixels of each row of its sub-box.)
+// The whole warp calls, with the same arguments but for `lane`.
 template <typename I>
-__device__ __forceinline__ void hz_draw_subbox(const HzView& P, const HzTri& T, int x0, int x1, int y0, int y1, int lane)
+__device__ __forceinline__ void
+hz_draw_subbox(const HzView& P, const HzTri& T, int x0, int x1, int y0, int y1, int lane, uint8_t* slots)
 {
     const HzEdges<I> E(T);
     if(E.box_outside(T, x0, x1, y0, y1)) return;
     const int px = x0 + lane;
-    if(px > x1) return;
+    const bool column = px <= x1;
     const I Px = (I)px * 256 + 128, Py = (I)y0 * 256 + 128;
     I e0 = E.dx0 * (Py - T.Y0) - E.dy0 * (Px - T.X0) - E.b0;      // >= 0 <=> inside, per edge
     I e1 = E.dx1 * (Py - T.Y1) - E.dy1 * (Px - T.X1) - E.b1;
     I e2 = E.dx2 * (Py - T.Y2) - E.dy2 * (Px - T.X2) - E.b2;
     const I sy0 = E.dx0 * 256, sy1 = E.dx1 * 256, sy2 = E.dx2 * 256;
-    for(int py = y0; py <= y1; py++)
+    const unsigned int below = (1u << lane) - 1u;
+    for(int yb = y0; yb <= y1; yb += 4)
     {
-        if((e0 | e1 | e2) >= 0) hz_fragment(P, T, px, py);
-        e0 += sy0; e1 += sy1; e2 += sy2;
+        unsigned int n = 0;                                       // covered pixel centres of these rows (the same in all lanes)
+        #pragma unroll
+        for(int r = 0; r < 4; r++)
+        {
+            const bool in = column && yb + r <= y1 && (e0 | e1 | e2) >= 0;
+            const unsigned int m = __ballot_sync(0xffffffffu, in);
+            if(in) slots[n + __popc(m & below)] = (uint8_t)((r << 5) | lane);
+            n += __popc(m);
+            e0 += sy0; e1 += sy1; e2 += sy2;
+        }
+        if(n == 0) continue;
+        __syncwarp();
+        for(unsigned int f = lane; f < n; f += 32)
+        {
+            const unsigned int code = slots[f];
+            hz_fragment(P, T, x0 + (int)(code & 31u), yb + (int)(code >> 5));
+        }
+        __syncwarp();
     }
 }
 
@@ -1368,9 +1433,11 @@ k_big(const HzView* __restrict__ V)
     HZ_KERNEL_PROLOGUE(V, P);
     // every slot below min(count, capacity) was written: with a record index or a triangle number, or poisoned by a
     // triangle that found the queue exhausted and drew itself (hz_raster_one)
+    __shared__ uint8_t s_slots[8][128];
     unsigned int count = *P.big_count;
     if(count > P.big_capacity) count = P.big_capacity;
     const int lane = threadIdx.x & 31;
+    uint8_t* slots = s_slots[threadIdx.x >> 5];
     const unsigned int nwarps = gridDim.x * (blockDim.x >> 5);
     for(unsigned int t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); t < count; t += nwarps)
     {
@@ -1385,8 +1452,8 @@ k_big(const HzView* __restrict__ V)
         const int rows = HZ_BIG_ROWS << ((entry.y >> 24) & 15u);
         const int y0 = T.py0 + (int)(entry.y & 0xFFFu) * rows,                y1 = min(y0 + rows - 1, T.py1);
         const int x0 = T.px0 + (int)((entry.y >> 12) & 0xFFFu) * HZ_BIG_COLS, x1 = min(x0 + HZ_BIG_COLS - 1, T.px1);
-        if(hz_tri_is_small(T)) hz_draw_subbox<int>(P, T, x0, x1, y0, y1, lane);
-        else                   hz_draw_subbox<long long>(P, T, x0, x1, y0, y1, lane);
+        if(hz_tri_is_small(T)) hz_draw_subbox<int>(P, T, x0, x1, y0, y1, lane, slots);
+        else                   hz_draw_subbox<long long>(P, T, x0, x1, y0, y1, lane, slots);
     }
 }
 
@@ -1435,48 +1502,47 @@ __device__ __forceinline__ HzResolve hz_resolve_params(const HzView& P)
     return R;
 }
 
-// 4 pixels per thread: 2x16 B of keys in, 12 B of BGR and 16 B of range out (per destination)
+// 4 pixels per thread: 2x16 B of keys in, 12 B of BGR and 16 B of range out (per destination).  32-bit index
+// arithmetic throughout (the launch falls back to k_resolve1 for targets of 2^31 pixels or more); the row of a CTA's
+// first group comes from one division that is the same for the whole CTA, the threads step on from there.
 __global__ void __launch_bounds__(256)
 k_resolve4(const HzView* __restrict__ V)
 {
     HZ_KERNEL_PROLOGUE(V, P);
     const HzResolve R = hz_resolve_params(P);
-    const int groups_per_row = R.Wt >> 2;
-    const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if(g >= (long long)groups_per_row * R.H) return;
-    const int y  = (int)(g / groups_per_row);          // GL row (0 = bottom)
-    const int x  = (int)(g % groups_per_row) << 2;
-    const size_t src = (size_t)y * R.Wt + x;
-    const size_t dst = (size_t)(R.H - 1 - y) * R.out_stride + R.out_x0 + x;   // top row first (lib:949-958, 1026-1038)
+    const unsigned int gpr = (unsigned int)R.Wt >> 2;                          // groups of 4 pixels per row
+    const unsigned int g0 = blockIdx.x * 256u;
+    unsigned int y = g0 / gpr, xg = g0 - y * gpr + threadIdx.x;                // GL row (0 = bottom), group within the row
+    if(xg >= gpr) { const unsigned int up = xg / gpr; y += up; xg -= up * gpr; }
+    if(y >= (unsigned int)R.H) return;
+    const unsigned int x = xg << 2;
+    const unsigned int src = y * (unsigned int)R.Wt + x;
+    const size_t dst = (size_t)((unsigned int)R.H - 1u - y) * (unsigned int)R.out_stride + (unsigned int)R.out_x0 + x;   // top row first (lib:949-958, 1026-1038)
 
-    const ulonglong2 k01 = *(const ulonglong2*)(R.vis + src);
-    const ulonglong2 k23 = *(const ulonglong2*)(R.vis + src + 2);
-    const unsigned long long k[4] = { k01.x, k01.y, k23.x, k23.y };
+    const ulonglong2 k01 = __ldcs((const ulonglong2*)(R.vis + src));           // read once: streaming
+    const ulonglong2 k23 = __ldcs((const ulonglong2*)(R.vis + src + 2));
+    const unsigned int q0 = (unsigned int)(k01.x >> 40), q1 = (unsigned int)(k01.y >> 40),
+                       q2 = (unsigned int)(k23.x >> 40), q3 = (unsigned int)(k23.y >> 40);
 
     // hit: (B,G,R) = (0,0,r8) ; sky: clear colour (0,0,1) read as BGR = (255,0,0)   lib:185, 938-939
-    unsigned char b[12];
-    #pragma unroll
-    for(int p = 0; p < 4; p++)
-    {
-        const bool hit = (unsigned int)(k[p] >> 40) != HZ_Q_MAX;
-        b[3 * p + 0] = hit ? 0 : 255;
-        b[3 * p + 1] = 0;
-        b[3 * p + 2] = hit ? (unsigned char)(k[p] & 0xFFu) : 0;
-    }
-    const uint32_t w0 = b[0] | (b[1] << 8) | (b[2]  << 16) | ((uint32_t)b[3]  << 24);
-    const uint32_t w1 = b[4] | (b[5] << 8) | (b[6]  << 16) | ((uint32_t)b[7]  << 24);
-    const uint32_t w2 = b[8] | (b[9] << 8) | (b[10] << 16) | ((uint32_t)b[11] << 24);
+    // bytes B0 G0 R0 B1 | G1 R1 B2 G2 | R2 B3 G3 R3
+    const unsigned int B0 = q0 != HZ_Q_MAX ? 0u : 255u, R0 = q0 != HZ_Q_MAX ? (unsigned int)k01.x & 0xFFu : 0u;
+    const unsigned int B1 = q1 != HZ_Q_MAX ? 0u : 255u, R1 = q1 != HZ_Q_MAX ? (unsigned int)k01.y & 0xFFu : 0u;
+    const unsigned int B2 = q2 != HZ_Q_MAX ? 0u : 255u, R2 = q2 != HZ_Q_MAX ? (unsigned int)k23.x & 0xFFu : 0u;
+    const unsigned int B3 = q3 != HZ_Q_MAX ? 0u : 255u, R3 = q3 != HZ_Q_MAX ? (unsigned int)k23.y & 0xFFu : 0u;
+    const uint32_t w0 = B0 | (R0 << 16) | (B1 << 24);
+    const uint32_t w1 = (R1 << 8) | (B2 << 16);
+    const uint32_t w2 = R2 | (B3 << 8) | (R3 << 24);
 
     float4 r = make_float4(-1.0f, -1.0f, -1.0f, -1.0f);
     // most groups of four pixels are sky: skip the FP64 conversion for them altogether
-    if(P.out_ranges[0] != nullptr &&
-       ((unsigned int)(k[0] >> 40) & (unsigned int)(k[1] >> 40) & (unsigned int)(k[2] >> 40) & (unsigned int)(k[3] >> 40)) != HZ_Q_MAX)
+    if(P.out_ranges[0] != nullptr && (q0 & q1 & q2 & q3) != HZ_Q_MAX)
     {
         const float t = R.tanel[y];
-        r.x = hz_range_of_key(k[0], t, R.znear, R.zfar);
-        r.y = hz_range_of_key(k[1], t, R.znear, R.zfar);
-        r.z = hz_range_of_key(k[2], t, R.znear, R.zfar);
-        r.w = hz_range_of_key(k[3], t, R.znear, R.zfar);
+        r.x = hz_range_of_key(k01.x, t, R.znear, R.zfar);
+        r.y = hz_range_of_key(k01.y, t, R.znear, R.zfar);
+        r.z = hz_range_of_key(k23.x, t, R.znear, R.zfar);
+        r.w = hz_range_of_key(k23.y, t, R.znear, R.zfar);
     }
     for(int d = 0; d < R.n_out; d++)
     {
@@ -1530,7 +1596,7 @@ bool hz_resolve_is_vectorisable(const HzView& v)
 cudaError_t hz_launch_resolve(const HzView& v, const HzView* d_v, int nviews, cudaStream_t stream)
 {
     const int Wt = v.x1 - v.x0;
-    if(hz_resolve_is_vectorisable(v))
+    if(hz_resolve_is_vectorisable(v) && (long long)Wt * v.H < (1ll << 31))
     {
         const long long n = (long long)(Wt / 4) * v.H;
         return hz_launch(k_resolve4, dim3((unsigned)((n + 255) / 256), (unsigned)nviews), dim3(256), stream, d_v);
