@@ -155,10 +155,12 @@ def ensure_tiles(rank, barrier):
     return TILES_DIR
 
 
-def viewpoints(n_ranks, rank, steps):
-    """Every rank renders the C2 viewpoint (BASELINE configs[1]) against its own copy of the DEM: the same work per
-    GPU, so that the N-GPU value measures how the machine scales and not how viewpoints differ."""
-    return [(C2["lat"], C2["lon"])] * steps
+def c5_grid(world, rank, g=64):
+    """BASELINE configs[4] ("C5"): the g x g grid of viewpoints over the central degree of the DEM, dealt to the ranks
+    in contiguous blocks of whole grid rows (disjoint; 4096 / world viewpoints each)."""
+    pts = [(33.5 + (j + 0.5) / g + 1.0 / 7200.0, -117.5 + (i + 0.5) / g + 1.0 / 7200.0) for j in range(g) for i in range(g)]
+    lo, hi = len(pts) * rank // world, len(pts) * (rank + 1) // world
+    return pts[lo:hi]
 
 
 # ------------------------------------------------------------------------------------------------ our arm
@@ -181,8 +183,46 @@ class StdoutToStderr:
             self.saved = None
 
 
+def load_reference_binding():
+    """The reference's own horizonator-pywrap.c, compiled unmodified against include/ and linked to the product library
+    (oracle/Makefile target `pywrap`; prebuilt, travels with the snapshot).  None where it was never built."""
+    import glob
+    import importlib.util
+    so = glob.glob(os.path.join(ROOT, "oracle", "_ref", "pywrap", "horizonator*.so"))
+    if not so:
+        return None
+    try:
+        spec = importlib.util.spec_from_file_location("horizonator", so[0])
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        return mod
+    except Exception as e:          # e.g. numpy ABI mismatch
+        sys.stderr.write("bench: reference binding not loadable: %r\n" % (e,))
+        return None
+
+
+def c3_sweep(render, n=48):
+    """BASELINE configs[2] ("C3"): pan/zoom re-render sweep through a Python render(az0, az1, znear=, zfar=) callable:
+    a pan around the circle at 60 degrees field of view, then a zoom from 120 to 2 degrees; per-render latency."""
+    import numpy as np
+    wins = [(c - 30.0, c + 30.0) for c in np.linspace(-150.0, 150.0, n // 2)]
+    wins += [(45.0 - f / 2, 45.0 + f / 2) for f in np.geomspace(120.0, 2.0, n - n // 2)]
+    for a0, a1 in wins[:3]:
+        render(float(a0), float(a1), znear=C2["znear"], zfar=C2["zfar"])
+    lat = []
+    for a0, a1 in wins:
+        t0 = time.perf_counter()
+        img, rng = render(float(a0), float(a1), znear=C2["znear"], zfar=C2["zfar"])
+        lat.append((time.perf_counter() - t0) * 1e3)
+    lat.sort()
+    return {"renders": len(lat), "median_ms": lat[len(lat) // 2], "p90_ms": lat[int(len(lat) * 0.9)], "max_ms": lat[-1],
+            "mean_ms": sum(lat) / len(lat)}
+
+
 def run_b200(args):
     quiet = StdoutToStderr()
+    import numpy as np
+    import ctypes as C
     import torch
     import torch.distributed as dist
 
@@ -192,12 +232,19 @@ def run_b200(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the renderer has no CPU path")
     torch.cuda.set_device(local)
+    os.environ["HORIZONATOR_DEVICE"] = str(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     def barrier():
         if world > 1:
             dist.barrier()
+
+    def max_over_ranks(x):
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
 
     tiles = ensure_tiles(rank, barrier)
     import horizonator_b200 as hz
@@ -210,42 +257,61 @@ def run_b200(args):
     W, H = C2["W"], C2["H"]
     h.set_zextents(C2["znear"], C2["zfar"])
     K, Wm = args.steps, args.warmup
-    pts = viewpoints(world, rank, K + Wm)
-    views = [(la, lo, C2["az0"], C2["az1"]) for la, lo in pts]
+    c2_view = (C2["lat"], C2["lon"], C2["az0"], C2["az1"])
+    peak, peak_src = measured_peak_gbs()
+    alg = algorithmic_bytes(R, W, H)
 
-    B = args.batch                      # panoramas per step: rendered concurrently on the library's render lanes
+    B = args.batch                      # panoramas per step: one call of the batch entry point
     d_img = torch.empty((B, H, W, 3), dtype=torch.uint8, device="cuda")
     d_rng = torch.empty((B, H, W), dtype=torch.float32, device="cuda")
-    stream = torch.cuda.current_stream()
+    # a stream of its own: the batch call takes stream NULL -- which is what torch's default stream is -- to mean "the
+    # context's stream, and wait for the result"; on a real stream it only enqueues, and successive calls overlap
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
 
-    # ---- latency of one panorama at a time ----
-    for k in range(Wm):
-        h.render_batch_device(views[k:k + 1], d_img.data_ptr(), d_rng.data_ptr(), stream.cuda_stream)
-    torch.cuda.synchronize()
-    n_lat = min(K, 50)
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record(stream)
-    for k in range(n_lat):
-        h.render_batch_device(views[Wm:Wm + 1], d_img.data_ptr(), d_rng.data_ptr(), stream.cuda_stream)
-    ev1.record(stream)
-    torch.cuda.synchronize()
-    latency_ms = ev0.elapsed_time(ev1) / n_lat
-    # ... and the same with CUDA events around every stage and the culling counters switched on
+    def render_dev(views):
+        h.render_batch_device(views, d_img.data_ptr(), d_rng.data_ptr(), stream.cuda_stream)
+
+    def lone_ms(view, reps=20):
+        for _ in range(3):
+            render_dev([view])
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(reps):
+            render_dev([view])
+        e1.record(stream)
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+
+    # ---- latency of one panorama at a time, then the same with CUDA events around every stage and the culling
+    # counters switched on
+    latency_ms = lone_ms(c2_view, min(K, 50))
     h.profile(True)
     h.profile_read()
     for k in range(20):
-        h.render_batch_device(views[Wm:Wm + 1], d_img.data_ptr(), d_rng.data_ptr(), stream.cuda_stream)
+        render_dev([c2_view])
     torch.cuda.synchronize()
     prof = h.profile_read()
     h.profile(False)
     stats = h.last_render_stats()
     counters = h.render_counters()
 
-    # ---- device-resident throughput: K steps of B panoramas ----
-    step_views = [views[Wm]] * B
+    # ---- device-resident throughput (the metric's configuration): K steps of B panoramas of the C2 viewpoint ----
+    step_views = [c2_view] * B
     for k in range(Wm):
-        h.render_batch_device(step_views, d_img.data_ptr(), d_rng.data_ptr(), stream.cuda_stream)
+        render_dev(step_views)
     torch.cuda.synchronize()
+    batch_launches = h.last_render_stats()["launches"]
+    # host time to enqueue a step, measured while nothing can block (the parameter rings are 16 deep): a few steps
+    # from an idle context
+    n_free = min(K, 4)
+    t0 = time.perf_counter()
+    for k in range(n_free):
+        render_dev(step_views)
+    host_enqueue_us = (time.perf_counter() - t0) / (n_free * B) * 1e6
+    torch.cuda.synchronize()
+
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -256,93 +322,142 @@ def run_b200(args):
     wall0 = time.time()
     ev0.record(stream)
     for k in range(K):
-        h.render_batch_device(step_views, d_img.data_ptr(), d_rng.data_ptr(), stream.cuda_stream)
+        render_dev(step_views)
     ev1.record(stream)
-    host_enqueue_s = time.time() - wall0
     torch.cuda.synchronize()
     barrier()
     wall1 = time.time()
     ms_total = ev0.elapsed_time(ev1)
     clocks = sampler.stop(wall0, wall1) if rank == 0 else None
-
-    t = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total_max = float(t.item())
+    ms_total_max = max_over_ranks(ms_total)
     value = world * K * B / (ms_total_max / 1e3)
 
+    # ---- C5: distinct viewpoints of the 64x64 grid, this rank's disjoint block, in calls of B ----
+    grid = [(la, lo, C2["az0"], C2["az1"]) for la, lo in c5_grid(world, rank)]
+    n_grid = len(grid) if args.grid_views <= 0 else min(len(grid), args.grid_views)
+    grid = grid[:n_grid]
+    for k in range(0, min(n_grid, 2 * B), B):
+        render_dev(grid[k:k + B])
+    barrier()
+    torch.cuda.synchronize()
+    ev0.record(stream)
+    for k in range(0, n_grid, B):
+        render_dev(grid[k:k + B])
+    ev1.record(stream)
+    torch.cuda.synchronize()
+    grid_ms = max_over_ranks(ev0.elapsed_time(ev1))
+    n_grid_all = int(max_over_ranks(float(n_grid)))        # (the same on every rank)
+    grid_value = world * n_grid_all / (grid_ms / 1e3)
+    sample = grid[:: max(1, n_grid // 16)][:16]
+    lone = sorted(lone_ms(v, 5) for v in sample)
+    hit = []
+    for v in sample[:4]:
+        render_dev([v])
+        torch.cuda.synchronize()
+        hit.append(float((d_rng[0] > 0).float().mean().item()))
+
+    # ---- expensive views: the eye high above the terrain, zoomed-in windows ----
+    special = {"eye_3km": c2_view + (3000.0,), "eye_12km": c2_view + (12000.0,),
+               "zoom_30deg": (C2["lat"], C2["lon"], 30.0, 60.0), "zoom_10deg": (C2["lat"], C2["lon"], 40.0, 50.0),
+               "zoom_5deg": (C2["lat"], C2["lon"], 42.5, 47.5)}
+    special_ms = {k: lone_ms(v, 5) for k, v in special.items()}
+
     # ---- end to end through the reference-facing call, host buffers ----
-    import numpy as np
-    import ctypes as C
     # host result buffers: page-locked (horizonator_host_alloc), reused across steps
     img = hz.pinned_array((H, W, 3), np.uint8)
     rng = hz.pinned_array((H, W), np.float32)
     ctx = C.byref(h.context)
 
-    def e2e_step(la, lo):
+    def e2e_step(la, lo, img, rng):
         # what horizonator-pywrap.c's render() does per call, minus the numpy allocation
         assert hz.lib.horizonator_pan_zoom(ctx, C2["az0"], C2["az1"])
         assert hz.lib.horizonator_move(ctx, None, la, lo)
         assert hz.lib.horizonator_set_zextents(ctx, C2["znear"], C2["zfar"], C2["znear"], C2["zfar"])
         assert hz.lib.horizonator_render_offscreen(ctx, img.ctypes.data, rng.ctypes.data)
 
-    for k in range(Wm):
-        e2e_step(*pts[k])
+    def e2e_rate(img, rng):
+        for k in range(Wm):
+            e2e_step(C2["lat"], C2["lon"], img, rng)
+        barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for k in range(K):
+            e2e_step(C2["lat"], C2["lon"], img, rng)
+        torch.cuda.synchronize()
+        return world * K / max_over_ranks(time.perf_counter() - t0)
+
+    e2e_value = e2e_rate(img, rng)
+    hit_fraction = float((rng > 0).mean())
+    # same call into ordinary pageable numpy arrays (what an unmodified caller of the reference passes)
+    img_p = np.zeros((H, W, 3), np.uint8)
+    rng_p = np.zeros((H, W), np.float32)
+    e2e_pageable = e2e_rate(img_p, rng_p)
+    same_pageable = bool(np.array_equal(img_p, img) and np.array_equal(rng_p, rng))
+
+    # how fast this box moves 7*W*H bytes per panorama from every GPU to page-locked host memory at once, with no
+    # rendering at all: the ceiling of any end-to-end number at this number of GPUs
+    d_flat = torch.empty((7 * W * H,), dtype=torch.uint8, device="cuda")
+    h_flat = torch.empty((7 * W * H,), dtype=torch.uint8).pin_memory()
+    for k in range(3):
+        h_flat.copy_(d_flat, non_blocking=True)
     barrier()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     for k in range(K):
-        e2e_step(*pts[Wm + k])
+        h_flat.copy_(d_flat, non_blocking=True)
     torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
-    t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = world * K / float(t.item())
-    hit_fraction = float((rng > 0).mean())
-
-    # same call into ordinary pageable numpy arrays (what an unmodified caller of the reference passes)
-    img_p = np.empty((H, W, 3), np.uint8)
-    rng_p = np.empty((H, W), np.float32)
-    img_p[:] = 0; rng_p[:] = 0
-    for k in range(2):
-        hz.lib.horizonator_render_offscreen(ctx, img_p.ctypes.data, rng_p.ctypes.data)
-    t0 = time.perf_counter()
-    for k in range(K):
-        hz.lib.horizonator_render_offscreen(ctx, img_p.ctypes.data, rng_p.ctypes.data)
-    e2e_pageable = K / (time.perf_counter() - t0)
+    d2h_ceiling = world * K / max_over_ranks(time.perf_counter() - t0)
+    del d_flat, h_flat
 
     # the additive host-pointer batch call: renders and device->host copies of different views overlap
-    bimg = hz.pinned_array((B, H, W, 3), np.uint8)
-    brng = hz.pinned_array((B, H, W), np.float32)
-    varr = h._views(step_views)
+    Bh = min(B, 16)
+    bimg = hz.pinned_array((Bh, H, W, 3), np.uint8)
+    brng = hz.pinned_array((Bh, H, W), np.float32)
+    varr = h._views([c2_view] * Bh)
     for k in range(2):
-        assert hz.lib.horizonator_render_batch(ctx, B, varr, bimg.ctypes.data, brng.ctypes.data)
-    n_b = max(3, K // B)
+        assert hz.lib.horizonator_render_batch(ctx, Bh, varr, bimg.ctypes.data, brng.ctypes.data)
+    n_b = max(3, K // Bh)
+    barrier()
     t0 = time.perf_counter()
     for k in range(n_b):
-        assert hz.lib.horizonator_render_batch(ctx, B, varr, bimg.ctypes.data, brng.ctypes.data)
-    e2e_batch = n_b * B / (time.perf_counter() - t0)
+        assert hz.lib.horizonator_render_batch(ctx, Bh, varr, bimg.ctypes.data, brng.ctypes.data)
+    e2e_batch = world * n_b * Bh / max_over_ranks(time.perf_counter() - t0)
+    del bimg, brng
+
+    # ---- C3: Python render() pan/zoom sweep -- through the reference's own compiled binding (fresh pageable numpy
+    # arrays per call, as it allocates them) and through the ctypes mirror (pooled page-locked arrays) ----
+    c3 = None
+    if rank == 0:
+        c3 = {"mirror": c3_sweep(h.render)}
+        ref_binding = load_reference_binding()
+        if ref_binding is not None:
+            hb = ref_binding.horizonator(C2["lat"], C2["lon"], W, H, SRTM1=True, dir_dems=tiles,
+                                         render_radius_m=C2["radius_m"])
+            c3["reference_binding"] = c3_sweep(hb.render)
+            del hb
+        else:
+            c3["reference_binding"] = None
+
+    # ---- C4 (N > 1): one 36000 x 4000 panorama by azimuth wedge over the ranks ----
+    c4 = c4_wedges(hz, tiles, world, rank, barrier, max_over_ranks) if world > 1 and not args.no_c4 else None
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
-    peak, peak_src = measured_peak_gbs()
-    alg = algorithmic_bytes(R, W, H)
     stages = {"prepare": "k_prepare", "near": "k_near+k_raster", "big_near": "k_big",
               "march": "bands: (k_tiles, k_blocks, k_mesh, k_raster) x 2", "big_far": "k_big", "resolve": "k_resolve"}
     # achieved: algorithmic bytes per panorama x panoramas/s of the whole device-resident job (kernels of
     # concurrent panoramas overlap, so a single kernel's duration no longer measures the machine)
-    achieved = alg * (K * B / (ms_total / 1e3)) / 1e9
-    traffic = None
-    tp = os.path.join(ROOT, "profiles", "dram_bytes_per_panorama.json")
-    if os.path.exists(tp):
-        try:
-            traffic = json.load(open(tp)).get("dram_bytes_per_panorama")
-        except Exception:
-            traffic = None
+    per_gpu = value / world
+    achieved = alg * per_gpu / 1e9
+    prof_batch = batch_profile()
+    sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
+    issue_peak = 148 * 4 * sm_mhz * 1e6
+
+    def frac_of_roof(ms):
+        return alg / (ms / 1e3) / 1e9 / peak
 
     mosaic_ms = h.time_mosaic(5)
     out = {
@@ -357,12 +472,14 @@ def run_b200(args):
                         "(R=%d cells, %d triangles), 3600x600 panorama + range image" % (R, h.context.Ntriangles),
             "az_deg": [C2["az0"], C2["az1"]], "znear_m": C2["znear"], "zfar_m": C2["zfar"],
             "panoramas_per_step_per_gpu": B,
-            "concurrency": "the %d panoramas of a step render concurrently on up to 16 render lanes (one CUDA stream "
-                           "and scratch set each) of one context; same viewpoint, nothing cached between them" % B,
+            "concurrency": "a step is one horizonator_render_batch_device() call of %d panoramas: chunks of up to 16 views, "
+                           "each chunk ONE chain of kernel launches with a view dimension (one parameter copy + one CUDA "
+                           "graph launch per chunk), chunks alternating between 2 streams; same viewpoint, nothing "
+                           "cached between views; distinct viewpoints: see aux.c5_grid" % B,
             "l2": "no explicit flush; inputs larger than L2: the int16 DEM square is %.0f MB and its culling pyramid "
-                  "%.0f MB, and the %d panoramas in flight cycle %d visibility buffers of %.0f MB each through the 126 MB "
+                  "%.0f MB, and the panoramas in flight cycle up to 32 visibility buffers of %.0f MB each through the 126 MB "
                   "L2 (hierarchical culling makes one panorama touch only a few tens of MB of the DEM, see "
-                  "roofline.traffic)" % (2 * (2 * R) ** 2 / 1e6, 4 * ((2 * R) // 4) ** 2 / 1e6, B, min(B, 16), 8 * W * H / 1e6),
+                  "roofline.traffic)" % (2 * (2 * R) ** 2 / 1e6, 4 * ((2 * R) // 4) ** 2 / 1e6, 8 * W * H / 1e6),
             "parallelism": "viewpoint batch, %d panoramas per GPU per step, DEM replicated, no data-path collective" % B,
         },
         "e2e": {"value": e2e_value, "unit": "panoramas/s",
@@ -370,37 +487,63 @@ def run_b200(args):
                 "note": "horizonator_pan_zoom+move+set_zextents+render_offscreen into page-locked host buffers; "
                         "per-step inputs are 7 scalars passed as kernel arguments (no H2D copy), outputs 7*W*H "
                         "bytes D2H; one panorama per call, calls back to back",
-                "pageable_host_buffers_value": e2e_pageable, "batch_call_value": e2e_batch,
+                "pageable_host_buffers_value": e2e_pageable, "pageable_equals_pinned": same_pageable,
+                "batch_call_value": e2e_batch,
                 "batch_call_note": "horizonator_render_batch() (additive API): %d views per call into page-locked host "
-                                   "memory, copies overlapping the next views' kernels" % B},
-        "gpu_launches": K * B * stats["launches"],
-        "roofline": {"bound": "hbm", "kernel": "whole panorama: 14 kernels replayed as one CUDA graph "
-                               "(k_prepare, k_near, k_raster, k_big, 2 x (k_tiles, k_blocks, k_mesh, k_raster), k_big, k_resolve)",
+                                   "memory, copies overlapping the next views' kernels" % Bh,
+                "d2h_ceiling_value": d2h_ceiling, "fraction_of_d2h_ceiling": e2e_value / d2h_ceiling,
+                "batch_call_fraction_of_d2h_ceiling": e2e_batch / d2h_ceiling,
+                "d2h_ceiling_note": "panoramas/s at which %d GPU(s) of this box move 7*W*H bytes each to page-locked host "
+                                    "memory concurrently with nothing else going on (plain cudaMemcpyAsync, measured "
+                                    "in this run)" % world},
+        "gpu_launches": K * ((B + 15) // 16) * batch_launches,
+        "roofline": {"bound": "hbm", "kernel": "whole panorama: a chain of %d kernels per chunk of up to 16 views, replayed as "
+                               "one CUDA graph (k_prepare, k_near, k_raster, k_big, 3 x (k_tiles, k_blocks, k_mesh, k_raster), "
+                               "k_big, k_resolve)" % batch_launches,
                      "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                     "frac": achieved / peak, "traffic": (prof_batch or {}).get("dram_bytes_per_panorama"),
+                     "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": alg,
                      "stage_ms_single_panorama": {"%s [%s]" % (k, stages[k]): prof[k] for k in stages},
                      "latency_ms_single_panorama": latency_ms,
+                     "frac_single_panorama": frac_of_roof(latency_ms),
                      # the resource that actually binds in batch mode: instruction issue.  Instructions per panorama
-                     # from the same ncu launch list as `traffic`; peak = SMs x 4 schedulers x SM clock
-                     "issue": {"warp_instructions_per_panorama": WARP_INST_PER_PANORAMA,
-                               "peak_warp_instructions_per_s": 148 * 4 * (clocks.get("sm_mhz") or 1965.0) * 1e6,
-                               "frac": value / world * WARP_INST_PER_PANORAMA
-                                       / (148 * 4 * (clocks.get("sm_mhz") or 1965.0) * 1e6),
-                               "source": "smsp__inst_executed.sum over the 14 kernels, profiles/r01A_kernels_per_panorama.txt"},
-                     "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum summed over the 14 kernels of one "
-                                     "panorama (one CUDA-graph launch), from the ncu capture summarised in "
-                                     "profiles/r01A_kernels_per_panorama.txt",
+                     # from an ncu capture of THIS configuration (batch of 16, 3 bands); peak = SMs x 4 schedulers x SM clock
+                     "issue": None if prof_batch is None else {
+                         "warp_instructions_per_panorama": prof_batch["warp_instructions_per_panorama"],
+                         "peak_warp_instructions_per_s": issue_peak,
+                         "frac": per_gpu * prof_batch["warp_instructions_per_panorama"] / issue_peak,
+                         "source": prof_batch["source"]},
+                     "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum over the kernels of one batched chain "
+                                     "divided by its views, from the ncu launch list named in issue.source",
                      "note": "achieved = algorithmic bytes per panorama (one read of the int16 DEM square + one write of "
-                             "image and range, SURVEY 8d) x measured panoramas/s over the whole timed region.  Hierarchical culling makes the kernels read far less DRAM than the "
-                             "algorithmic figure (see traffic) and leaves them latency-bound, which is why several "
-                             "panoramas are kept in flight"},
+                             "image and range, SURVEY 8d) x measured panoramas/s over the whole timed region.  Hierarchical "
+                             "culling makes the kernels read far less DRAM than the algorithmic figure (see traffic): HBM "
+                             "is not what binds, instruction issue is (see issue)"},
         "clocks": clocks,
         "aux": {"init_s": t_init, "mosaic_decode_ms": mosaic_ms,
                 "mosaic_decode_gbs": 4 * (2 * R) ** 2 / (mosaic_ms / 1e3) / 1e9,
                 "triangles_rasterised": stats["triangles_rasterised"], "big_entries": stats["big_entries"],
                 "terrain_pixel_fraction": hit_fraction, "culling": counters,
-                "host_enqueue_us_per_panorama": host_enqueue_s / (K * B) * 1e6},
+                "host_enqueue_us_per_panorama": host_enqueue_us,
+                "host_enqueue_fraction_of_device_period": host_enqueue_us / (1e6 / per_gpu),
+                "host_enqueue_note": "host time of %d back-to-back batch calls from an idle context (nothing to wait "
+                                     "for), per panorama; device period = 1/value per GPU" % n_free,
+                "c5_grid": {"value": grid_value, "unit": "panoramas/s", "viewpoints_per_gpu": n_grid_all,
+                            "what": "BASELINE configs[4]: DISTINCT viewpoints of the 64x64 grid over the central degree "
+                                    "(33.5..34.5 N, 117.5..116.5 W), eye 1 m above the local terrain, full circle; "
+                                    "each rank renders its own contiguous block of the grid in calls of %d" % B,
+                            "ratio_to_single_viewpoint_value": grid_value / value,
+                            "roofline_frac": alg * (grid_value / world) / 1e9 / peak,
+                            "lone_ms": {"min": lone[0], "median": lone[len(lone) // 2], "max": lone[-1], "n": len(lone),
+                                        "roofline_frac_min_median_max": [frac_of_roof(lone[-1]), frac_of_roof(lone[len(lone) // 2]),
+                                                                         frac_of_roof(lone[0])],
+                                        "max_over_c2_view": lone[-1] / latency_ms},
+                            "terrain_pixel_fraction_sample": hit},
+                "lone_ms_special_views": dict(special_ms, note="device time of one panorama at a time; eye_*: explicit "
+                                              "viewer_z above sea level over the C2 position (full circle); zoom_*: azimuth "
+                                              "window of that width around 45 degrees"),
+                "c3_sweep": c3, "c4_wedge": c4},
     }
     if world == 1 and not args.no_cpu_baseline:
         port = cpu_baseline(tiles, use_ref=False, steps=3)
@@ -412,6 +555,90 @@ def run_b200(args):
     print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def batch_profile():
+    """Instructions and DRAM bytes per panorama of the batch configuration, from the committed ncu launch list of
+    `tools/batch_sweep.py --once 16` (profiles/README.md says how it was taken)."""
+    p = os.path.join(ROOT, "profiles", "batch_profile.json")
+    try:
+        return json.load(open(p))
+    except Exception:
+        return None
+
+
+def c4_wedges(hz, tiles, world, rank, barrier, max_over_ranks):
+    """BASELINE configs[3]: one 36000 x 4000 full-circle panorama split by azimuth wedge over the ranks, assembled
+    (a) in every rank's device memory by the resolve kernel's peer stores over NVLink, (b) in ONE host buffer that all
+    ranks share, each rank copying its own wedge over its own PCIe link; against one GPU doing the whole panorama."""
+    import torch
+    from horizonator_b200 import sharding
+    W, H = 36000, 4000
+    try:
+        h = hz.horizonator(C2["lat"], C2["lon"], W, H, SRTM1=True, dir_dems=tiles, render_radius_m=C2["radius_m"])
+        h.set_zextents(C2["znear"], C2["zfar"])
+        h.pan_zoom(-180.0 + 180.0 / W, 180.0 - 180.0 / W)
+        h.move(C2["lat"], C2["lon"])
+        n = 3
+
+        def timed(fn):
+            for _ in range(2):
+                fn()
+            torch.cuda.synchronize()
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(n):
+                fn()
+            torch.cuda.synchronize()
+            return max_over_ranks((time.perf_counter() - t0) / n * 1e3)
+
+        pp = sharding.PeerPanorama(h)
+        peer_ms = timed(lambda: pp.render())
+        peer_ck = int(pp.image.sum(dtype=torch.int64).item()), float(pp.ranges.double().sum().item())
+        timeouts = pp.timeouts()
+        pp.close()
+        hp = sharding.HostPanorama(h)
+        host_ms = timed(lambda: hp.render())
+        barrier()
+        host_ck = (int(hp.image.astype("int64").sum()), float(hp.ranges.astype("float64").sum())) if rank == 0 else None
+        # one GPU doing all of it: device-resident, and delivered to the same host buffer
+        whole_dev_ms = whole_host_ms = None
+        whole_ck = None
+        if rank == 0:
+            fi = torch.empty((H, W, 3), dtype=torch.uint8, device="cuda")
+            fr = torch.empty((H, W), dtype=torch.float32, device="cuda")
+            st = torch.cuda.current_stream().cuda_stream
+            for _ in range(2):
+                h.render_wedge_device(0, W, fi.data_ptr(), fr.data_ptr(), st)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(n):
+                h.render_wedge_device(0, W, fi.data_ptr(), fr.data_ptr(), st)
+            torch.cuda.synchronize()
+            whole_dev_ms = (time.perf_counter() - t0) / n * 1e3
+            whole_ck = int(fi.sum(dtype=torch.int64).item()), float(fr.double().sum().item())
+            del fi, fr
+            hp.render_whole()
+            t0 = time.perf_counter()
+            for _ in range(n):
+                hp.render_whole()
+            whole_host_ms = (time.perf_counter() - t0) / n * 1e3
+        barrier()
+        hp.close()
+        del h
+        if rank != 0:
+            return None
+        return {"what": "BASELINE configs[3]: 36000x4000 full circle, C2 DEM, one azimuth wedge per rank",
+                "peer_store_ms_per_panorama": peer_ms, "peer_barrier_timeouts": timeouts,
+                "host_delivered_ms_per_panorama": host_ms,
+                "one_gpu_device_resident_ms": whole_dev_ms, "one_gpu_host_delivered_ms": whole_host_ms,
+                "speedup_host_delivered": whole_host_ms / host_ms, "speedup_device_resident": whole_dev_ms / peer_ms,
+                "checksums_equal": bool(peer_ck == whole_ck and host_ck == whole_ck), "checksum": list(whole_ck),
+                "bytes_per_panorama": 7 * W * H}
+    except Exception as e:      # the headline numbers must survive a failure here
+        import traceback
+        traceback.print_exc()
+        return {"error": repr(e)}
 
 
 # ------------------------------------------------------------------------------------------------ CPU legs
@@ -598,7 +825,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--batch", type=int, default=16, help="panoramas per step (rendered concurrently)")
+    ap.add_argument("--batch", type=int, default=64, help="panoramas per step (one call of the batch entry point)")
+    ap.add_argument("--grid-views", type=int, default=0, help="viewpoints of the C5 grid per GPU (0 = its whole block)")
+    ap.add_argument("--no-c4", action="store_true", help="skip the 36000x4000 wedge panorama (N > 1)")
     ap.add_argument("--llvmpipe-child", action="store_true", help=argparse.SUPPRESS)
     args = ap.parse_args()
     if args.llvmpipe_child:

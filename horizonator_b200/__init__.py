@@ -110,6 +110,9 @@ def _declare(lib):
         "horizonator_render_wedge_peers": (b, [ctx, i, i, i, P(vp), P(vp), vp]),
         "horizonator_peer_barrier": (b, [ctx, i, i, P(vp), C.c_uint, vp]),
         "horizonator_reload_tunables": (b, [ctx]),
+        "horizonator_render_wedge_host": (b, [ctx, i, i, vp, vp]),
+        "horizonator_host_register": (b, [vp, C.c_size_t]),
+        "horizonator_host_unregister": (b, [vp]),
         "horizonator_host_alloc": (vp, [C.c_size_t]),
         "horizonator_host_free": (None, [vp]),
         "horizonator_profile_enable": (b, [ctx, b]),
@@ -141,6 +144,7 @@ EXPORTED_SYMBOLS = (
     "horizonator_render_counters", "horizonator_horizon_profile_device", "horizonator_set_earth_curvature", "horizonator_set_seam_wrap",
     "horizonator_peer_alloc", "horizonator_peer_open", "horizonator_peer_close", "horizonator_peer_free",
     "horizonator_render_wedge_peers", "horizonator_peer_barrier", "horizonator_reload_tunables",
+    "horizonator_render_wedge_host", "horizonator_host_register", "horizonator_host_unregister",
 )
 
 if not os.path.exists(LIBRARY_PATH):
@@ -290,6 +294,13 @@ class horizonator:
         if not lib.horizonator_render_wedge_device(C.byref(self._ctx), int(x0), int(x1),
                                                    d_image or None, d_ranges or None, stream or None):
             raise RuntimeError("horizonator_render_wedge_device() failed")
+
+    def render_wedge_host(self, x0, x1, image=None, ranges=None):
+        """Columns [x0, x1) of the current view into FULL-size host arrays (H,W,3) uint8 / (H,W) float32."""
+        if not lib.horizonator_render_wedge_host(C.byref(self._ctx), int(x0), int(x1),
+                                                 image.ctypes.data if image is not None else None,
+                                                 ranges.ctypes.data if ranges is not None else None):
+            raise RuntimeError("horizonator_render_wedge_host() failed")
 
     def set_seam_wrap(self, on=True):
         """Opt-in (off by default; the reference drops them): draw triangles across the +-180 degree seam at both

@@ -15,7 +15,11 @@
 #include <cstddef>
 #include <cstdlib>
 #include <cstring>
+#include <atomic>
+#include <chrono>
+#include <condition_variable>
 #include <mutex>
+#include <thread>
 #include <vector>
 
 namespace {
@@ -100,7 +104,9 @@ struct ViewSet
     cudaStream_t last_stream = nullptr;
     bool busy_recorded = false;
     // the standard chain, captured on first use per (number of views, shape)
-    struct Graph { int m; bool big_per_band; cudaGraphExec_t exec; int launches; };
+    // (several executable instances each, used in turn: an instance that is still in flight makes the next launch of
+    // the SAME instance wait on the host)
+    struct Graph { int m; bool big_per_band; std::vector<cudaGraphExec_t> exec; size_t next; int launches; };
     std::vector<Graph> graphs;
     bool graph_failed = false;
 };
@@ -126,7 +132,7 @@ struct Slot
     struct Bands { int n; int end[MAX_BANDS]; };
     Bands bands_single = { 2, { 48, 1 << 20, 0, 0, 0, 0 } };
     Bands bands_batch  = { 3, { 24, 72, 1 << 20, 0, 0, 0 } };
-    int views_per_set = 16, n_sets_max = 2;
+    int views_per_set = 16, n_sets_max = 4, graph_instances = 2;
 
     // target
     int W = 0, H = 0;
@@ -134,6 +140,11 @@ struct Slot
     float*   d_ranges = nullptr;
     size_t   target_pixels = 0;      // capacity of the buffers above
     uint32_t tri_capacity = 0, big_capacity = 0, bigtri_capacity = 0;
+
+    // page-locked staging for results that go to pageable host memory (copy_to_pageable): made on first use
+    char*  h_stage = nullptr;
+    size_t h_stage_bytes = 0;
+    std::vector<cudaEvent_t> stage_ev;
 
     // host-side cache of tan(elevation) row tables (tanf() per row is not free; callers re-render the same few windows)
     struct TanelRow { TanelKey key; std::vector<float> row; };
@@ -188,7 +199,7 @@ struct DeviceGuard
 
 void drop_graphs(ViewSet& vs)
 {
-    for(ViewSet::Graph& g : vs.graphs) if(g.exec) cudaGraphExecDestroy(g.exec);
+    for(ViewSet::Graph& g : vs.graphs) for(cudaGraphExec_t e : g.exec) cudaGraphExecDestroy(e);
     vs.graphs.clear();
     vs.graph_failed = false;
 }
@@ -239,6 +250,9 @@ void free_target(Slot& s)
     for(ViewSet* g : s.sets) free_set_target(*g);
     cudaFree(s.d_image);  s.d_image = nullptr;
     cudaFree(s.d_ranges); s.d_ranges = nullptr;
+    cudaFreeHost(s.h_stage); s.h_stage = nullptr; s.h_stage_bytes = 0;
+    for(cudaEvent_t e : s.stage_ev) cudaEventDestroy(e);
+    s.stage_ev.clear();
     s.target_pixels = 0;
     s.tanel_cache.clear();
 }
@@ -484,12 +498,12 @@ bool launch_chain(Slot& s, ViewSet& set, const HzView* hv, int m, bool big_per_b
 // Captures the standard chain (full width, vectorised resolve, grids sized for any eye position) for m views of the
 // set; every later standard render of m views is one cudaGraphLaunch after the parameter copy.  A dozen separate
 // launches cost more host time than the GPU needs for the render.
-const ViewSet::Graph* capture_graph(Slot& s, ViewSet& set, const HzView* hv, int m, bool big_per_band)
+ViewSet::Graph* capture_graph(Slot& s, ViewSet& set, const HzView* hv, int m, bool big_per_band)
 {
     cudaStream_t cs = nullptr;
     if(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); return nullptr; }
     cudaGraph_t g = nullptr;
-    cudaGraphExec_t exec = nullptr;
+    std::vector<cudaGraphExec_t> exec;
     bool ok = cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
     int launches = 0;
     if(ok)
@@ -497,7 +511,12 @@ const ViewSet::Graph* capture_graph(Slot& s, ViewSet& set, const HzView* hv, int
         ok = launch_chain(s, set, hv, m, big_per_band, true, true, cs, nullptr, &launches);
         if(cudaStreamEndCapture(cs, &g) != cudaSuccess) ok = false;
     }
-    if(ok && cudaGraphInstantiate(&exec, g, 0) != cudaSuccess) { ok = false; exec = nullptr; }
+    for(int k = 0; ok && k < s.graph_instances; k++)
+    {
+        cudaGraphExec_t e = nullptr;
+        if(cudaGraphInstantiate(&e, g, 0) != cudaSuccess) ok = false; else exec.push_back(e);
+    }
+    if(!ok) for(cudaGraphExec_t e : exec) cudaGraphExecDestroy(e);
     if(g) cudaGraphDestroy(g);
     cudaStreamDestroy(cs);
     if(!ok)
@@ -506,7 +525,7 @@ const ViewSet::Graph* capture_graph(Slot& s, ViewSet& set, const HzView* hv, int
         MSG("CUDA graph capture of the render chain failed; launching the kernels one by one instead");
         return nullptr;
     }
-    set.graphs.push_back(ViewSet::Graph{ m, big_per_band, exec, launches });
+    set.graphs.push_back(ViewSet::Graph{ m, big_per_band, exec, 0, launches });
     return &set.graphs.back();
 }
 
@@ -589,9 +608,27 @@ void fill_view(const Slot& s, const ViewSet& set, const Scratch& sc, const ViewS
 
 // Enqueues one render of columns [x0,x1) of m views (m <= what ensure_views() gave) on stream st: view k uses scratch
 // set.sc[k] and writes to outs[k] (device memory).  All views of one call must have the same kinds of output.
+// HORIZONATOR_TRACE_HOST=1: where the host time of enqueue_views() goes, printed when the context is destroyed
+struct HostTrace
+{
+    bool on = getenv("HORIZONATOR_TRACE_HOST") != nullptr;
+    double wait_ring = 0, fill = 0, copy = 0, launch = 0;
+    long calls = 0, views = 0;
+    static double now() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+    ~HostTrace()
+    {
+        if(on && calls)
+            fprintf(stderr, "horizonator host trace: %ld enqueues, %ld views; per enqueue: ring wait %.1f us, fill %.1f us, "
+                    "parameter copy %.1f us, launch %.1f us\n", calls, views, wait_ring / calls * 1e6, fill / calls * 1e6,
+                    copy / calls * 1e6, launch / calls * 1e6);
+    }
+};
+HostTrace g_trace;
+
 bool enqueue_views(Slot& s, ViewSet& set, int m, const ViewState* vs, int x0, int x1, const OutSpec* outs, cudaStream_t st)
 {
     if(s.W <= 0 || s.H <= 0 || m < 1 || m > (int)set.sc.size()) return false;
+    const double t_begin = g_trace.on ? HostTrace::now() : 0;
     const bool want_image = outs[0].image[0] != nullptr, want_ranges = outs[0].ranges[0] != nullptr;
     // a set serves one render at a time: if its previous render went to another stream, wait for that one
     if(set.busy_recorded && set.last_stream != st) CUDA_TRY(cudaStreamWaitEvent(st, set.busy, 0));
@@ -601,6 +638,7 @@ bool enqueue_views(Slot& s, ViewSet& set, int m, const ViewState* vs, int x0, in
     const int slot = set.ring_next;
     set.ring_next = (set.ring_next + 1) % PARAM_RING;
     CUDA_TRY(cudaEventSynchronize(set.ring_ev[slot]));            // the copies that last used this slot are done
+    const double t_ring = g_trace.on ? HostTrace::now() : 0;
     HzView* hv = set.h_views + (size_t)slot * set.cap * HZ_V_COUNT;
     const Slot::Bands& bands = bands_of(s, set);
     bool big_per_band = false, vectorisable = true;
@@ -639,8 +677,20 @@ bool enqueue_views(Slot& s, ViewSet& set, int m, const ViewState* vs, int x0, in
             sc.tanel_key.valid = true; sc.tanel_key.daz = vs[k].az_deg1 - vs[k].az_deg0; sc.tanel_key.W = s.W; sc.tanel_key.H = s.H;
         }
     }
+    const double t_fill = g_trace.on ? HostTrace::now() : 0;
     CUDA_TRY(cudaMemcpyAsync(set.d_views, hv, (size_t)m * HZ_V_COUNT * sizeof(HzView), cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaEventRecord(set.ring_ev[slot], st));
+    const double t_copy = g_trace.on ? HostTrace::now() : 0;
+    struct TraceEnd
+    {
+        double a, b, c, d; int m;
+        ~TraceEnd()
+        {
+            if(!g_trace.on) return;
+            g_trace.wait_ring += b - a; g_trace.fill += c - b; g_trace.copy += d - c; g_trace.launch += HostTrace::now() - d;
+            g_trace.calls++; g_trace.views += m;
+        }
+    } trace_end{ t_begin, t_ring, t_fill, t_copy, m };
 
     // ---- the kernels: a replay of the captured graph where the chain has its standard shape, one by one otherwise
     const bool is_main = (&set == &s.main);
@@ -648,12 +698,13 @@ bool enqueue_views(Slot& s, ViewSet& set, int m, const ViewState* vs, int x0, in
                           outs[0].n == 1 && hv[0].out_stride == s.W && outs[0].x_off == 0 && vectorisable;
     if(standard && !set.graph_failed)
     {
-        const ViewSet::Graph* g = nullptr;
-        for(const ViewSet::Graph& c : set.graphs) if(c.m == m && c.big_per_band == big_per_band) g = &c;
+        ViewSet::Graph* g = nullptr;
+        for(ViewSet::Graph& c : set.graphs) if(c.m == m && c.big_per_band == big_per_band) g = &c;
         if(g == nullptr && (g = capture_graph(s, set, hv, m, big_per_band)) == nullptr) set.graph_failed = true;
         if(g != nullptr)
         {
-            CUDA_TRY(cudaGraphLaunch(g->exec, st));
+            CUDA_TRY(cudaGraphLaunch(g->exec[g->next], st));
+            g->next = (g->next + 1) % g->exec.size();
             CUDA_TRY(cudaEventRecord(set.busy, st)); set.last_stream = st; set.busy_recorded = true;
             s.launches_last = g->launches;
             if(is_main) s.have_render = true;
@@ -716,6 +767,7 @@ void read_tunables(Slot& s)
     if(const char* env = getenv("HORIZONATOR_BANDS")) { parse_bands(env, s.bands_single); s.bands_batch = s.bands_single; }
     if(const char* env = getenv("HORIZONATOR_BANDS_BATCH")) parse_bands(env, s.bands_batch);
     if(const char* env = getenv("HORIZONATOR_GRAPHS")) s.use_graphs = atoi(env) != 0;
+    if(const char* env = getenv("HORIZONATOR_GRAPH_INSTANCES")) s.graph_instances = atoi(env) < 1 ? 1 : (atoi(env) > 16 ? 16 : atoi(env));
     // HORIZONATOR_LANES: most views of a batch rendered by one chain of launches; HORIZONATOR_SETS: how many such
     // sets may be in flight (each on its own stream)
     if(const char* env = getenv("HORIZONATOR_LANES")) s.views_per_set = atoi(env) < 1 ? 1 : (atoi(env) > 64 ? 64 : atoi(env));
@@ -748,9 +800,170 @@ bool compute_move(const horizonator_context_t* ctx, float* viewer_z, float lat, 
     return true;
 }
 
-// Device -> caller's host buffer on `st`.  Page-locked destinations (cudaHostAlloc / cudaHostRegister /
-// horizonator_host_alloc) are written by DMA at PCIe speed; for ordinary pageable memory the driver stages the
-// copy itself, which measured faster here than a private pinned bounce buffer plus memcpy.
+// ---- results into pageable host memory ------------------------------------------------------------------------
+//
+// What an unmodified caller of the reference passes to horizonator_render_offscreen() is ordinary pageable memory
+// (horizonator-pywrap.c:234-250 allocates fresh numpy arrays for every render).  A device->host copy into such memory
+// goes through a page-locked staging buffer one way or another; the driver's own staging moves a 15 MB result at about
+// a third of the PCIe rate, single-threaded.  Here the result is copied in chunks into the context's page-locked
+// staging buffer, an event after each chunk, and a few host threads (this one and a small process-wide pool) copy each
+// chunk on to the caller's memory as soon as its event has fired: the DMA and the memcpys overlap, and the memcpys
+// (and the page faults of a freshly allocated destination) run in parallel.
+
+class HostCopyPool
+{
+public:
+    struct Part { char* dst; const char* src; size_t bytes; cudaEvent_t ready; };
+
+    // copies every part (after its event) with the pool's threads and the calling one; returns when all are done
+    void run(int device, const std::vector<Part>& parts)
+    {
+        std::unique_lock<std::mutex> call(call_mutex_);          // one job at a time, process-wide
+        start_workers();
+        {
+            std::lock_guard<std::mutex> lk(m_);
+            parts_ = &parts; device_ = device; next_ = 0; pending_ = parts.size(); generation_++;
+        }
+        cv_work_.notify_all();
+        work();
+        std::unique_lock<std::mutex> lk(m_);
+        cv_done_.wait(lk, [this] { return pending_ == 0; });
+        parts_ = nullptr;
+    }
+
+    static HostCopyPool& instance() { static HostCopyPool* p = new HostCopyPool; return *p; }    // never destroyed: no
+                                                                      // join at exit, the threads die with the process
+    int threads() { start_workers(); return (int)workers_.size() + 1; }
+
+private:
+    void start_workers()
+    {
+        if(started_) return;
+        started_ = true;
+        int n = 3;
+        if(const char* env = getenv("HORIZONATOR_COPY_THREADS")) n = atoi(env) - 1;
+        const int hw = (int)std::thread::hardware_concurrency();
+        if(hw > 0 && n > hw - 1) n = hw - 1;
+        for(int k = 0; k < n; k++) workers_.emplace_back([this] { loop(); });
+        for(std::thread& t : workers_) t.detach();
+    }
+    void loop()
+    {
+        unsigned long long seen = 0;
+        for(;;)
+        {
+            {
+                std::unique_lock<std::mutex> lk(m_);
+                cv_work_.wait(lk, [&] { return generation_ != seen; });
+                seen = generation_;
+            }
+            work();
+        }
+    }
+    void work()
+    {
+        int dev_set = -1;
+        for(;;)
+        {
+            const std::vector<Part>* parts;
+            size_t k;
+            int dev;
+            {
+                std::lock_guard<std::mutex> lk(m_);
+                parts = parts_;
+                if(parts == nullptr || next_ >= parts->size()) return;
+                k = next_++; dev = device_;
+            }
+            if(dev_set != dev) { cudaSetDevice(dev); dev_set = dev; }
+            const Part& p = (*parts)[k];
+            cudaEventSynchronize(p.ready);
+            memcpy(p.dst, p.src, p.bytes);
+            {
+                std::lock_guard<std::mutex> lk(m_);
+                if(--pending_ == 0) cv_done_.notify_all();
+            }
+        }
+    }
+
+    std::mutex call_mutex_, m_;
+    std::condition_variable cv_work_, cv_done_;
+    std::vector<std::thread> workers_;
+    bool started_ = false;
+    const std::vector<Part>* parts_ = nullptr;
+    int device_ = 0;
+    size_t next_ = 0, pending_ = 0;
+    unsigned long long generation_ = 0;
+};
+
+bool is_pageable(const void* p)
+{
+    cudaPointerAttributes a{};
+    if(cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeUnregistered;
+}
+
+constexpr size_t STAGE_MAX_BYTES = (size_t)256 << 20;       // larger results take the driver's path
+
+// Device -> caller's host buffers on `st`, and waits for them.  image / ranges: destination or null; d_image /
+// d_ranges: the rendered outputs (px pixels).
+bool copy_results_to_host(Slot& s, char* image, float* ranges, const uint8_t* d_image, const float* d_ranges, size_t px,
+                          cudaStream_t st)
+{
+    struct Out { char* dst; const char* src; size_t bytes; };
+    Out outs[2] = { { image, (const char*)d_image, px * 3 }, { (char*)ranges, (const char*)d_ranges, px * sizeof(float) } };
+    std::vector<HostCopyPool::Part> parts;
+    size_t staged = 0;
+    static const bool pipeline = [] { const char* e = getenv("HORIZONATOR_COPY_THREADS"); return e == nullptr || atoi(e) > 0; }();
+    for(const Out& o : outs)
+    {
+        if(o.dst == nullptr) continue;
+        // Page-locked destinations (cudaHostAlloc / cudaHostRegister / horizonator_host_alloc) are written by DMA at
+        // PCIe speed
+        if(!pipeline || staged + o.bytes > STAGE_MAX_BYTES || !is_pageable(o.dst))
+        {
+            CUDA_TRY(cudaMemcpyAsync(o.dst, o.src, o.bytes, cudaMemcpyDeviceToHost, st));
+            continue;
+        }
+        if(s.h_stage == nullptr)
+        {
+            const size_t want = px * 7 < STAGE_MAX_BYTES ? px * 7 : STAGE_MAX_BYTES;
+            if(cudaMallocHost(&s.h_stage, want) != cudaSuccess)
+            {
+                cudaGetLastError(); s.h_stage = nullptr;
+                CUDA_TRY(cudaMemcpyAsync(o.dst, o.src, o.bytes, cudaMemcpyDeviceToHost, st));
+                continue;
+            }
+            s.h_stage_bytes = want;
+        }
+        if(staged + o.bytes > s.h_stage_bytes)
+        {
+            CUDA_TRY(cudaMemcpyAsync(o.dst, o.src, o.bytes, cudaMemcpyDeviceToHost, st));
+            continue;
+        }
+        // chunks of about 1 MB, at most 64 per output
+        size_t chunk = (size_t)1 << 20;
+        if(o.bytes / chunk > 64) chunk = (o.bytes / 64 + 4095) & ~(size_t)4095;
+        for(size_t off = 0; off < o.bytes; off += chunk)
+        {
+            const size_t n = o.bytes - off < chunk ? o.bytes - off : chunk;
+            if(parts.size() >= s.stage_ev.size())
+            {
+                cudaEvent_t e;
+                CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+                s.stage_ev.push_back(e);
+            }
+            CUDA_TRY(cudaMemcpyAsync(s.h_stage + staged + off, o.src + off, n, cudaMemcpyDeviceToHost, st));
+            CUDA_TRY(cudaEventRecord(s.stage_ev[parts.size()], st));
+            parts.push_back({ o.dst + off, s.h_stage + staged + off, n, s.stage_ev[parts.size()] });
+        }
+        staged += o.bytes;
+    }
+    if(!parts.empty()) HostCopyPool::instance().run(s.device, parts);
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return true;
+}
+
+// plain asynchronous device -> host copy (the batch call: its destinations are written while later views render)
 bool copy_to_host(void* dst, const void* src, size_t bytes, cudaStream_t st)
 {
     CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, st));
@@ -987,10 +1200,7 @@ bool horizonator_render_offscreen(const horizonator_context_t* ctx, char* image,
     const size_t px = (size_t)s->W * s->H;
     if(!enqueue_render(*s, s->view, 0, s->W,
                        single_out(image ? s->d_image : nullptr, ranges ? s->d_ranges : nullptr), s->stream)) return false;
-    if(image  && !copy_to_host(image,  s->d_image,  px * 3, s->stream)) return false;
-    if(ranges && !copy_to_host(ranges, s->d_ranges, px * sizeof(float), s->stream)) return false;
-    CUDA_TRY(cudaStreamSynchronize(s->stream));
-    return true;
+    return copy_results_to_host(*s, image, ranges, s->d_image, s->d_ranges, px, s->stream);
 }
 
 bool horizonator_pick(const horizonator_context_t* ctx, float* lat, float* lon, int x, int y)
@@ -1106,8 +1316,10 @@ static bool render_batch_common(const horizonator_context_t* ctx, Slot* s, int n
     int n_sets = 0, chunk = 0;
     if(n > 1)
     {
+        // (no fewer than 8 to a chunk where there are that many: a launch pays off with views to share it)
         n_sets = s->n_sets_max;
         chunk = (n + n_sets - 1) / n_sets;
+        if(chunk < 8) chunk = n < 8 ? n : 8;
         if(chunk > s->views_per_set) chunk = s->views_per_set;
         n_sets = (n + chunk - 1) / chunk < n_sets ? (n + chunk - 1) / chunk : n_sets;
         for(int g = 0; g < n_sets; g++)
@@ -1211,6 +1423,49 @@ bool horizonator_render_wedge_device(const horizonator_context_t* ctx, int x0, i
     cudaStream_t st = stream ? (cudaStream_t)stream : s->stream;
     if(!enqueue_render(*s, s->view, x0, x1, single_out((uint8_t*)d_image, (float*)d_ranges), st)) return false;
     if(stream == nullptr) CUDA_TRY(cudaStreamSynchronize(st));
+    return true;
+}
+
+bool horizonator_render_wedge_host(const horizonator_context_t* ctx, int x0, int x1, char* image, float* ranges)
+{
+    Slot* s = slot_of(ctx);
+    if(s == nullptr) return false;
+    if(x0 < 0 || x1 > s->W || x0 >= x1)
+    {
+        MSG("wedge columns [%d,%d) are not inside [0,%d)", x0, x1, s->W);
+        return false;
+    }
+    if(image == nullptr && ranges == nullptr) return true;
+    DeviceGuard g(s->device);
+    cudaStream_t st = s->stream;
+    // the context's own output buffers serve as the slab [H][x1-x0]; from there straight into the caller's columns
+    const size_t w = (size_t)(x1 - x0);
+    if(!enqueue_render(*s, s->view, x0, x1, single_out(image ? s->d_image : nullptr, ranges ? s->d_ranges : nullptr), st)) return false;
+    if(image)  CUDA_TRY(cudaMemcpy2DAsync(image + (size_t)x0 * 3, (size_t)s->W * 3, s->d_image, w * 3, w * 3, (size_t)s->H,
+                                          cudaMemcpyDeviceToHost, st));
+    if(ranges) CUDA_TRY(cudaMemcpy2DAsync(ranges + x0, (size_t)s->W * sizeof(float), s->d_ranges, w * sizeof(float),
+                                          w * sizeof(float), (size_t)s->H, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return true;
+}
+
+bool horizonator_host_register(void* p, size_t bytes)
+{
+    if(p == nullptr || bytes == 0) return false;
+    const cudaError_t e = cudaHostRegister(p, bytes, cudaHostRegisterPortable);
+    if(e != cudaSuccess)
+    {
+        MSG("cudaHostRegister(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
+        cudaGetLastError();
+        return false;
+    }
+    return true;
+}
+
+bool horizonator_host_unregister(void* p)
+{
+    if(p == nullptr) return false;
+    if(cudaHostUnregister(p) != cudaSuccess) { cudaGetLastError(); return false; }
     return true;
 }
 
@@ -1359,6 +1614,7 @@ bool horizonator_reload_tunables(const horizonator_context_t* ctx)
         s->small_max_pix = d.small_max_pix; s->mid_max_pix = d.mid_max_pix; s->grid_percent_single = d.grid_percent_single;
         s->grid_percent_batch = d.grid_percent_batch; s->bands_single = d.bands_single; s->bands_batch = d.bands_batch;
         s->use_graphs = d.use_graphs; s->views_per_set = d.views_per_set; s->n_sets_max = d.n_sets_max;
+        s->graph_instances = d.graph_instances;
     }
     read_tunables(*s);
     return true;

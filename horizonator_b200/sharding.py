@@ -171,14 +171,22 @@ class PeerPanorama:
                 self.opened += [pi, pr, pf]
                 self.img_dst.append(pi); self.rng_dst.append(pr); self.flag_dst.append(pf)
         self.epoch = 0
+        self._timeouts_seen = 0
         self.image = torch.as_tensor(_DeviceArray(self.img_ptr, (H, W, 3), "|u1"), device="cuda")
         self.ranges = torch.as_tensor(_DeviceArray(self.rng_ptr, (H, W), "<f4"), device="cuda")
         if self.world > 1:
             dist.barrier(group=group)                        # everybody has mapped everything
 
-    def render(self, root=None):
+    def render(self, root=None, strict=False):
         """Renders this rank's wedge of h's current view into everybody's buffers (root=None), or only into rank
-        `root`'s (the others' buffers are then left as they were); all ranks call it together."""
+        `root`'s (the others' buffers are then left as they were); all ranks call it together.
+
+        The GPU-side barriers give up on a rank that does not arrive within their spin bound (a rank that died, or
+        lags badly: first-call graph capture, host jitter) instead of hanging the GPU, and only count the time-out.
+        The returned tensors are therefore complete only if timeouts() has not changed: strict=True checks that after
+        waiting for the render (a host synchronisation per call) and raises RuntimeError if it has; callers that
+        pipeline several renders should check timeouts() themselves once at the end."""
+        before = self._timeouts_seen if strict else 0
         x0, x1 = self.edges[self.rank], self.edges[self.rank + 1]
         stream = torch.cuda.current_stream().cuda_stream
         img_dst = self.img_dst if root is None else [self.img_dst[root]]
@@ -187,6 +195,11 @@ class PeerPanorama:
         self._barrier(stream)                       # nobody's stream is still reading the previous panorama
         self.h.render_wedge_peers(x0, x1, img_dst, rng_dst, stream)
         self._barrier(stream)                       # every wedge has landed everywhere
+        if strict:
+            now = self.timeouts()
+            self._timeouts_seen = now
+            if now != before:
+                raise RuntimeError("PeerPanorama: %d GPU-side barrier(s) timed out; the panorama may be incomplete" % (now - before))
         return self.image, self.ranges
 
     def _barrier(self, stream):
@@ -210,6 +223,68 @@ class PeerPanorama:
             self.image = self.ranges = self.flags = None
             self.h.peer_free(self.img_ptr); self.h.peer_free(self.rng_ptr); self.h.peer_free(self.flag_ptr)
             self.img_ptr = self.rng_ptr = self.flag_ptr = None
+
+
+class HostPanorama:
+    """One panorama split by azimuth wedge over the ranks and delivered to ONE host buffer -- where the reference's
+    API puts its results (horizonator_render_offscreen) -- that all ranks share: a file in /dev/shm that every rank
+    maps and page-locks, so that each rank's wedge travels over its own GPU's PCIe link (one GPU delivering the whole
+    36000 x 4000 panorama moves 1 GB over a single link).  No collective on the data path; a barrier tells the ranks
+    that the panorama is complete.  Build once per context and size (collective), render() many times; rank 0 owns the
+    file.  `image` (H,W,3) uint8 and `ranges` (H,W) float32 are numpy views of the shared buffer."""
+
+    def __init__(self, h, group=None, directory="/dev/shm"):
+        import os
+        import numpy as np
+        from . import lib
+        self.h, self.group, self._lib = h, group, lib
+        self.world, self.rank = _world(group)
+        W, H = h.width, h.height
+        self.W, self.H = W, H
+        # column edges on multiples of 4 so that every wedge takes the vectorised resolve path
+        self.edges = [((W * g // self.world) // 4) * 4 for g in range(self.world)] + [W]
+        name = [os.path.join(directory, "horizonator_pano_%d_%dx%d" % (os.getpid(), W, H))]
+        nbytes = 7 * W * H
+        if self.rank == 0:
+            with open(name[0], "wb") as f:
+                f.truncate(nbytes)
+        if self.world > 1:
+            dist.broadcast_object_list(name, src=0, group=group)      # also: the file exists
+        self.path = name[0]
+        self.buf = np.memmap(self.path, dtype=np.uint8, mode="r+", shape=(nbytes,))
+        self.buf[::4096] = 0                                          # fault the pages in before they are locked
+        self.registered = bool(lib.horizonator_host_register(self.buf.ctypes.data, nbytes))
+        self.ranges = self.buf[:4 * W * H].view(np.float32).reshape(H, W)
+        self.image = self.buf[4 * W * H:].reshape(H, W, 3)
+        if self.world > 1:
+            dist.barrier(group=group)
+
+    def render(self):
+        """Every rank renders its wedge of h's current view into the shared buffer; returns when all have."""
+        self.h.render_wedge_host(self.edges[self.rank], self.edges[self.rank + 1], self.image, self.ranges)
+        if self.world > 1:
+            dist.barrier(group=self.group)
+        return self.image, self.ranges
+
+    def render_whole(self):
+        """This rank alone renders all columns into the buffer (the one-GPU baseline)."""
+        self.h.render_wedge_host(0, self.W, self.image, self.ranges)
+        return self.image, self.ranges
+
+    def close(self):
+        import os
+        if self.buf is not None:
+            if self.registered:
+                self._lib.horizonator_host_unregister(self.buf.ctypes.data)
+            self.image = self.ranges = None
+            self.buf = None
+            if self.world > 1:
+                dist.barrier(group=self.group)
+            if self.rank == 0:
+                try:
+                    os.unlink(self.path)
+                except OSError:
+                    pass
 
 
 def render_batch_sharded(h, views, group=None, gather_profiles=True):

@@ -52,6 +52,17 @@ bool horizonator_render_wedge_device(const horizonator_context_t* ctx,
                                      void* d_image, void* d_ranges,
                                      void* stream);
 
+/* The same columns into HOST memory laid out as the FULL panorama: image = H*W*3 bytes, ranges = H*W floats (as
+ * horizonator_render_offscreen() takes them; either may be NULL), of which only columns [x0, x1) are written.
+ * Synchronous.  Several contexts -- one per GPU, in one process or in several that share the buffer -- can fill
+ * one panorama this way, each over its own PCIe link; page-lock the buffer (horizonator_host_alloc(), or
+ * horizonator_host_register() for memory that exists already, e.g. a shared mapping) for DMA speed. */
+bool horizonator_render_wedge_host(const horizonator_context_t* ctx,
+                                   int x0, int x1,
+                                   char* image, float* ranges);
+bool horizonator_host_register(void* p, size_t bytes);
+bool horizonator_host_unregister(void* p);
+
 /* A wedge-sharded panorama assembled by the renderer itself over NVLink: instead of rendering its wedge
  * into a private slab that a collective then gathers, a rank's final kernel stores the wedge's pixels
  * straight into the FULL W x H image / range buffers of every rank (peer memory).

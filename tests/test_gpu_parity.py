@@ -404,10 +404,17 @@ def test_ragged_mixed_batch_equals_single_renders(hz, tiles_c1, lanes, sets):
         views.append((la, lo, c - half, c + half - (0.1 if half == 180.0 else 0.0), z))
     di = torch.empty((len(views), H, W, 3), dtype=torch.uint8, device="cuda")
     dr = torch.empty((len(views), H, W), dtype=torch.float32, device="cuda")
+    d2 = torch.empty_like(di)
+    r2 = torch.empty_like(dr)
+    stream = torch.cuda.Stream()        # a real stream: the calls only enqueue (stream 0 = NULL would make them synchronous)
     for rep in range(2):        # the second pass replays the captured graphs
-        di.zero_(); dr.zero_()
-        h.render_batch_device(views, di.data_ptr(), dr.data_ptr(), torch.cuda.current_stream().cuda_stream)
+        di.zero_(); dr.zero_(); d2.zero_(); r2.zero_()
         torch.cuda.synchronize()
+        # two calls back to back without waiting: the second reuses the view sets while the first is still in flight
+        h.render_batch_device(views, di.data_ptr(), dr.data_ptr(), stream.cuda_stream)
+        h.render_batch_device(views[::-1], d2.data_ptr(), r2.data_ptr(), stream.cuda_stream)
+        torch.cuda.synchronize()
+        assert torch.equal(d2.flip(0), di) and torch.equal(r2.flip(0), dr)
         bi, br = di.cpu().numpy(), dr.cpu().numpy()
         hi, hr = h.render_batch(views)
         assert np.array_equal(hi, bi) and np.array_equal(hr, br)

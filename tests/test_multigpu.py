@@ -55,6 +55,18 @@ def _worker(rank, world, port, tiles, q):
         dist.barrier()
         pp.close()
 
+        # ... and delivered to ONE host buffer that all ranks share, each rank copying its own wedge (its own PCIe link)
+        hp = sharding.HostPanorama(h)
+        for _ in range(2):
+            hi_, hr_ = hp.render()
+            ok = ok and np.array_equal(hi_, full_i) and np.array_equal(hr_, full_r)
+        hp.close()
+        # strict mode of the peer barrier: a time-out would raise instead of returning a stale panorama
+        pp2 = sharding.PeerPanorama(h)
+        pi, pr = pp2.render(strict=True)
+        ok = ok and np.array_equal(pi.cpu().numpy(), full_i)
+        dist.barrier()
+        pp2.close()
         views = [(LAT + 0.01 * k, LON - 0.008 * k, -180.05, 179.95) for k in range(5)]
         img, rng, (lo, hi), prof = sharding.render_batch_sharded(h, views)
         torch.cuda.synchronize()

@@ -38,6 +38,8 @@ def main():
     ap.add_argument("--last", type=int, default=0)
     ap.add_argument("--views", type=int, default=1)
     ap.add_argument("--each", action="store_true", help="list every launch instead of sums per kernel")
+    ap.add_argument("--json", default=None, help="also write {warp_instructions_per_panorama, dram_bytes_per_panorama, ...}")
+    ap.add_argument("--source", default=None, help="what the list is (goes into the json)")
     a = ap.parse_args()
     rows = read(a.csv)
     if a.last:
@@ -64,6 +66,14 @@ def main():
             e["tinst"] / e["inst"] if e["inst"] else 0, e["rd"] / 1e6 / V, e["wr"] / 1e6 / V, e["grid"]))
     print("%-12s %4d %9.1f %7s %9.3f %8s %9.2f %9.2f   (per view, %d view(s))" % (
         "total", tot["n"], tot["us"] / V, "", tot["inst"] / 1e6 / V, "", tot["rd"] / 1e6 / V, tot["wr"] / 1e6 / V, V))
+
+
+    if a.json:
+        import json
+        json.dump({"warp_instructions_per_panorama": tot["inst"] / V, "dram_bytes_per_panorama": (tot["rd"] + tot["wr"]) / V,
+                   "kernel_us_sum_per_panorama": tot["us"] / V, "launches": int(tot["n"]), "views_per_launch": V,
+                   "per_kernel_Minst": {e["name"]: round(e["inst"] / 1e6 / V, 3) for e in agg.values()},
+                   "source": a.source or a.csv}, open(a.json, "w"), indent=1)
 
 
 if __name__ == "__main__":

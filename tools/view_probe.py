@@ -49,7 +49,8 @@ class Probe:
         self.h.set_zextents(100., 150000.)
         self.d_img = torch.empty((600, 3600, 3), dtype=torch.uint8, device="cuda")
         self.d_rng = torch.empty((600, 3600), dtype=torch.float32, device="cuda")
-        self.st = torch.cuda.current_stream()
+        self.st = torch.cuda.Stream()        # (stream 0 would make the batch call synchronous)
+        torch.cuda.set_stream(self.st)
 
     def render(self, v, n=1):
         for _ in range(n):
