@@ -110,6 +110,7 @@ def _declare(lib):
         "horizonator_render_wedge_peers": (b, [ctx, i, i, i, P(vp), P(vp), vp]),
         "horizonator_peer_barrier": (b, [ctx, i, i, P(vp), C.c_uint, vp]),
         "horizonator_reload_tunables": (b, [ctx]),
+        "horizonator_debug_device_math": (b, [i, vp, vp, vp, vp, vp, vp]),
         "horizonator_render_wedge_host": (b, [ctx, i, i, vp, vp]),
         "horizonator_host_register": (b, [vp, C.c_size_t]),
         "horizonator_host_unregister": (b, [vp]),
@@ -145,6 +146,7 @@ EXPORTED_SYMBOLS = (
     "horizonator_peer_alloc", "horizonator_peer_open", "horizonator_peer_close", "horizonator_peer_free",
     "horizonator_render_wedge_peers", "horizonator_peer_barrier", "horizonator_reload_tunables",
     "horizonator_render_wedge_host", "horizonator_host_register", "horizonator_host_unregister",
+    "horizonator_debug_device_math",
 )
 
 if not os.path.exists(LIBRARY_PATH):

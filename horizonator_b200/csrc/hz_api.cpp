@@ -1595,6 +1595,26 @@ bool horizonator_set_earth_curvature(const horizonator_context_t* ctx, bool on, 
     return true;
 }
 
+bool horizonator_debug_device_math(int n, const float* e, const float* north, const float* h, const float* d2,
+                                   float* az, float* el)
+{
+    if(n < 0 || (n > 0 && (!e || !north || !h || !d2 || !az || !el))) return false;
+    if(n == 0) return true;
+    float* d = nullptr;
+    const size_t bytes = (size_t)n * sizeof(float);
+    CUDA_TRY(cudaMalloc(&d, 6 * bytes));
+    bool ok = cudaMemcpy(d, e, bytes, cudaMemcpyHostToDevice) == cudaSuccess &&
+              cudaMemcpy(d + n, north, bytes, cudaMemcpyHostToDevice) == cudaSuccess &&
+              cudaMemcpy(d + 2 * (size_t)n, h, bytes, cudaMemcpyHostToDevice) == cudaSuccess &&
+              cudaMemcpy(d + 3 * (size_t)n, d2, bytes, cudaMemcpyHostToDevice) == cudaSuccess &&
+              hz_launch_math_probe(n, d, d + n, d + 2 * (size_t)n, d + 3 * (size_t)n, d + 4 * (size_t)n, d + 5 * (size_t)n, nullptr) == cudaSuccess &&
+              cudaMemcpy(az, d + 4 * (size_t)n, bytes, cudaMemcpyDeviceToHost) == cudaSuccess &&
+              cudaMemcpy(el, d + 5 * (size_t)n, bytes, cudaMemcpyDeviceToHost) == cudaSuccess;
+    if(!ok) MSG("CUDA error in horizonator_debug_device_math: %s", cudaGetErrorString(cudaGetLastError()));
+    cudaFree(d);
+    return ok;
+}
+
 bool horizonator_reload_tunables(const horizonator_context_t* ctx)
 {
     Slot* s = slot_of(ctx);

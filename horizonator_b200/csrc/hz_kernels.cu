@@ -1667,3 +1667,24 @@ cudaError_t hz_launch_horizon(const float* ranges, int n, int W, int H, int* row
     k_horizon<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(ranges, n, W, H, rows, range);
     return cudaGetLastError();
 }
+
+// ================================================================================================
+// k_math_probe (tests only): the projection's two angle functions on arrays of arguments
+// ================================================================================================
+
+__global__ void k_math_probe(int n, const float* __restrict__ e, const float* __restrict__ nn, const float* __restrict__ h,
+                             const float* __restrict__ d2, float* __restrict__ az, float* __restrict__ el)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if(k >= n) return;
+    az[k] = hz_atan2_az(e[k], nn[k]);
+    el[k] = hz_atan_el(h[k], d2[k]);
+}
+
+cudaError_t hz_launch_math_probe(int n, const float* e, const float* nn, const float* h, const float* d2, float* az, float* el,
+                                 cudaStream_t stream)
+{
+    if(n <= 0) return cudaSuccess;
+    k_math_probe<<<(n + 255) / 256, 256, 0, stream>>>(n, e, nn, h, d2, az, el);
+    return cudaGetLastError();
+}

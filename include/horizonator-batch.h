@@ -116,6 +116,12 @@ bool horizonator_set_seam_wrap(const horizonator_context_t* ctx, bool on);
  * go back to their defaults.  For parameter sweeps inside one process; the images do not depend on them. */
 bool horizonator_reload_tunables(const horizonator_context_t* ctx);
 
+/* Test hook: the renderer's own fp32 angle functions (csrc/hz_math.cuh) evaluated on the current CUDA device for n
+ * argument sets in host arrays: az[k] = atan2(e[k], north[k]) (vertex.glsl:136), el[k] = atan(h[k] / sqrt(d2[k]))
+ * (vertex.glsl:153).  tests/test_device_math.py measures their error in ulp against double precision. */
+bool horizonator_debug_device_math(int n, const float* e, const float* north, const float* h, const float* d2,
+                                   float* az, float* el);
+
 /* Page-locked host memory for output buffers.  horizonator_render_offscreen() and
  * horizonator_render_batch() accept any host pointer; into memory from this allocator (or any
  * other CUDA-registered host memory) the results arrive by DMA at PCIe speed, into ordinary

@@ -20,6 +20,29 @@ REF_SO = os.path.join(HERE, "_ref", "libhorizonator_ref.so")
 MESA_SO = os.path.join(HERE, "_ref", "libhorizonator_mesa.so")
 
 
+class _dem_context_t(C.Structure):
+    """/root/reference/dem.h: horizonator_dem_context_t (352 bytes).  Declared here, not imported from the product
+    package, so that nothing of the product is loaded by the reference arm."""
+    _fields_ = [("dems", (C.c_void_p * 4) * 4), ("mmap_sizes", (C.c_size_t * 4) * 4), ("mmap_fd", (C.c_int * 4) * 4),
+                ("origin_dem_lon_lat", C.c_int * 2), ("origin_dem_cellij", C.c_int * 2), ("Ndems_ij", C.c_int * 2),
+                ("radius_cells", C.c_int), ("cells_per_deg", C.c_int)]
+
+
+class _offscreen_t(C.Structure):
+    _fields_ = [("inited", C.c_bool), ("frameBufID", C.c_uint32), ("renderBufID", C.c_uint32), ("depthBufID", C.c_uint32),
+                ("width", C.c_int), ("height", C.c_int)]
+
+
+class context_t(C.Structure):
+    """/root/reference/horizonator.h: horizonator_context_t (472 bytes)."""
+    _fields_ = [("Ntriangles", C.c_int), ("render_texture", C.c_bool), ("use_glut", C.c_bool), ("glut_window", C.c_int),
+                ("uniforms", C.c_int32 * 17), ("program", C.c_uint32), ("viewer_lat", C.c_float), ("viewer_lon", C.c_float),
+                ("dems", _dem_context_t), ("offscreen", _offscreen_t)]
+
+
+assert C.sizeof(_dem_context_t) == 352 and C.sizeof(context_t) == 472
+
+
 def build(ref=True):
     """make liboracle.so (+ _ref, on the fake GL and on Mesa, when /root/reference is present)."""
     targets = ["liboracle.so"] + (["ref", "mesa"] if ref else [])
@@ -194,7 +217,6 @@ class Reference:
 
     def __init__(self, lat, lon, width, height, SRTM1=False, dir_dems=None,
                  render_radius_cells=-1, render_radius_m=-1., viewer_z=None, threads=1):
-        from horizonator_b200 import context_t   # layout only; no product code runs
         L = self.lib()
         self._set_threads(threads)
         self.ctx = None
@@ -226,6 +248,16 @@ class Reference:
     def dem_sample(self, i, j):
         return self.lib().horizonator_dem_sample(C.byref(self.ctx.dems), i, j)
 
+    def mosaic(self):
+        """The whole DEM square through the reference's own horizonator_dem_sample() (dem.c:264-309), one call per
+        cell as horizonator-lib.c:435-439 does it, in a C loop (oracle/fakegl/fakegl.c: ref_sample_square)."""
+        n = 2 * self.ctx.dems.radius_cells
+        out = np.empty((n, n), np.int16)
+        L = self.lib()
+        L.ref_sample_square.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        L.ref_sample_square(C.byref(self.ctx.dems), n, out.ctypes.data)
+        return out
+
     def render(self, az_deg0, az_deg1, lat=-1000., lon=-1000., znear=100., zfar=40000.,
                znear_color=-1., zfar_color=-1.):
         L = self.lib()
@@ -242,6 +274,35 @@ class Reference:
         ranges = np.empty((self.H, self.W), np.float32)
         assert L.horizonator_render_offscreen(C.byref(self.ctx), image.ctypes.data, ranges.ctypes.data)
         return image, ranges
+
+
+class ReferenceDem:
+    """Only the DEM layer of the reference (dem.c, unmodified, out of _ref/libhorizonator_ref.so): horizonator_dem_init()
+    and the whole square through horizonator_dem_sample().  No GL context, no mesh."""
+
+    def __init__(self, lat, lon, SRTM1=False, dir_dems=None, render_radius_cells=-1, render_radius_m=-1., threads=1):
+        self.L = Reference.lib()
+        self.L.fakegl_set_threads(threads)
+        self.dems = _dem_context_t()
+        if not self.L.horizonator_dem_init(C.byref(self.dems), lat, lon, render_radius_cells, render_radius_m,
+                                           os.fsencode(dir_dems), SRTM1):
+            self.dems = None
+            raise RuntimeError("reference horizonator_dem_init() failed")
+
+    def mosaic(self):
+        n = 2 * self.dems.radius_cells
+        out = np.empty((n, n), np.int16)
+        self.L.ref_sample_square.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        self.L.ref_sample_square(C.byref(self.dems), n, out.ctypes.data)
+        return out
+
+    def close(self):
+        if self.dems is not None:
+            self.L.horizonator_dem_deinit(C.byref(self.dems))
+            self.dems = None
+
+    def __del__(self):
+        self.close()
 
 
 class MesaReference(Reference):

@@ -49,6 +49,19 @@ static int    g_threads = 1;
 
 void fakegl_set_threads(int n) { g_threads = n < 1 ? 1 : n; }
 
+/* Test helper, not GL: the whole n x n DEM square through the reference's OWN sampler (dem.c:264-309, compiled
+ * unmodified into this library), one call per cell in the order horizonator-lib.c:435-439 makes them.  out[j*n+i]. */
+#include <stdint.h>
+struct horizonator_dem_context_t;
+int16_t horizonator_dem_sample(const struct horizonator_dem_context_t* ctx, int i, int j);
+void ref_sample_square(const void* dem_ctx, int n, int16_t* out)
+{
+    #pragma omp parallel for schedule(static) num_threads(g_threads)
+    for(int j = 0; j < n; j++)
+        for(int i = 0; i < n; i++)
+            out[(size_t)j * n + i] = horizonator_dem_sample((const struct horizonator_dem_context_t*)dem_ctx, i, j);
+}
+
 /* ---- misc ---- */
 GLenum glGetError(void) { return GL_NO_ERROR; }
 const unsigned char* glGetString(GLenum name)

@@ -29,6 +29,22 @@ def pair_c2(tiles_c2):
     return h, o
 
 
+def test_config2_mosaic_bit_exact_against_the_reference_sampler(pair_c2, tiles_c2):
+    """K1 at BASELINE configs[1] size, all 137 M cells, against dem.c itself (compiled unmodified, oracle/_ref):
+    horizonator_dem_sample() once per cell, as horizonator-lib.c:435-439 calls it."""
+    from oracle import binding
+    if not binding.have_ref():
+        pytest.skip("oracle/_ref was not built (needs /root/reference at build time)")
+    h, _ = pair_c2
+    rd = binding.ReferenceDem(C2_LAT, C2_LON, SRTM1=True, dir_dems=tiles_c2, render_radius_m=150000., threads=os.cpu_count() or 1)
+    want = rd.mosaic()
+    rd.close()
+    got = h.mosaic()
+    assert got.shape == want.shape == (11716, 11716)
+    assert np.array_equal(got, want)
+    assert int(want.max()) > 1000 and int((want == 0).sum()) > 0        # real terrain, and voids clamped to 0
+
+
 def test_config2_mosaic_bit_exact_on_a_sample(pair_c2):
     h, o = pair_c2
     m = h.mosaic()

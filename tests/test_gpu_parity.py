@@ -49,6 +49,13 @@ def test_mosaic_bit_exact(hz, tiles_c1, R):
         want = _numpy_mosaic(tiles_c1, h.context.dems)
     assert got.dtype == np.int16 and got.shape == (2 * R, 2 * R)
     assert np.array_equal(got, want)
+    # ... and for every cell against the REFERENCE's own sampler: dem.c compiled unmodified (oracle/_ref), called once
+    # per cell in a C loop like horizonator-lib.c:435-439 does
+    from oracle import binding
+    if binding.have_ref():
+        rd = binding.ReferenceDem(C1_LAT, C1_LON, dir_dems=tiles_c1, render_radius_cells=R, threads=os.cpu_count() or 1)
+        assert np.array_equal(got, rd.mosaic())
+        rd.close()
     # and the host-side sampler of the product agrees with the device copy on a scattered subset
     rs = np.random.default_rng(R)
     for _ in range(200):

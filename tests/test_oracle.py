@@ -152,3 +152,17 @@ def test_oracle_shared_edges_are_watertight(tiles_c1):
             holes += (hit[-1] - hit[0] + 1) - len(hit)
     # back-facing slopes seen from above are legitimately empty only where they are in front of sky; allow a few
     assert holes <= 0.002 * 720 * 120, holes
+
+
+def test_reference_sampler_loop_equals_oracle_port(tiles_c1, tiles_holes):
+    """ReferenceDem.mosaic() -- dem.c's horizonator_dem_sample() itself, once per cell in a C loop, what the GPU tests
+    check k_mosaic against at full size -- equals the oracle's restatement cell by cell (incl. missing/empty tiles)."""
+    from oracle import binding
+    if not binding.have_ref():
+        pytest.skip("oracle/_ref was not built (needs /root/reference at build time)")
+    for tiles, R in ((tiles_c1, 130), (tiles_holes, 90)):
+        rd = binding.ReferenceDem(C1_LAT, C1_LON, dir_dems=tiles, render_radius_cells=R, threads=2)
+        got = rd.mosaic()
+        rd.close()
+        o = binding.Oracle(C1_LAT, C1_LON, 64, 16, dir_dems=tiles, render_radius_cells=R)
+        assert np.array_equal(got, o.mosaic())
