@@ -940,12 +940,15 @@ bool copy_results_to_host(Slot& s, char* image, float* ranges, const uint8_t* d_
             CUDA_TRY(cudaMemcpyAsync(o.dst, o.src, o.bytes, cudaMemcpyDeviceToHost, st));
             continue;
         }
-        // chunks of about 1 MB, at most 64 per output
+        // chunks of about 1 MB (at most ~64 per output), the last two of them cut into quarters: what remains to be
+        // done after the last byte has crossed the bus is the memcpy of the last chunk
         size_t chunk = (size_t)1 << 20;
         if(o.bytes / chunk > 64) chunk = (o.bytes / 64 + 4095) & ~(size_t)4095;
-        for(size_t off = 0; off < o.bytes; off += chunk)
+        size_t n = 0;
+        for(size_t off = 0; off < o.bytes; off += n)
         {
-            const size_t n = o.bytes - off < chunk ? o.bytes - off : chunk;
+            const size_t left = o.bytes - off, want = left > 2 * chunk ? chunk : chunk / 4;
+            n = left < want ? left : want;
             if(parts.size() >= s.stage_ev.size())
             {
                 cudaEvent_t e;

@@ -51,8 +51,10 @@ def test_mosaic_bit_exact(hz, tiles_c1, R):
     assert np.array_equal(got, want)
     # ... and for every cell against the REFERENCE's own sampler: dem.c compiled unmodified (oracle/_ref), called once
     # per cell in a C loop like horizonator-lib.c:435-439 does
+    # (not for R = 1: there the square starts on cell 0 of a tile, where the reference reads out of bounds -- SURVEY Q10,
+    # it segfaults -- and the product defines the result instead)
     from oracle import binding
-    if binding.have_ref():
+    if binding.have_ref() and R > 1:
         rd = binding.ReferenceDem(C1_LAT, C1_LON, dir_dems=tiles_c1, render_radius_cells=R, threads=os.cpu_count() or 1)
         assert np.array_equal(got, rd.mosaic())
         rd.close()
