@@ -123,15 +123,18 @@ struct Slot
     short2 *d_mm_block = nullptr, *d_mm_tile = nullptr;   // culling pyramid
     int nb = 0, nt = 0;
     int near_rings = 2;
-    int occl_tile_max_pix = 64, occl_block_max_pix = 32, small_max_pix = 16, mid_max_pix = 64;
+    // largest screen box one thread checks against the visibility buffer: a lone view is latency-bound and a long walk
+    // by one thread holds its kernel up; the views of a batch hide that behind each other and gain from the extra culling
+    int occl_tile_max_pix = 64, occl_block_max_pix = 32, occl_tile_max_pix_batch = 256, occl_block_max_pix_batch = 64;
+    int small_max_pix = 16, mid_max_pix = 64;
     int grid_percent_single = 150, grid_percent_batch = 200;   // see hz_grid() in hz_kernels.cu
     // Rings (in tiles around the eye's tile) at which the bands end; the last band runs to the edge of the mesh.
     // More bands = more of the mesh culled by what nearer bands drew, but four more kernels each.  A lone view is
-    // latency-bound and gets two bands; the views of a batch overlap each other's latencies and get three (measured
-    // over a grid of viewpoints: +18 % throughput, see profiles/).  The image is the same either way.
+    // latency-bound and gets two bands; the views of a batch overlap each other's latencies and get five (measured
+    // over a grid of viewpoints: +13 % throughput over three, profiles/r02k_*).  The image is the same either way.
     struct Bands { int n; int end[MAX_BANDS]; };
     Bands bands_single = { 2, { 48, 1 << 20, 0, 0, 0, 0 } };
-    Bands bands_batch  = { 3, { 24, 72, 1 << 20, 0, 0, 0 } };
+    Bands bands_batch  = { 5, { 10, 24, 56, 120, 1 << 20, 0 } };
     int views_per_set = 16, n_sets_max = 4, graph_instances = 2;
 
     // target
@@ -577,8 +580,11 @@ void fill_view(const Slot& s, const ViewSet& set, const Scratch& sc, const ViewS
     v.tile_queue = sc.d_tile_queue; v.block_queue = sc.d_block_queue;
     v.tri_queue = sc.d_tri_queue; v.tri_capacity = s.tri_capacity;
     v.bigtri = sc.d_bigtri; v.bigtri_count = sc.d_counters + 3; v.bigtri_capacity = s.bigtri_capacity;
-    v.occl_tile_max_pix = s.occl_tile_max_pix; v.occl_block_max_pix = s.occl_block_max_pix;
-    v.small_max_pix = s.small_max_pix; v.mid_max_pix = s.mid_max_pix;
+    v.occl_tile_max_pix  = set.batch ? s.occl_tile_max_pix_batch  : s.occl_tile_max_pix;
+    v.occl_block_max_pix = set.batch ? s.occl_block_max_pix_batch : s.occl_block_max_pix;
+    // (middle-sized triangles are drawn by their own threads only in zoomed-in views, where whole warps have them; in a
+    // wide view they sit right around the eye, and walking them in k_raster holds that kernel up for nothing)
+    v.small_max_pix = s.small_max_pix; v.mid_max_pix = big_after_every_band(s, vs) ? s.mid_max_pix : 0;
     v.grid_percent = set.batch ? s.grid_percent_batch : s.grid_percent_single;
     v.big_capacity = s.big_capacity;
 
@@ -744,8 +750,11 @@ bool enqueue_render(Slot& s, const ViewState& vs, int x0, int x1, const OutSpec&
 void read_tunables(Slot& s)
 {
     if(const char* env = getenv("HORIZONATOR_NEAR_RINGS")) s.near_rings = atoi(env) < 0 ? 0 : atoi(env);
-    if(const char* env = getenv("HORIZONATOR_OCCL_TILE_PIX"))  s.occl_tile_max_pix  = atoi(env);
-    if(const char* env = getenv("HORIZONATOR_OCCL_BLOCK_PIX")) s.occl_block_max_pix = atoi(env);
+    // (the plain variable sets both; ..._BATCH the value for the views of a batch only)
+    if(const char* env = getenv("HORIZONATOR_OCCL_TILE_PIX"))  s.occl_tile_max_pix  = s.occl_tile_max_pix_batch  = atoi(env);
+    if(const char* env = getenv("HORIZONATOR_OCCL_BLOCK_PIX")) s.occl_block_max_pix = s.occl_block_max_pix_batch = atoi(env);
+    if(const char* env = getenv("HORIZONATOR_OCCL_TILE_PIX_BATCH"))  s.occl_tile_max_pix_batch  = atoi(env);
+    if(const char* env = getenv("HORIZONATOR_OCCL_BLOCK_PIX_BATCH")) s.occl_block_max_pix_batch = atoi(env);
     if(const char* env = getenv("HORIZONATOR_SMALL_PIX"))      s.small_max_pix = atoi(env);
     if(const char* env = getenv("HORIZONATOR_MID_PIX"))        s.mid_max_pix = atoi(env);
     if(const char* env = getenv("HORIZONATOR_GRID_SCALE"))       s.grid_percent_single = atoi(env);
@@ -1634,6 +1643,7 @@ bool horizonator_reload_tunables(const horizonator_context_t* ctx)
     {
         const Slot d;       // the defaults
         s->near_rings = d.near_rings; s->occl_tile_max_pix = d.occl_tile_max_pix; s->occl_block_max_pix = d.occl_block_max_pix;
+        s->occl_tile_max_pix_batch = d.occl_tile_max_pix_batch; s->occl_block_max_pix_batch = d.occl_block_max_pix_batch;
         s->small_max_pix = d.small_max_pix; s->mid_max_pix = d.mid_max_pix; s->grid_percent_single = d.grid_percent_single;
         s->grid_percent_batch = d.grid_percent_batch; s->bands_single = d.bands_single; s->bands_batch = d.bands_batch;
         s->use_graphs = d.use_graphs; s->views_per_set = d.views_per_set; s->n_sets_max = d.n_sets_max;

@@ -1061,24 +1061,6 @@ cudaError_t hz_launch_near(const HzView& v, const HzView* d_v, int nviews, cudaS
 // Everything a band draws is in the visibility buffer before the next band is tested against it, and within a
 // band whatever has already been drawn helps too.
 
-// k-th tile of the ring walk around (0,0): k = 0 is the centre, ring r >= 1 holds the 8r tiles k in [(2r-1)^2, (2r+1)^2)
-__device__ __forceinline__ void hz_ring_walk(unsigned int k, int& dx, int& dy)
-{
-    if(k == 0) { dx = 0; dy = 0; return; }
-    int r = (int)ceilf((sqrtf((float)k + 1.0f) - 1.0f) * 0.5f);
-    while((unsigned int)((2 * r + 1) * (2 * r + 1)) <= k) r++;
-    while(r > 1 && (unsigned int)((2 * r - 1) * (2 * r - 1)) > k) r--;
-    const unsigned int off = k - (unsigned int)((2 * r - 1) * (2 * r - 1));
-    const int side = (int)(off / (unsigned int)(2 * r)), pos = (int)(off % (unsigned int)(2 * r));
-    switch(side)
-    {
-    case 0:  dx = -r + pos; dy = -r;       break;
-    case 1:  dx =  r;       dy = -r + pos; break;
-    case 2:  dx =  r - pos; dy =  r;       break;
-    default: dx = -r;       dy =  r - pos; break;
-    }
-}
-
 // Eight keys are fetched per round, walking the box row by row, so that the L2 round trips overlap whatever the
 // shape of the box; the walk ends at the first round that shows something not nearer.
 __device__ __forceinline__ bool hz_box_occluded_thread(const HzView& P, const HzBox& B, int max_pix)
@@ -1154,23 +1136,25 @@ k_tiles(const HzView* __restrict__ V)
     __shared__ unsigned int s_stats[4];
     const int nt = P.nt, N = P.N;
     const int rmax = max(max(P.eye_ti, nt - 1 - P.eye_ti), max(P.eye_tj, nt - 1 - P.eye_tj));
-    const int ring_hi = min(P.ring_hi, rmax + 1);
-    if(P.ring_lo >= ring_hi) return;
-    const unsigned int first = (unsigned int)((2 * P.ring_lo - 1) * (2 * P.ring_lo - 1));
-    const unsigned int last  = (unsigned int)((2 * ring_hi - 1) * (2 * ring_hi - 1));
+    const int ring_hi = min(P.ring_hi, rmax + 1), ring_lo = P.ring_lo;
+    if(ring_lo >= ring_hi) return;
+    // the band = the tiles of Chebyshev distance [ring_lo, ring_hi) from the eye's tile: the threads walk the part of
+    // its bounding square that lies inside the mesh, row by row, and skip the hole in the middle
+    const int tx0 = max(P.eye_ti - (ring_hi - 1), 0), tx1 = min(P.eye_ti + (ring_hi - 1), nt - 1);
+    const int ty0 = max(P.eye_tj - (ring_hi - 1), 0), ty1 = min(P.eye_tj + (ring_hi - 1), nt - 1);
+    const unsigned int bw = (unsigned int)(tx1 - tx0 + 1), last = bw * (unsigned int)(ty1 - ty0 + 1);
     const unsigned int nth = gridDim.x * blockDim.x;
     unsigned int n_all = 0, n_far = 0, n_window = 0, n_occl = 0;
-    for(unsigned int k0 = first + blockIdx.x * blockDim.x; k0 < last; k0 += nth)      // the same trip count CTA-wide
+    for(unsigned int k0 = blockIdx.x * blockDim.x; k0 < last; k0 += nth)      // the same trip count CTA-wide
     {
         const unsigned int k = k0 + threadIdx.x;
         bool on = false;
         unsigned int id = 0;
         if(k < last)
         {
-            int dx, dy;
-            hz_ring_walk(k, dx, dy);
-            const int ti = P.eye_ti + dx, tj = P.eye_tj + dy;
-            if(ti >= 0 && ti < nt && tj >= 0 && tj < nt)
+            const unsigned int row = k / bw;
+            const int ti = tx0 + (int)(k - row * bw), tj = ty0 + (int)row;
+            if(max(abs(ti - P.eye_ti), abs(tj - P.eye_tj)) >= ring_lo)
             {
                 n_all++;
                 const int tc0 = ti * HZ_TILE_CELLS, tr0 = tj * HZ_TILE_CELLS;
@@ -1368,7 +1352,8 @@ cudaError_t hz_launch_band(const HzView& v, const HzView* d_v, int nviews, bool 
                                 : max(max(v.eye_ti, v.nt - 1 - v.eye_ti), max(v.eye_tj, v.nt - 1 - v.eye_tj));
     const int ring_hi = min(v.ring_hi, rmax + 1);
     if(v.ring_lo >= ring_hi) return cudaSuccess;
-    const long long ntiles = (long long)(2 * ring_hi - 1) * (2 * ring_hi - 1) - (long long)(2 * v.ring_lo - 1) * (2 * v.ring_lo - 1);
+    // (the threads walk the band's bounding square, clipped to the mesh)
+    const long long side = min(2 * ring_hi - 1, v.nt), ntiles = side * side;
     long long ctas = (ntiles + 255) / 256;
     if(ctas > (long long)hz_grid(v, 8, nviews)) ctas = hz_grid(v, 8, nviews);
     const unsigned int ny = (unsigned int)nviews;
