@@ -127,7 +127,7 @@ struct Slot
     // by one thread holds its kernel up; the views of a batch hide that behind each other and gain from the extra culling
     int occl_tile_max_pix = 64, occl_block_max_pix = 32, occl_tile_max_pix_batch = 256, occl_block_max_pix_batch = 64;
     int small_max_pix = 16, mid_max_pix = 64;
-    int grid_percent_single = 150, grid_percent_batch = 200;   // see hz_grid() in hz_kernels.cu
+    int grid_percent_single = 100, grid_percent_batch = 200;   // see hz_grid() in hz_kernels.cu
     // Rings (in tiles around the eye's tile) at which the bands end; the last band runs to the edge of the mesh.
     // More bands = more of the mesh culled by what nearer bands drew, but four more kernels each.  A lone view is
     // latency-bound and gets two bands; the views of a batch overlap each other's latencies and get five (measured

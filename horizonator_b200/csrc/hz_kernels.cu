@@ -1061,8 +1061,11 @@ cudaError_t hz_launch_near(const HzView& v, const HzView* d_v, int nviews, cudaS
 // Everything a band draws is in the visibility buffer before the next band is tested against it, and within a
 // band whatever has already been drawn helps too.
 
-// Eight keys are fetched per round, walking the box row by row, so that the L2 round trips overlap whatever the
+// HZ_OCCL_FETCH keys are fetched per round, walking the box row by row, so that the L2 round trips overlap whatever the
 // shape of the box; the walk ends at the first round that shows something not nearer.
+#ifndef HZ_OCCL_FETCH
+#define HZ_OCCL_FETCH 8            /* (16 and 32 measured no better, lone or batched) */
+#endif
 __device__ __forceinline__ bool hz_box_occluded_thread(const HzView& P, const HzBox& B, int max_pix)
 {
     const int w = B.px1 - B.px0 + 1, h = B.py1 - B.py0 + 1;
@@ -1071,11 +1074,11 @@ __device__ __forceinline__ bool hz_box_occluded_thread(const HzView& P, const Hz
     const size_t Wt = (size_t)(P.x1 - P.x0);
     const unsigned long long* row = P.vis + (size_t)B.py0 * Wt + (size_t)(B.px0 - P.x0);
     int x = 0;
-    for(int p = 0; p < npix; p += 8)
+    for(int p = 0; p < npix; p += HZ_OCCL_FETCH)
     {
         unsigned int farthest = 0;
         #pragma unroll
-        for(int u = 0; u < 8; u++)
+        for(int u = 0; u < HZ_OCCL_FETCH; u++)
         {
             if(p + u < npix)
             {

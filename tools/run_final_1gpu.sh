@@ -1,0 +1,15 @@
+# Round-end evidence on one B200: tests, both bench arms, per-view costs, ncu launch lists and one full capture.
+T=${1:-r02}
+M=gpu__time_duration.sum,smsp__inst_executed.sum,smsp__thread_inst_executed.sum,dram__bytes_read.sum,dram__bytes_write.sum
+python -m pytest tests -m gpu -q 2>&1 | tail -4 | tee gpurun_out/${T}_pytest_tail.txt
+python bench.py > gpurun_out/${T}_bench.json 2> gpurun_out/${T}_bench.err; tail -2 gpurun_out/${T}_bench.err
+python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/${T}_bench_ref.json 2> gpurun_out/${T}_bench_ref.err
+python tools/view_probe.py --grid --out gpurun_out/${T}_views.json > gpurun_out/${T}_views.log 2>&1; head -1 gpurun_out/${T}_views.log
+for v in c2 gridworst eye12km zoom10; do
+  ncu --metrics $M --clock-control none --csv --log-file gpurun_out/${T}_launch_$v.csv python tools/view_probe.py --ncu $v --reps 2 > /dev/null 2>&1
+done
+ncu --metrics $M --clock-control none --csv --log-file gpurun_out/${T}_launch_batch64.csv python tools/batch_sweep.py --once 64 > /dev/null 2>&1
+# one full capture of the batch configuration's kernels (one chunk of 16 views: 26 kernels; the third call is the timed one)
+ncu --set full --clock-control none --import-source on -k regex:"k_mesh|k_blocks|k_raster|k_tiles|k_big|k_resolve4|k_near|k_prepare" -s 208 -c 26 -o gpurun_out/${T}_batch_chain python tools/batch_sweep.py --once 64 > gpurun_out/${T}_ncu_full.log 2>&1
+HORIZONATOR_TRACE_HOST=1 python tools/batch_sweep.py --reps 10 --batches 16,64,256 --out gpurun_out/${T}_sweep.jsonl "" 2>&1 | tail -2 | tee gpurun_out/${T}_host_trace.txt
+ls -la gpurun_out | tail -20
