@@ -281,7 +281,7 @@ struct HzTri
     unsigned int id;
 };
 
-enum { HZ_SETUP_NOTHING = 0, HZ_SETUP_OK = 1, HZ_SETUP_TOO_WIDE = -1 };
+enum { HZ_SETUP_NOTHING = 0, HZ_SETUP_OK = 1, HZ_SETUP_TOO_WIDE = -1, HZ_SETUP_QUEUE_FULL = -2 };
 
 // geometry.glsl:21-27, guard band, back-face cull, bounding box.  HZ_SETUP_OK, or why the triangle produces nothing.
 __device__ __forceinline__ int
@@ -737,17 +737,17 @@ __device__ __forceinline__ unsigned int hz_big_layout(const HzView& P, const HzT
     return nx * ny;
 }
 
-// Queues a large triangle: `slot` = first of its n = nx*ny reserved queue slots, `rec` = its reserved record.
-__device__ __forceinline__ void
+// Queues a large triangle: `slot` = first of its n = nx*ny reserved queue slots, `rec` = its reserved record.  False if
+// the queue is full: the reserved slots are poisoned (k_big skips those) and the caller has to draw the triangle itself
+// (hz_draw_slow; not from here: that call in the middle of k_raster's loop cost it 16 registers and spills).
+__device__ __forceinline__ bool
 hz_big_enqueue(const HzView& P, const HzTri& T, unsigned int id, int copy, unsigned int nx, unsigned int k, unsigned int n,
                unsigned int slot, unsigned int rec)
 {
     if(slot + n > P.big_capacity)
     {
-        // queue full: draw it here, and poison the queue slots it reserved (k_big skips those)
         for(unsigned int q = slot; q < min(slot + n, P.big_capacity); q++) P.big_queue[q] = make_uint2(0xFFFFFFFFu, 0u);
-        hz_draw_slow(P, id, copy);
-        return;
+        return false;
     }
     // the set-up triangle goes to the record pool; if that is full the entries carry the triangle's number instead and
     // k_big repeats the set-up (slower, still one warp per sub-box)
@@ -758,6 +758,7 @@ hz_big_enqueue(const HzView& P, const HzTri& T, unsigned int id, int copy, unsig
     for(unsigned int by = 0; by < ny; by++)
         for(unsigned int bx = 0; bx < nx; bx++)
             P.big_queue[slot + by * nx + bx] = make_uint2(first, by | (bx << 12) | tag);
+    return true;
 }
 
 // The two seam copies of a triangle that came out too wide (opt-in seam wrap; rare): one thread does it all, with
@@ -773,10 +774,19 @@ __device__ __noinline__ unsigned int hz_raster_seam_copies(const HzView& P, unsi
         const unsigned int n = hz_big_layout(P, T, nx, k);
         if(n == 0) { hz_draw_box<int>(P, T); continue; }
         const unsigned int slot = atomicAdd(P.big_count, n), rec = atomicAdd(P.bigtri_count, 1u);
-        hz_big_enqueue(P, T, id, copy, nx, k, n, slot, rec);
-        queued += n;
+        if(hz_big_enqueue(P, T, id, copy, nx, k, n, slot, rec)) queued += n;
+        else hz_draw_slow(P, id, copy);
     }
     return queued;
+}
+
+// k_raster's rare cases for one triangle: the large-triangle queue was full -> drawn by this thread, whatever its size;
+// too wide as it stands and the opt-in seam wrap is on -> its two seam copies.  Returns the queue entries made.
+__device__ __noinline__ unsigned int hz_raster_rare(const HzView& P, unsigned int id, int status)
+{
+    if(status == HZ_SETUP_QUEUE_FULL) { hz_draw_slow(P, id, 0); return 0; }
+    if(status == HZ_SETUP_TOO_WIDE && P.seam_period > 0.0f) return hz_raster_seam_copies(P, id);
+    return 0;
 }
 
 __device__ __forceinline__ unsigned int hz_warp_sum(unsigned int v)
@@ -966,6 +976,42 @@ hz_stage_flush_cta(const HzView& P, const HzMeshWarp& M, int count, unsigned int
     }
 }
 
+// What a meshing warp does from the moment the stage's triangle list is full (never on the normal path; tests shrink
+// the list to get here): it draws what it has staged, then meshes the rest of its blocks with every passing triangle
+// drawn on the spot.  One out-of-line function with its own register allocation, called once at the end of the kernel:
+// inlined, its calls to hz_draw_slow() made ptxas keep the hot meshing loop's registers in local memory.
+// b: first block of the group the warp stopped in (already projected, to be resumed at block k_resume), ids: that
+// group's blocks; the warp's later groups start `stride` blocks on.  near: k_near's blocks are not queued but counted
+// off a rectangle of the block grid (G), k_mesh's come from P.block_queue (G = null).
+struct HzNearGrid { int bj0, bi0, nbi; };
+
+__device__ __noinline__ void
+hz_mesh_slow_tail(const HzView& P, HzMeshWarp& M, int staged, unsigned int b, unsigned int n, unsigned int stride, int per,
+                  unsigned int ids, int k_resume, const HzNearGrid* G, unsigned int& n_meshed, unsigned int& n_tris)
+{
+    const int lane = (int)(threadIdx.x & 31u);
+    const HzLaneMap map = hz_lane_map(lane);
+    hz_stage_draw_slow(P, M.stage, staged);
+    int count = 0;
+    for(bool first = true; b < n; b += stride, first = false)
+    {
+        const int nblk = (int)min((unsigned int)per, n - b);
+        if(!first)
+        {
+            if(G != nullptr)
+            {
+                const int bk = (int)min(b + (unsigned int)lane, n - 1u);
+                ids = ((unsigned int)(G->bj0 + bk / G->nbi) << 16) | (unsigned int)(G->bi0 + bk % G->nbi);
+            }
+            else ids = (b + lane < n && lane < per) ? P.block_queue[b + lane] : 0u;
+            hz_group_project(P, ids, nblk, lane, map, hz_group_heights(P, ids, nblk, map), M);
+            n_meshed += (unsigned int)nblk;
+        }
+        hz_group_triangles<true>(P, ids, first ? k_resume : 0, nblk, lane, M, count, n_tris);
+        __syncwarp();
+    }
+}
+
 // ================================================================================================
 // k_near: the tiles around the eye, one warp per block, no pyramid and no occlusion tests
 // ================================================================================================
@@ -1010,22 +1056,15 @@ k_near(const HzView* __restrict__ V)
     }
     if(k_resume >= 0)
     {
-        // the triangle list is full: this warp draws everything else it finds itself (b already points at the next group)
-        hz_stage_draw_slow(P, M.stage, count);
-        count = 0;
+        // the triangle list is full: this warp draws everything else it finds itself (b already points at the next
+        // group; the one it stopped in is still projected)
         b -= nwarps * per;
-        for(bool first = true; b < nblocks; b += nwarps * per, first = false)
-        {
-            const int nblk = min(per, nblocks - b), bk = min(b + lane, nblocks - 1);
-            const unsigned int ids = ((unsigned int)(bj0 + bk / nbi) << 16) | (unsigned int)(bi0 + bk % nbi);
-            if(!first)
-            {
-                n_blocks += (unsigned int)nblk;
-                hz_group_project(P, ids, nblk, lane, map, hz_group_heights(P, ids, nblk, map), M);
-            }
-            hz_group_triangles<true>(P, ids, first ? k_resume : 0, nblk, lane, M, count, n_tris);
-            __syncwarp();
-        }
+        const HzNearGrid G = { bj0, bi0, nbi };
+        const int bk = min(b + lane, nblocks - 1);
+        const unsigned int ids = ((unsigned int)(bj0 + bk / nbi) << 16) | (unsigned int)(bi0 + bk % nbi);
+        hz_mesh_slow_tail(P, M, count, (unsigned int)b, (unsigned int)nblocks, (unsigned int)(nwarps * per), per, ids, k_resume, &G,
+                          n_blocks, n_tris);
+        count = 0;
     }
     hz_stage_flush_cta(P, s_warp[wib], count, &s_total, &s_base);
     if(P.stats && lane == 0 && n_blocks)
@@ -1252,21 +1291,9 @@ k_mesh(const HzView* __restrict__ V)
     if(k_resume >= 0)
     {
         // the triangle list is full: this warp draws everything else it finds itself (b, ids: the group it stopped in,
-        // already projected)
-        hz_stage_draw_slow(P, M.stage, count);
+        // already projected).  Out of line, with its own registers: see hz_mesh_slow_tail.
+        hz_mesh_slow_tail(P, M, count, b, n, nwarps * per, (int)per, ids, k_resume, nullptr, n_meshed, n_tris);
         count = 0;
-        for(bool first = true; b < n; b += nwarps * per, first = false)
-        {
-            const int nblk = (int)min(per, n - b);
-            if(!first)
-            {
-                ids = (b + lane < n && lane < per) ? P.block_queue[b + lane] : 0u;
-                hz_group_project(P, ids, nblk, lane, map, hz_group_heights(P, ids, nblk, map), M);
-                n_meshed += (unsigned int)nblk;
-            }
-            hz_group_triangles<true>(P, ids, first ? k_resume : 0, nblk, lane, M, count, n_tris);
-            __syncwarp();
-        }
     }
     hz_stage_flush_cta(P, s_warp[wib], count, &s_total, &s_base);
     if(P.stats && lane == 0 && n_meshed)
@@ -1331,11 +1358,15 @@ k_raster(const HzView* __restrict__ V)
             slot0 = __shfl_sync(0xffffffffu, slot0, 0); rec0 = __shfl_sync(0xffffffffu, rec0, 0);
             if(nsub != 0)
             {
-                hz_big_enqueue(P, T, id, 0, nx, k, nsub, slot0 + incl - nsub, rec0 + __popc(ballot & ((1u << lane) - 1u)));
-                n_big += nsub;
+                if(hz_big_enqueue(P, T, id, 0, nx, k, nsub, slot0 + incl - nsub, rec0 + __popc(ballot & ((1u << lane) - 1u))))
+                    n_big += nsub;
+                else
+                    st = HZ_SETUP_QUEUE_FULL;
             }
         }
-        if(st == HZ_SETUP_TOO_WIDE && P.seam_period > 0.0f) n_big += hz_raster_seam_copies(P, id);
+        // the rare cases, out of line and only here, where nothing of the triangle's set-up is live any more: the queue
+        // was full (never on the normal path) or the triangle straddles the seam (opt-in seam wrap)
+        if(st < 0) n_big += hz_raster_rare(P, id, st);
     }
     n_big = hz_warp_sum(n_big);
     if(P.stats && lane == 0 && n_big) atomicAdd(P.stats + HZ_STAT_BIG_ENTRIES, n_big);
