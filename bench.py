@@ -1,26 +1,34 @@
 #!/usr/bin/env python
 """bench.py -- panoramas/s of the render hot path on N B200s (BASELINE.json metric), one JSON line.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--batch B]
 
 Workload (N=1 and per rank for N>1): BASELINE.json configs[1] ("C2") -- synthetic SRTM1 tiles N32..N35 x
 W119..W116, viewer (34+1/7200, -117+1/7200), render_radius_m = 150 km (R = 5858 cells, 137 M vertices, 274 M
 triangles), 3600x600 panorama + range image, az [-180.05, 179.95], znear 100 m, zfar 150 km.  A step is one
-call of horizonator_render_batch_device() with --batch (default 16) panoramas per rank, which the library renders
-concurrently on its render lanes (the kernels of one panorama are short and latency-bound; several in flight
-fill the machine).  With N>1 every rank does the same against its own copy of the DEM (weak scaling, no
-collective on the data path; NCCL only for the barrier/max of times).
+call of horizonator_render_batch_device() with --batch (default 64) panoramas per rank on a real CUDA stream: the
+library renders them in chunks of up to 16 views, each chunk ONE chain of kernel launches with a view dimension,
+chunks alternating between 4 streams.  With N>1 every rank does the same against its own copy of the DEM (weak
+scaling, no collective on the data path; NCCL only for the barrier/max of times).
 
 value      device-resident throughput: K steps x batch panoramas / time; outputs stay in HBM, CUDA events on the
            stream the work is queued on, max over ranks
 e2e        the same metric through the reference-facing call horizonator_render_offscreen(): one panorama per
-           call into (page-locked) HOST buffers, device->host copy inside the timed region
+           call into (page-locked) HOST buffers, device->host copy inside the timed region; also into pageable
+           buffers, through the batch call, and against the box's concurrent device->host ceiling measured in the run
 roofline   achieved = algorithmic bytes per panorama (2*(2R)^2 + 7*W*H) x measured panoramas/s against
-           MEASURED_PEAKS.json hbm_gbs; plus the per-stage CUDA-event times and the latency of a lone panorama
-cpu_baseline  the CPU oracle timed on the host cores (rank 0, N=1), a bounded sample of the same workload
+           MEASURED_PEAKS.json hbm_gbs; issue = warp instructions per panorama (ncu capture of this configuration,
+           profiles/batch_profile.json) x panoramas/s against the SMs' issue peak; per-stage times and the latency of
+           a lone panorama
+aux        c5_grid: BASELINE configs[4], the 64x64 grid of DISTINCT viewpoints, each rank its own rows;
+           lone_ms_special_views: eye 3/12 km up, zoomed-in windows; c3_sweep: configs[2], Python render() pan/zoom
+           sweep through the reference's own compiled binding and through the ctypes mirror; c4_wedge (N > 1):
+           configs[3], one 36000x4000 panorama by azimuth wedge, assembled in device memory (peer stores over NVLink)
+           and in one shared host buffer (every rank over its own PCIe link)
+cpu_baseline  the unmodified reference on Mesa llvmpipe on the host cores (rank 0, N=1): one steady-state frame
 
---impl reference: the reference's own horizonator-lib.c + dem.c (compiled unmodified, oracle/_ref) rendering
-the same workload on the host cores through a software GL restatement (no GL driver can run in this image).
+--impl reference: the reference's own horizonator-lib.c + dem.c + GLSL (compiled unmodified, oracle/_ref) rendering
+the same workload on the host cores on Mesa llvmpipe (fallback: on the oracle's software-GL restatement).
 """
 import argparse
 import json
@@ -157,10 +165,10 @@ def ensure_tiles(rank, barrier):
 
 def c5_grid(world, rank, g=64):
     """BASELINE configs[4] ("C5"): the g x g grid of viewpoints over the central degree of the DEM, dealt to the ranks
-    in contiguous blocks of whole grid rows (disjoint; 4096 / world viewpoints each)."""
-    pts = [(33.5 + (j + 0.5) / g + 1.0 / 7200.0, -117.5 + (i + 0.5) / g + 1.0 / 7200.0) for j in range(g) for i in range(g)]
-    lo, hi = len(pts) * rank // world, len(pts) * (rank + 1) // world
-    return pts[lo:hi]
+    by grid row, round-robin (disjoint; 4096 / world viewpoints each; neighbouring rows cost about the same, so the
+    ranks get equal work -- contiguous blocks of rows would give each rank a different kind of terrain)."""
+    rows = range(rank, g, world)
+    return [(33.5 + (j + 0.5) / g + 1.0 / 7200.0, -117.5 + (i + 0.5) / g + 1.0 / 7200.0) for j in rows for i in range(g)]
 
 
 # ------------------------------------------------------------------------------------------------ our arm
@@ -532,7 +540,7 @@ def run_b200(args):
                 "c5_grid": {"value": grid_value, "unit": "panoramas/s", "viewpoints_per_gpu": n_grid_all,
                             "what": "BASELINE configs[4]: DISTINCT viewpoints of the 64x64 grid over the central degree "
                                     "(33.5..34.5 N, 117.5..116.5 W), eye 1 m above the local terrain, full circle; "
-                                    "each rank renders its own contiguous block of the grid in calls of %d" % B,
+                                    "each rank renders its own rows of the grid (rows rank, rank + N, ...) in calls of %d" % B,
                             "ratio_to_single_viewpoint_value": grid_value / value,
                             "roofline_frac": alg * (grid_value / world) / 1e9 / peak,
                             "lone_ms": {"min": lone[0], "median": lone[len(lone) // 2], "max": lone[-1], "n": len(lone),
