@@ -103,6 +103,7 @@ def _declare(lib):
         "horizonator_horizon_profile_device": (b, [ctx, vp, i, vp, vp, vp]),
         "horizonator_set_earth_curvature": (b, [ctx, b, f]),
         "horizonator_set_seam_wrap": (b, [ctx, b]),
+        "horizonator_set_lod": (b, [ctx, f]),
         "horizonator_peer_alloc": (b, [ctx, C.c_size_t, P(vp), P(C.c_ubyte * 64)]),
         "horizonator_peer_open": (b, [ctx, P(C.c_ubyte * 64), P(vp)]),
         "horizonator_peer_close": (b, [ctx, vp]),
@@ -146,7 +147,7 @@ EXPORTED_SYMBOLS = (
     "horizonator_peer_alloc", "horizonator_peer_open", "horizonator_peer_close", "horizonator_peer_free",
     "horizonator_render_wedge_peers", "horizonator_peer_barrier", "horizonator_reload_tunables",
     "horizonator_render_wedge_host", "horizonator_host_register", "horizonator_host_unregister",
-    "horizonator_debug_device_math",
+    "horizonator_debug_device_math", "horizonator_set_lod",
 )
 
 if not os.path.exists(LIBRARY_PATH):
@@ -309,6 +310,12 @@ class horizonator:
         edges of a full-circle panorama.  See horizonator-batch.h."""
         if not lib.horizonator_set_seam_wrap(C.byref(self._ctx), bool(on)):
             raise RuntimeError("horizonator_set_seam_wrap() failed")
+
+    def set_lod(self, max_cell_pixels=0.5):
+        """Opt-in level of detail (0 = off, the default; the reference always draws every DEM cell): coarser far mesh
+        where a coarser cell still is at most `max_cell_pixels` pixels across.  See horizonator-batch.h."""
+        if not lib.horizonator_set_lod(C.byref(self._ctx), float(max_cell_pixels)):
+            raise RuntimeError("horizonator_set_lod() failed")
 
     def set_earth_curvature(self, on=True, refraction=0.13):
         """Opt-in accuracy mode (off by default; the reference is flat-earth): see horizonator-batch.h."""

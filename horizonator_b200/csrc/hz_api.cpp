@@ -169,6 +169,7 @@ struct Slot
 
     // optional per-kernel timing: PROF_EVENTS events per recorded render
     bool profiling = false;
+    float lod_pixels = 0.f;          // opt-in (horizonator_set_lod); 0 = every band meshed at full density like the reference
     bool  seam_wrap = false;         // opt-in (horizonator_set_seam_wrap); false = seam triangles dropped like the reference
     float curvature = 0.f;           // opt-in (horizonator_set_earth_curvature); 0 = flat earth like the reference
     bool use_graphs = true;
@@ -458,6 +459,12 @@ const Slot::Bands& bands_of(const Slot& s, const ViewSet& set)
     return set.batch ? s.bands_batch : s.bands_single;
 }
 
+// bands of a render chain: the configured ones, plus two more where the opt-in level of detail changes (fill: enqueue_views)
+int n_bands_of(const Slot& s, const ViewSet& set)
+{
+    return bands_of(s, set).n + (s.lod_pixels > 0.f ? HZ_MAX_LOD : 0);
+}
+
 // Zoomed-in views (small angle per pixel) show triangles many pixels large even far from the eye: each band then draws
 // its large triangles before the next band is tested against the visibility buffer.  In wide views the far bands have
 // hardly any, and one k_big after the last band saves a launch per band.
@@ -480,10 +487,10 @@ bool launch_chain(Slot& s, ViewSet& set, const HzView* hv, int m, bool big_per_b
     if(ev) CUDA_TRY(cudaEventRecord(ev[2], st));
     CUDA_TRY(hz_launch_big(hv[HZ_V_NEAR], dv + HZ_V_NEAR, m, st)); n++;
     if(ev) CUDA_TRY(cudaEventRecord(ev[3], st));
-    const Slot::Bands& bands = bands_of(s, set);
-    for(int b = 0; b < bands.n; b++)
+    const int n_bands = n_bands_of(s, set);
+    for(int b = 0; b < n_bands; b++)
     {
-        const bool last = (b + 1 == bands.n);
+        const bool last = (b + 1 == n_bands);
         int k = 0;
         CUDA_TRY(hz_launch_band(hv[HZ_V_BAND0 + b], dv + HZ_V_BAND0 + b, m, worst_case, st, &k));
         n += k;
@@ -586,6 +593,7 @@ void fill_view(const Slot& s, const ViewSet& set, const Scratch& sc, const ViewS
     // wide view they sit right around the eye, and walking them in k_raster holds that kernel up for nothing)
     v.small_max_pix = s.small_max_pix; v.mid_max_pix = big_after_every_band(s, vs) ? s.mid_max_pix : 0;
     v.grid_percent = set.batch ? s.grid_percent_batch : s.grid_percent_single;
+    v.lod_capable = s.lod_pixels > 0.f;
     v.big_capacity = s.big_capacity;
 
     // the eye's tile, and how many rings of tiles around it form the foreground pass
@@ -662,16 +670,40 @@ bool enqueue_views(Slot& s, ViewSet& set, int m, const ViewState* vs, int x0, in
         {
             hk[j].big_queue = sc.d_big_queue + s.big_capacity;      hk[j].big_count = sc.d_counters + 1;
         }
+        // The bands: the configured ring limits -- plus, with the opt-in level of detail, the two rings from which on a
+        // cell of 2x2 / 4x4 DEM cells, seen from that ring's nearest edge, is at most lod_pixels pixels across: the level
+        // is then the same throughout a band, and the image does not depend on how the bands were configured.
+        int ends[HZ_MAX_BANDS], n_ends = 0;
+        for(int b = 0; b < bands.n; b++) ends[n_ends++] = bands.end[b];
+        int lod_from[HZ_MAX_LOD + 1] = { 0, 1 << 30, 1 << 30 };
+        if(s.lod_pixels > 0.f)
+        {
+            // cell / distance * pixels per radian, distance = (ring - 1) tiles of HZ_TILE_CELLS cells
+            const double k_px = fabs((double)hk[0].az_ndc_per_rad) * 0.5 * (double)s.W / (double)HZ_TILE_CELLS;
+            for(int l = 1; l <= HZ_MAX_LOD; l++)
+            {
+                const double r = ceil(k_px * (double)(1 << l) / (double)s.lod_pixels) + 1.0;
+                lod_from[l] = r < 2.0 ? 2 : (r > 1e9 ? 1 << 30 : (int)r);
+                int at = n_ends;
+                while(at > 0 && ends[at - 1] > lod_from[l]) { ends[at] = ends[at - 1]; at--; }
+                ends[at] = lod_from[l];
+                n_ends++;
+            }
+        }
         int lo = s.near_rings + 1;
-        for(int b = 0; b < bands.n; b++)
+        for(int b = 0; b < n_ends; b++)
         {
             HzView& vb = hk[HZ_V_BAND0 + b];
-            vb.ring_lo = lo; vb.ring_hi = bands.end[b] > lo ? bands.end[b] : lo;
+            vb.ring_lo = lo; vb.ring_hi = ends[b] > lo ? ends[b] : lo;
             vb.tile_count = sc.d_counters + 4 + 4 * b; vb.block_count = sc.d_counters + 5 + 4 * b;
             vb.tri_count  = sc.d_counters + 6 + 4 * b;
             // one k_big per band: each band counts its own entries from 0 (the queue memory is reused, the bands run
             // one after the other); one k_big at the end: all bands append to the same count
             vb.big_count  = sc.d_counters + 7 + (big_per_band ? 4 * b : 0);
+            int lod = 0;
+            while(lod < HZ_MAX_LOD && vb.ring_lo >= lod_from[lod + 1]) lod++;
+            vb.lod = lod;
+            vb.cell_diag2 = hk[0].cell_diag2 * (float)((1 << lod) * (1 << lod));
             lo = vb.ring_hi;
         }
         // the row table of this view's window, unless the scratch still holds it from its previous render
@@ -763,7 +795,7 @@ void read_tunables(Slot& s)
     // of a batch; the first also sets the second unless that is given); the last band always runs to the edge
     auto parse_bands = [](const char* env, Slot::Bands& out) {
         int n = 0;
-        for(const char* p = env; *p && n < MAX_BANDS - 1; )
+        for(const char* p = env; *p && n < MAX_BANDS - HZ_MAX_LOD - 1; )
         {
             const int r = atoi(p);
             if(r > 0) out.end[n++] = r;
@@ -1591,6 +1623,30 @@ bool horizonator_set_seam_wrap(const horizonator_context_t* ctx, bool on)
     Slot* s = slot_of(ctx);
     if(s == nullptr) return false;
     s->seam_wrap = on;
+    return true;
+}
+
+bool horizonator_set_lod(const horizonator_context_t* ctx, float max_cell_pixels)
+{
+    Slot* s = slot_of(ctx);
+    if(s == nullptr) return false;
+    if(!(max_cell_pixels >= 0.f))
+    {
+        MSG("max_cell_pixels %g is negative", (double)max_cell_pixels);
+        return false;
+    }
+    if((max_cell_pixels > 0.f) != (s->lod_pixels > 0.f))
+    {
+        // the captured chains launch a different instantiation of k_blocks: wait for what is in flight, drop them
+        DeviceGuard g(s->device);
+        CUDA_TRY(cudaStreamSynchronize(s->stream));
+        for(ViewSet* v : s->sets) CUDA_TRY(cudaStreamSynchronize(v->stream));
+        if(s->main.busy_recorded) CUDA_TRY(cudaEventSynchronize(s->main.busy));
+        for(ViewSet* v : s->sets) if(v->busy_recorded) CUDA_TRY(cudaEventSynchronize(v->busy));
+        drop_graphs(s->main);
+        for(ViewSet* v : s->sets) drop_graphs(*v);
+    }
+    s->lod_pixels = max_cell_pixels;
     return true;
 }
 

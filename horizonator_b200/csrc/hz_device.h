@@ -9,7 +9,9 @@
 //     [63:40] q    window depth quantised to 24 bits (the GL_DEPTH_COMPONENT renderbuffer of
 //                  horizonator-lib.c:646; smaller = nearer)
 //     [39: 8] id   triangle number in the reference's draw order (horizonator-lib.c:496-508):
-//                  2*(j*(2R-1)+i) + {0: (j,i),(j+1,i+1),(j+1,i)   1: (j,i),(j,i+1),(j+1,i+1)}
+//                  2*(j*(2R-1)+i) + {0: (j,i),(j+1,i+1),(j+1,i)   1: (j,i),(j,i+1),(j+1,i+1)}   (< 2^29)
+//                  bits [30:29] of it: the opt-in level of detail of the triangle (0 in the reference's mesh: the
+//                  triangle then spans (1 << lod) cells from (j,i))
 //     [ 7: 0] r8   the fragment's red channel (fragment.glsl:16 after unorm8 conversion)
 // min() over keys == GL_LESS with in-order drawing: nearest q wins, equal q -> first drawn wins.
 // The result is independent of the order in which threads get to a pixel.
@@ -32,10 +34,12 @@ constexpr int HZ_MAX_OUT     = 8;   // destinations of one resolve (ranks of a w
 constexpr int HZ_BLOCK_CELLS = 4;
 constexpr int HZ_TILE_BLOCKS = 8;
 constexpr int HZ_TILE_CELLS  = HZ_BLOCK_CELLS * HZ_TILE_BLOCKS;
-// The blocks along the far edges of the mesh may reach up to 3 vertices beyond its last row/column: the mosaic has this
+// The blocks along the far edges of the mesh may reach beyond its last row/column (by up to 3 vertices; with the
+// opt-in level of detail by up to a coarse block): the mosaic has this
 // many extra (zero) rows, its pitch covers as many extra columns, and the axis tables as many extra entries, so that the
 // meshing kernels read those vertices without clamping (their triangles are left out).
-constexpr int HZ_MESH_PAD    = 4;
+constexpr int HZ_MAX_LOD     = 2;                       // opt-in level of detail: blocks of (4 << lod)^2 cells (HzView::lod)
+constexpr int HZ_MESH_PAD    = HZ_BLOCK_CELLS << HZ_MAX_LOD;
 
 // ---- counters a render leaves behind (diagnostics; bench.py and the tests read them) -----------
 enum HzStat
@@ -93,6 +97,8 @@ struct HzView
     // it is tested against it.
     int eye_ti, eye_tj, near_rings;
     int ring_lo, ring_hi;        // the band this launch works on
+    int lod;                     // 0 = the reference's mesh.  Opt-in (horizonator_set_lod): the band is meshed with every
+                                 // (1 << lod)-th vertex -- blocks of (4 << lod)^2 cells, still 5x5 vertices and 32 triangles
     uint32_t* tile_queue;        // live tiles of the band (tj << 16 | ti)
     uint32_t* tile_count;
     uint32_t* block_queue;       // live blocks of the band (bj << 16 | bi)
@@ -102,6 +108,7 @@ struct HzView
     uint32_t  tri_capacity;
     int occl_tile_max_pix, occl_block_max_pix;   // largest screen box one thread checks against the visibility buffer
     int grid_percent;            // host only: scale of the device-counted kernels' grids (hz_grid)
+    int lod_capable;             // host only: some view of the launch may have lod > 0 (picks k_blocks' instantiation)
     int small_max_pix;           // a lane rasterises bounding boxes up to this many pixels itself; larger ones go to k_big
     int mid_max_pix;             // ... and up to this many where enough lanes of its warp have one (k_raster)
 
@@ -136,7 +143,7 @@ struct HzView
 // queue/counter/band fields: the kernels take a pointer to their variant, so that the same captured CUDA graph can
 // be replayed for every view after one small host->device copy.
 enum { HZ_V_NEAR = 0, HZ_V_FAR = 1, HZ_V_BAND0 = 2 };
-constexpr int HZ_MAX_BANDS = 6;
+constexpr int HZ_MAX_BANDS = 8;
 constexpr int HZ_V_COUNT   = HZ_V_BAND0 + HZ_MAX_BANDS;
 
 // flags of the GPU-side barrier between the ranks of a wedge-sharded panorama (k_peer_barrier)

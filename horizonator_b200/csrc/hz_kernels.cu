@@ -260,14 +260,19 @@ __device__ __forceinline__ int hz_snap(float a)
     return (int)t;
 }
 
-// triangle number -> its three vertices (row j, column i), lib:496-508
+#define HZ_ID_LOD_SHIFT 29                     /* see the visibility key in hz_device.h */
+#define HZ_ID_CELL_MASK 0x1FFFFFFFu
+
+// triangle number -> its three vertices (row j, column i), lib:496-508; s = 1 unless the triangle belongs to a band
+// meshed at a coarser (opt-in) level of detail
 __device__ __forceinline__ void hz_tri_vertices(unsigned int id, int N, int vj[3], int vi[3])
 {
-    const unsigned int cell = id >> 1;
+    const int s = 1 << (id >> HZ_ID_LOD_SHIFT);
+    const unsigned int cell = (id & HZ_ID_CELL_MASK) >> 1;
     const int j = (int)(cell / (unsigned int)(N - 1)), i = (int)(cell % (unsigned int)(N - 1));
     vj[0] = j; vi[0] = i;
-    if((id & 1u) == 0) { vj[1] = j + 1; vi[1] = i + 1; vj[2] = j + 1; vi[2] = i;     }
-    else               { vj[1] = j;     vi[1] = i + 1; vj[2] = j + 1; vi[2] = i + 1; }
+    if((id & 1u) == 0) { vj[1] = j + s; vi[1] = i + s; vj[2] = j + s; vi[2] = i;     }
+    else               { vj[1] = j;     vi[1] = i + s; vj[2] = j + s; vi[2] = i + s; }
 }
 
 struct HzTri
@@ -828,12 +833,12 @@ __device__ __forceinline__ HzLaneMap hz_lane_map(int lane)
 // of the group); false beyond the group's last vertex.  All lanes call.  The mosaic and the axis tables are padded
 // (HZ_MESH_PAD), so the vertices of blocks that hang over the mesh's last row/column need no clamping: their triangles
 // are left out later.
-__device__ __forceinline__ bool hz_group_vertex(unsigned int ids, int nblk, unsigned int code, int& vj, int& vi)
+__device__ __forceinline__ bool hz_group_vertex(unsigned int ids, int nblk, unsigned int code, int lod, int& vj, int& vi)
 {
     const int k = (int)(code & 7u);
     const unsigned int id = __shfl_sync(0xffffffffu, ids, k);
-    vj = (int)(id >> 16) * HZ_BLOCK_CELLS + (int)((code >> 8) & 7u);
-    vi = (int)(id & 0xFFFFu) * HZ_BLOCK_CELLS + (int)(code >> 16);
+    vj = ((int)(id >> 16) * HZ_BLOCK_CELLS + (int)((code >> 8) & 7u)) << lod;
+    vi = ((int)(id & 0xFFFFu) * HZ_BLOCK_CELLS + (int)(code >> 16)) << lod;
     return k < nblk;
 }
 
@@ -846,11 +851,12 @@ __device__ __forceinline__ HzGroupZ hz_group_heights(const HzView& P, unsigned i
     HzGroupZ g;
     const int16_t* mosaic = P.mosaic;
     const unsigned int pitch = (unsigned int)P.pitch;
+    const int lod = P.lod;
     #pragma unroll
     for(int round = 0; round < HZ_MESH_ROUNDS; round++)
     {
         int vj, vi;
-        g.z[round] = hz_group_vertex(ids, nblk, map.code[round], vj, vi)
+        g.z[round] = hz_group_vertex(ids, nblk, map.code[round], lod, vj, vi)
                          ? (float)__ldg(mosaic + (unsigned int)vj * pitch + (unsigned int)vi) : 0.f;
     }
     return g;
@@ -886,13 +892,14 @@ hz_group_project(const HzView& P, unsigned int ids, int nblk, int lane, const Hz
     const float halfW = 0.5f * (float)P.W, halfH = 0.5f * (float)P.H;
     const float* e_tab = P.e_tab;
     const float* n_tab = P.n_tab;
+    const int lod = P.lod;
     #pragma unroll 1            // one projection's registers at a time (unrolled, ptxas interleaves the four and spills)
     for(int round = 0; round < HZ_MESH_ROUNDS; round++)
     {
         int vj, vi;
         const float z = round == 0 ? Z.z[0] : round == 1 ? Z.z[1] : round == 2 ? Z.z[2] : Z.z[3];
         const unsigned int code = round == 0 ? map.code[0] : round == 1 ? map.code[1] : round == 2 ? map.code[2] : map.code[3];
-        if(hz_group_vertex(ids, nblk, code, vj, vi))
+        if(hz_group_vertex(ids, nblk, code, lod, vj, vi))
             M.verts[round * 32 + lane] = hz_lane_vertex(P, __ldg(e_tab + vi), __ldg(n_tab + vj), z, halfW, halfH);
     }
     __syncwarp();
@@ -910,8 +917,9 @@ __device__ __forceinline__ int
 hz_group_triangles(const HzView& P, unsigned int ids, int k0, int nblk, int lane, HzMeshWarp& M, int& count, unsigned int& passed)
 {
     // (copies: P lives in shared memory like M, and every store to M would make the compiler read these again)
-    const int N1 = P.N - 1, x0 = P.x0, x1 = P.x1, H = P.H;
+    const int N1 = P.N - 1, x0 = P.x0, x1 = P.x1, H = P.H, lod = P.lod;
     const int wide = P.seam_period > 0.0f ? P.W * 64 - 1024 : 0x7FFFFFFF;      // see hz_tri_alive
+    const int jmax = N1 - (1 << lod);                                           // last row/column a triangle may start at
     // cell (cr, cc) of the block, its lower-left vertex a, upper-right vertex d, and the third one
     // lib:496-508: even triangle (j,i),(j+1,i+1),(j+1,i) ; odd triangle (j,i),(j,i+1),(j+1,i+1)
     const int cell = lane >> 1, cr = cell >> 2, cc = cell & 3;
@@ -920,14 +928,15 @@ hz_group_triangles(const HzView& P, unsigned int ids, int k0, int nblk, int lane
     for(int k = k0; k < nblk; k++)
     {
         const unsigned int id = __shfl_sync(0xffffffffu, ids, k);
-        const int j = (int)(id >> 16) * HZ_BLOCK_CELLS + cr, i = (int)(id & 0xFFFFu) * HZ_BLOCK_CELLS + cc;
+        const int j = ((int)(id >> 16) * HZ_BLOCK_CELLS + cr) << lod, i = ((int)(id & 0xFFFFu) * HZ_BLOCK_CELLS + cc) << lod;
         // (one evaluation with selected operands: under an odd/even branch each half would run with half the lanes)
         const HzLaneVtx* vb = M.verts + 25 * k;
         const HzLaneVtx a = vb[ia], d = vb[id_], o = vb[io];
-        const bool on = j < N1 && i < N1 && hz_tri_alive(x0, x1, H, wide, a, odd ? o : d, odd ? d : o);
+        const bool on = j <= jmax && i <= jmax && hz_tri_alive(x0, x1, H, wide, a, odd ? o : d, odd ? d : o);
         const unsigned int ballot = __ballot_sync(0xffffffffu, on);
         if(ballot == 0) continue;
-        const unsigned int tri = 2u * ((unsigned int)j * (unsigned int)N1 + (unsigned int)i) + (unsigned int)(lane & 1);
+        const unsigned int tri = (2u * ((unsigned int)j * (unsigned int)N1 + (unsigned int)i) + (unsigned int)(lane & 1)) |
+                                 ((unsigned int)lod << HZ_ID_LOD_SHIFT);
         passed += (unsigned int)__popc(ballot);
         if(SLOW)
         {
@@ -1215,6 +1224,9 @@ k_tiles(const HzView* __restrict__ V)
     if(P.stats) hz_cta_stats4(s_stats, P.stats + HZ_STAT_TILES, n_all, n_far, n_window, n_occl);
 }
 
+// LOD = false: the reference's mesh (lod = 0 known at compile time: fewer registers, more resident warps); true: the
+// instantiation launched once the caller has opted into a coarser far field, P.lod says how coarse this band is
+template <bool LOD>
 __global__ void __launch_bounds__(256)
 k_blocks(const HzView* __restrict__ V)
 {
@@ -1222,25 +1234,39 @@ k_blocks(const HzView* __restrict__ V)
     __shared__ HzCtaAppend s_app;
     __shared__ unsigned int s_stats[4];
     const int nb = P.nb, N = P.N;
-    const unsigned int total = *P.tile_count * (unsigned int)(HZ_TILE_BLOCKS * HZ_TILE_BLOCKS);
+    // blocks of (4 << lod) cells: (8 >> lod)^2 of them per tile
+    const int lod = LOD ? P.lod : 0, sh = 3 - lod, side = 1 << sh, cells = HZ_BLOCK_CELLS << lod;
+    const unsigned int total = *P.tile_count << (2 * sh);
     const unsigned int nth = gridDim.x * blockDim.x;
     unsigned int n_all = 0, n_far = 0, n_window = 0, n_occl = 0;
-    for(unsigned int t0 = blockIdx.x * blockDim.x; t0 < total; t0 += nth)     // total is a multiple of 64: no ragged end
+    for(unsigned int t0 = blockIdx.x * blockDim.x; t0 < total; t0 += nth)     // (the same trip count CTA-wide)
     {
         const unsigned int t = t0 + threadIdx.x;
         bool on = false;
         unsigned int id = 0;
         if(t < total)
         {
-            const unsigned int tile = P.tile_queue[t >> 6];
+            const unsigned int tile = P.tile_queue[t >> (2 * sh)];
             const int tj = (int)(tile >> 16), ti = (int)(tile & 0xFFFFu);
-            const int bj = tj * HZ_TILE_BLOCKS + (int)((t >> 3) & 7u), bi = ti * HZ_TILE_BLOCKS + (int)(t & 7u);
-            if(bj < nb && bi < nb)
+            const int bj = tj * side + (int)((t >> sh) & (unsigned int)(side - 1)), bi = ti * side + (int)(t & (unsigned int)(side - 1));
+            if((bj << lod) < nb && (bi << lod) < nb)
             {
-                const short2 mm = __ldg(P.mm_block + (size_t)bj * nb + bi);
+                short2 mm = __ldg(P.mm_block + (size_t)(bj << lod) * nb + (bi << lod));
+                if(lod > 0)
+                {
+                    // (min, max) over the 4x4-cell blocks the coarse block is made of
+                    int lo = mm.x, hi = mm.y;
+                    for(int y = bj << lod; y < min((bj + 1) << lod, nb); y++)
+                        for(int x = bi << lod; x < min((bi + 1) << lod, nb); x++)
+                        {
+                            const short2 c = __ldg(P.mm_block + (size_t)y * nb + x);
+                            lo = min(lo, (int)c.x); hi = max(hi, (int)c.y);
+                        }
+                    mm = make_short2((short)lo, (short)hi);
+                }
                 HzBox B;
-                const int c0 = bi * HZ_BLOCK_CELLS, r0 = bj * HZ_BLOCK_CELLS;
-                const int r = hz_rect_test(P, c0, min(c0 + HZ_BLOCK_CELLS, N - 1), r0, min(r0 + HZ_BLOCK_CELLS, N - 1),
+                const int c0 = bi * cells, r0 = bj * cells;
+                const int r = hz_rect_test(P, c0, min(c0 + cells, N - 1), r0, min(r0 + cells, N - 1),
                                            (float)mm.x, (float)mm.y, B);
                 n_all++;
                 if(r == HZ_RECT_DEAD_FAR)         n_far++;
@@ -1393,7 +1419,7 @@ cudaError_t hz_launch_band(const HzView& v, const HzView* d_v, int nviews, bool 
     const unsigned int ny = (unsigned int)nviews;
     cudaError_t e;
     if((e = hz_launch(k_tiles,  dim3((unsigned)ctas, ny), dim3(256), stream, d_v)) != cudaSuccess) return e;
-    if((e = hz_launch(k_blocks, dim3(hz_grid(v, 8, nviews), ny), dim3(256), stream, d_v)) != cudaSuccess) return e;
+    if((e = hz_launch(v.lod_capable ? k_blocks<true> : k_blocks<false>, dim3(hz_grid(v, 8, nviews), ny), dim3(256), stream, d_v)) != cudaSuccess) return e;
     if((e = hz_launch(k_mesh,   dim3(hz_grid(v, 4, nviews), ny), dim3(HZ_WARPS_PER_CTA * 32), stream, d_v)) != cudaSuccess) return e;
     if((e = hz_launch(k_raster, dim3(hz_grid(v, 6, nviews), ny), dim3(256), stream, d_v)) != cudaSuccess) return e;
     *launches = 4;

@@ -111,6 +111,16 @@ bool horizonator_set_earth_curvature(const horizonator_context_t* ctx, bool on, 
  * that are too wide for another reason stay dropped. */
 bool horizonator_set_seam_wrap(const horizonator_context_t* ctx, bool on);
 
+/* Opt-in level of detail; OFF (0) by default and in every parity test: the reference draws every cell of the DEM
+ * however far away it is (README.org:169-185 lists a coarser far mesh as future work).  With max_cell_pixels > 0 the
+ * parts of the mesh beyond the foreground are drawn with every 2nd or 4th vertex only -- cells of 2x2 or 4x4 DEM cells
+ * -- wherever such a coarser cell, seen from the nearest edge of its distance band, is still at most max_cell_pixels
+ * pixels across (0.5 is a sensible value: half a pixel).  The foreground is never coarsened.  Where two levels meet,
+ * hairline cracks are possible; the image differs from the full render only by sub-pixel shifts of far silhouettes
+ * (tests/test_gpu_large.py reports the differences), and views that see much distant terrain render several times
+ * faster.  Applies to all later renders of the context. */
+bool horizonator_set_lod(const horizonator_context_t* ctx, float max_cell_pixels);
+
 /* Reads the HORIZONATOR_* tuning variables again -- they are otherwise read once, by
  * horizonator_init() -- after waiting for everything the context has in flight.  Variables that are not set
  * go back to their defaults.  For parameter sweeps inside one process; the images do not depend on them. */

@@ -248,3 +248,59 @@ def test_pageable_destinations_get_what_page_locked_ones_get(tiles_c2, W, H):
     ar = np.full((H, W), 7, np.float32)
     h.render_into(None, ar)
     assert np.array_equal(ar, pr)
+
+
+def test_lod_is_opt_in_and_stays_within_subpixel_error(tiles_c2):
+    """Opt-in level of detail (horizonator_set_lod; N4): off by default -- every other test runs without it -- and
+    switching it off again restores the full render bit for bit.  On (coarser cells up to half a pixel across), the
+    image may differ from the full render only by sub-pixel shifts of far silhouettes: reported here, and bounded."""
+    import torch
+    import horizonator_b200 as hz
+    W, H = 3600, 600
+    h = hz.horizonator(C2_LAT, C2_LON, W, H, SRTM1=True, dir_dems=tiles_c2, render_radius_m=150000.)
+    h.set_zextents(100., 150000.)
+    stream = torch.cuda.Stream()
+    d_img = torch.empty((2, H, W, 3), dtype=torch.uint8, device="cuda")
+    d_rng = torch.empty((2, H, W), dtype=torch.float32, device="cuda")
+    views = {"c2": (C2_LAT, C2_LON, -180.05, 179.95), "eye_12km": (C2_LAT, C2_LON, -180.05, 179.95, 12000.),
+             "grid": (33.5 + 1.5 / 8 + 1.0 / 7200.0, -117.5 + 5.5 / 8 + 1.0 / 7200.0, -180.05, 179.95)}
+
+    def render(v, slot):
+        t = []
+        for rep in range(4):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            h.render_batch_device([v], d_img[slot].data_ptr(), d_rng[slot].data_ptr(), stream.cuda_stream)
+            e1.record(stream)
+            torch.cuda.synchronize()
+            t.append(e0.elapsed_time(e1))
+        return d_img[slot].cpu().numpy(), d_rng[slot].cpu().numpy(), min(t)
+
+    for name, v in views.items():
+        h.set_lod(0.)
+        fi, fr, t_full = render(v, 0)
+        for px in (0.5, 1.0, 2.0):
+            h.set_lod(px)
+            li, lr, t_lod = render(v, 1)
+            s = compare_renders(li, lr, fi, fr)
+            both = (lr > 0) & (fr > 0)
+            rel = np.abs(lr[both].astype(np.float64) - fr[both]) / fr[both]
+            print("LOD %.1f px vs full, %s: %.3f ms -> %.3f ms; coverage agreement %.5f, agreement incl. range %.5f, "
+                  "off-silhouette %d, range error median %.2e / p99 %.2e" %
+                  (px, name, t_full, t_lod, s["coverage_agreement"], s["agreement"], s["off_silhouette"], float(np.median(rel)),
+                   float(np.quantile(rel, 0.99))))
+            if px == 0.5:
+                assert s["coverage_agreement"] >= 0.995 and s["sky_ok"] and s["bg_channels_ok"]
+                assert float(np.quantile(rel, 0.99)) < 5e-3          # a few metres at a few kilometres
+        h.set_lod(0.)
+        bi, br, _ = render(v, 1)
+        assert np.array_equal(bi, fi) and np.array_equal(br, fr)
+    # batches take the same path
+    h.set_lod(0.5)
+    bi, br = h.render_batch([views["c2"], views["grid"]])
+    h.pan_zoom(-180.05, 179.95)
+    for k, name in enumerate(("c2", "grid")):
+        h.move(views[name][0], views[name][1])
+        wi = hz.pinned_array((H, W, 3), np.uint8); wr = hz.pinned_array((H, W), np.float32)
+        h.render_into(wi, wr)
+        assert np.array_equal(bi[k], wi) and np.array_equal(br[k], wr), name
