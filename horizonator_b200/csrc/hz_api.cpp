@@ -80,6 +80,10 @@ struct Scratch
     // reading the row when it is replaced)
     float*    d_tanel = nullptr;       // [H]
     TanelKey  tanel_key;
+    // renders made with this visibility buffer since it was allocated: the epoch of the keys counts down from 7 with it,
+    // and the buffer is cleared only when that wraps (hz_device.h, the visibility key)
+    unsigned int renders = 0;
+    unsigned int last_epoch = 0;       // of the most recent render (horizonator_pick decodes main's keys with it)
 };
 
 // Up to `cap` views that are rendered TOGETHER: one chain of kernel launches whose grids have a view dimension
@@ -216,6 +220,7 @@ void free_scratch_target(Scratch& c)
     c.d_vis = nullptr; c.d_image = nullptr; c.d_ranges = nullptr;
     c.d_tri_queue = nullptr; c.d_big_queue = nullptr; c.d_bigtri = nullptr; c.d_tanel = nullptr;
     c.tanel_key = TanelKey{};
+    c.renders = 0;
 }
 
 bool alloc_scratch_target(const Slot& s, Scratch& c, bool staging)
@@ -662,6 +667,11 @@ bool enqueue_views(Slot& s, ViewSet& set, int m, const ViewState* vs, int x0, in
         Scratch& sc = set.sc[k];
         HzView* hk = hv + (size_t)k * HZ_V_COUNT;
         fill_view(s, set, sc, vs[k], x0, x1, outs[k], hk[0]);
+        // the epoch of this render's keys; a fresh or wrapped buffer is cleared first, all of it
+        hk[0].epoch = HZ_KEY_EPOCHS - 1u - sc.renders % HZ_KEY_EPOCHS;
+        hk[0].clear_keys = (sc.renders % HZ_KEY_EPOCHS == 0) ? (unsigned int)s.target_pixels : 0u;
+        sc.last_epoch = hk[0].epoch;
+        sc.renders++;
         vectorisable = vectorisable && hz_resolve_is_vectorisable(hk[0]);
         for(int j = 1; j < HZ_V_COUNT; j++) hk[j] = hk[0];
         hk[HZ_V_NEAR].tri_count = sc.d_counters + 2;
@@ -1256,7 +1266,7 @@ bool horizonator_pick(const horizonator_context_t* ctx, float* lat, float* lon, 
     unsigned long long key = 0;
     CUDA_TRY(cudaStreamSynchronize(s->stream));
     CUDA_TRY(cudaMemcpy(&key, s->main.sc[0].d_vis + (size_t)(s->H - 1 - y) * s->W + x, sizeof(key), cudaMemcpyDeviceToHost));
-    const float depth = (float)((double)(unsigned)(key >> 40) * (1.0 / 16777215.0));
+    const float depth = (float)((double)hz_key_q(key, s->main.sc[0].last_epoch) * (1.0 / 16777215.0));
     if(depth >= 1.0f) return false;                                     // lib:1272
     // lib:1282-1295: the depth is treated as horizontal distance
     const double range_en = depth * (s->zfar - s->znear) + s->znear;

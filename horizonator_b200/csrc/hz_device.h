@@ -5,18 +5,33 @@
 #include <cuda_runtime.h>
 
 // ---- visibility key --------------------------------------------------------------------------
-// One 64-bit word per pixel, resolved with atomicMin:
-//     [63:40] q    window depth quantised to 24 bits (the GL_DEPTH_COMPONENT renderbuffer of
+// One 64-bit word per pixel, resolved with a min() reduction (red.global.min.u64):
+//     [63:61] ep   epoch of the render that wrote the key, counting DOWN from 7: a key of an earlier render is larger
+//                  than any key of the current one, i.e. it loses every min() and reads as "nothing drawn yet" -- so
+//                  the buffer only has to be cleared when the epoch wraps, every eighth render (17 MB of stores per
+//                  3600x600 view otherwise)
+//     [60:37] q    window depth quantised to 24 bits (the GL_DEPTH_COMPONENT renderbuffer of
 //                  horizonator-lib.c:646; smaller = nearer)
-//     [39: 8] id   triangle number in the reference's draw order (horizonator-lib.c:496-508):
-//                  2*(j*(2R-1)+i) + {0: (j,i),(j+1,i+1),(j+1,i)   1: (j,i),(j,i+1),(j+1,i+1)}   (< 2^29)
-//                  bits [30:29] of it: the opt-in level of detail of the triangle (0 in the reference's mesh: the
-//                  triangle then spans (1 << lod) cells from (j,i))
+//     [36: 8] id   triangle number in the reference's draw order (horizonator-lib.c:496-508):
+//                  2*(j*(2R-1)+i) + {0: (j,i),(j+1,i+1),(j+1,i)   1: (j,i),(j,i+1),(j+1,i+1)}   (< 2^29: R <= 7200)
 //     [ 7: 0] r8   the fragment's red channel (fragment.glsl:16 after unorm8 conversion)
 // min() over keys == GL_LESS with in-order drawing: nearest q wins, equal q -> first drawn wins.
 // The result is independent of the order in which threads get to a pixel.
-#define HZ_KEY_CLEAR 0xFFFFFFFFFFFFFFFFull   /* q = 0xFFFFFF = cleared depth 1.0 */
+// (Triangle numbers in the queues carry the opt-in level of detail in bits [30:29]; the key only takes the low 29.)
+#define HZ_KEY_CLEAR 0xFFFFFFFFFFFFFFFFull   /* epoch 7, q = 0xFFFFFF = cleared depth 1.0 */
 #define HZ_Q_MAX     0xFFFFFFu
+#define HZ_KEY_Q_SHIFT     37
+#define HZ_KEY_EPOCHS      8u
+
+// epoch and depth of a key as one number: what occlusion tests compare (a key of an earlier epoch compares as farther
+// than anything)
+static __host__ __device__ inline unsigned int hz_key_top(unsigned long long key) { return (unsigned int)(key >> HZ_KEY_Q_SHIFT); }
+// the depth a key holds for a render of epoch `ep`: HZ_Q_MAX (cleared) if the key is an earlier render's
+static __host__ __device__ inline unsigned int hz_key_q(unsigned long long key, unsigned int ep)
+{
+    const unsigned int top = hz_key_top(key);
+    return (top >> 24) == ep ? (top & HZ_Q_MAX) : HZ_Q_MAX;
+}
 
 // ---- tiles as uploaded (raw file bytes) ------------------------------------------------------
 struct HzTiles
@@ -90,6 +105,8 @@ struct HzView
     int W, H;
     int x0, x1;
     unsigned long long* vis;     // [H][x1-x0], GL row order (row 0 = bottom)
+    unsigned int epoch;          // of this render's keys (see the visibility key)
+    unsigned int clear_keys;     // k_prepare clears this many keys (the whole allocation when the epoch wrapped, else 0)
 
     // The mesh is walked outwards from the eye.  Tiles within `near_rings` (Chebyshev distance in tiles) of the
     // eye's tile go first and completely (k_near + k_big), then bands of rings [ring_lo, ring_hi), each through

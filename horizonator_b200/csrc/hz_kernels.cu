@@ -186,18 +186,22 @@ k_prepare(const HzView* __restrict__ V)
     const unsigned int tid = blockIdx.x * blockDim.x + threadIdx.x;
     const unsigned int nth = gridDim.x * blockDim.x;
 
-    // glClear: depth 1.0 everywhere.  Keys are cleared two at a time (16-byte stores), four stores per trip.
-    const size_t nkeys = (size_t)P.H * (size_t)(P.x1 - P.x0);
-    const unsigned int npairs = (unsigned int)(nkeys / 2);
-    ulonglong2* v2 = (ulonglong2*)P.vis;
-    const ulonglong2 clear2 = make_ulonglong2(HZ_KEY_CLEAR, HZ_KEY_CLEAR);
-    unsigned int k = tid;
-    for(; k + 3u * nth < npairs; k += 4u * nth)
+    // glClear: depth 1.0 everywhere -- only when the epoch of the keys has wrapped (see the visibility key): then the
+    // whole buffer is cleared, two keys at a time (16-byte stores), four stores per trip
+    const size_t nkeys = P.clear_keys;
+    if(nkeys)
     {
-        v2[k] = clear2; v2[k + nth] = clear2; v2[k + 2u * nth] = clear2; v2[k + 3u * nth] = clear2;
+        const unsigned int npairs = (unsigned int)(nkeys / 2);
+        ulonglong2* v2 = (ulonglong2*)P.vis;
+        const ulonglong2 clear2 = make_ulonglong2(HZ_KEY_CLEAR, HZ_KEY_CLEAR);
+        unsigned int k = tid;
+        for(; k + 3u * nth < npairs; k += 4u * nth)
+        {
+            v2[k] = clear2; v2[k + nth] = clear2; v2[k + 2u * nth] = clear2; v2[k + 3u * nth] = clear2;
+        }
+        for(; k < npairs; k += nth) v2[k] = clear2;
+        if(tid == 0 && (nkeys & 1)) P.vis[nkeys - 1] = HZ_KEY_CLEAR;
     }
-    for(; k < npairs; k += nth) v2[k] = clear2;
-    if(tid == 0 && (nkeys & 1)) P.vis[nkeys - 1] = HZ_KEY_CLEAR;
 
     // vertex.glsl:128-130, operator by operator:
     //   e = (i - viewer_cell_i) * DEG_PER_CELL * Rearth * pi/180. * cos_viewer_lat
@@ -433,7 +437,8 @@ __device__ __forceinline__ void hz_fragment(const HzView& P, const HzTri& T, int
     float r = T.r0 + (T.drdx * ddx + T.drdy * ddy);
     r = fmaxf(fminf(r, 1.0f), 0.0f);
     const unsigned int r8 = (unsigned int)(r * 255.0f + 0.5f);              // F8
-    const unsigned long long key = ((unsigned long long)q << 40) | ((unsigned long long)T.id << 8) | r8;
+    const unsigned long long key = ((unsigned long long)((P.epoch << 24) | q) << HZ_KEY_Q_SHIFT) |
+                                   ((unsigned long long)(T.id & HZ_ID_CELL_MASK) << 8) | r8;
     hz_red_min(&P.vis[(size_t)py * (size_t)(P.x1 - P.x0) + (size_t)(px - P.x0)], key);
 }
 
@@ -580,7 +585,7 @@ hz_rect_test(const HzView& P, int c_lo, int c_hi, int r_lo, int r_hi, float zmin
         const float sep = s2 * rsqrtf(s2);
         const float lo  = (len - P.znear - 4.004f * sep) * P.inv_zrange - 2e-5f;
         if(lo > 1.0f) return HZ_RECT_DEAD_FAR;             // every fragment fails the far clip
-        B.qmin = (lo <= 0.0f) ? 0u : (unsigned int)(lo * 16777215.0f);
+        B.qmin = (P.epoch << 24) | ((lo <= 0.0f) ? 0u : (unsigned int)(lo * 16777215.0f));    // as hz_key_top() gives it
     }
     if(e_in || n_in) return HZ_RECT_ALIVE;                 // touches an axis through the eye: not worth a box
 
@@ -609,13 +614,6 @@ hz_rect_test(const HzView& P, int c_lo, int c_hi, int r_lo, int r_hi, float zmin
     B.px0 = max((int)fx0, P.x0); B.px1 = min((int)fx1, P.x1 - 1);
     B.py0 = max((int)fy0, 0);    B.py1 = min((int)fy1, P.H - 1);
     return HZ_RECT_BOXED;
-}
-
-// the visibility buffer is being written by other warps: read through to L2; a stale (older, larger) key only
-// makes the test more cautious
-__device__ __forceinline__ unsigned int hz_vis_depth(const HzView& P, int px, int py)
-{
-    return (unsigned int)(__ldcg(P.vis + (size_t)py * (size_t)(P.x1 - P.x0) + (size_t)(px - P.x0)) >> 40);
 }
 
 // ================================================================================================
@@ -1130,7 +1128,7 @@ __device__ __forceinline__ bool hz_box_occluded_thread(const HzView& P, const Hz
         {
             if(p + u < npix)
             {
-                farthest = max(farthest, (unsigned int)(__ldcg(row + x) >> 40));
+                farthest = max(farthest, hz_key_top(__ldcg(row + x)));
                 if(++x == w) { x = 0; row += Wt; }
             }
         }
@@ -1512,9 +1510,8 @@ cudaError_t hz_launch_big(const HzView& v, const HzView* d_v, int nviews, cudaSt
 // ================================================================================================
 
 // lib:1013-1025 for one pixel: depth as glReadPixels(GL_DEPTH_COMPONENT, GL_FLOAT) returns it -> range
-__device__ __forceinline__ float hz_range_of_key(unsigned long long key, float tanel, float znear, float zfar)
+__device__ __forceinline__ float hz_range_of_q(unsigned int q, float tanel, float znear, float zfar)
 {
-    const unsigned int q = (unsigned int)(key >> 40);
     // lib:1016 "depth == 1.0f -> -1": of the 24-bit values only the cleared one reads back as 1.0f (the next lower
     // one is 1 - 2^-24, exactly representable).  Checked first: most of a panorama is sky, and the rest of this
     // function is FP64.
@@ -1566,8 +1563,8 @@ k_resolve4(const HzView* __restrict__ V)
 
     const ulonglong2 k01 = __ldcs((const ulonglong2*)(R.vis + src));           // read once: streaming
     const ulonglong2 k23 = __ldcs((const ulonglong2*)(R.vis + src + 2));
-    const unsigned int q0 = (unsigned int)(k01.x >> 40), q1 = (unsigned int)(k01.y >> 40),
-                       q2 = (unsigned int)(k23.x >> 40), q3 = (unsigned int)(k23.y >> 40);
+    const unsigned int ep = P.epoch;
+    const unsigned int q0 = hz_key_q(k01.x, ep), q1 = hz_key_q(k01.y, ep), q2 = hz_key_q(k23.x, ep), q3 = hz_key_q(k23.y, ep);
 
     // hit: (B,G,R) = (0,0,r8) ; sky: clear colour (0,0,1) read as BGR = (255,0,0)   lib:185, 938-939
     // bytes B0 G0 R0 B1 | G1 R1 B2 G2 | R2 B3 G3 R3
@@ -1584,10 +1581,10 @@ k_resolve4(const HzView* __restrict__ V)
     if(P.out_ranges[0] != nullptr && (q0 & q1 & q2 & q3) != HZ_Q_MAX)
     {
         const float t = R.tanel[y];
-        r.x = hz_range_of_key(k01.x, t, R.znear, R.zfar);
-        r.y = hz_range_of_key(k01.y, t, R.znear, R.zfar);
-        r.z = hz_range_of_key(k23.x, t, R.znear, R.zfar);
-        r.w = hz_range_of_key(k23.y, t, R.znear, R.zfar);
+        r.x = hz_range_of_q(q0, t, R.znear, R.zfar);
+        r.y = hz_range_of_q(q1, t, R.znear, R.zfar);
+        r.z = hz_range_of_q(q2, t, R.znear, R.zfar);
+        r.w = hz_range_of_q(q3, t, R.znear, R.zfar);
     }
     for(int d = 0; d < R.n_out; d++)
     {
@@ -1613,8 +1610,9 @@ k_resolve1(const HzView* __restrict__ V)
     const int y = (int)(g / R.Wt), x = (int)(g % R.Wt);
     const unsigned long long key = R.vis[g];
     const size_t dst = (size_t)(R.H - 1 - y) * R.out_stride + R.out_x0 + x;
-    const bool hit = (unsigned int)(key >> 40) != HZ_Q_MAX;
-    const float range = (P.out_ranges[0] != nullptr) ? hz_range_of_key(key, R.tanel[y], R.znear, R.zfar) : -1.0f;
+    const unsigned int q = hz_key_q(key, P.epoch);
+    const bool hit = q != HZ_Q_MAX;
+    const float range = (P.out_ranges[0] != nullptr) ? hz_range_of_q(q, R.tanel[y], R.znear, R.zfar) : -1.0f;
     for(int d = 0; d < R.n_out; d++)
     {
         uint8_t* image = P.out_image[d];
