@@ -596,7 +596,9 @@ void fill_view(const Slot& s, const ViewSet& set, const Scratch& sc, const ViewS
     v.occl_block_max_pix = set.batch ? s.occl_block_max_pix_batch : s.occl_block_max_pix;
     // (middle-sized triangles are drawn by their own threads only in zoomed-in views, where whole warps have them; in a
     // wide view they sit right around the eye, and walking them in k_raster holds that kernel up for nothing)
-    v.small_max_pix = s.small_max_pix; v.mid_max_pix = big_after_every_band(s, vs) ? s.mid_max_pix : 0;
+    // (... and in such views the threads walk boxes twice as large themselves: measured 5 % faster)
+    const bool zoomed = big_after_every_band(s, vs);
+    v.small_max_pix = zoomed ? 2 * s.small_max_pix : s.small_max_pix; v.mid_max_pix = zoomed ? s.mid_max_pix : 0;
     v.grid_percent = set.batch ? s.grid_percent_batch : s.grid_percent_single;
     v.lod_capable = s.lod_pixels > 0.f;
     v.big_capacity = s.big_capacity;

@@ -624,7 +624,9 @@ hz_rect_test(const HzView& P, int c_lo, int c_hi, int r_lo, int r_hi, float zmin
 #ifndef HZ_MESH_CTAS
 #define HZ_MESH_CTAS 4             /* resident CTAs per SM the meshing kernels are compiled for (register budget) */
 #endif
-#define HZ_BIG_ROWS      4         /* large bounding boxes are cut into sub-boxes of this size for k_big: */
+#ifndef HZ_BIG_ROWS
+#define HZ_BIG_ROWS      16        /* large bounding boxes are cut into sub-boxes of this size for k_big (4 and 8 rows: */
+#endif                             /* the per-sub-box set-up weighs more, measured slower in zoomed-in views and batches): */
 #define HZ_BIG_COLS      32        /* lane = column, a few rows each (more for very large triangles) */
 #define HZ_BIG_MAX_ENTRIES 64u
 #define HZ_MID_LANES     16        /* lanes of a warp with a middle-sized triangle from which on they draw them themselves */
