@@ -418,7 +418,7 @@ def run_b200(args):
     del d_flat, h_flat
 
     # the additive host-pointer batch call: renders and device->host copies of different views overlap
-    Bh = min(B, 16)
+    Bh = min(B, 64)
     bimg = hz.pinned_array((Bh, H, W, 3), np.uint8)
     brng = hz.pinned_array((Bh, H, W), np.float32)
     varr = h._views([c2_view] * Bh)

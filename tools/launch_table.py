@@ -20,7 +20,7 @@ def read(path):
     for r in rd:
         key = r["ID"]
         if cur is None or cur["id"] != key:
-            cur = {"id": key, "name": r["Kernel Name"].split("(")[0], "grid": r.get("Grid Size", ""), "m": {}}
+            cur = {"id": key, "name": r["Kernel Name"].split("(")[0].replace("void ", "").split("<")[0], "grid": r.get("Grid Size", ""), "m": {}}
             rows.append(cur)
         try:
             v = float(r["Metric Value"].replace(",", ""))
