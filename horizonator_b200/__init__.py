@@ -278,8 +278,10 @@ class horizonator:
     def render_batch(self, views, return_image=True, return_range=True):
         """views: sequence of (lat, lon, az_deg0, az_deg1[, viewer_z]).  Host arrays (n,H,W,3), (n,H,W)."""
         n, W, H = len(views), self.width, self.height
-        image = np.empty((n, H, W, 3), dtype=np.uint8) if return_image else None
-        ranges = np.empty((n, H, W), dtype=np.float32) if return_range else None
+        # page-locked blocks from the recycling pool, like render(): the copies of different views then run by DMA and
+        # overlap the next views' kernels (into pageable arrays each copy would go through the driver's staging)
+        image = _pool.array((n, H, W, 3), np.uint8) if return_image else None
+        ranges = _pool.array((n, H, W), np.float32) if return_range else None
         if not lib.horizonator_render_batch(C.byref(self._ctx), n, self._views(views),
                                             image.ctypes.data if image is not None else None,
                                             ranges.ctypes.data if ranges is not None else None):

@@ -868,20 +868,22 @@ class HostCopyPool
 public:
     struct Part { char* dst; const char* src; size_t bytes; cudaEvent_t ready; };
 
-    // copies every part (after its event) with the pool's threads and the calling one; returns when all are done
-    void run(int device, const std::vector<Part>& parts)
+    // copies every part (after its event) with the pool's threads and the calling one; returns when all are done:
+    // false if waiting for some part's event failed (that part was not copied)
+    bool run(int device, const std::vector<Part>& parts)
     {
         std::unique_lock<std::mutex> call(call_mutex_);          // one job at a time, process-wide
         start_workers();
         {
             std::lock_guard<std::mutex> lk(m_);
-            parts_ = &parts; device_ = device; next_ = 0; pending_ = parts.size(); generation_++;
+            parts_ = &parts; device_ = device; next_ = 0; pending_ = parts.size(); failed_ = false; generation_++;
         }
         cv_work_.notify_all();
         work();
         std::unique_lock<std::mutex> lk(m_);
         cv_done_.wait(lk, [this] { return pending_ == 0; });
         parts_ = nullptr;
+        return !failed_;
     }
 
     static HostCopyPool& instance() { static HostCopyPool* p = new HostCopyPool; return *p; }    // never destroyed: no
@@ -929,10 +931,11 @@ private:
             }
             if(dev_set != dev) { cudaSetDevice(dev); dev_set = dev; }
             const Part& p = (*parts)[k];
-            cudaEventSynchronize(p.ready);
-            memcpy(p.dst, p.src, p.bytes);
+            const bool ok = cudaEventSynchronize(p.ready) == cudaSuccess;
+            if(ok) memcpy(p.dst, p.src, p.bytes);
             {
                 std::lock_guard<std::mutex> lk(m_);
+                if(!ok) failed_ = true;
                 if(--pending_ == 0) cv_done_.notify_all();
             }
         }
@@ -945,6 +948,7 @@ private:
     const std::vector<Part>* parts_ = nullptr;
     int device_ = 0;
     size_t next_ = 0, pending_ = 0;
+    bool failed_ = false;
     unsigned long long generation_ = 0;
 };
 
@@ -1014,8 +1018,13 @@ bool copy_results_to_host(Slot& s, char* image, float* ranges, const uint8_t* d_
         }
         staged += o.bytes;
     }
-    if(!parts.empty()) HostCopyPool::instance().run(s.device, parts);
+    const bool copied = parts.empty() || HostCopyPool::instance().run(s.device, parts);
     CUDA_TRY(cudaStreamSynchronize(st));
+    if(!copied)
+    {
+        MSG("CUDA error while the result was copied to host memory: %s", cudaGetErrorString(cudaGetLastError()));
+        return false;
+    }
     return true;
 }
 

@@ -1329,12 +1329,94 @@ k_mesh(const HzView* __restrict__ V)
     }
 }
 
+// ---- the triangles the lanes of a warp draw themselves (bounding boxes of a few dozen pixels at most) -----------------
+//
+// Coverage and shading are separated here as in k_big: every lane walks the bounding box of ITS triangle one pixel
+// centre per step, stepping 32-bit edge functions, and the covered ones of all lanes are compacted into a small list in
+// shared memory (owner lane, offset in the box); whenever the list holds 32 the lanes shade 32 fragments at once, each
+// fetching its fragment's plane equations from the owner's row of a table in shared memory.  Walking and shading in
+// the same loop instead leaves most lanes idle through the ~45 instructions of every fragment: a triangle covers a few
+// of the pixel centres of its box, and every lane's are somewhere else.
+struct HzFragAttr          // what hz_fragment needs of a triangle; one row per lane, 16 words
+{
+    float xw0, yw0, z0w, dzdx, dzdy, zw_lo, zw_hi, r0, drdx, drdy;
+    unsigned int id;
+    int px0, py0;
+    int pad[3];
+};
+struct HzRasterWarp
+{
+    HzFragAttr   attr[32];
+    unsigned int frag[64];         // owner | dx << 5 | dy << 11
+};
+
+__device__ __forceinline__ void hz_shade_listed(const HzView& P, const HzRasterWarp& S, unsigned int entry)
+{
+    const HzFragAttr& A = S.attr[entry & 31u];
+    HzTri T;                       // (only the members hz_fragment reads)
+    T.xw0 = A.xw0; T.yw0 = A.yw0; T.z0w = A.z0w; T.dzdx = A.dzdx; T.dzdy = A.dzdy; T.zw_lo = A.zw_lo; T.zw_hi = A.zw_hi;
+    T.r0 = A.r0; T.drdx = A.drdx; T.drdy = A.drdy; T.id = A.id;
+    hz_fragment(P, T, A.px0 + (int)((entry >> 5) & 63u), A.py0 + (int)(entry >> 11));
+}
+
+// All lanes of the warp call; `mine`: this lane has a set-up triangle T to draw (its box at most 64 x 64 pixels and
+// hz_tri_is_small).
+__device__ __forceinline__ void hz_draw_boxes_warp(const HzView& P, const HzTri& T, bool mine, HzRasterWarp& S, unsigned int lane)
+{
+    const unsigned int any = __ballot_sync(0xffffffffu, mine);
+    if(any == 0) return;
+    int bw = 0, npx = 0;
+    int e0 = 0, e1 = 0, e2 = 0, sx0 = 0, sx1 = 0, sx2 = 0, wr0 = 0, wr1 = 0, wr2 = 0;
+    if(mine)
+    {
+        HzFragAttr& A = S.attr[lane];
+        A.xw0 = T.xw0; A.yw0 = T.yw0; A.z0w = T.z0w; A.dzdx = T.dzdx; A.dzdy = T.dzdy; A.zw_lo = T.zw_lo; A.zw_hi = T.zw_hi;
+        A.r0 = T.r0; A.drdx = T.drdx; A.drdy = T.drdy; A.id = T.id; A.px0 = T.px0; A.py0 = T.py0;
+        const HzEdges<int> E(T);
+        const int Px = T.px0 * 256 + 128, Py = T.py0 * 256 + 128;
+        e0 = E.dx0 * (Py - T.Y0) - E.dy0 * (Px - T.X0) - E.b0;      // >= 0 <=> inside, per edge
+        e1 = E.dx1 * (Py - T.Y1) - E.dy1 * (Px - T.X1) - E.b1;
+        e2 = E.dx2 * (Py - T.Y2) - E.dy2 * (Px - T.X2) - E.b2;
+        bw = T.px1 - T.px0 + 1;
+        npx = bw * (T.py1 - T.py0 + 1);
+        sx0 = E.dy0 * 256; sx1 = E.dy1 * 256; sx2 = E.dy2 * 256;   // one pixel to the right: E -= dy * 256
+        wr0 = E.dx0 * 256 + bw * sx0; wr1 = E.dx1 * 256 + bw * sx1; wr2 = E.dx2 * 256 + bw * sx2;   // up a row and back to its left end
+    }
+    const int steps = __reduce_max_sync(0xffffffffu, npx);
+    const unsigned int below = (1u << lane) - 1u;
+    unsigned int count = 0;        // entries in the list (the same in all lanes)
+    int x = 0, y = 0;
+    __syncwarp();
+    for(int s = 0; s < steps; s++)
+    {
+        const bool in = s < npx && (e0 | e1 | e2) >= 0;
+        const unsigned int m = __ballot_sync(0xffffffffu, in);
+        if(in) S.frag[count + __popc(m & below)] = lane | ((unsigned int)x << 5) | ((unsigned int)y << 11);
+        count += __popc(m);
+        e0 -= sx0; e1 -= sx1; e2 -= sx2;
+        if(++x == bw) { x = 0; y++; e0 += wr0; e1 += wr1; e2 += wr2; }
+        if(count >= 32u)
+        {
+            __syncwarp();
+            hz_shade_listed(P, S, S.frag[lane]);
+            const unsigned int rest = (lane < count - 32u) ? S.frag[32u + lane] : 0u;
+            __syncwarp();
+            if(lane < count - 32u) S.frag[lane] = rest;
+            count -= 32u;
+        }
+    }
+    __syncwarp();
+    if(lane < count) hz_shade_listed(P, S, S.frag[lane]);
+    __syncwarp();                  // the table and the list are free for the next trip
+}
+
 // ---- k_raster: one thread per triangle of a stage's list
 
 __global__ void __launch_bounds__(256, 3)
 k_raster(const HzView* __restrict__ V)
 {
     HZ_KERNEL_PROLOGUE(V, P);
+    __shared__ HzRasterWarp s_warp[8];
     const unsigned int n = min(*P.tri_count, P.tri_capacity);
     const unsigned int nth = gridDim.x * blockDim.x;
     const unsigned int lane = threadIdx.x & 31u;
@@ -1349,23 +1431,18 @@ k_raster(const HzView* __restrict__ V)
         {
             id = P.tri_queue[t];
             st = hz_tri_setup(P, id, 0, T);
-            if(st == HZ_SETUP_OK)
-            {
-                nsub = hz_big_layout(P, T, nx, k);
-                if(nsub == 0) hz_draw_box<int>(P, T);
-            }
+            if(st == HZ_SETUP_OK) nsub = hz_big_layout(P, T, nx, k);
         }
-        // Middle-sized bounding boxes (up to P.mid_max_pix pixels): a warp of its own in k_big is a lot for a few dozen
-        // pixels, and a lone lane walking them here holds up its 31 neighbours.  But where many lanes of the warp have
-        // one -- zoomed-in views, where neighbouring triangles are all that size -- they walk them side by side.
+        // Who draws what: bounding boxes up to P.small_max_pix pixels are drawn here.  Middle-sized ones (up to
+        // P.mid_max_pix) too where many lanes of the warp have one -- zoomed-in views, where neighbouring triangles are
+        // all that size; for a few of them a warp of its own in k_big is the better deal.  Everything else is queued.
+        bool mine = (st == HZ_SETUP_OK && nsub == 0);
         {
-            const bool mid = nsub != 0 && (T.px1 - T.px0 + 1) * (T.py1 - T.py0 + 1) <= P.mid_max_pix && hz_tri_is_small(T);
-            if(__popc(__ballot_sync(0xffffffffu, mid)) >= HZ_MID_LANES && mid)
-            {
-                hz_draw_box<int>(P, T);
-                nsub = 0;
-            }
+            const bool mid = st == HZ_SETUP_OK && nsub != 0 && (T.px1 - T.px0 + 1) * (T.py1 - T.py0 + 1) <= P.mid_max_pix &&
+                             hz_tri_is_small(T) && T.px1 - T.px0 < 64 && T.py1 - T.py0 < 64;
+            if(__popc(__ballot_sync(0xffffffffu, mid)) >= HZ_MID_LANES && mid) { mine = true; nsub = 0; }
         }
+        hz_draw_boxes_warp(P, T, mine, s_warp[threadIdx.x >> 5], lane);
         // the large ones of the warp reserve their queue slots and records with ONE atomic each: in a zoomed-in view
         // nearly every triangle is large, and a million same-address atomics would be the whole kernel
         const unsigned int ballot = __ballot_sync(0xffffffffu, nsub != 0);
@@ -1410,8 +1487,11 @@ cudaError_t hz_launch_band(const HzView& v, const HzView* d_v, int nviews, bool 
     *launches = 0;
     const int rmax = worst_case ? v.nt - 1
                                 : max(max(v.eye_ti, v.nt - 1 - v.eye_ti), max(v.eye_tj, v.nt - 1 - v.eye_tj));
-    const int ring_hi = min(v.ring_hi, rmax + 1);
-    if(v.ring_lo >= ring_hi) return cudaSuccess;
+    // (With the opt-in level of detail the bands' limits depend on each view's azimuth window: a launch that serves
+    // several views, or a captured graph that will be replayed for others, must not be shaped by this one's.)
+    const bool any_band = worst_case && v.lod_capable;
+    const int ring_hi = any_band ? v.nt : min(v.ring_hi, rmax + 1);
+    if(!any_band && v.ring_lo >= ring_hi) return cudaSuccess;
     // (the threads walk the band's bounding square, clipped to the mesh)
     const long long side = min(2 * ring_hi - 1, v.nt), ntiles = side * side;
     long long ctas = (ntiles + 255) / 256;
