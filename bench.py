@@ -482,10 +482,10 @@ def run_b200(args):
             "panoramas_per_step_per_gpu": B,
             "concurrency": "a step is one horizonator_render_batch_device() call of %d panoramas: chunks of up to 16 views, "
                            "each chunk ONE chain of kernel launches with a view dimension (one parameter copy + one CUDA "
-                           "graph launch per chunk), chunks alternating between 2 streams; same viewpoint, nothing "
+                           "graph launch per chunk), chunks alternating between 4 streams; same viewpoint, nothing "
                            "cached between views; distinct viewpoints: see aux.c5_grid" % B,
             "l2": "no explicit flush; inputs larger than L2: the int16 DEM square is %.0f MB and its culling pyramid "
-                  "%.0f MB, and the panoramas in flight cycle up to 32 visibility buffers of %.0f MB each through the 126 MB "
+                  "%.0f MB, and the panoramas in flight cycle up to 64 visibility buffers of %.0f MB each through the 126 MB "
                   "L2 (hierarchical culling makes one panorama touch only a few tens of MB of the DEM, see "
                   "roofline.traffic)" % (2 * (2 * R) ** 2 / 1e6, 4 * ((2 * R) // 4) ** 2 / 1e6, 8 * W * H / 1e6),
             "parallelism": "viewpoint batch, %d panoramas per GPU per step, DEM replicated, no data-path collective" % B,
@@ -506,7 +506,7 @@ def run_b200(args):
                                     "in this run)" % world},
         "gpu_launches": K * ((B + 15) // 16) * batch_launches,
         "roofline": {"bound": "hbm", "kernel": "whole panorama: a chain of %d kernels per chunk of up to 16 views, replayed as "
-                               "one CUDA graph (k_prepare, k_near, k_raster, k_big, 3 x (k_tiles, k_blocks, k_mesh, k_raster), "
+                               "one CUDA graph (k_prepare, k_near, k_raster, k_big, 5 x (k_tiles, k_blocks, k_mesh, k_raster), "
                                "k_big, k_resolve)" % batch_launches,
                      "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": (prof_batch or {}).get("dram_bytes_per_panorama"),
