@@ -177,6 +177,9 @@ struct Slot
     bool  seam_wrap = false;         // opt-in (horizonator_set_seam_wrap); false = seam triangles dropped like the reference
     float curvature = 0.f;           // opt-in (horizonator_set_earth_curvature); 0 = flat earth like the reference
     bool use_graphs = true;
+    // blocks of live tiles tested in two levels (k_blocks_mid: fewer tests, one more in a row): the views of a batch
+    int mid_level_single = 0, mid_level_batch = 1;
+    int pdl_single = 1, pdl_batch = 1;   // programmatic dependent launch of the chain's kernels
     bool collect_stats = false;      // culling counters (horizonator_render_counters); off: the kernels skip them
     std::vector<cudaEvent_t> prof_events;
     size_t prof_used = 0;
@@ -601,6 +604,8 @@ void fill_view(const Slot& s, const ViewSet& set, const Scratch& sc, const ViewS
     v.small_max_pix = zoomed ? 2 * s.small_max_pix : s.small_max_pix; v.mid_max_pix = zoomed ? s.mid_max_pix : 0;
     v.grid_percent = set.batch ? s.grid_percent_batch : s.grid_percent_single;
     v.lod_capable = s.lod_pixels > 0.f;
+    v.mid_level = set.batch ? s.mid_level_batch : s.mid_level_single;
+    v.no_pdl = (set.batch ? s.pdl_batch : s.pdl_single) ? 0 : 1;
     v.big_capacity = s.big_capacity;
 
     // the eye's tile, and how many rings of tiles around it form the foreground pass
@@ -820,6 +825,10 @@ void read_tunables(Slot& s)
     if(const char* env = getenv("HORIZONATOR_BANDS")) { parse_bands(env, s.bands_single); s.bands_batch = s.bands_single; }
     if(const char* env = getenv("HORIZONATOR_BANDS_BATCH")) parse_bands(env, s.bands_batch);
     if(const char* env = getenv("HORIZONATOR_GRAPHS")) s.use_graphs = atoi(env) != 0;
+    if(const char* env = getenv("HORIZONATOR_MID_LEVEL"))       s.mid_level_single = s.mid_level_batch = atoi(env) != 0;
+    if(const char* env = getenv("HORIZONATOR_MID_LEVEL_BATCH")) s.mid_level_batch = atoi(env) != 0;
+    if(const char* env = getenv("HORIZONATOR_PDL"))       s.pdl_single = s.pdl_batch = atoi(env) != 0;
+    if(const char* env = getenv("HORIZONATOR_PDL_BATCH")) s.pdl_batch = atoi(env) != 0;
     if(const char* env = getenv("HORIZONATOR_GRAPH_INSTANCES")) s.graph_instances = atoi(env) < 1 ? 1 : (atoi(env) > 16 ? 16 : atoi(env));
     // HORIZONATOR_LANES: most views of a batch rendered by one chain of launches; HORIZONATOR_SETS: how many such
     // sets may be in flight (each on its own stream)
@@ -1724,7 +1733,7 @@ bool horizonator_reload_tunables(const horizonator_context_t* ctx)
         s->small_max_pix = d.small_max_pix; s->mid_max_pix = d.mid_max_pix; s->grid_percent_single = d.grid_percent_single;
         s->grid_percent_batch = d.grid_percent_batch; s->bands_single = d.bands_single; s->bands_batch = d.bands_batch;
         s->use_graphs = d.use_graphs; s->views_per_set = d.views_per_set; s->n_sets_max = d.n_sets_max;
-        s->graph_instances = d.graph_instances;
+        s->graph_instances = d.graph_instances; s->mid_level_single = d.mid_level_single; s->mid_level_batch = d.mid_level_batch; s->pdl_single = d.pdl_single; s->pdl_batch = d.pdl_batch;
     }
     read_tunables(*s);
     return true;

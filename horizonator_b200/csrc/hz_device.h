@@ -126,6 +126,8 @@ struct HzView
     int occl_tile_max_pix, occl_block_max_pix;   // largest screen box one thread checks against the visibility buffer
     int grid_percent;            // host only: scale of the device-counted kernels' grids (hz_grid)
     int lod_capable;             // host only: some view of the launch may have lod > 0 (picks k_blocks' instantiation)
+    int mid_level;               // host only: the blocks of live tiles are tested in two levels (k_blocks_mid)
+    int no_pdl;                  // host only: launch without programmatic dependent launch (see hz_launch)
     int small_max_pix;           // a lane rasterises bounding boxes up to this many pixels itself; larger ones go to k_big
     int mid_max_pix;             // ... and up to this many where enough lanes of its warp have one (k_raster)
 

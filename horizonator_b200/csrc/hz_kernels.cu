@@ -44,10 +44,15 @@ __device__ __forceinline__ void hz_wait_for_previous_kernel()
 // kernel, so that those reads overlap that kernel's tail instead of following it; afterwards every P.field is a
 // shared-memory read.
 // One launch serves gridDim.y views: view y reads its copy of the launch's variant, HZ_V_COUNT elements per view on.
+// (Every render kernel runs CTAs of HZ_CTA_THREADS threads and the block has fewer words than that: one guarded load
+// per thread.  Written as a loop striding by blockDim.x the compiler does not know the trip count and works it out
+// with an integer division -- some 50 instructions at the head of every warp of every launch.)
+#define HZ_CTA_THREADS 256
+static_assert(sizeof(HzView) % 4 == 0 && sizeof(HzView) / 4 <= HZ_CTA_THREADS, "HzView must fit one word per thread");
 #define HZ_KERNEL_PROLOGUE(V, P)                                                                           \
     __shared__ HzView hz_s_view;                                                                           \
-    for(unsigned int hz_i = threadIdx.x; hz_i < sizeof(HzView) / 4; hz_i += blockDim.x)                    \
-        ((uint32_t*)&hz_s_view)[hz_i] = __ldg((const uint32_t*)((V) + blockIdx.y * HZ_V_COUNT) + hz_i);    \
+    if(threadIdx.x < sizeof(HzView) / 4)                                                                   \
+        ((uint32_t*)&hz_s_view)[threadIdx.x] = __ldg((const uint32_t*)((V) + blockIdx.y * HZ_V_COUNT) + threadIdx.x); \
     __syncthreads();                                                                                       \
     hz_wait_for_previous_kernel();                                                                         \
     const HzView& P = hz_s_view
@@ -66,13 +71,13 @@ static unsigned int hz_grid(const HzView& v, unsigned int ctas_per_sm, int nview
 }
 
 template <typename... KArgs, typename... Args>
-static cudaError_t hz_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, cudaStream_t stream, Args&&... args)
+static cudaError_t hz_launch(const HzView& v, void (*kernel)(KArgs...), dim3 grid, dim3 block, cudaStream_t stream, Args&&... args)
 {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = 0; cfg.stream = stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    attr[0].val.programmaticStreamSerializationAllowed = v.no_pdl ? 0 : 1;   // (without it the wait in the prologue is a no-op)
     cfg.attrs = attr; cfg.numAttrs = 1;
     return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
@@ -223,7 +228,7 @@ cudaError_t hz_launch_prepare(const HzView& v, const HzView* d_v, int nviews, cu
     if(nviews > 1) blocks = 148u * 8u / (unsigned int)nviews;
     if(blocks < 16u) blocks = 16u;
     (void)v;
-    return hz_launch(k_prepare, dim3(blocks, (unsigned)nviews), dim3(256), stream, d_v);
+    return hz_launch(v, k_prepare, dim3(blocks, (unsigned)nviews), dim3(256), stream, d_v);
 }
 
 // ================================================================================================
@@ -1092,7 +1097,7 @@ cudaError_t hz_launch_near(const HzView& v, const HzView* d_v, int nviews, cudaS
     const int cap = max(148 * 8 / max(nviews, 1), 37);
     if(ctas > cap) ctas = cap;
     if(ctas < 1) ctas = 1;
-    return hz_launch(k_near, dim3(ctas, (unsigned)nviews), dim3(HZ_WARPS_PER_CTA * 32), stream, d_v);
+    return hz_launch(v, k_near, dim3(ctas, (unsigned)nviews), dim3(HZ_WARPS_PER_CTA * 32), stream, d_v);
 }
 
 // ================================================================================================
@@ -1109,32 +1114,33 @@ cudaError_t hz_launch_near(const HzView& v, const HzView* d_v, int nviews, cudaS
 // Everything a band draws is in the visibility buffer before the next band is tested against it, and within a
 // band whatever has already been drawn helps too.
 
-// HZ_OCCL_FETCH keys are fetched per round, walking the box row by row, so that the L2 round trips overlap whatever the
-// shape of the box; the walk ends at the first round that shows something not nearer.
+// The box is walked row by row, HZ_OCCL_FETCH keys per round (so that the L2 round trips overlap); only the upper half
+// of a key is fetched -- epoch and depth sit in its top 27 bits -- and the walk ends at the first round that shows
+// something not nearer.  (Round 2 walked the box as one run of pixels: the wrap to the next row, tested per pixel,
+// cost as much as the fetch and the comparison together.)
 #ifndef HZ_OCCL_FETCH
 #define HZ_OCCL_FETCH 8            /* (16 and 32 measured no better, lone or batched) */
 #endif
 __device__ __forceinline__ bool hz_box_occluded_thread(const HzView& P, const HzBox& B, int max_pix)
 {
     const int w = B.px1 - B.px0 + 1, h = B.py1 - B.py0 + 1;
-    const int npix = w * h;
-    if(npix > max_pix) return false;
-    const size_t Wt = (size_t)(P.x1 - P.x0);
-    const unsigned long long* row = P.vis + (size_t)B.py0 * Wt + (size_t)(B.px0 - P.x0);
-    int x = 0;
-    for(int p = 0; p < npix; p += HZ_OCCL_FETCH)
+    if(w * h > max_pix) return false;
+    const unsigned int Wt2 = 2u * (unsigned int)(P.x1 - P.x0);                // 32-bit words per row of keys
+    // (upper word of the first key of the box)
+    const unsigned int* row = (const unsigned int*)P.vis + ((size_t)B.py0 * Wt2 + 2u * (unsigned int)(B.px0 - P.x0) + 1u);
+    const unsigned int qmin_hi = B.qmin << (HZ_KEY_Q_SHIFT - 32);             // the bound, placed like the key's upper word
+    for(int y = 0; y < h; y++, row += Wt2)
     {
-        unsigned int farthest = 0;
-        #pragma unroll
-        for(int u = 0; u < HZ_OCCL_FETCH; u++)
+        for(int x = 0; x < w; x += HZ_OCCL_FETCH)
         {
-            if(p + u < npix)
-            {
-                farthest = max(farthest, hz_key_top(__ldcg(row + x)));
-                if(++x == w) { x = 0; row += Wt; }
-            }
+            unsigned int farthest = 0;
+            #pragma unroll
+            for(int u = 0; u < HZ_OCCL_FETCH; u++)
+                if(x + u < w) farthest = max(farthest, __ldcg(row + 2 * (x + u)));
+            // (the upper word holds epoch | depth | the top 5 bits of the triangle number: comparing it whole against
+            // the bound with those 5 bits clear is the same test as comparing the top 27 bits)
+            if(farthest >= qmin_hi) return false;
         }
-        if(farthest >= B.qmin) return false;
     }
     return true;
 }
@@ -1276,6 +1282,109 @@ k_blocks(const HzView* __restrict__ V)
             }
         }
         hz_cta_append(s_app, on, id, P.block_queue, P.block_count);
+    }
+    if(P.stats) hz_cta_stats4(s_stats, P.stats + HZ_STAT_BLOCKS, n_all, n_far, n_window, n_occl);
+}
+
+// ---- k_blocks with a level in between (MID) ----------------------------------------------------------------------------
+//
+// Most of a live tile is dead at the block level (seen at a grazing angle a stretch of terrain is a fraction of a pixel
+// high and holds no pixel centre; what does is mostly hidden), and a rectangle test costs a few hundred instructions.
+// The MID variant therefore tests the 16 "mids" of every live tile first -- squares of 2x2 blocks = 8x8 cells, (min, max)
+// taken from the four blocks' entries of the pyramid -- one per thread, collects the survivors in shared memory, and then
+// tests their four blocks each, densely again (thread = (surviving mid, block), 256 at a time): about half the rectangle
+// tests per live tile, in full warps.  It is what the views of a batch use (throughput); a lone view is latency-bound
+// and keeps the one-level kernel, whose threads have one test each behind them instead of two.
+enum { HZ_RECT_OCCLUDED = 4 };
+
+__device__ __forceinline__ int
+hz_rect_cull(const HzView& P, int c_lo, int c_hi, int r_lo, int r_hi, float zmin, float zmax, int max_pix)
+{
+    HzBox B;
+    const int r = hz_rect_test(P, c_lo, c_hi, r_lo, r_hi, zmin, zmax, B);
+    return (r == HZ_RECT_BOXED && hz_box_occluded_thread(P, B, max_pix)) ? (int)HZ_RECT_OCCLUDED : r;
+}
+
+// appends `value` of the threads with `on` to list[*n ...] in shared memory; every thread of the CTA calls, *n was zeroed
+// (and the CTA synchronised) before, and the caller synchronises before it reads the list
+__device__ __forceinline__ void hz_smem_append(bool on, unsigned int value, unsigned int* list, unsigned int* n)
+{
+    const unsigned int lane = threadIdx.x & 31u;
+    const unsigned int ballot = __ballot_sync(0xffffffffu, on);
+    unsigned int base = 0;
+    if(lane == 0 && ballot) base = atomicAdd(n, (unsigned int)__popc(ballot));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if(on) list[base + __popc(ballot & ((1u << lane) - 1u))] = value;
+}
+
+__global__ void __launch_bounds__(256)
+k_blocks_mid(const HzView* __restrict__ V)
+{
+    HZ_KERNEL_PROLOGUE(V, P);
+    __shared__ HzCtaAppend s_app;
+    __shared__ unsigned int s_mids[256], s_nmids;
+    __shared__ unsigned int s_stats[4];
+    const int nb = P.nb, N = P.N;
+    const int mid_pix = P.occl_tile_max_pix, block_pix = P.occl_block_max_pix;
+    const unsigned int total = *P.tile_count * 16u;
+    const unsigned int nth = gridDim.x * blockDim.x;
+    unsigned int n_all = 0, n_far = 0, n_window = 0, n_occl = 0;
+    for(unsigned int t0 = blockIdx.x * blockDim.x; t0 < total; t0 += nth)     // (the same trip counts CTA-wide, here and below)
+    {
+        __syncthreads();
+        if(threadIdx.x == 0) s_nmids = 0;
+        __syncthreads();
+        {
+            const unsigned int t = t0 + threadIdx.x;
+            bool on = false;
+            unsigned int id = 0;
+            if(t < total)
+            {
+                const unsigned int tile = P.tile_queue[t >> 4];
+                const int mj = (int)(tile >> 16) * 4 + (int)((t >> 2) & 3u), mi = (int)(tile & 0xFFFFu) * 4 + (int)(t & 3u);
+                const int bj = 2 * mj, bi = 2 * mi;
+                if(bj < nb && bi < nb)
+                {
+                    const short2* mm = P.mm_block + (size_t)bj * nb + bi;
+                    const bool right = bi + 1 < nb, up = bj + 1 < nb;
+                    const short2 a = __ldg(mm), b = right ? __ldg(mm + 1) : a, c = up ? __ldg(mm + nb) : a,
+                                 d = (right && up) ? __ldg(mm + nb + 1) : a;
+                    const int lo = min(min((int)a.x, (int)b.x), min((int)c.x, (int)d.x));
+                    const int hi = max(max((int)a.y, (int)b.y), max((int)c.y, (int)d.y));
+                    const int c0 = bi * HZ_BLOCK_CELLS, r0 = bj * HZ_BLOCK_CELLS;
+                    const int r = hz_rect_cull(P, c0, min(c0 + 2 * HZ_BLOCK_CELLS, N - 1), r0, min(r0 + 2 * HZ_BLOCK_CELLS, N - 1),
+                                               (float)lo, (float)hi, mid_pix);
+                    on = r == HZ_RECT_ALIVE || r == HZ_RECT_BOXED;
+                    id = ((unsigned int)mj << 16) | (unsigned int)mi;
+                }
+            }
+            hz_smem_append(on, id, s_mids, &s_nmids);
+        }
+        __syncthreads();
+        const unsigned int items = s_nmids * 4u;
+        for(unsigned int jb = 0; jb < items; jb += 256u)
+        {
+            const unsigned int item = jb + threadIdx.x;
+            bool on = false;
+            unsigned int id = 0;
+            if(item < items)
+            {
+                const unsigned int mid = s_mids[item >> 2];
+                const int bj = (int)(mid >> 16) * 2 + (int)((item >> 1) & 1u), bi = (int)(mid & 0xFFFFu) * 2 + (int)(item & 1u);
+                if(bj < nb && bi < nb)
+                {
+                    const short2 mm = __ldg(P.mm_block + (size_t)bj * nb + bi);
+                    const int c0 = bi * HZ_BLOCK_CELLS, r0 = bj * HZ_BLOCK_CELLS;
+                    const int r = hz_rect_cull(P, c0, min(c0 + HZ_BLOCK_CELLS, N - 1), r0, min(r0 + HZ_BLOCK_CELLS, N - 1),
+                                               (float)mm.x, (float)mm.y, block_pix);
+                    n_all++;
+                    n_far += (r == HZ_RECT_DEAD_FAR); n_window += (r == HZ_RECT_DEAD_WINDOW); n_occl += (r == HZ_RECT_OCCLUDED);
+                    on = r == HZ_RECT_ALIVE || r == HZ_RECT_BOXED;
+                    id = ((unsigned int)bj << 16) | (unsigned int)bi;
+                }
+            }
+            hz_cta_append(s_app, on, id, P.block_queue, P.block_count);
+        }
     }
     if(P.stats) hz_cta_stats4(s_stats, P.stats + HZ_STAT_BLOCKS, n_all, n_far, n_window, n_occl);
 }
@@ -1477,7 +1586,7 @@ k_raster(const HzView* __restrict__ V)
 
 cudaError_t hz_launch_raster(const HzView& v, const HzView* d_v, int nviews, cudaStream_t stream)
 {
-    return hz_launch(k_raster, dim3(hz_grid(v, 6, nviews), (unsigned)nviews), dim3(256), stream, d_v);
+    return hz_launch(v, k_raster, dim3(hz_grid(v, 6, nviews), (unsigned)nviews), dim3(256), stream, d_v);
 }
 
 // `worst_case`: size the tile kernel for any eye position (a CUDA graph is captured once per context and replayed
@@ -1498,11 +1607,12 @@ cudaError_t hz_launch_band(const HzView& v, const HzView* d_v, int nviews, bool 
     if(ctas > (long long)hz_grid(v, 8, nviews)) ctas = hz_grid(v, 8, nviews);
     const unsigned int ny = (unsigned int)nviews;
     cudaError_t e;
-    if((e = hz_launch(k_tiles,  dim3((unsigned)ctas, ny), dim3(256), stream, d_v)) != cudaSuccess) return e;
-    if((e = hz_launch(v.lod_capable ? k_blocks<true> : k_blocks<false>, dim3(hz_grid(v, 8, nviews), ny), dim3(256), stream, d_v)) != cudaSuccess) return e;
-    if((e = hz_launch(k_mesh,   dim3(hz_grid(v, 4, nviews), ny), dim3(HZ_WARPS_PER_CTA * 32), stream, d_v)) != cudaSuccess) return e;
-    if((e = hz_launch(k_raster, dim3(hz_grid(v, 6, nviews), ny), dim3(256), stream, d_v)) != cudaSuccess) return e;
+    void (*blocks)(const HzView*) = v.lod_capable ? k_blocks<true> : (v.mid_level ? k_blocks_mid : k_blocks<false>);
+    if((e = hz_launch(v, k_tiles, dim3((unsigned)ctas, ny), dim3(256), stream, d_v)) != cudaSuccess) return e;
+    if((e = hz_launch(v, blocks,  dim3(hz_grid(v, 8, nviews), ny), dim3(256), stream, d_v)) != cudaSuccess) return e;
     *launches = 4;
+    if((e = hz_launch(v, k_mesh,   dim3(hz_grid(v, 4, nviews), ny), dim3(HZ_WARPS_PER_CTA * 32), stream, d_v)) != cudaSuccess) return e;
+    if((e = hz_launch(v, k_raster, dim3(hz_grid(v, 6, nviews), ny), dim3(256), stream, d_v)) != cudaSuccess) return e;
     return cudaSuccess;
 }
 
@@ -1584,7 +1694,7 @@ k_big(const HzView* __restrict__ V)
 
 cudaError_t hz_launch_big(const HzView& v, const HzView* d_v, int nviews, cudaStream_t stream)
 {
-    return hz_launch(k_big, dim3(hz_grid(v, 8, nviews), (unsigned)nviews), dim3(256), stream, d_v);
+    return hz_launch(v, k_big, dim3(hz_grid(v, 8, nviews), (unsigned)nviews), dim3(256), stream, d_v);
 }
 
 // ================================================================================================
@@ -1626,58 +1736,73 @@ __device__ __forceinline__ HzResolve hz_resolve_params(const HzView& P)
     return R;
 }
 
-// 4 pixels per thread: 2x16 B of keys in, 12 B of BGR and 16 B of range out (per destination).  32-bit index
-// arithmetic throughout (the launch falls back to k_resolve1 for targets of 2^31 pixels or more); the row of a CTA's
-// first group comes from one division that is the same for the whole CTA, the threads step on from there.
-__global__ void __launch_bounds__(256)
+// 4 pixels per thread and trip: 2x16 B of keys in, 12 B of BGR and 16 B of range out (per destination).  One CTA per
+// row of the target: no index arithmetic to speak of (round 2's version spent more instructions on finding its row,
+// a division, than on its four pixels), the row's tan(elevation) is read once, and the next trip's keys are on their
+// way while this trip's pixels are converted.
+__global__ void __launch_bounds__(HZ_CTA_THREADS)
 k_resolve4(const HzView* __restrict__ V)
 {
     HZ_KERNEL_PROLOGUE(V, P);
-    const HzResolve R = hz_resolve_params(P);
-    const unsigned int gpr = (unsigned int)R.Wt >> 2;                          // groups of 4 pixels per row
-    const unsigned int g0 = blockIdx.x * 256u;
-    unsigned int y = g0 / gpr, xg = g0 - y * gpr + threadIdx.x;                // GL row (0 = bottom), group within the row
-    if(xg >= gpr) { const unsigned int up = xg / gpr; y += up; xg -= up * gpr; }
-    if(y >= (unsigned int)R.H) return;
-    const unsigned int x = xg << 2;
-    const unsigned int src = y * (unsigned int)R.Wt + x;
-    const size_t dst = (size_t)((unsigned int)R.H - 1u - y) * (unsigned int)R.out_stride + (unsigned int)R.out_x0 + x;   // top row first (lib:949-958, 1026-1038)
-
-    const ulonglong2 k01 = __ldcs((const ulonglong2*)(R.vis + src));           // read once: streaming
-    const ulonglong2 k23 = __ldcs((const ulonglong2*)(R.vis + src + 2));
+    const unsigned int Wt = (unsigned int)(P.x1 - P.x0), gpr = Wt >> 2;        // groups of 4 pixels per row
+    const unsigned int y = blockIdx.x;                                         // GL row (0 = bottom)
     const unsigned int ep = P.epoch;
-    const unsigned int q0 = hz_key_q(k01.x, ep), q1 = hz_key_q(k01.y, ep), q2 = hz_key_q(k23.x, ep), q3 = hz_key_q(k23.y, ep);
+    const float znear = P.znear, zfar = P.zfar;
+    const int n_out = P.n_out;
+    uint8_t* const image0 = P.out_image[0];
+    float* const ranges0 = P.out_ranges[0];
+    const float tanel = ranges0 != nullptr ? __ldg(P.tanel + y) : 0.0f;
+    const ulonglong2* src = (const ulonglong2*)(P.vis + (size_t)y * Wt);
+    const size_t dst_row = (size_t)((unsigned int)P.H - 1u - y) * (unsigned int)P.out_stride + (unsigned int)P.out_x0;   // top row first (lib:949-958, 1026-1038)
 
-    // hit: (B,G,R) = (0,0,r8) ; sky: clear colour (0,0,1) read as BGR = (255,0,0)   lib:185, 938-939
-    // bytes B0 G0 R0 B1 | G1 R1 B2 G2 | R2 B3 G3 R3
-    const unsigned int B0 = q0 != HZ_Q_MAX ? 0u : 255u, R0 = q0 != HZ_Q_MAX ? (unsigned int)k01.x & 0xFFu : 0u;
-    const unsigned int B1 = q1 != HZ_Q_MAX ? 0u : 255u, R1 = q1 != HZ_Q_MAX ? (unsigned int)k01.y & 0xFFu : 0u;
-    const unsigned int B2 = q2 != HZ_Q_MAX ? 0u : 255u, R2 = q2 != HZ_Q_MAX ? (unsigned int)k23.x & 0xFFu : 0u;
-    const unsigned int B3 = q3 != HZ_Q_MAX ? 0u : 255u, R3 = q3 != HZ_Q_MAX ? (unsigned int)k23.y & 0xFFu : 0u;
-    const uint32_t w0 = B0 | (R0 << 16) | (B1 << 24);
-    const uint32_t w1 = (R1 << 8) | (B2 << 16);
-    const uint32_t w2 = R2 | (B3 << 8) | (R3 << 24);
+    unsigned int xg = threadIdx.x;
+    ulonglong2 k01 = make_ulonglong2(0, 0), k23 = k01;
+    if(xg < gpr) { k01 = __ldcs(src + 2 * xg); k23 = __ldcs(src + 2 * xg + 1); }   // read once: streaming
+    while(xg < gpr)
+    {
+        const unsigned int xg_next = xg + HZ_CTA_THREADS;
+        ulonglong2 n01 = k01, n23 = k23;
+        if(xg_next < gpr) { n01 = __ldcs(src + 2 * xg_next); n23 = __ldcs(src + 2 * xg_next + 1); }
 
-    float4 r = make_float4(-1.0f, -1.0f, -1.0f, -1.0f);
-    // most groups of four pixels are sky: skip the FP64 conversion for them altogether
-    if(P.out_ranges[0] != nullptr && (q0 & q1 & q2 & q3) != HZ_Q_MAX)
-    {
-        const float t = R.tanel[y];
-        r.x = hz_range_of_q(q0, t, R.znear, R.zfar);
-        r.y = hz_range_of_q(q1, t, R.znear, R.zfar);
-        r.z = hz_range_of_q(q2, t, R.znear, R.zfar);
-        r.w = hz_range_of_q(q3, t, R.znear, R.zfar);
-    }
-    for(int d = 0; d < R.n_out; d++)
-    {
-        uint8_t* image = P.out_image[d];
-        float* ranges = P.out_ranges[d];
-        if(image)
+        const unsigned int q0 = hz_key_q(k01.x, ep), q1 = hz_key_q(k01.y, ep), q2 = hz_key_q(k23.x, ep), q3 = hz_key_q(k23.y, ep);
+        // hit: (B,G,R) = (0,0,r8) ; sky: clear colour (0,0,1) read as BGR = (255,0,0)   lib:185, 938-939
+        // bytes B0 G0 R0 B1 | G1 R1 B2 G2 | R2 B3 G3 R3
+        const unsigned int B0 = q0 != HZ_Q_MAX ? 0u : 255u, R0 = q0 != HZ_Q_MAX ? (unsigned int)k01.x & 0xFFu : 0u;
+        const unsigned int B1 = q1 != HZ_Q_MAX ? 0u : 255u, R1 = q1 != HZ_Q_MAX ? (unsigned int)k01.y & 0xFFu : 0u;
+        const unsigned int B2 = q2 != HZ_Q_MAX ? 0u : 255u, R2 = q2 != HZ_Q_MAX ? (unsigned int)k23.x & 0xFFu : 0u;
+        const unsigned int B3 = q3 != HZ_Q_MAX ? 0u : 255u, R3 = q3 != HZ_Q_MAX ? (unsigned int)k23.y & 0xFFu : 0u;
+        const uint32_t w0 = B0 | (R0 << 16) | (B1 << 24);
+        const uint32_t w1 = (R1 << 8) | (B2 << 16);
+        const uint32_t w2 = R2 | (B3 << 8) | (R3 << 24);
+
+        float4 r = make_float4(-1.0f, -1.0f, -1.0f, -1.0f);
+        // most groups of four pixels are sky: skip the FP64 conversion for them altogether
+        if(ranges0 != nullptr && (q0 & q1 & q2 & q3) != HZ_Q_MAX)
         {
-            uint32_t* o = (uint32_t*)(image + dst * 3);    // dst*3 is a multiple of 4 because x, x0 and the stride are
+            r.x = hz_range_of_q(q0, tanel, znear, zfar);
+            r.y = hz_range_of_q(q1, tanel, znear, zfar);
+            r.z = hz_range_of_q(q2, tanel, znear, zfar);
+            r.w = hz_range_of_q(q3, tanel, znear, zfar);
+        }
+        const size_t dst = dst_row + 4u * xg;
+        if(image0)
+        {
+            uint32_t* o = (uint32_t*)(image0 + dst * 3);       // dst*3 is a multiple of 4 because x, x0 and the stride are
             o[0] = w0; o[1] = w1; o[2] = w2;
         }
-        if(ranges) *(float4*)(ranges + dst) = r;
+        if(ranges0) *(float4*)(ranges0 + dst) = r;
+        for(int d = 1; d < n_out; d++)                         // (the other ranks of a wedge-sharded panorama)
+        {
+            uint8_t* image = P.out_image[d];
+            float* ranges = P.out_ranges[d];
+            if(image)
+            {
+                uint32_t* o = (uint32_t*)(image + dst * 3);
+                o[0] = w0; o[1] = w1; o[2] = w2;
+            }
+            if(ranges) *(float4*)(ranges + dst) = r;
+        }
+        xg = xg_next; k01 = n01; k23 = n23;
     }
 }
 
@@ -1721,15 +1846,12 @@ bool hz_resolve_is_vectorisable(const HzView& v)
 cudaError_t hz_launch_resolve(const HzView& v, const HzView* d_v, int nviews, cudaStream_t stream)
 {
     const int Wt = v.x1 - v.x0;
-    if(hz_resolve_is_vectorisable(v) && (long long)Wt * v.H < (1ll << 31))
-    {
-        const long long n = (long long)(Wt / 4) * v.H;
-        return hz_launch(k_resolve4, dim3((unsigned)((n + 255) / 256), (unsigned)nviews), dim3(256), stream, d_v);
-    }
+    if(hz_resolve_is_vectorisable(v))
+        return hz_launch(v, k_resolve4, dim3((unsigned)v.H, (unsigned)nviews), dim3(HZ_CTA_THREADS), stream, d_v);
     else
     {
         const long long n = (long long)Wt * v.H;
-        return hz_launch(k_resolve1, dim3((unsigned)((n + 255) / 256), (unsigned)nviews), dim3(256), stream, d_v);
+        return hz_launch(v, k_resolve1, dim3((unsigned)((n + 255) / 256), (unsigned)nviews), dim3(256), stream, d_v);
     }
 }
 

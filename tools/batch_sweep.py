@@ -21,7 +21,7 @@ from tools import synth  # noqa: E402
 
 C2_LAT, C2_LON = 34.0 + 1.0 / 7200.0, -117.0 + 1.0 / 7200.0
 KEYS = ("LANES", "SETS", "GRID_SCALE_BATCH", "GRID_SCALE", "BANDS", "BANDS_BATCH", "NEAR_RINGS", "OCCL_TILE_PIX",
-        "OCCL_BLOCK_PIX", "OCCL_TILE_PIX_BATCH", "OCCL_BLOCK_PIX_BATCH", "SMALL_PIX", "MID_PIX", "GRAPHS", "GRAPH_INSTANCES")
+        "OCCL_BLOCK_PIX", "OCCL_TILE_PIX_BATCH", "OCCL_BLOCK_PIX_BATCH", "SMALL_PIX", "MID_PIX", "GRAPHS", "GRAPH_INSTANCES", "MID_LEVEL", "MID_LEVEL_BATCH", "PDL", "PDL_BATCH")
 
 
 def grid_views(g=8):
@@ -64,6 +64,8 @@ def main():
     ap.add_argument("--batches", default="16,64")
     ap.add_argument("--once", type=int, default=0, help="for ncu: after two warm-up calls, ONE call of this many "
                     "panoramas of the benchmark viewpoint, nothing else")
+    ap.add_argument("--grid", action="store_true", help="with --once: the distinct viewpoints of the 8x8 grid (C5 flavour) "
+                    "instead of the benchmark viewpoint repeated")
     ap.add_argument("configs", nargs="*", default=[""])
     a = ap.parse_args()
     tiles = synth.config2_tiles(os.environ.get("HZ_BENCH_TILES", "/tmp/hz_tiles_c2"))
@@ -74,7 +76,7 @@ def main():
     d_img = torch.empty((Bmax, 600, 3600, 3), dtype=torch.uint8, device="cuda")
     d_rng = torch.empty((Bmax, 600, 3600), dtype=torch.float32, device="cuda")
     if a.once:
-        v = [(C2_LAT, C2_LON, -180.05, 179.95)] * a.once
+        v = (grid_views() * (1 + a.once // 64))[:a.once] if a.grid else [(C2_LAT, C2_LON, -180.05, 179.95)] * a.once
         for _ in range(3):
             h.render_batch_device(v, d_img.data_ptr(), d_rng.data_ptr(), torch.cuda.current_stream().cuda_stream)
             torch.cuda.synchronize()
