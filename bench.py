@@ -6,8 +6,8 @@
 Workload (N=1 and per rank for N>1): BASELINE.json configs[1] ("C2") -- synthetic SRTM1 tiles N32..N35 x
 W119..W116, viewer (34+1/7200, -117+1/7200), render_radius_m = 150 km (R = 5858 cells, 137 M vertices, 274 M
 triangles), 3600x600 panorama + range image, az [-180.05, 179.95], znear 100 m, zfar 150 km.  A step is one
-call of horizonator_render_batch_device() with --batch (default 64) panoramas per rank on a real CUDA stream: the
-library renders them in chunks of up to 16 views, each chunk ONE chain of kernel launches with a view dimension,
+call of horizonator_render_batch_device() with --batch (default 256) panoramas per rank on a real CUDA stream: the
+library renders them in chunks of up to 64 views, each chunk ONE chain of kernel launches with a view dimension,
 chunks alternating between 4 streams.  With N>1 every rank does the same against its own copy of the DEM (weak
 scaling, no collective on the data path; NCCL only for the barrier/max of times).
 
@@ -44,7 +44,6 @@ sys.path.insert(0, ROOT)
 C2 = dict(lat=34.0 + 1.0 / 7200.0, lon=-117.0 + 1.0 / 7200.0, W=3600, H=600, radius_m=150000.0,
           az0=-180.05, az1=179.95, znear=100.0, zfar=150000.0, R=5858)
 TILES_DIR = os.environ.get("HZ_BENCH_TILES", "/tmp/hz_tiles_c2")
-WARP_INST_PER_PANORAMA = 42.29e6    # ncu smsp__inst_executed.sum, all kernels of one C2 panorama (profiles/r01A_*)
 
 
 def algorithmic_bytes(R, W, H):
@@ -270,6 +269,9 @@ def run_b200(args):
     alg = algorithmic_bytes(R, W, H)
 
     B = args.batch                      # panoramas per step: one call of the batch entry point
+    # (how the library cuts a call into chunks: spread evenly over its 4 view sets, 8 to 64 views each -- render_batch_common())
+    chunk = max(min(-(-B // 4), 64), min(B, 8))
+    n_chunks = -(-B // chunk)
     d_img = torch.empty((B, H, W, 3), dtype=torch.uint8, device="cuda")
     d_rng = torch.empty((B, H, W), dtype=torch.float32, device="cuda")
     # a stream of its own: the batch call takes stream NULL -- which is what torch's default stream is -- to mean "the
@@ -480,10 +482,10 @@ def run_b200(args):
                         "(R=%d cells, %d triangles), 3600x600 panorama + range image" % (R, h.context.Ntriangles),
             "az_deg": [C2["az0"], C2["az1"]], "znear_m": C2["znear"], "zfar_m": C2["zfar"],
             "panoramas_per_step_per_gpu": B,
-            "concurrency": "a step is one horizonator_render_batch_device() call of %d panoramas: chunks of up to 16 views, "
+            "concurrency": "a step is one horizonator_render_batch_device() call of %d panoramas: %d chunks of %d views, "
                            "each chunk ONE chain of kernel launches with a view dimension (one parameter copy + one CUDA "
                            "graph launch per chunk), chunks alternating between 4 streams; same viewpoint, nothing "
-                           "cached between views; distinct viewpoints: see aux.c5_grid" % B,
+                           "cached between views; distinct viewpoints: see aux.c5_grid" % (B, n_chunks, chunk),
             "l2": "no explicit flush; inputs larger than L2: the int16 DEM square is %.0f MB and its culling pyramid "
                   "%.0f MB, and the panoramas in flight cycle up to 64 visibility buffers of %.0f MB each through the 126 MB "
                   "L2 (hierarchical culling makes one panorama touch only a few tens of MB of the DEM, see "
@@ -504,10 +506,10 @@ def run_b200(args):
                 "d2h_ceiling_note": "panoramas/s at which %d GPU(s) of this box move 7*W*H bytes each to page-locked host "
                                     "memory concurrently with nothing else going on (plain cudaMemcpyAsync, measured "
                                     "in this run)" % world},
-        "gpu_launches": K * ((B + 15) // 16) * batch_launches,
-        "roofline": {"bound": "hbm", "kernel": "whole panorama: a chain of %d kernels per chunk of up to 16 views, replayed as "
-                               "one CUDA graph (k_prepare, k_near, k_raster, k_big, 5 x (k_tiles, k_blocks, k_mesh, k_raster), "
-                               "k_big, k_resolve)" % batch_launches,
+        "gpu_launches": K * n_chunks * batch_launches,
+        "roofline": {"bound": "hbm", "kernel": "whole panorama: a chain of %d kernels per chunk of up to 64 views, replayed as "
+                               "one CUDA graph (k_prepare, k_near, k_raster, k_big, 10 x (k_tiles, k_blocks_mid, k_mesh, "
+                               "k_raster), k_big, k_resolve4)" % batch_launches,
                      "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": (prof_batch or {}).get("dram_bytes_per_panorama"),
                      "peak_source": peak_src,
@@ -516,7 +518,7 @@ def run_b200(args):
                      "latency_ms_single_panorama": latency_ms,
                      "frac_single_panorama": frac_of_roof(latency_ms),
                      # the resource that actually binds in batch mode: instruction issue.  Instructions per panorama
-                     # from an ncu capture of THIS configuration (batch of 16, 3 bands); peak = SMs x 4 schedulers x SM clock
+                     # from an ncu capture of THIS configuration (profiles/batch_profile.json); peak = SMs x 4 schedulers x SM clock
                      "issue": None if prof_batch is None else {
                          "warp_instructions_per_panorama": prof_batch["warp_instructions_per_panorama"],
                          "peak_warp_instructions_per_s": issue_peak,
@@ -835,7 +837,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--batch", type=int, default=64, help="panoramas per step (one call of the batch entry point)")
+    ap.add_argument("--batch", type=int, default=256, help="panoramas per step (one call of the batch entry point)")
     ap.add_argument("--grid-views", type=int, default=0, help="viewpoints of the C5 grid per GPU (0 = its whole block)")
     ap.add_argument("--no-c4", action="store_true", help="skip the 36000x4000 wedge panorama (N > 1)")
     ap.add_argument("--llvmpipe-child", action="store_true", help=argparse.SUPPRESS)

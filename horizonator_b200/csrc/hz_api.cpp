@@ -129,17 +129,19 @@ struct Slot
     int near_rings = 2;
     // largest screen box one thread checks against the visibility buffer: a lone view is latency-bound and a long walk
     // by one thread holds its kernel up; the views of a batch hide that behind each other and gain from the extra culling
-    int occl_tile_max_pix = 64, occl_block_max_pix = 32, occl_tile_max_pix_batch = 256, occl_block_max_pix_batch = 64;
+    int occl_tile_max_pix = 64, occl_block_max_pix = 32, occl_tile_max_pix_batch = 128, occl_block_max_pix_batch = 128;
     int small_max_pix = 16, mid_max_pix = 64;
     int grid_percent_single = 100, grid_percent_batch = 200;   // see hz_grid() in hz_kernels.cu
     // Rings (in tiles around the eye's tile) at which the bands end; the last band runs to the edge of the mesh.
     // More bands = more of the mesh culled by what nearer bands drew, but four more kernels each.  A lone view is
-    // latency-bound and gets two bands; the views of a batch overlap each other's latencies and get five (measured
-    // over a grid of viewpoints: +13 % throughput over three, profiles/r02k_*).  The image is the same either way.
+    // latency-bound and gets two bands.  The views of a batch share their launches -- up to 64 views per chain, so a
+    // launch costs next to nothing per view -- and get ten, each reaching about 1.5 times as far as the one before
+    // (measured on 256 distinct viewpoints, profiles/r02s_sweep.jsonl: 13.4k panoramas/s with five bands and 16 views
+    // per chain, 15.6k with ten and 64; the benchmark viewpoint repeated 30.3k -> 33.0k).  The image is the same either way.
     struct Bands { int n; int end[MAX_BANDS]; };
-    Bands bands_single = { 2, { 48, 1 << 20, 0, 0, 0, 0 } };
-    Bands bands_batch  = { 5, { 10, 24, 56, 120, 1 << 20, 0 } };
-    int views_per_set = 16, n_sets_max = 4, graph_instances = 2;
+    Bands bands_single = { 2, { 48, 1 << 20 } };
+    Bands bands_batch  = { 10, { 5, 8, 12, 18, 27, 40, 60, 90, 135, 1 << 20 } };
+    int views_per_set = 64, n_sets_max = 4, graph_instances = 2;
 
     // target
     int W = 0, H = 0;

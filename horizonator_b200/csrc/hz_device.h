@@ -162,7 +162,7 @@ struct HzView
 // queue/counter/band fields: the kernels take a pointer to their variant, so that the same captured CUDA graph can
 // be replayed for every view after one small host->device copy.
 enum { HZ_V_NEAR = 0, HZ_V_FAR = 1, HZ_V_BAND0 = 2 };
-constexpr int HZ_MAX_BANDS = 8;
+constexpr int HZ_MAX_BANDS = 14;
 constexpr int HZ_V_COUNT   = HZ_V_BAND0 + HZ_MAX_BANDS;
 
 // flags of the GPU-side barrier between the ranks of a wedge-sharded panorama (k_peer_barrier)

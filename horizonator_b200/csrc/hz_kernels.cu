@@ -1114,10 +1114,10 @@ cudaError_t hz_launch_near(const HzView& v, const HzView* d_v, int nviews, cudaS
 // Everything a band draws is in the visibility buffer before the next band is tested against it, and within a
 // band whatever has already been drawn helps too.
 
-// The box is walked row by row, HZ_OCCL_FETCH keys per round (so that the L2 round trips overlap); only the upper half
-// of a key is fetched -- epoch and depth sit in its top 27 bits -- and the walk ends at the first round that shows
-// something not nearer.  (Round 2 walked the box as one run of pixels: the wrap to the next row, tested per pixel,
-// cost as much as the fetch and the comparison together.)
+// The box is walked along its longer side, HZ_OCCL_FETCH keys per round (so that the L2 round trips overlap: a lone view
+// waits for every one of them); only the upper half of a key is fetched -- epoch and depth sit in its top 27 bits --
+// and the walk ends at the first round that shows something not nearer.  (The first version walked the box as one run
+// of pixels: the wrap to the next row, tested per pixel, cost as much as the fetch and the comparison together.)
 #ifndef HZ_OCCL_FETCH
 #define HZ_OCCL_FETCH 8            /* (16 and 32 measured no better, lone or batched) */
 #endif
@@ -1127,16 +1127,20 @@ __device__ __forceinline__ bool hz_box_occluded_thread(const HzView& P, const Hz
     if(w * h > max_pix) return false;
     const unsigned int Wt2 = 2u * (unsigned int)(P.x1 - P.x0);                // 32-bit words per row of keys
     // (upper word of the first key of the box)
-    const unsigned int* row = (const unsigned int*)P.vis + ((size_t)B.py0 * Wt2 + 2u * (unsigned int)(B.px0 - P.x0) + 1u);
+    const unsigned int* line = (const unsigned int*)P.vis + ((size_t)B.py0 * Wt2 + 2u * (unsigned int)(B.px0 - P.x0) + 1u);
     const unsigned int qmin_hi = B.qmin << (HZ_KEY_Q_SHIFT - 32);             // the bound, placed like the key's upper word
-    for(int y = 0; y < h; y++, row += Wt2)
+    const bool rows = w >= h;                                                 // lines = rows of the box, or its columns
+    const int n_lines = rows ? h : w, n_along = rows ? w : h;
+    const unsigned int step_line = rows ? Wt2 : 2u, step_along = rows ? 2u : Wt2;
+    for(int l = 0; l < n_lines; l++, line += step_line)
     {
-        for(int x = 0; x < w; x += HZ_OCCL_FETCH)
+        const unsigned int* p = line;
+        for(int a = 0; a < n_along; a += HZ_OCCL_FETCH, p += HZ_OCCL_FETCH * step_along)
         {
             unsigned int farthest = 0;
             #pragma unroll
             for(int u = 0; u < HZ_OCCL_FETCH; u++)
-                if(x + u < w) farthest = max(farthest, __ldcg(row + 2 * (x + u)));
+                if(a + u < n_along) farthest = max(farthest, __ldcg(p + u * step_along));
             // (the upper word holds epoch | depth | the top 5 bits of the triangle number: comparing it whole against
             // the bound with those 5 bits clear is the same test as comparing the top 27 bits)
             if(farthest >= qmin_hi) return false;
@@ -1736,16 +1740,21 @@ __device__ __forceinline__ HzResolve hz_resolve_params(const HzView& P)
     return R;
 }
 
-// 4 pixels per thread and trip: 2x16 B of keys in, 12 B of BGR and 16 B of range out (per destination).  One CTA per
-// row of the target: no index arithmetic to speak of (round 2's version spent more instructions on finding its row,
-// a division, than on its four pixels), the row's tan(elevation) is read once, and the next trip's keys are on their
-// way while this trip's pixels are converted.
+// 4 pixels per thread and trip: 2x16 B of keys in, 12 B of BGR and 16 B of range out (per destination).  A CTA works on
+// one row of the target: no index arithmetic to speak of (the first version spent more instructions on finding its
+// row, a division, than on its four pixels), the row's tan(elevation) is read once, and the next trip's keys are on
+// their way while this trip's pixels are converted.  Two launch shapes: for several views one CTA per row (grid x = row),
+// whose threads take a few trips each -- fewest instructions; for a lone view, which is latency-bound and whose
+// terrain pixels each cost a double-precision square root, the row is spread over as many CTAs as it has groups of
+// 256 (grid x = part of the row, grid z = row): one trip per thread.
 __global__ void __launch_bounds__(HZ_CTA_THREADS)
 k_resolve4(const HzView* __restrict__ V)
 {
     HZ_KERNEL_PROLOGUE(V, P);
     const unsigned int Wt = (unsigned int)(P.x1 - P.x0), gpr = Wt >> 2;        // groups of 4 pixels per row
-    const unsigned int y = blockIdx.x;                                         // GL row (0 = bottom)
+    const bool spread = gridDim.z > 1;
+    const unsigned int y = spread ? blockIdx.z : blockIdx.x;                    // GL row (0 = bottom)
+    const unsigned int stride = spread ? HZ_CTA_THREADS * gridDim.x : HZ_CTA_THREADS;
     const unsigned int ep = P.epoch;
     const float znear = P.znear, zfar = P.zfar;
     const int n_out = P.n_out;
@@ -1755,12 +1764,12 @@ k_resolve4(const HzView* __restrict__ V)
     const ulonglong2* src = (const ulonglong2*)(P.vis + (size_t)y * Wt);
     const size_t dst_row = (size_t)((unsigned int)P.H - 1u - y) * (unsigned int)P.out_stride + (unsigned int)P.out_x0;   // top row first (lib:949-958, 1026-1038)
 
-    unsigned int xg = threadIdx.x;
+    unsigned int xg = threadIdx.x + (spread ? HZ_CTA_THREADS * blockIdx.x : 0u);
     ulonglong2 k01 = make_ulonglong2(0, 0), k23 = k01;
     if(xg < gpr) { k01 = __ldcs(src + 2 * xg); k23 = __ldcs(src + 2 * xg + 1); }   // read once: streaming
     while(xg < gpr)
     {
-        const unsigned int xg_next = xg + HZ_CTA_THREADS;
+        const unsigned int xg_next = xg + stride;
         ulonglong2 n01 = k01, n23 = k23;
         if(xg_next < gpr) { n01 = __ldcs(src + 2 * xg_next); n23 = __ldcs(src + 2 * xg_next + 1); }
 
@@ -1847,7 +1856,12 @@ cudaError_t hz_launch_resolve(const HzView& v, const HzView* d_v, int nviews, cu
 {
     const int Wt = v.x1 - v.x0;
     if(hz_resolve_is_vectorisable(v))
+    {
+        const unsigned int parts = (unsigned)((Wt / 4 + HZ_CTA_THREADS - 1) / HZ_CTA_THREADS);
+        if(nviews == 1 && v.H > 1 && v.H <= 65535)
+            return hz_launch(v, k_resolve4, dim3(parts, 1u, (unsigned)v.H), dim3(HZ_CTA_THREADS), stream, d_v);
         return hz_launch(v, k_resolve4, dim3((unsigned)v.H, (unsigned)nviews), dim3(HZ_CTA_THREADS), stream, d_v);
+    }
     else
     {
         const long long n = (long long)Wt * v.H;

@@ -66,6 +66,7 @@ def main():
                     "panoramas of the benchmark viewpoint, nothing else")
     ap.add_argument("--grid", action="store_true", help="with --once: the distinct viewpoints of the 8x8 grid (C5 flavour) "
                     "instead of the benchmark viewpoint repeated")
+    ap.add_argument("--grid-size", type=int, default=8, help="distinct viewpoints: a g x g grid over the central degree")
     ap.add_argument("configs", nargs="*", default=[""])
     a = ap.parse_args()
     tiles = synth.config2_tiles(os.environ.get("HZ_BENCH_TILES", "/tmp/hz_tiles_c2"))
@@ -76,12 +77,13 @@ def main():
     d_img = torch.empty((Bmax, 600, 3600, 3), dtype=torch.uint8, device="cuda")
     d_rng = torch.empty((Bmax, 600, 3600), dtype=torch.float32, device="cuda")
     if a.once:
-        v = (grid_views() * (1 + a.once // 64))[:a.once] if a.grid else [(C2_LAT, C2_LON, -180.05, 179.95)] * a.once
+        g = grid_views(a.grid_size)
+        v = (g * (1 + a.once // len(g)))[:a.once] if a.grid else [(C2_LAT, C2_LON, -180.05, 179.95)] * a.once
         for _ in range(3):
             h.render_batch_device(v, d_img.data_ptr(), d_rng.data_ptr(), torch.cuda.current_stream().cuda_stream)
             torch.cuda.synchronize()
         return
-    grid = grid_views()
+    grid = grid_views(a.grid_size)
     out = open(a.out, "a") if a.out else None
     for cfg in a.configs:
         env = {"HORIZONATOR_" + k: None for k in KEYS}

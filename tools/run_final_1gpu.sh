@@ -8,8 +8,13 @@ python tools/view_probe.py --grid --out gpurun_out/${T}_views.json > gpurun_out/
 for v in c2 gridworst eye12km zoom10; do
   ncu --metrics $M --clock-control none --csv --log-file gpurun_out/${T}_launch_$v.csv python tools/view_probe.py --ncu $v --reps 2 > /dev/null 2>&1
 done
-ncu --metrics $M --clock-control none --csv --log-file gpurun_out/${T}_launch_batch64.csv python tools/batch_sweep.py --once 64 > /dev/null 2>&1
-# one full capture of the batch configuration's kernels (one chunk of 16 views: 26 kernels; the third call is the timed one)
-ncu --set full --clock-control none --import-source on -k regex:"k_mesh|k_blocks|k_raster|k_tiles|k_big|k_resolve4|k_near|k_prepare" -s 208 -c 26 -o gpurun_out/${T}_batch_chain python tools/batch_sweep.py --once 64 > gpurun_out/${T}_ncu_full.log 2>&1
-HORIZONATOR_TRACE_HOST=1 python tools/batch_sweep.py --reps 10 --batches 16,64,256 --out gpurun_out/${T}_sweep.jsonl "" 2>&1 | tail -2 | tee gpurun_out/${T}_host_trace.txt
+# the batch configuration bench.py times: one call of 256 panoramas = 4 chunks of 64 views x 46 kernels (the third call is listed)
+ncu --metrics $M --clock-control none --csv --log-file gpurun_out/${T}_launch_batch256.csv python tools/batch_sweep.py --once 256 > /dev/null 2>&1
+python tools/launch_table.py gpurun_out/${T}_launch_batch256.csv --last 184 --views 256 --json gpurun_out/${T}_batch_profile.json --source profiles/${T}_launch_batch256.csv | tail -12
+# ... and the same for 256 distinct viewpoints (16x16 grid over the central degree: the C5 workload)
+ncu --metrics $M --clock-control none --csv --log-file gpurun_out/${T}_launch_grid256.csv python tools/batch_sweep.py --once 256 --grid --grid-size 16 > /dev/null 2>&1
+python tools/launch_table.py gpurun_out/${T}_launch_grid256.csv --last 184 --views 256 | tail -12
+# one full capture of the batch configuration's kernels (one chunk of 64 views: 46 kernels of the third call)
+ncu --set full --clock-control none --import-source on -k regex:"k_mesh|k_blocks|k_raster|k_tiles|k_big|k_resolve4|k_near|k_prepare" -s 368 -c 46 -o gpurun_out/${T}_batch_chain python tools/batch_sweep.py --once 256 > gpurun_out/${T}_ncu_full.log 2>&1
+HORIZONATOR_TRACE_HOST=1 python tools/batch_sweep.py --reps 4 --batches 16,64,256 --grid-size 16 --out gpurun_out/${T}_sweep.jsonl "" 2>&1 | tail -2 | tee gpurun_out/${T}_host_trace.txt
 ls -la gpurun_out | tail -20
