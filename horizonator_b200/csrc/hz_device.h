@@ -74,7 +74,7 @@ enum HzStat
 };
 
 // ---- one render ------------------------------------------------------------------------------
-struct HzView
+struct alignas(16) HzView      // (16-byte units: the kernels fetch their copy with 128-bit loads, see HZ_KERNEL_PROLOGUE)
 {
     // terrain (resident in HBM): N x N int16, row j = north index, column i = east index
     const int16_t* mosaic;       // [N + HZ_MESH_PAD][pitch]
@@ -127,7 +127,6 @@ struct HzView
     int grid_percent;            // host only: scale of the device-counted kernels' grids (hz_grid)
     int lod_capable;             // host only: some view of the launch may have lod > 0 (picks k_blocks' instantiation)
     int mid_level;               // host only: the blocks of live tiles are tested in two levels (k_blocks_mid)
-    int no_pdl;                  // host only: launch without programmatic dependent launch (see hz_launch)
     int small_max_pix;           // a lane rasterises bounding boxes up to this many pixels itself; larger ones go to k_big
     int mid_max_pix;             // ... and up to this many where enough lanes of its warp have one (k_raster)
 

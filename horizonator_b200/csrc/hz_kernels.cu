@@ -44,15 +44,15 @@ __device__ __forceinline__ void hz_wait_for_previous_kernel()
 // kernel, so that those reads overlap that kernel's tail instead of following it; afterwards every P.field is a
 // shared-memory read.
 // One launch serves gridDim.y views: view y reads its copy of the launch's variant, HZ_V_COUNT elements per view on.
-// (Every render kernel runs CTAs of HZ_CTA_THREADS threads and the block has fewer words than that: one guarded load
-// per thread.  Written as a loop striding by blockDim.x the compiler does not know the trip count and works it out
-// with an integer division -- some 50 instructions at the head of every warp of every launch.)
+// (Every render kernel runs CTAs of HZ_CTA_THREADS threads and the block has fewer 16-byte units than that: one guarded
+// 128-bit load per thread.  Written as a loop striding by blockDim.x the compiler does not know the trip count and
+// works it out with an integer division -- some 50 instructions at the head of every warp of every launch.)
 #define HZ_CTA_THREADS 256
-static_assert(sizeof(HzView) % 4 == 0 && sizeof(HzView) / 4 <= HZ_CTA_THREADS, "HzView must fit one word per thread");
+static_assert(sizeof(HzView) % 16 == 0 && sizeof(HzView) / 16 <= HZ_CTA_THREADS && alignof(HzView) == 16, "HzView: whole 16-byte units");
 #define HZ_KERNEL_PROLOGUE(V, P)                                                                           \
     __shared__ HzView hz_s_view;                                                                           \
-    if(threadIdx.x < sizeof(HzView) / 4)                                                                   \
-        ((uint32_t*)&hz_s_view)[threadIdx.x] = __ldg((const uint32_t*)((V) + blockIdx.y * HZ_V_COUNT) + threadIdx.x); \
+    if(threadIdx.x < sizeof(HzView) / 16)                                                                  \
+        ((uint4*)&hz_s_view)[threadIdx.x] = __ldg((const uint4*)((V) + blockIdx.y * HZ_V_COUNT) + threadIdx.x); \
     __syncthreads();                                                                                       \
     hz_wait_for_previous_kernel();                                                                         \
     const HzView& P = hz_s_view
@@ -71,13 +71,13 @@ static unsigned int hz_grid(const HzView& v, unsigned int ctas_per_sm, int nview
 }
 
 template <typename... KArgs, typename... Args>
-static cudaError_t hz_launch(const HzView& v, void (*kernel)(KArgs...), dim3 grid, dim3 block, cudaStream_t stream, Args&&... args)
+static cudaError_t hz_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, cudaStream_t stream, Args&&... args)
 {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = 0; cfg.stream = stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = v.no_pdl ? 0 : 1;   // (without it the wait in the prologue is a no-op)
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
     return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
@@ -228,7 +228,7 @@ cudaError_t hz_launch_prepare(const HzView& v, const HzView* d_v, int nviews, cu
     if(nviews > 1) blocks = 148u * 8u / (unsigned int)nviews;
     if(blocks < 16u) blocks = 16u;
     (void)v;
-    return hz_launch(v, k_prepare, dim3(blocks, (unsigned)nviews), dim3(256), stream, d_v);
+    return hz_launch(k_prepare, dim3(blocks, (unsigned)nviews), dim3(256), stream, d_v);
 }
 
 // ================================================================================================
@@ -1097,7 +1097,7 @@ cudaError_t hz_launch_near(const HzView& v, const HzView* d_v, int nviews, cudaS
     const int cap = max(148 * 8 / max(nviews, 1), 37);
     if(ctas > cap) ctas = cap;
     if(ctas < 1) ctas = 1;
-    return hz_launch(v, k_near, dim3(ctas, (unsigned)nviews), dim3(HZ_WARPS_PER_CTA * 32), stream, d_v);
+    return hz_launch(k_near, dim3(ctas, (unsigned)nviews), dim3(HZ_WARPS_PER_CTA * 32), stream, d_v);
 }
 
 // ================================================================================================
@@ -1137,10 +1137,18 @@ __device__ __forceinline__ bool hz_box_occluded_thread(const HzView& P, const Hz
         const unsigned int* p = line;
         for(int a = 0; a < n_along; a += HZ_OCCL_FETCH, p += HZ_OCCL_FETCH * step_along)
         {
+            // all fetches of the round first, none of them conditional (beyond the end of the line the last key is
+            // fetched again).  Whether the loads really go out together hangs on ptxas's register heuristics: one
+            // build of k_tiles came out with 40 instead of 48 registers, two or three loads in flight instead of
+            // eight, and a lone panorama 12 us slower.  The culling kernels therefore say __launch_bounds__(256, 3):
+            // with a stated register budget (85) ptxas schedules for the loads, and uses 48 (tools/sass_census.py).
+            unsigned int k[HZ_OCCL_FETCH];
+            const int last = n_along - 1 - a;
+            #pragma unroll
+            for(int u = 0; u < HZ_OCCL_FETCH; u++) k[u] = __ldcg(p + (unsigned int)min(u, last) * step_along);
             unsigned int farthest = 0;
             #pragma unroll
-            for(int u = 0; u < HZ_OCCL_FETCH; u++)
-                if(a + u < n_along) farthest = max(farthest, __ldcg(p + u * step_along));
+            for(int u = 0; u < HZ_OCCL_FETCH; u++) farthest = max(farthest, k[u]);
             // (the upper word holds epoch | depth | the top 5 bits of the triangle number: comparing it whole against
             // the bound with those 5 bits clear is the same test as comparing the top 27 bits)
             if(farthest >= qmin_hi) return false;
@@ -1189,7 +1197,7 @@ __device__ __forceinline__ void hz_cta_stats4(unsigned int* s4, unsigned int* gl
     if(threadIdx.x < 4 && s4[threadIdx.x]) atomicAdd(global4 + threadIdx.x, s4[threadIdx.x]);
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)
 k_tiles(const HzView* __restrict__ V)
 {
     HZ_KERNEL_PROLOGUE(V, P);
@@ -1237,7 +1245,7 @@ k_tiles(const HzView* __restrict__ V)
 // LOD = false: the reference's mesh (lod = 0 known at compile time: fewer registers, more resident warps); true: the
 // instantiation launched once the caller has opted into a coarser far field, P.lod says how coarse this band is
 template <bool LOD>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)
 k_blocks(const HzView* __restrict__ V)
 {
     HZ_KERNEL_PROLOGUE(V, P);
@@ -1321,7 +1329,7 @@ __device__ __forceinline__ void hz_smem_append(bool on, unsigned int value, unsi
     if(on) list[base + __popc(ballot & ((1u << lane) - 1u))] = value;
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)
 k_blocks_mid(const HzView* __restrict__ V)
 {
     HZ_KERNEL_PROLOGUE(V, P);
@@ -1590,7 +1598,7 @@ k_raster(const HzView* __restrict__ V)
 
 cudaError_t hz_launch_raster(const HzView& v, const HzView* d_v, int nviews, cudaStream_t stream)
 {
-    return hz_launch(v, k_raster, dim3(hz_grid(v, 6, nviews), (unsigned)nviews), dim3(256), stream, d_v);
+    return hz_launch(k_raster, dim3(hz_grid(v, 6, nviews), (unsigned)nviews), dim3(256), stream, d_v);
 }
 
 // `worst_case`: size the tile kernel for any eye position (a CUDA graph is captured once per context and replayed
@@ -1612,11 +1620,11 @@ cudaError_t hz_launch_band(const HzView& v, const HzView* d_v, int nviews, bool 
     const unsigned int ny = (unsigned int)nviews;
     cudaError_t e;
     void (*blocks)(const HzView*) = v.lod_capable ? k_blocks<true> : (v.mid_level ? k_blocks_mid : k_blocks<false>);
-    if((e = hz_launch(v, k_tiles, dim3((unsigned)ctas, ny), dim3(256), stream, d_v)) != cudaSuccess) return e;
-    if((e = hz_launch(v, blocks,  dim3(hz_grid(v, 8, nviews), ny), dim3(256), stream, d_v)) != cudaSuccess) return e;
+    if((e = hz_launch(k_tiles, dim3((unsigned)ctas, ny), dim3(256), stream, d_v)) != cudaSuccess) return e;
+    if((e = hz_launch(blocks,  dim3(hz_grid(v, 8, nviews), ny), dim3(256), stream, d_v)) != cudaSuccess) return e;
     *launches = 4;
-    if((e = hz_launch(v, k_mesh,   dim3(hz_grid(v, 4, nviews), ny), dim3(HZ_WARPS_PER_CTA * 32), stream, d_v)) != cudaSuccess) return e;
-    if((e = hz_launch(v, k_raster, dim3(hz_grid(v, 6, nviews), ny), dim3(256), stream, d_v)) != cudaSuccess) return e;
+    if((e = hz_launch(k_mesh,   dim3(hz_grid(v, 4, nviews), ny), dim3(HZ_WARPS_PER_CTA * 32), stream, d_v)) != cudaSuccess) return e;
+    if((e = hz_launch(k_raster, dim3(hz_grid(v, 6, nviews), ny), dim3(256), stream, d_v)) != cudaSuccess) return e;
     return cudaSuccess;
 }
 
@@ -1698,7 +1706,7 @@ k_big(const HzView* __restrict__ V)
 
 cudaError_t hz_launch_big(const HzView& v, const HzView* d_v, int nviews, cudaStream_t stream)
 {
-    return hz_launch(v, k_big, dim3(hz_grid(v, 8, nviews), (unsigned)nviews), dim3(256), stream, d_v);
+    return hz_launch(k_big, dim3(hz_grid(v, 8, nviews), (unsigned)nviews), dim3(256), stream, d_v);
 }
 
 // ================================================================================================
@@ -1859,13 +1867,13 @@ cudaError_t hz_launch_resolve(const HzView& v, const HzView* d_v, int nviews, cu
     {
         const unsigned int parts = (unsigned)((Wt / 4 + HZ_CTA_THREADS - 1) / HZ_CTA_THREADS);
         if(nviews == 1 && v.H > 1 && v.H <= 65535)
-            return hz_launch(v, k_resolve4, dim3(parts, 1u, (unsigned)v.H), dim3(HZ_CTA_THREADS), stream, d_v);
-        return hz_launch(v, k_resolve4, dim3((unsigned)v.H, (unsigned)nviews), dim3(HZ_CTA_THREADS), stream, d_v);
+            return hz_launch(k_resolve4, dim3(parts, 1u, (unsigned)v.H), dim3(HZ_CTA_THREADS), stream, d_v);
+        return hz_launch(k_resolve4, dim3((unsigned)v.H, (unsigned)nviews), dim3(HZ_CTA_THREADS), stream, d_v);
     }
     else
     {
         const long long n = (long long)Wt * v.H;
-        return hz_launch(v, k_resolve1, dim3((unsigned)((n + 255) / 256), (unsigned)nviews), dim3(256), stream, d_v);
+        return hz_launch(k_resolve1, dim3((unsigned)((n + 255) / 256), (unsigned)nviews), dim3(256), stream, d_v);
     }
 }
 

@@ -21,7 +21,7 @@ from tools import synth  # noqa: E402
 
 C2_LAT, C2_LON = 34.0 + 1.0 / 7200.0, -117.0 + 1.0 / 7200.0
 KEYS = ("LANES", "SETS", "GRID_SCALE_BATCH", "GRID_SCALE", "BANDS", "BANDS_BATCH", "NEAR_RINGS", "OCCL_TILE_PIX",
-        "OCCL_BLOCK_PIX", "OCCL_TILE_PIX_BATCH", "OCCL_BLOCK_PIX_BATCH", "SMALL_PIX", "MID_PIX", "GRAPHS", "GRAPH_INSTANCES", "MID_LEVEL", "MID_LEVEL_BATCH", "PDL", "PDL_BATCH")
+        "OCCL_BLOCK_PIX", "OCCL_TILE_PIX_BATCH", "OCCL_BLOCK_PIX_BATCH", "SMALL_PIX", "MID_PIX", "GRAPHS", "GRAPH_INSTANCES", "MID_LEVEL", "MID_LEVEL_BATCH", "FORK", "FORK_BATCH")
 
 
 def grid_views(g=8):
