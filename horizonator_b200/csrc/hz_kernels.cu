@@ -1533,7 +1533,10 @@ __device__ __forceinline__ void hz_draw_boxes_warp(const HzView& P, const HzTri&
 
 // ---- k_raster: one thread per triangle of a stage's list
 
-__global__ void __launch_bounds__(256, 3)
+#ifndef HZ_RASTER_CTAS
+#define HZ_RASTER_CTAS 3           /* resident CTAs per SM k_raster is compiled for (register budget 80) */
+#endif
+__global__ void __launch_bounds__(256, HZ_RASTER_CTAS)
 k_raster(const HzView* __restrict__ V)
 {
     HZ_KERNEL_PROLOGUE(V, P);

@@ -73,7 +73,7 @@ def main():
     h = hz.horizonator(C2_LAT, C2_LON, 3600, 600, SRTM1=True, dir_dems=tiles, render_radius_m=150000.)
     h.set_zextents(100., 150000.)
     torch.cuda.set_stream(torch.cuda.Stream())
-    Bmax = max(int(b) for b in a.batches.split(","))
+    Bmax = max([int(b) for b in a.batches.split(",")] + [a.once])
     d_img = torch.empty((Bmax, 600, 3600, 3), dtype=torch.uint8, device="cuda")
     d_rng = torch.empty((Bmax, 600, 3600), dtype=torch.float32, device="cuda")
     if a.once:
