@@ -354,7 +354,11 @@ def test_reference_python_binding_on_this_library(hz, tiles_c1):
     {"HORIZONATOR_BANDS": "4,9,20", "HORIZONATOR_NEAR_RINGS": "0"},       # other band structures
     {"HORIZONATOR_BANDS": "100000", "HORIZONATOR_NEAR_RINGS": "5", "HORIZONATOR_SMALL_PIX": "1"},
     {"HORIZONATOR_GRAPHS": "0", "HORIZONATOR_OCCL_TILE_PIX": "0", "HORIZONATOR_OCCL_BLOCK_PIX": "0"},
-], ids=["tri_overflow", "big_overflow", "record_overflow", "bands3", "one_band", "no_graph_no_occlusion"])
+    {"HORIZONATOR_MID_LEVEL": "1", "HORIZONATOR_FORK": "0"},             # two-level block test for lone views too; k_big in line
+    {"HORIZONATOR_MID_LEVEL_BATCH": "0", "HORIZONATOR_FORK_BATCH": "0", "HORIZONATOR_BANDS_BATCH": "10,24,56,120",
+     "HORIZONATOR_OCCL_TILE_PIX_BATCH": "256", "HORIZONATOR_OCCL_BLOCK_PIX_BATCH": "64"},    # the batch defaults the round started with
+], ids=["tri_overflow", "big_overflow", "record_overflow", "bands3", "one_band", "no_graph_no_occlusion", "mid_level_no_fork",
+        "old_batch_defaults"])
 def test_overflow_paths_and_tunables_do_not_change_the_image(hz, tiles_c1, env, monkeypatch):
     """Queue overflows fall back to a slow in-kernel path, and the band/occlusion tunables only move work around:
     the image must be the one the default configuration produces, bit for bit."""
