@@ -6,16 +6,17 @@
 //   k_prepare  (render)  clear visibility keys, per-column/row metre tables    glClear, lib:896; vertex.glsl:128-130
 //   k_near     (render)  the tiles around the eye: mesh generation, projection,  lib:496-508 (index pattern), vertex.glsl,
 //                        exact integer cull -> list of triangles                  GL cull/clip
-//   k_tiles, k_blocks, k_mesh (render)
-//                        the rest of the mesh in bands outwards from the eye: whole tiles, then blocks, are dropped
-//                        by conservative tests (beyond zfar, no pixel centre of the target inside their screen box,
-//                        everything in that box already nearer in the visibility buffer); what is left goes
-//                        through the same exact stages as in k_near -> list of triangles
+//   k_tiles, k_blocks / k_blocks_mid, k_mesh (render)
+//                        the rest of the mesh in bands outwards from the eye: whole tiles, then blocks (for the views
+//                        of a batch with 8x8-cell squares in between: k_blocks_mid), are dropped by conservative tests
+//                        (beyond zfar, no pixel centre of the target inside their screen box, everything in that box
+//                        already nearer in the visibility buffer); what is left goes through the same exact stages
+//                        as in k_near -> list of triangles
 //   k_raster   (render)  set-up, rasterisation and depth test of a list,          vertex.glsl, geometry.glsl, GL raster,
 //                        one thread per triangle                                  depth test, fragment.glsl
 //   k_big      (render)  the triangles with large bounding boxes, one warp per 32-column sub-box (lane = column)
 //   k_peer_barrier (multi-GPU)  barrier between the ranks of a wedge-sharded panorama through peer memory
-//   k_resolve  (render)  keys -> BGR8 image + float range image, top row first lib:936-1048
+//   k_resolve4 / k_resolve1 (render)  keys -> BGR8 image + float range image, top row first   lib:936-1048
 //   k_horizon  (extra)   range image -> per-column topmost terrain row and its range
 //
 // The mesh is never materialised: triangle t of the reference's index buffer is (cell = t>>1, half = t&1)
