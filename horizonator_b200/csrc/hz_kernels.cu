@@ -1678,7 +1678,11 @@ hz_draw_subbox(const HzView& P, const HzTri& T, int x0, int x1, int y0, int y1, 
     }
 }
 
-__global__ void __launch_bounds__(256)
+#ifndef HZ_BIG_CTAS
+#define HZ_BIG_CTAS 4              /* resident CTAs per SM k_big is compiled for: 64 registers (left to itself ptxas takes 72, */
+                                   /* 3 CTAs: measured 2 % slower in batches, 4 % in the 5-degree zoom) */
+#endif
+__global__ void __launch_bounds__(256, HZ_BIG_CTAS)
 k_big(const HzView* __restrict__ V)
 {
     HZ_KERNEL_PROLOGUE(V, P);
