@@ -1535,7 +1535,8 @@ __device__ __forceinline__ void hz_draw_boxes_warp(const HzView& P, const HzTri&
 // ---- k_raster: one thread per triangle of a stage's list
 
 #ifndef HZ_RASTER_CTAS
-#define HZ_RASTER_CTAS 3           /* resident CTAs per SM k_raster is compiled for (register budget 80) */
+#define HZ_RASTER_CTAS 3           /* resident CTAs per SM k_raster is compiled for (register budget 80; measured: 2 CTAs, 108 */
+                                   /* registers and no spills, 3-4 % slower; 4 CTAs, 64 registers, +1.5 % in batches, lone views 1 % slower) */
 #endif
 __global__ void __launch_bounds__(256, HZ_RASTER_CTAS)
 k_raster(const HzView* __restrict__ V)
