@@ -30,7 +30,10 @@ typedef struct
 
 /* Renders n views with the context's current z extents and image size (W x H).
  * d_images: n*H*W*3 bytes (B,G,R, top row first) or NULL; d_ranges: n*H*W floats or NULL;
- * both DEVICE pointers.  Leaves the context's own eye/azimuth state as it was. */
+ * both DEVICE pointers.  Leaves the context's own eye/azimuth state as it was.
+ * The views are rendered in chunks that share every kernel launch (8 to 64 views each, spread over up to 4 streams):
+ * throughput grows with n up to about 256 views per call (measured at 3600x600: 16 views 16 k panoramas/s, 64 views
+ * 26 k, 256 views 33 k); each view in flight takes ~140 MB of scratch, allocated on first use. */
 bool horizonator_render_batch_device(const horizonator_context_t* ctx,
                                      int n, const horizonator_view_t* views,
                                      void* d_images, void* d_ranges,
